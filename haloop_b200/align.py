@@ -1,0 +1,33 @@
+"""Alignment paths: greedy argmax decode (ha/recognizer.py:48-59) and CTC Viterbi forced alignment."""
+import torch
+
+from . import ops
+
+
+def greedy_decode(log_probs, input_lengths=None):
+    """TemporalClassifier.decode's hot part (ha/recognizer.py:51-57) on the GPU.
+
+    log_probs (N,T,C).  Returns (hypotheses, output_lengths, alignments, scores) where alignments
+    and scores are torch.max(dim=-1) bit for bit (first index wins ties), hypotheses is the
+    collapsed (unique_consecutive, blanks dropped) label sequence padded with -1 to (N,T) and
+    output_lengths its lengths.  input_lengths=None reproduces the reference, which ignores lengths
+    (ha/recognizer.py:51); pass them to stop the collapse at each utterance's end.
+    """
+    ali, sc, hyp, hl = ops.greedy_decode(log_probs, input_lengths)
+    return hyp, hl, ali, sc
+
+
+def greedy_decode_nested(log_probs, input_lengths=None):
+    """Same, with hypotheses as the nested tensor the reference returns (ha/recognizer.py:52-55)."""
+    hyp, hl, ali, sc = greedy_decode(log_probs, input_lengths)
+    lens = hl.tolist()
+    nested = torch.nested.nested_tensor([hyp[i, :n] for i, n in enumerate(lens)])
+    return nested, hl, ali, sc, None
+
+
+def ctc_viterbi_align(log_probs, targets, input_lengths, target_lengths):
+    """Best CTC alignment (max-semiring of ha/ctc.py:144-167; not in the reference).
+
+    log_probs (T,N,C) -> (alignment (N,T) int64 class per frame, -1 beyond the input length;
+    score (N,) log-prob of that path)."""
+    return ops.ctc_viterbi(log_probs, targets, input_lengths, target_lengths)

@@ -1,0 +1,475 @@
+// api.cu — the C ABI of libha_b200.so (include/ha_b200.h): argument checks, workspace carving,
+// kernel selection and launches.  No allocation, no synchronisation, no global state.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/ha_b200.h"
+#include "align.cuh"
+#include "common.cuh"
+#include "ctc.cuh"
+#include "rnnt.cuh"
+#include "star.cuh"
+
+using namespace hab;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(HA_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return HA_OK;
+}
+
+constexpr size_t kMaxSmem = 227 * 1024;       // opt-in dynamic shared memory per CTA on sm_100
+constexpr size_t kRowSmemTarget = 100 * 1024; // two row-kernel CTAs per SM
+
+template <typename K>
+int set_smem(K kernel, size_t bytes, const char* what) {
+    if (bytes > kMaxSmem) return fail(HA_ERR_UNSUPPORTED_SHAPE, "%s needs %zu B of shared memory", what, bytes);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(HA_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    return HA_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// warps per CTA and ring depth for a warp-per-row streaming kernel with `row_floats` per stage
+struct RowCfg { int nwarps, nstage, rows_per_warp; size_t smem; bool ok; };
+
+template <typename F>
+RowCfg pick_row_cfg(int T, F smem_of /* (nstage, nwarps) -> bytes */) {
+    RowCfg c{8, 4, 1, 0, false};
+    for (int nw = 8; nw >= 1 && !c.ok; nw >>= 1) {
+        for (int ns = 4; ns >= 2; --ns) {
+            size_t b = smem_of(ns, nw);
+            if (b <= kRowSmemTarget || (ns == 2 && b <= kMaxSmem)) { c.nwarps = nw; c.nstage = ns; c.smem = b; c.ok = true; break; }
+        }
+    }
+    int rpw = (T + c.nwarps * 4 - 1) / (c.nwarps * 4);
+    c.rows_per_warp = rpw < 1 ? 1 : (rpw > 16 ? 16 : rpw);
+    return c;
+}
+
+int common_checks(const void* x, int T, int N, int V, int S, const void* ws, size_t ws_bytes, size_t need) {
+    if (!x || !ws) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+    if (T <= 0 || N <= 0 || V <= 0 || S < 0) return fail(HA_ERR_INVALID_ARGUMENT, "bad sizes T=%d N=%d V=%d S=%d", T, N, V, S);
+    if (N > 65535) return fail(HA_ERR_UNSUPPORTED_SHAPE, "N=%d > 65535", N);
+    if (!aligned16(ws)) return fail(HA_ERR_INVALID_ARGUMENT, "workspace must be 16-byte aligned");
+    if (ws_bytes < need) return fail(HA_ERR_WORKSPACE_TOO_SMALL, "workspace %zu < %zu", ws_bytes, need);
+    return HA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ha_b200_version(void) { return 100; }
+const char* ha_b200_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------- CTC ---
+size_t ha_ctc_workspace_bytes(int T, int N, int V, int S) {
+    (void)V;
+    if (T <= 0 || N <= 0 || S < 0) return 0;
+    return ctc_ws_layout(T, N, S).total;
+}
+
+static int ctc_trellis_launch(const TrellisParams& tp, int nslot_max, int N, cudaStream_t st) {
+    TrellisParams p = tp;
+    // ring depth: as deep as shared memory allows, at most 8
+    int ns = 8;
+    while (ns >= 2 && (size_t)4 * trellis_warp_bytes(p.E, p.SPX, ns) > 200 * 1024) --ns;
+    if (ns < 2) return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length too large for the trellis kernel");
+    p.nstage = ns;
+    p.warp_bytes = trellis_warp_bytes(p.E, p.SPX, ns);
+    const size_t smem = (size_t)4 * p.warp_bytes;
+    const dim3 grid((N + 1) / 2), block(128);
+    int rc;
+#define HAB_LAUNCH_TRELLIS(JJ)                                                        \
+    do {                                                                              \
+        if ((rc = set_smem(ctc_trellis_kernel<JJ>, smem, "ctc_trellis"))) return rc; \
+        ctc_trellis_kernel<JJ><<<grid, block, smem, st>>>(p);                         \
+    } while (0)
+    if (nslot_max <= 1) HAB_LAUNCH_TRELLIS(1);
+    else if (nslot_max <= 2) HAB_LAUNCH_TRELLIS(2);
+    else if (nslot_max <= 4) HAB_LAUNCH_TRELLIS(4);
+    else if (nslot_max <= 8) HAB_LAUNCH_TRELLIS(8);
+    else if (nslot_max <= 12) HAB_LAUNCH_TRELLIS(12);
+    else if (nslot_max <= 16) HAB_LAUNCH_TRELLIS(16);
+    else if (nslot_max <= 24) HAB_LAUNCH_TRELLIS(24);
+    else if (nslot_max <= 32) HAB_LAUNCH_TRELLIS(32);
+    else return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length > 1023 is not supported");
+#undef HAB_LAUNCH_TRELLIS
+    return check_launch("ctc_trellis_kernel");
+}
+
+int ha_ctc_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
+               const void* targets, int64_t tgt_stride, int S, int targets_i64,
+               const void* in_len, const void* tgt_len, int lengths_i64,
+               int from_logits, float* loss, void* ws, size_t ws_bytes, void* stream) {
+    const CtcWs w = ctc_ws_layout(T, N, S);
+    int rc = common_checks(x, T, N, V, S, ws, ws_bytes, w.total);
+    if (rc) return rc;
+    if (!in_len || !tgt_len || !loss || (S > 0 && !targets)) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* base = (unsigned char*)ws;
+
+    PrepParams pp{};
+    pp.targets = targets; pp.tgt_stride = tgt_stride; pp.tgt64 = targets_i64;
+    pp.in_len = in_len; pp.tgt_len = tgt_len; pp.len64 = lengths_i64;
+    pp.T = T; pp.N = N; pp.V = V; pp.S = S; pp.Sp = w.Sp;
+    pp.meta = (int4*)(base + w.meta); pp.order = (int*)(base + w.order);
+    pp.tgt = (int*)(base + w.tgt); pp.dupnext = (int*)(base + w.dupnext); pp.star = 0;
+    ctc_prep_kernel<<<N, 128, (size_t)(S > 0 ? S : 1) * 4, st>>>(pp);
+    if ((rc = check_launch("ctc_prep_kernel"))) return rc;
+
+    RowsParams rp{};
+    rp.x = x; rp.sx_t = sx_t; rp.sx_n = sx_n; rp.T = T; rp.N = N; rp.V = V;
+    rp.meta = pp.meta; rp.tgt = pp.tgt; rp.Sp = w.Sp;
+    rp.lse2 = (float*)(base + w.lse2); rp.em = (float*)(base + w.em); rp.E = w.E;
+    rp.from_logits = from_logits;
+    const bool vec = (V % 4 == 0) && aligned16(x) && (sx_t % 4 == 0) && (sx_n % 4 == 0);
+    rp.use_bulk = vec ? 1 : 0;
+    RowCfg rc_ = pick_row_cfg(T, [&](int ns, int nw) { return rows_smem_bytes(w.Sp, V, ns, nw); });
+    if (!rc_.ok) return fail(HA_ERR_UNSUPPORTED_SHAPE, "V=%d too large for the row kernel", V);
+    rp.nstage = rc_.nstage; rp.nwarps = rc_.nwarps; rp.rows_per_warp = rc_.rows_per_warp;
+    {
+        const dim3 grid((T + rp.nwarps * rp.rows_per_warp - 1) / (rp.nwarps * rp.rows_per_warp), N);
+        const dim3 block(32 * rp.nwarps);
+        if (vec) {
+            if ((rc = set_smem(ctc_rows_kernel<true>, rc_.smem, "ctc_rows"))) return rc;
+            ctc_rows_kernel<true><<<grid, block, rc_.smem, st>>>(rp);
+        } else {
+            if ((rc = set_smem(ctc_rows_kernel<false>, rc_.smem, "ctc_rows"))) return rc;
+            ctc_rows_kernel<false><<<grid, block, rc_.smem, st>>>(rp);
+        }
+        if ((rc = check_launch("ctc_rows_kernel"))) return rc;
+    }
+
+    TrellisParams tp{};
+    tp.T = T; tp.N = N; tp.meta = pp.meta; tp.order = pp.order; tp.tgt = pp.tgt; tp.Sp = w.Sp;
+    tp.em = rp.em; tp.E = w.E; tp.tr = (float*)(base + w.tr); tp.SPX = w.SPX; tp.JWp = w.JWp;
+    tp.loss = loss; tp.loss_ws = (float*)(base + w.loss);
+    if ((rc = ctc_trellis_launch(tp, (S + 1 + 31) / 32, N, st))) return rc;
+
+    return HA_OK;
+}
+
+int ha_ctc_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V, int S,
+               const float* grad_loss, int from_logits,
+               float* gx, int64_t sg_t, int64_t sg_n,
+               void* ws, size_t ws_bytes, void* stream) {
+    const CtcWs w = ctc_ws_layout(T, N, S);
+    int rc = common_checks(gx, T, N, V, S, ws, ws_bytes, w.total);
+    if (rc) return rc;
+    if (!grad_loss || (from_logits && !x)) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* base = (unsigned char*)ws;
+    GradParams gp{};
+    gp.x = x; gp.sx_t = sx_t; gp.sx_n = sx_n; gp.gx = gx; gp.sg_t = sg_t; gp.sg_n = sg_n;
+    gp.T = T; gp.N = N; gp.V = V;
+    gp.meta = (const int4*)(base + w.meta); gp.tgt = (const int*)(base + w.tgt);
+    gp.dupnext = (const int*)(base + w.dupnext); gp.Sp = w.Sp;
+    gp.lse2 = (const float*)(base + w.lse2); gp.occ = (const float*)(base + w.em); gp.E = w.E;
+    gp.gout = grad_loss; gp.loss = (const float*)(base + w.loss); gp.from_logits = from_logits;
+    const bool vec = (V % 4 == 0) && aligned16(gx) && (sg_t % 4 == 0) && (sg_n % 4 == 0) &&
+                     (!from_logits || (aligned16(x) && (sx_t % 4 == 0) && (sx_n % 4 == 0)));
+    gp.use_bulk = vec ? 1 : 0;
+    RowCfg rc_ = pick_row_cfg(T, [&](int ns, int nw) { return grad_smem_bytes(w.Sp, V, w.E, ns, nw); });
+    if (!rc_.ok) return fail(HA_ERR_UNSUPPORTED_SHAPE, "V=%d too large for the gradient kernel", V);
+    gp.nstage = rc_.nstage; gp.nwarps = rc_.nwarps; gp.rows_per_warp = rc_.rows_per_warp;
+    const dim3 grid((T + gp.nwarps * gp.rows_per_warp - 1) / (gp.nwarps * gp.rows_per_warp), N);
+    const dim3 block(32 * gp.nwarps);
+    if (vec) {
+        if ((rc = set_smem(ctc_grad_kernel<true>, rc_.smem, "ctc_grad"))) return rc;
+        ctc_grad_kernel<true><<<grid, block, rc_.smem, st>>>(gp);
+    } else {
+        if ((rc = set_smem(ctc_grad_kernel<false>, rc_.smem, "ctc_grad"))) return rc;
+        ctc_grad_kernel<false><<<grid, block, rc_.smem, st>>>(gp);
+    }
+    return check_launch("ctc_grad_kernel");
+}
+
+// -------------------------------------------------------------------------------- star-CTC ---
+size_t ha_star_workspace_bytes(int T, int N, int V, int S) {
+    (void)V;
+    if (T <= 0 || N <= 0 || S < 0) return 0;
+    return star_ws_layout(T, N, S).total;
+}
+
+static int star_trellis_launch(const StarTrellisParams& tp, int nslot_max, int N, cudaStream_t st) {
+    StarTrellisParams p = tp;
+    int ns = 8;
+    while (ns >= 2 && (size_t)4 * trellis_warp_bytes(p.E, p.SPX, ns) > 200 * 1024) --ns;
+    if (ns < 2) return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length too large for the star trellis kernel");
+    p.nstage = ns;
+    p.warp_bytes = trellis_warp_bytes(p.E, p.SPX, ns);
+    const size_t smem = (size_t)4 * p.warp_bytes;
+    const dim3 grid((N + 1) / 2), block(128);
+    int rc;
+#define HAB_LAUNCH_STAR(JJ)                                                            \
+    do {                                                                               \
+        if ((rc = set_smem(star_trellis_kernel<JJ>, smem, "star_trellis"))) return rc; \
+        star_trellis_kernel<JJ><<<grid, block, smem, st>>>(p);                         \
+    } while (0)
+    if (nslot_max <= 1) HAB_LAUNCH_STAR(1);
+    else if (nslot_max <= 2) HAB_LAUNCH_STAR(2);
+    else if (nslot_max <= 4) HAB_LAUNCH_STAR(4);
+    else if (nslot_max <= 8) HAB_LAUNCH_STAR(8);
+    else if (nslot_max <= 12) HAB_LAUNCH_STAR(12);
+    else if (nslot_max <= 16) HAB_LAUNCH_STAR(16);
+    else return fail(HA_ERR_UNSUPPORTED_SHAPE, "star-CTC target length > 511 is not supported");
+#undef HAB_LAUNCH_STAR
+    return check_launch("star_trellis_kernel");
+}
+
+int ha_star_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
+                const void* targets, int64_t tgt_stride, int S, int targets_i64,
+                const void* in_len, const void* tgt_len, int lengths_i64,
+                float star_penalty, int from_logits, float* loss,
+                void* ws, size_t ws_bytes, void* stream) {
+    const StarWs w = star_ws_layout(T, N, S);
+    int rc = common_checks(x, T, N, V, S, ws, ws_bytes, w.total);
+    if (rc) return rc;
+    if (!in_len || !tgt_len || !loss || (S > 0 && !targets)) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+    if (V < 2) return fail(HA_ERR_UNSUPPORTED_SHAPE, "star-CTC needs at least one non-blank class");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* base = (unsigned char*)ws;
+
+    PrepParams pp{};
+    pp.targets = targets; pp.tgt_stride = tgt_stride; pp.tgt64 = targets_i64;
+    pp.in_len = in_len; pp.tgt_len = tgt_len; pp.len64 = lengths_i64;
+    pp.T = T; pp.N = N; pp.V = V; pp.S = S; pp.Sp = w.Sp;
+    pp.meta = (int4*)(base + w.meta); pp.order = (int*)(base + w.order);
+    pp.tgt = (int*)(base + w.tgt); pp.dupnext = (int*)(base + w.dupnext); pp.star = 1;
+    ctc_prep_kernel<<<N, 128, (size_t)(S > 0 ? S : 1) * 4, st>>>(pp);
+    if ((rc = check_launch("ctc_prep_kernel"))) return rc;
+
+    StarRowsParams rp{};
+    rp.x = x; rp.sx_t = sx_t; rp.sx_n = sx_n; rp.T = T; rp.N = N; rp.V = V; rp.S = S;
+    rp.meta = pp.meta; rp.tgt = pp.tgt; rp.Sp = w.Sp;
+    rp.lse2 = (float*)(base + w.lse2); rp.em = (float*)(base + w.em); rp.E = w.E;
+    rp.from_logits = from_logits;
+    const bool vec = (V % 4 == 0) && aligned16(x) && (sx_t % 4 == 0) && (sx_n % 4 == 0);
+    rp.use_bulk = vec ? 1 : 0;
+    RowCfg rc_ = pick_row_cfg(T, [&](int ns, int nw) { return rows_smem_bytes(w.Sp, V, ns, nw); });
+    if (!rc_.ok) return fail(HA_ERR_UNSUPPORTED_SHAPE, "V=%d too large for the row kernel", V);
+    rp.nstage = rc_.nstage; rp.nwarps = rc_.nwarps; rp.rows_per_warp = rc_.rows_per_warp;
+    {
+        const dim3 grid((T + rp.nwarps * rp.rows_per_warp - 1) / (rp.nwarps * rp.rows_per_warp), N);
+        const dim3 block(32 * rp.nwarps);
+        if (vec) {
+            if ((rc = set_smem(star_rows_kernel<true>, rc_.smem, "star_rows"))) return rc;
+            star_rows_kernel<true><<<grid, block, rc_.smem, st>>>(rp);
+        } else {
+            if ((rc = set_smem(star_rows_kernel<false>, rc_.smem, "star_rows"))) return rc;
+            star_rows_kernel<false><<<grid, block, rc_.smem, st>>>(rp);
+        }
+        if ((rc = check_launch("star_rows_kernel"))) return rc;
+    }
+
+    StarTrellisParams tp{};
+    tp.T = T; tp.N = N; tp.S = S; tp.meta = pp.meta; tp.order = pp.order; tp.tgt = pp.tgt; tp.Sp = w.Sp;
+    tp.em = rp.em; tp.E = w.E; tp.tr = (float*)(base + w.tr); tp.SPX = w.SPX; tp.JWp = w.JWp;
+    tp.loss = loss; tp.loss_ws = (float*)(base + w.loss);
+    tp.pen2 = star_penalty * kLog2e;
+    return star_trellis_launch(tp, (S + 1 + 31) / 32, N, st);
+}
+
+int ha_star_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V, int S,
+                const float* grad_loss, int from_logits,
+                float* gx, int64_t sg_t, int64_t sg_n,
+                void* ws, size_t ws_bytes, void* stream) {
+    const StarWs w = star_ws_layout(T, N, S);
+    int rc = common_checks(gx, T, N, V, S, ws, ws_bytes, w.total);
+    if (rc) return rc;
+    if (!grad_loss || !x) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* base = (unsigned char*)ws;
+    StarGradParams gp{};
+    gp.x = x; gp.sx_t = sx_t; gp.sx_n = sx_n; gp.gx = gx; gp.sg_t = sg_t; gp.sg_n = sg_n;
+    gp.T = T; gp.N = N; gp.V = V; gp.S = S;
+    gp.meta = (const int4*)(base + w.meta); gp.tgt = (const int*)(base + w.tgt);
+    gp.dupnext = (const int*)(base + w.dupnext); gp.Sp = w.Sp;
+    gp.lse2 = (const float*)(base + w.lse2); gp.occ = (const float*)(base + w.em); gp.E = w.E;
+    gp.gout = grad_loss; gp.loss = (const float*)(base + w.loss); gp.from_logits = from_logits;
+    const bool vec = (V % 4 == 0) && aligned16(gx) && (sg_t % 4 == 0) && (sg_n % 4 == 0) &&
+                     aligned16(x) && (sx_t % 4 == 0) && (sx_n % 4 == 0);
+    gp.use_bulk = vec ? 1 : 0;
+    RowCfg rc_ = pick_row_cfg(T, [&](int ns, int nw) { return grad_smem_bytes(w.Sp, V, w.E, ns, nw); });
+    if (!rc_.ok) return fail(HA_ERR_UNSUPPORTED_SHAPE, "V=%d too large for the gradient kernel", V);
+    gp.nstage = rc_.nstage; gp.nwarps = rc_.nwarps; gp.rows_per_warp = rc_.rows_per_warp;
+    const dim3 grid((T + gp.nwarps * gp.rows_per_warp - 1) / (gp.nwarps * gp.rows_per_warp), N);
+    const dim3 block(32 * gp.nwarps);
+    if (vec) {
+        if ((rc = set_smem(star_grad_kernel<true>, rc_.smem, "star_grad"))) return rc;
+        star_grad_kernel<true><<<grid, block, rc_.smem, st>>>(gp);
+    } else {
+        if ((rc = set_smem(star_grad_kernel<false>, rc_.smem, "star_grad"))) return rc;
+        star_grad_kernel<false><<<grid, block, rc_.smem, st>>>(gp);
+    }
+    return check_launch("star_grad_kernel");
+}
+
+// ----------------------------------------------------------------------------------- RNN-T ---
+size_t ha_rnnt_workspace_bytes(int N, int T, int U1, int V) {
+    (void)V;
+    if (T <= 0 || N <= 0 || U1 <= 0) return 0;
+    return rnnt_ws_layout(N, T, U1).total;
+}
+
+int ha_rnnt_fwd(const float* joint, int N, int T, int U1, int V,
+                const void* targets, int64_t tgt_stride, int targets_i64,
+                const void* in_len, const void* tgt_len, int lengths_i64,
+                int from_logits, float* loss, void* ws, size_t ws_bytes, void* stream) {
+    if (U1 <= 0) return fail(HA_ERR_INVALID_ARGUMENT, "U1 must be >= 1");
+    const RnntWs w = rnnt_ws_layout(N, T, U1);
+    int rc = common_checks(joint, T, N, V, U1 - 1, ws, ws_bytes, w.total);
+    if (rc) return rc;
+    if (!in_len || !tgt_len || !loss || (U1 > 1 && !targets)) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+    if (U1 > 1024) return fail(HA_ERR_UNSUPPORTED_SHAPE, "U+1 > 1024 is not supported");
+    if ((long long)T * U1 >= (1ll << 31)) return fail(HA_ERR_UNSUPPORTED_SHAPE, "T*(U+1) too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* base = (unsigned char*)ws;
+
+    RnntPrepParams pp{};
+    pp.targets = targets; pp.tgt_stride = tgt_stride; pp.tgt64 = targets_i64;
+    pp.in_len = in_len; pp.tgt_len = tgt_len; pp.len64 = lengths_i64;
+    pp.N = N; pp.T = T; pp.U = U1 - 1; pp.V = V; pp.Up = w.Up;
+    pp.meta = (int4*)(base + w.meta); pp.tgt = (int*)(base + w.tgt);
+    rnnt_prep_kernel<<<N, 128, 0, st>>>(pp);
+    if ((rc = check_launch("rnnt_prep_kernel"))) return rc;
+
+    RnntRowsParams rp{};
+    rp.x = joint; rp.N = N; rp.T = T; rp.U1 = U1; rp.V = V;
+    rp.meta = pp.meta; rp.tgt = pp.tgt; rp.Up = w.Up;
+    rp.lse2 = (float*)(base + w.lse2); rp.bl = (float*)(base + w.bl); rp.lb = (float*)(base + w.lb); rp.D = w.D;
+    rp.from_logits = from_logits;
+    const bool vec = (V % 4 == 0) && aligned16(joint);
+    rp.use_bulk = vec ? 1 : 0;
+    const int nodes = T * U1;
+    RowCfg rc_ = pick_row_cfg(nodes, [&](int ns, int nw) { return rnnt_rows_smem_bytes(V, ns, nw); });
+    if (!rc_.ok) return fail(HA_ERR_UNSUPPORTED_SHAPE, "V=%d too large for the row kernel", V);
+    rp.nstage = rc_.nstage; rp.nwarps = rc_.nwarps; rp.rows_per_warp = rc_.rows_per_warp;
+    {
+        const dim3 grid((nodes + rp.nwarps * rp.rows_per_warp - 1) / (rp.nwarps * rp.rows_per_warp), N);
+        const dim3 block(32 * rp.nwarps);
+        if (vec) {
+            if ((rc = set_smem(rnnt_rows_kernel<true>, rc_.smem, "rnnt_rows"))) return rc;
+            rnnt_rows_kernel<true><<<grid, block, rc_.smem, st>>>(rp);
+        } else {
+            if ((rc = set_smem(rnnt_rows_kernel<false>, rc_.smem, "rnnt_rows"))) return rc;
+            rnnt_rows_kernel<false><<<grid, block, rc_.smem, st>>>(rp);
+        }
+        if ((rc = check_launch("rnnt_rows_kernel"))) return rc;
+    }
+
+    RnntLatticeParams lp{};
+    lp.N = N; lp.T = T; lp.U1 = U1; lp.D = w.D; lp.meta = pp.meta;
+    lp.bl = rp.bl; lp.lb = rp.lb; lp.alpha = (double*)(base + w.alpha); lp.occ = (float2*)(base + w.occ);
+    lp.loss = loss; lp.loss_ws = (float*)(base + w.loss);
+    rnnt_lattice_kernel<<<N, round_up(U1, 32), 0, st>>>(lp);
+    return check_launch("rnnt_lattice_kernel");
+}
+
+int ha_rnnt_bwd(const float* joint, int N, int T, int U1, int V,
+                const float* grad_loss, int from_logits, float* gjoint,
+                void* ws, size_t ws_bytes, void* stream) {
+    if (U1 <= 0) return fail(HA_ERR_INVALID_ARGUMENT, "U1 must be >= 1");
+    const RnntWs w = rnnt_ws_layout(N, T, U1);
+    int rc = common_checks(gjoint, T, N, V, U1 - 1, ws, ws_bytes, w.total);
+    if (rc) return rc;
+    if (!grad_loss || (from_logits && !joint)) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* base = (unsigned char*)ws;
+    RnntGradParams gp{};
+    gp.x = joint; gp.gx = gjoint; gp.N = N; gp.T = T; gp.U1 = U1; gp.V = V;
+    gp.meta = (const int4*)(base + w.meta); gp.tgt = (const int*)(base + w.tgt); gp.Up = w.Up;
+    gp.lse2 = (const float*)(base + w.lse2); gp.occ = (const float2*)(base + w.occ); gp.D = w.D;
+    gp.gout = grad_loss; gp.loss = (const float*)(base + w.loss); gp.from_logits = from_logits;
+    const bool vec = (V % 4 == 0) && aligned16(gjoint) && (!from_logits || aligned16(joint));
+    gp.use_bulk = vec ? 1 : 0;
+    const int nodes = T * U1;
+    RowCfg rc_ = pick_row_cfg(nodes, [&](int ns, int nw) { return rnnt_rows_smem_bytes(V, ns, nw); });
+    if (!rc_.ok) return fail(HA_ERR_UNSUPPORTED_SHAPE, "V=%d too large for the gradient kernel", V);
+    gp.nstage = rc_.nstage; gp.nwarps = rc_.nwarps; gp.rows_per_warp = rc_.rows_per_warp;
+    {
+        const dim3 grid((nodes + 63) / 64, N);
+        rnnt_zero_kernel<<<grid, 256, 0, st>>>(gp);
+        if ((rc = check_launch("rnnt_zero_kernel"))) return rc;
+    }
+    const dim3 grid((nodes + gp.nwarps * gp.rows_per_warp - 1) / (gp.nwarps * gp.rows_per_warp), N);
+    const dim3 block(32 * gp.nwarps);
+    if (vec) {
+        if ((rc = set_smem(rnnt_grad_kernel<true>, rc_.smem, "rnnt_grad"))) return rc;
+        rnnt_grad_kernel<true><<<grid, block, rc_.smem, st>>>(gp);
+    } else {
+        if ((rc = set_smem(rnnt_grad_kernel<false>, rc_.smem, "rnnt_grad"))) return rc;
+        rnnt_grad_kernel<false><<<grid, block, rc_.smem, st>>>(gp);
+    }
+    return check_launch("rnnt_grad_kernel");
+}
+
+// ------------------------------------------------------------------------------- alignment ---
+int ha_greedy_decode(const float* x, int64_t sx_n, int64_t sx_t, int N, int T, int V,
+                     const void* in_len, int lengths_i64,
+                     int64_t* alignment, float* score, int64_t* hyp, int64_t* hyp_len, void* stream) {
+    if (!x || !alignment || !score || !hyp || !hyp_len) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+    if (N <= 0 || T <= 0 || V <= 0 || N > 65535) return fail(HA_ERR_INVALID_ARGUMENT, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    GreedyParams p{};
+    p.x = x; p.sx_n = sx_n; p.sx_t = sx_t; p.N = N; p.T = T; p.V = V;
+    p.in_len = in_len; p.len64 = lengths_i64;
+    p.alignment = (long long*)alignment; p.score = score; p.hyp = (long long*)hyp; p.hyp_len = (long long*)hyp_len;
+    greedy_argmax_kernel<<<dim3((T + 7) / 8, N), 256, 0, st>>>(p);
+    int rc = check_launch("greedy_argmax_kernel");
+    if (rc) return rc;
+    greedy_collapse_kernel<<<N, 256, 0, st>>>(p);
+    return check_launch("greedy_collapse_kernel");
+}
+
+size_t ha_ctc_viterbi_workspace_bytes(int T, int N, int V, int S) {
+    (void)V;
+    if (T <= 0 || N <= 0 || S < 0) return 0;
+    return viterbi_ws_layout(T, N, S).total;
+}
+
+int ha_ctc_viterbi(const float* lp, int64_t sx_t, int64_t sx_n, int T, int N, int V,
+                   const void* targets, int64_t tgt_stride, int S, int targets_i64,
+                   const void* in_len, const void* tgt_len, int lengths_i64,
+                   int64_t* alignment, float* score, void* ws, size_t ws_bytes, void* stream) {
+    const ViterbiWs w = viterbi_ws_layout(T, N, S);
+    int rc = common_checks(lp, T, N, V, S, ws, ws_bytes, w.total);
+    if (rc) return rc;
+    if (!in_len || !tgt_len || !alignment || !score || (S > 0 && !targets)) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* base = (unsigned char*)ws;
+    PrepParams pp{};
+    pp.targets = targets; pp.tgt_stride = tgt_stride; pp.tgt64 = targets_i64;
+    pp.in_len = in_len; pp.tgt_len = tgt_len; pp.len64 = lengths_i64;
+    pp.T = T; pp.N = N; pp.V = V; pp.S = S; pp.Sp = w.Sp;
+    pp.meta = (int4*)(base + w.meta); pp.order = (int*)(base + w.order);
+    pp.tgt = (int*)(base + w.tgt); pp.dupnext = (int*)(base + w.dupnext); pp.star = 0;
+    ctc_prep_kernel<<<N, 128, (size_t)(S > 0 ? S : 1) * 4, st>>>(pp);
+    if ((rc = check_launch("ctc_prep_kernel"))) return rc;
+    ViterbiParams vp{};
+    vp.lp = lp; vp.sx_t = sx_t; vp.sx_n = sx_n; vp.T = T; vp.N = N; vp.V = V; vp.S_ = w.S_;
+    vp.meta = pp.meta; vp.tgt = pp.tgt; vp.Sp = w.Sp; vp.bp = base + w.bp;
+    vp.alignment = (long long*)alignment; vp.score = score;
+    const size_t smem = (size_t)w.S_ * 12;
+    if ((rc = set_smem(ctc_viterbi_kernel, smem, "ctc_viterbi"))) return rc;
+    ctc_viterbi_kernel<<<N, 256, smem, st>>>(vp);
+    return check_launch("ctc_viterbi_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,317 @@
+"""PyTorch custom ops (with autograd) over the C-ABI library: the thin shim between the
+reference-named Python functions and libha_b200.so.
+
+Forward ops return (loss, workspace); the workspace tensor is the saved-for-backward state
+(row log-sum-exps and posterior occupancies), never a second B x T x V tensor.  Backward ops
+return the gradient with the SAME strides as the input view (ha/recognizer.py:70,78 hands the loss
+a permuted view of an (N,T,C) buffer), multiplied by the per-utterance grad_output.
+"""
+import torch
+
+from . import _lib
+
+_F32 = torch.float32
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _check_cuda_f32(x, name):
+    if not x.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor: haloop_b200 has no CPU path")
+    if x.dtype != _F32:
+        raise ValueError(f"{name} must be float32 (got {x.dtype}); the reference forces fp32 too "
+                         "(ha/recognizer.py:68-70)")
+
+
+def _idx(t, device, name):
+    """int32/int64 index tensor on `device`, contiguous; returns (tensor, is64)."""
+    if t.dtype not in (torch.int32, torch.int64):
+        if t.is_floating_point() or t.dtype == torch.bool:
+            raise ValueError(f"{name} must be an integer tensor")
+        t = t.to(torch.int64)
+    if t.device != device:
+        t = t.to(device)
+    return t.contiguous(), int(t.dtype == torch.int64)
+
+
+def _unit_class_stride(x):
+    return x if x.stride(-1) == 1 else x.contiguous()
+
+
+def _empty_like_strided(x):
+    """Fresh tensor with x's shape and strides (when x is dense), else contiguous."""
+    if x.is_contiguous() or x.numel() == 0:
+        return torch.empty_like(x, memory_format=torch.contiguous_format)
+    try:
+        # dense + non-overlapping views (a permuted contiguous buffer) keep their strides
+        perm = sorted(range(x.dim()), key=lambda d: (-x.stride(d), d))
+        dense = True
+        expect = 1
+        for d in reversed(perm):
+            if x.size(d) != 1 and x.stride(d) != expect:
+                dense = False
+                break
+            expect *= x.size(d)
+        if dense:
+            return torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device)
+    except Exception:
+        pass
+    return torch.empty(x.shape, dtype=x.dtype, device=x.device)
+
+
+# ------------------------------------------------------------------------------------------- CTC
+@torch.library.custom_op("ha_b200::ctc_fwd", mutates_args=())
+def ctc_fwd(x: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, tgt_len: torch.Tensor,
+            from_logits: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    _check_cuda_f32(x, "emissions")
+    x = _unit_class_stride(x)
+    T, N, V = x.shape
+    tg, tg64 = _idx(targets, x.device, "targets")
+    il, il64 = _idx(in_len, x.device, "emission_lengths")
+    tl, tl64 = _idx(tgt_len, x.device, "target_lengths")
+    if il64 != tl64:
+        il, tl, il64 = il.to(torch.int64), tl.to(torch.int64), 1
+    if tg.dim() != 2 or tg.shape[0] != N or il.shape != (N,) or tl.shape != (N,):
+        raise ValueError("expected targets (N,S), emission_lengths (N,), target_lengths (N,)")
+    S = tg.shape[1]
+    L = _lib.lib()
+    nbytes = L.ha_ctc_workspace_bytes(T, N, V, S)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    loss = torch.empty(N, dtype=_F32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.ha_ctc_fwd(x.data_ptr(), x.stride(0), x.stride(1), T, N, V,
+                          tg.data_ptr() if S else None, tg.stride(0) if S else 0, S, tg64,
+                          il.data_ptr(), tl.data_ptr(), il64, int(from_logits),
+                          loss.data_ptr(), ws.data_ptr(), nbytes, _stream(x))
+    _lib.check(rc, "ha_ctc_fwd")
+    return loss, ws
+
+
+@ctc_fwd.register_fake
+def _(x, targets, in_len, tgt_len, from_logits):
+    T, N, V = x.shape
+    return x.new_empty(N), x.new_empty(1, dtype=torch.uint8)
+
+
+@torch.library.custom_op("ha_b200::ctc_bwd", mutates_args=())
+def ctc_bwd(x: torch.Tensor, ws: torch.Tensor, grad_loss: torch.Tensor, S: int,
+            from_logits: bool) -> torch.Tensor:
+    xs = _unit_class_stride(x)
+    T, N, V = xs.shape
+    gx = _empty_like_strided(xs)
+    g = grad_loss.to(_F32).contiguous()
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        rc = L.ha_ctc_bwd(xs.data_ptr(), xs.stride(0), xs.stride(1), T, N, V, S, g.data_ptr(),
+                          int(from_logits), gx.data_ptr(), gx.stride(0), gx.stride(1),
+                          ws.data_ptr(), ws.numel(), _stream(x))
+    _lib.check(rc, "ha_ctc_bwd")
+    return gx
+
+
+@ctc_bwd.register_fake
+def _(x, ws, grad_loss, S, from_logits):
+    return torch.empty_like(x)
+
+
+def _ctc_setup(ctx, inputs, output):
+    x, targets, _, _, from_logits = inputs
+    _, ws = output
+    ctx.save_for_backward(x, ws)
+    ctx.S = targets.shape[1]
+    ctx.from_logits = from_logits
+
+
+def _ctc_backward(ctx, grad_loss, _grad_ws):
+    x, ws = ctx.saved_tensors
+    return ctc_bwd(x, ws, grad_loss, ctx.S, ctx.from_logits), None, None, None, None
+
+
+ctc_fwd.register_autograd(_ctc_backward, setup_context=_ctc_setup)
+
+
+# -------------------------------------------------------------------------------------- star-CTC
+@torch.library.custom_op("ha_b200::star_fwd", mutates_args=())
+def star_fwd(x: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, tgt_len: torch.Tensor,
+             star_penalty: float, from_logits: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    _check_cuda_f32(x, "emissions")
+    x = _unit_class_stride(x)
+    T, N, V = x.shape
+    tg, tg64 = _idx(targets, x.device, "targets")
+    il, il64 = _idx(in_len, x.device, "emission_lengths")
+    tl, tl64 = _idx(tgt_len, x.device, "target_lengths")
+    if il64 != tl64:
+        il, tl, il64 = il.to(torch.int64), tl.to(torch.int64), 1
+    if tg.dim() != 2 or tg.shape[0] != N or il.shape != (N,) or tl.shape != (N,):
+        raise ValueError("expected targets (N,S), emission_lengths (N,), target_lengths (N,)")
+    S = tg.shape[1]
+    L = _lib.lib()
+    nbytes = L.ha_star_workspace_bytes(T, N, V, S)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    loss = torch.empty(N, dtype=_F32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.ha_star_fwd(x.data_ptr(), x.stride(0), x.stride(1), T, N, V,
+                           tg.data_ptr() if S else None, tg.stride(0) if S else 0, S, tg64,
+                           il.data_ptr(), tl.data_ptr(), il64, float(star_penalty), int(from_logits),
+                           loss.data_ptr(), ws.data_ptr(), nbytes, _stream(x))
+    _lib.check(rc, "ha_star_fwd")
+    return loss, ws
+
+
+@star_fwd.register_fake
+def _(x, targets, in_len, tgt_len, star_penalty, from_logits):
+    T, N, V = x.shape
+    return x.new_empty(N), x.new_empty(1, dtype=torch.uint8)
+
+
+@torch.library.custom_op("ha_b200::star_bwd", mutates_args=())
+def star_bwd(x: torch.Tensor, ws: torch.Tensor, grad_loss: torch.Tensor, S: int,
+             from_logits: bool) -> torch.Tensor:
+    xs = _unit_class_stride(x)
+    T, N, V = xs.shape
+    gx = _empty_like_strided(xs)
+    g = grad_loss.to(_F32).contiguous()
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        rc = L.ha_star_bwd(xs.data_ptr(), xs.stride(0), xs.stride(1), T, N, V, S, g.data_ptr(),
+                           int(from_logits), gx.data_ptr(), gx.stride(0), gx.stride(1),
+                           ws.data_ptr(), ws.numel(), _stream(x))
+    _lib.check(rc, "ha_star_bwd")
+    return gx
+
+
+@star_bwd.register_fake
+def _(x, ws, grad_loss, S, from_logits):
+    return torch.empty_like(x)
+
+
+def _star_setup(ctx, inputs, output):
+    x, targets, _, _, _, from_logits = inputs
+    _, ws = output
+    ctx.save_for_backward(x, ws)
+    ctx.S = targets.shape[1]
+    ctx.from_logits = from_logits
+
+
+def _star_backward(ctx, grad_loss, _grad_ws):
+    x, ws = ctx.saved_tensors
+    return star_bwd(x, ws, grad_loss, ctx.S, ctx.from_logits), None, None, None, None, None
+
+
+star_fwd.register_autograd(_star_backward, setup_context=_star_setup)
+
+
+# ----------------------------------------------------------------------------------------- RNN-T
+@torch.library.custom_op("ha_b200::rnnt_fwd", mutates_args=())
+def rnnt_fwd(joint: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, tgt_len: torch.Tensor,
+             from_logits: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    _check_cuda_f32(joint, "joint")
+    joint = joint.contiguous()
+    N, T, U1, V = joint.shape
+    tg, tg64 = _idx(targets, joint.device, "targets")
+    il, il64 = _idx(in_len, joint.device, "joint_lengths")
+    tl, tl64 = _idx(tgt_len, joint.device, "target_lengths")
+    if il64 != tl64:
+        il, tl, il64 = il.to(torch.int64), tl.to(torch.int64), 1
+    if tg.dim() != 2 or tg.shape != (N, U1 - 1) or il.shape != (N,) or tl.shape != (N,):
+        raise ValueError("expected joint (N,T,U+1,V), targets (N,U), joint_lengths (N,), target_lengths (N,)")
+    L = _lib.lib()
+    nbytes = L.ha_rnnt_workspace_bytes(N, T, U1, V)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=joint.device)
+    loss = torch.empty(N, dtype=_F32, device=joint.device)
+    with torch.cuda.device(joint.device):
+        rc = L.ha_rnnt_fwd(joint.data_ptr(), N, T, U1, V,
+                           tg.data_ptr() if U1 > 1 else None, tg.stride(0) if U1 > 1 else 0, tg64,
+                           il.data_ptr(), tl.data_ptr(), il64, int(from_logits),
+                           loss.data_ptr(), ws.data_ptr(), nbytes, _stream(joint))
+    _lib.check(rc, "ha_rnnt_fwd")
+    return loss, ws
+
+
+@rnnt_fwd.register_fake
+def _(joint, targets, in_len, tgt_len, from_logits):
+    return joint.new_empty(joint.shape[0]), joint.new_empty(1, dtype=torch.uint8)
+
+
+@torch.library.custom_op("ha_b200::rnnt_bwd", mutates_args=())
+def rnnt_bwd(joint: torch.Tensor, ws: torch.Tensor, grad_loss: torch.Tensor,
+             from_logits: bool) -> torch.Tensor:
+    joint = joint.contiguous()
+    N, T, U1, V = joint.shape
+    gj = torch.empty_like(joint, memory_format=torch.contiguous_format)
+    g = grad_loss.to(_F32).contiguous()
+    L = _lib.lib()
+    with torch.cuda.device(joint.device):
+        rc = L.ha_rnnt_bwd(joint.data_ptr(), N, T, U1, V, g.data_ptr(), int(from_logits), gj.data_ptr(),
+                           ws.data_ptr(), ws.numel(), _stream(joint))
+    _lib.check(rc, "ha_rnnt_bwd")
+    return gj
+
+
+@rnnt_bwd.register_fake
+def _(joint, ws, grad_loss, from_logits):
+    return torch.empty_like(joint)
+
+
+def _rnnt_setup(ctx, inputs, output):
+    joint, _, _, _, from_logits = inputs
+    _, ws = output
+    ctx.save_for_backward(joint, ws)
+    ctx.from_logits = from_logits
+
+
+def _rnnt_backward(ctx, grad_loss, _grad_ws):
+    joint, ws = ctx.saved_tensors
+    return rnnt_bwd(joint, ws, grad_loss, ctx.from_logits), None, None, None, None
+
+
+rnnt_fwd.register_autograd(_rnnt_backward, setup_context=_rnnt_setup)
+
+
+# ------------------------------------------------------------------------------------- alignment
+def greedy_decode(x, in_len=None):
+    """x (N,T,V) -> alignment (N,T) i64, score (N,T) f32, hyp (N,T) i64 padded with -1, hyp_len (N,)."""
+    _check_cuda_f32(x, "log_probs")
+    x = _unit_class_stride(x)
+    N, T, V = x.shape
+    dev = x.device
+    ali = torch.empty(N, T, dtype=torch.int64, device=dev)
+    sc = torch.empty(N, T, dtype=_F32, device=dev)
+    hyp = torch.empty(N, T, dtype=torch.int64, device=dev)
+    hl = torch.empty(N, dtype=torch.int64, device=dev)
+    il, il64 = (None, 0) if in_len is None else _idx(in_len, dev, "input_lengths")
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        rc = L.ha_greedy_decode(x.data_ptr(), x.stride(0), x.stride(1), N, T, V,
+                                il.data_ptr() if il is not None else None, il64,
+                                ali.data_ptr(), sc.data_ptr(), hyp.data_ptr(), hl.data_ptr(), _stream(x))
+    _lib.check(rc, "ha_greedy_decode")
+    return ali, sc, hyp, hl
+
+
+def ctc_viterbi(lp, targets, in_len, tgt_len):
+    """lp (T,N,V) log-probs -> alignment (N,T) i64 (class per frame, -1 padded), score (N,) f32."""
+    _check_cuda_f32(lp, "log_probs")
+    lp = _unit_class_stride(lp)
+    T, N, V = lp.shape
+    dev = lp.device
+    tg, tg64 = _idx(targets, dev, "targets")
+    il, il64 = _idx(in_len, dev, "input_lengths")
+    tl, tl64 = _idx(tgt_len, dev, "target_lengths")
+    if il64 != tl64:
+        il, tl, il64 = il.to(torch.int64), tl.to(torch.int64), 1
+    S = tg.shape[1]
+    L = _lib.lib()
+    nbytes = L.ha_ctc_viterbi_workspace_bytes(T, N, V, S)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ali = torch.empty(N, T, dtype=torch.int64, device=dev)
+    sc = torch.empty(N, dtype=_F32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.ha_ctc_viterbi(lp.data_ptr(), lp.stride(0), lp.stride(1), T, N, V,
+                              tg.data_ptr() if S else None, tg.stride(0) if S else 0, S, tg64,
+                              il.data_ptr(), tl.data_ptr(), il64,
+                              ali.data_ptr(), sc.data_ptr(), ws.data_ptr(), nbytes, _stream(lp))
+    _lib.check(rc, "ha_ctc_viterbi")
+    return ali, sc

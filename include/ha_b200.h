@@ -1,0 +1,100 @@
+/*
+ * ha_b200.h — C ABI of libha_b200.so: B200 (sm_100a) alignment losses for haloop.
+ *
+ * The reference (proger/haloop) has no FFI: its hot path is four Python functions imported by
+ * name into ha/recognizer.py:6-8.  Each entry point below names the reference function whose
+ * arithmetic it replaces; haloop_b200/ops.py binds them with ctypes and registers them as
+ * PyTorch custom ops with autograd (INTEGRATION.md shows the binding and the call-site patch).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; no torch types
+ *   - the library never allocates, never synchronises and keeps no global state: scratch and
+ *     saved-for-backward state live in a caller-owned workspace sized by *_workspace_bytes()
+ *   - `stream` is a cudaStream_t passed as void*
+ *   - return value: 0 = ok, otherwise an HA_ERR_* code; ha_b200_last_error() (thread-local)
+ *     describes it
+ *   - logits/log-probs are float32 with unit stride along the class axis; strides are in elements
+ *   - targets are 0-padded, blank = 0 (ha/ctc.py:123, ha/star.py:85, ha/transducer.py:190)
+ *   - from_logits = 1: input is raw logits, the op applies log-softmax itself and the gradient is
+ *     d loss / d logits = (softmax - occupancy) * grad_loss.  from_logits = 0: input is log-probs
+ *     used as they are (the reference signature) and the gradient is what autograd yields at the
+ *     reference's `emissions` / `joint` argument, -occupancy * grad_loss.
+ *   - an infeasible alignment returns loss = +inf and a zero gradient (the reference returns
+ *     ~3.4e38, ha/ctc.py:135); an utterance with out-of-range lengths or labels returns NaN.
+ */
+#ifndef HA_B200_H
+#define HA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HA_OK 0
+#define HA_ERR_INVALID_ARGUMENT 1
+#define HA_ERR_WORKSPACE_TOO_SMALL 2
+#define HA_ERR_UNSUPPORTED_SHAPE 3
+#define HA_ERR_CUDA 4
+
+int ha_b200_version(void);
+const char* ha_b200_last_error(void);
+
+/* ---- CTC: ha/ctc.py:110-174 ctc_forward_score3 (+ its autograd backward) ------------------- */
+size_t ha_ctc_workspace_bytes(int T, int N, int V, int S);
+/* x (T,N,V) viewed through (sx_t, sx_n, 1); targets (N,S) int32/int64; loss (N) */
+int ha_ctc_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
+               const void* targets, int64_t tgt_stride, int S, int targets_i64,
+               const void* in_len, const void* tgt_len, int lengths_i64,
+               int from_logits, float* loss, void* ws, size_t ws_bytes, void* stream);
+/* needs the workspace ha_ctc_fwd filled for the same x; grad_loss (N); gx strided like x */
+int ha_ctc_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V, int S,
+               const float* grad_loss, int from_logits,
+               float* gx, int64_t sg_t, int64_t sg_n,
+               void* ws, size_t ws_bytes, void* stream);
+
+/* ---- star-CTC: ha/star.py:65-163 star_ctc_forward_score (+ intersperse_stars :8-49) --------- */
+size_t ha_star_workspace_bytes(int T, int N, int V, int S);
+int ha_star_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
+                const void* targets, int64_t tgt_stride, int S, int targets_i64,
+                const void* in_len, const void* tgt_len, int lengths_i64,
+                float star_penalty, int from_logits, float* loss,
+                void* ws, size_t ws_bytes, void* stream);
+int ha_star_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V, int S,
+                const float* grad_loss, int from_logits,
+                float* gx, int64_t sg_t, int64_t sg_n,
+                void* ws, size_t ws_bytes, void* stream);
+
+/* ---- RNN-T: ha/transducer.py:175-205 transducer_forward_score (+ ha/scan.py:88-126) --------- */
+size_t ha_rnnt_workspace_bytes(int N, int T, int U1, int V);
+/* joint (N,T,U1,V) contiguous, U1 = U+1; targets (N,U) */
+int ha_rnnt_fwd(const float* joint, int N, int T, int U1, int V,
+                const void* targets, int64_t tgt_stride, int targets_i64,
+                const void* in_len, const void* tgt_len, int lengths_i64,
+                int from_logits, float* loss, void* ws, size_t ws_bytes, void* stream);
+int ha_rnnt_bwd(const float* joint, int N, int T, int U1, int V,
+                const float* grad_loss, int from_logits, float* gjoint,
+                void* ws, size_t ws_bytes, void* stream);
+
+/* ---- greedy alignment: ha/recognizer.py:48-59 TemporalClassifier.decode -------------------- */
+/* x (N,T,V) through (sx_n, sx_t, 1).  alignment (N,T) int64 = per-frame argmax (first index wins,
+ * as torch.max), score (N,T) = the max, hyp (N,T) int64 = collapsed repeats with blanks dropped,
+ * padded with -1, hyp_len (N) int64.  in_len may be NULL (the reference ignores lengths, :51). */
+int ha_greedy_decode(const float* x, int64_t sx_n, int64_t sx_t, int N, int T, int V,
+                     const void* in_len, int lengths_i64,
+                     int64_t* alignment, float* score, int64_t* hyp, int64_t* hyp_len, void* stream);
+
+/* ---- CTC Viterbi forced alignment (max-semiring of ha/ctc.py:144-167; not in the reference) - */
+size_t ha_ctc_viterbi_workspace_bytes(int T, int N, int V, int S);
+/* lp (T,N,V) log-probs through (sx_t, sx_n, 1); alignment (N,T) int64 class per frame (-1 beyond
+ * the input length); score (N) best-path log-prob */
+int ha_ctc_viterbi(const float* lp, int64_t sx_t, int64_t sx_n, int T, int N, int V,
+                   const void* targets, int64_t tgt_stride, int S, int targets_i64,
+                   const void* in_len, const void* tgt_len, int lengths_i64,
+                   int64_t* alignment, float* score, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HA_B200_H */

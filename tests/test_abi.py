@@ -1,0 +1,77 @@
+"""CPU-side checks of the C-ABI boundary: the library builds/loads and exports exactly what
+include/ha_b200.h declares; argument validation works without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from haloop_b200 import _lib
+
+
+@pytest.fixture(scope="module")
+def L():
+    _lib.build()
+    return _lib.lib()
+
+
+def _declared():
+    src = open(_lib.HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ha_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(L):
+    names = _declared()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/ha_b200.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+
+
+def test_version_and_workspace_queries(L):
+    assert L.ha_b200_version() >= 100
+    # BASELINE configs: workspaces are a fraction of the logits they serve and fit 180 GB easily
+    assert 0 < L.ha_ctc_workspace_bytes(1500, 256, 1024, 300) < 2 * 1500 * 256 * 1024 * 4
+    assert 0 < L.ha_star_workspace_bytes(1000, 128, 512, 200) < 4 * 1000 * 128 * 512 * 4
+    assert 0 < L.ha_rnnt_workspace_bytes(32, 500, 101, 1024) < 32 * 500 * 101 * 1024 * 4 // 50
+    assert L.ha_ctc_workspace_bytes(0, 1, 1, 1) == 0
+
+
+def test_argument_validation_without_gpu(L):
+    """Bad arguments are rejected before any CUDA call, with a message."""
+    rc = L.ha_ctc_fwd(None, 0, 0, 4, 2, 8, None, 0, 2, 1, None, None, 1, 1, None, None, 0, None)
+    assert rc == 1
+    assert b"null" in L.ha_b200_last_error()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.addressof(buf)
+    p = (p + 15) // 16 * 16
+    rc = L.ha_ctc_fwd(p, 16, 8, 4, 2, 8, p, 2, 2, 1, p, p, 1, 1, p, p, 16, None)
+    assert rc == 2 and b"workspace" in L.ha_b200_last_error()
+    rc = L.ha_rnnt_fwd(p, 2, 4, 0, 8, p, 1, 1, p, p, 1, 1, p, p, 16, None)
+    assert rc == 1
+
+
+def test_no_fallback_off_gpu():
+    """The product path refuses CPU tensors instead of silently computing elsewhere."""
+    import torch
+    import haloop_b200 as hb
+    x = torch.zeros(4, 2, 8)
+    tg = torch.ones(2, 2, dtype=torch.long)
+    with pytest.raises(ValueError, match="CUDA"):
+        hb.ctc_forward_score3(x, tg, torch.tensor([4, 4]), torch.tensor([2, 2]))
+    with pytest.raises(ValueError, match="CUDA"):
+        hb.star_ctc_forward_score(x, tg, torch.tensor([4, 4]), torch.tensor([2, 2]))
+    with pytest.raises(ValueError, match="CUDA"):
+        hb.transducer_forward_score(torch.zeros(2, 4, 3, 8), tg, torch.tensor([4, 4]), torch.tensor([2, 2]))
+
+
+def test_product_does_not_import_oracle():
+    """Nothing under haloop_b200/ may import, link or execute the oracle."""
+    root = os.path.dirname(_lib.HEADER).replace("include", "haloop_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                for pat in (r"import\s+oracle", r"from\s+oracle", r"libha_oracle", r"ha_oracle_", r"oracle\."):
+                    assert not re.search(pat, txt), f"{f} references the oracle ({pat})"

@@ -1,0 +1,309 @@
+"""Parity of the CUDA hot path (through the Python API -> custom op -> C ABI) against the golden
+vectors of the reference (float64 runs of ha/ctc.py, ha/star.py, ha/transducer.py) and against the
+CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): loss within 1e-4 relative, logit gradients within 1e-5
+absolute, both against float64 gold; the reference's own float32 deviation (golden *_ref32_*) is
+2e-6 .. 8e-5 on the same cases, i.e. the bar is tighter than the reference's fp32 noise floor.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden_path
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+GRAD_ATOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def hb():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import haloop_b200
+    return haloop_b200
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _cases(kind):
+    return [os.path.basename(p)[:-4] for p in sorted(glob.glob(os.path.join(GOLDEN, kind + "_*.npz")))]
+
+
+def _x_of(d, shape):
+    if "x" in d:
+        return torch.from_numpy(d["x"])
+    g = torch.Generator().manual_seed(int(d["seed"]))
+    x = torch.randn(*shape, generator=g, dtype=torch.float32) * float(d["x_scale"] if "x_scale" in d else 1.0)
+    assert abs(float(x.double().sum()) - float(d["x_checksum"])) < 1e-6, "torch RNG drifted"
+    return x
+
+
+def _assert_loss(loss, ref):
+    loss = loss.detach().double().cpu().numpy()
+    np.testing.assert_allclose(loss, ref, rtol=LOSS_RTOL)
+
+
+def _grad_check(grad, d, batch_axis):
+    g = grad.double().cpu().numpy()
+    if "grad" in d:
+        err = np.abs(g - d["grad"]).max()
+    else:
+        err = np.abs(np.take(g, d["grad_rows"], axis=batch_axis) - d["grad_sub"]).max()
+        assert abs(np.abs(g).sum() / float(d["grad_abs_sum"]) - 1) < 1e-5
+    assert err < GRAD_ATOL, f"grad abs err {err:.3e} (reference fp32 itself: {float(d['ref32_grad_dev']):.3e})"
+
+
+@pytest.mark.parametrize("name", _cases("ctc"))
+def test_ctc_golden(hb, name):
+    d = np.load(golden_path(name))
+    T, N, V, S = d["shape"]
+    x = _x_of(d, (T, N, V)).to(dev()).requires_grad_(True)
+    tg, il, tl = (torch.from_numpy(d[k]).to(dev()) for k in ("targets", "in_len", "tgt_len"))
+    loss = hb.ctc_forward_score3(x, tg, il, tl, from_logits=True)
+    _assert_loss(loss, d["loss"])
+    assert abs(float(hb.ctc_reduce_mean(loss, tl)) / float(d["reduce_mean"]) - 1) < LOSS_RTOL
+    loss.sum().backward()
+    _grad_check(x.grad, d, 1)
+    for n in range(N):
+        assert not x.grad[int(il[n]):, n].any(), "rows beyond the input length must be exactly zero"
+    if "lpgrad" in d:
+        # reference contract: log-probs in, autograd gives -occupancy at the emissions boundary
+        lp = _x_of(d, (T, N, V)).double().log_softmax(-1).float().to(dev()).requires_grad_(True)
+        l2 = hb.ctc_forward_score3(lp, tg, il, tl)
+        _assert_loss(l2, d["loss"])
+        l2.sum().backward()
+        assert np.abs(lp.grad.double().cpu().numpy() - d["lpgrad"]).max() < GRAD_ATOL
+
+
+@pytest.mark.parametrize("name", _cases("star"))
+def test_star_golden(hb, name):
+    d = np.load(golden_path(name))
+    T, N, V, S = d["shape"]
+    pen = float(d["star_penalty"])
+    x = _x_of(d, (T, N, V)).to(dev()).requires_grad_(True)
+    tg, il, tl = (torch.from_numpy(d[k]).to(dev()) for k in ("targets", "in_len", "tgt_len"))
+    loss = hb.star_ctc_forward_score(x, tg, il, tl, star_penalty=pen, from_logits=True)
+    _assert_loss(loss, d["loss"])
+    loss.sum().backward()
+    _grad_check(x.grad, d, 1)
+    if "lpgrad" in d:
+        lp = _x_of(d, (T, N, V)).double().log_softmax(-1).float().to(dev()).requires_grad_(True)
+        l2 = hb.star_ctc_forward_score(lp, tg, il, tl, star_penalty=pen)
+        _assert_loss(l2, d["loss"])
+        l2.sum().backward()
+        assert np.abs(lp.grad.double().cpu().numpy() - d["lpgrad"]).max() < GRAD_ATOL
+
+
+@pytest.mark.parametrize("name", _cases("rnnt"))
+def test_rnnt_golden(hb, name):
+    d = np.load(golden_path(name))
+    N, T, U, V = d["shape"]
+    x = _x_of(d, (N, T, U + 1, V)).to(dev()).requires_grad_(True)
+    tg, il, tl = (torch.from_numpy(d[k]).to(dev()) for k in ("targets", "in_len", "tgt_len"))
+    loss = hb.transducer_forward_score(x, tg, il, tl, from_logits=True)
+    _assert_loss(loss, d["loss"])
+    loss.sum().backward()
+    _grad_check(x.grad, d, 0)
+    if "lpgrad" in d:
+        lp = _x_of(d, (N, T, U + 1, V)).double().log_softmax(-1).float().to(dev()).requires_grad_(True)
+        l2 = hb.transducer_forward_score(lp, tg.int(), il.int(), tl.int())     # int32, as ha/transducer.py:217-218
+        _assert_loss(l2, d["loss"])
+        l2.sum().backward()
+        assert np.abs(lp.grad.double().cpu().numpy() - d["lpgrad"]).max() < GRAD_ATOL
+
+
+def test_kat_appendix_d(hb):
+    d = np.load(golden_path("kat_appendix_d"))
+    x = torch.from_numpy(d["x"]).float().to(dev())
+    tg, il, tl = (torch.from_numpy(d[k]).to(dev()) for k in ("targets", "in_len", "tgt_len"))
+    _assert_loss(hb.ctc_forward_score3(x, tg, il, tl, from_logits=True), d["ctc_loss"])
+    _assert_loss(hb.star_ctc_forward_score(x, tg, il, tl, star_penalty=-0.5, from_logits=True), d["star_loss"])
+    j = torch.from_numpy(d["joint"]).float().to(dev())
+    tg, il, tl = (torch.from_numpy(d[k]).to(dev()) for k in ("rnnt_targets", "rnnt_in_len", "rnnt_tgt_len"))
+    _assert_loss(hb.transducer_forward_score(j, tg, il, tl, from_logits=True), d["rnnt_loss"])
+
+
+def _rand_ctc(seed, T, N, V, S, var=True, scale=1.0, repeats=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(T, N, V, generator=g) * scale
+    tg = torch.randint(1, 3 if repeats else V, (N, S), generator=g)
+    if var:
+        il = torch.randint(T // 2, T + 1, (N,), generator=g); il[0] = T
+        tl = torch.randint(S // 2, S + 1, (N,), generator=g); tl[0] = S
+    else:
+        il = torch.full((N,), T); tl = torch.full((N,), S)
+    return x, tg, il, tl
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(T=300, N=5, V=64, S=100),                 # 4 slots
+    dict(T=700, N=3, V=128, S=300),                # 10 slots -> J=12 (the C2 target length)
+    dict(T=97, N=7, V=37, S=11),                   # V % 4 != 0: scalar (non-bulk) path
+    dict(T=400, N=4, V=32, S=40, scale=5.0),       # peaky posteriors
+    dict(T=260, N=4, V=8, S=120, repeats=True),    # many repeated labels, T barely feasible for some
+])
+def test_ctc_vs_oracle(hb, oracle, cfg):
+    c = dict(cfg)
+    x, tg, il, tl = _rand_ctc(100 + c["T"], c.pop("T"), c.pop("N"), c.pop("V"), c.pop("S"), **c)
+    go = torch.linspace(0.5, 2.0, x.shape[1])
+    ol, og = oracle.ctc(x.numpy(), tg.numpy(), il.numpy(), tl.numpy(), grad_out=go.numpy())
+    xd = x.to(dev()).requires_grad_(True)
+    loss = hb.ctc_forward_score3(xd, tg.to(dev()), il.to(dev()), tl.to(dev()), from_logits=True)
+    (loss * go.to(dev())).sum().backward()
+    lo = loss.detach().double().cpu().numpy()
+    fin = np.isfinite(ol)
+    np.testing.assert_allclose(lo[fin], ol[fin], rtol=LOSS_RTOL)
+    assert (np.isinf(lo) == np.isinf(ol)).all()
+    err = np.abs(xd.grad.double().cpu().numpy() - og).max()
+    assert err < GRAD_ATOL, f"{err:.3e}"
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(T=300, N=5, V=64, S=60),
+    dict(T=500, N=3, V=128, S=200),                # 7 slots -> J=8 (the C3 target length)
+    dict(T=97, N=6, V=37, S=11),
+    dict(T=300, N=4, V=32, S=40, scale=4.0),
+    dict(T=200, N=4, V=8, S=50, repeats=True),
+])
+def test_star_vs_oracle(hb, oracle, cfg):
+    c = dict(cfg)
+    x, tg, il, tl = _rand_ctc(200 + c["T"], c.pop("T"), c.pop("N"), c.pop("V"), c.pop("S"), **c)
+    for n in range(tg.shape[0]):
+        tg[n, tl[n]:] = 0                          # Collator pads with 0 (ha/loop.py:40)
+    go = torch.linspace(0.5, 2.0, x.shape[1])
+    ol, og = oracle.star(x.numpy(), tg.numpy(), il.numpy(), tl.numpy(), star_penalty=-0.5, grad_out=go.numpy())
+    xd = x.to(dev()).requires_grad_(True)
+    loss = hb.star_ctc_forward_score(xd, tg.to(dev()), il.to(dev()), tl.to(dev()), star_penalty=-0.5,
+                                     from_logits=True)
+    (loss * go.to(dev())).sum().backward()
+    np.testing.assert_allclose(loss.detach().double().cpu().numpy(), ol, rtol=LOSS_RTOL)
+    err = np.abs(xd.grad.double().cpu().numpy() - og).max()
+    assert err < GRAD_ATOL, f"{err:.3e}"
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(N=3, T=50, U=20, V=64),
+    dict(N=2, T=33, U=70, V=32),                   # U+1 spans 3 warps
+    dict(N=4, T=61, U=9, V=37),                    # V % 4 != 0
+    dict(N=2, T=150, U=100, V=16),                 # the C4 lattice width
+])
+def test_rnnt_vs_oracle(hb, oracle, cfg):
+    N, T, U, V = cfg["N"], cfg["T"], cfg["U"], cfg["V"]
+    g = torch.Generator().manual_seed(300 + T)
+    x = torch.randn(N, T, U + 1, V, generator=g)
+    tg = torch.randint(0, V, (N, U), generator=g)           # label 0 allowed, as ha/transducer.py:216
+    il = torch.randint(T // 2, T + 1, (N,), generator=g); il[0] = T
+    tl = torch.randint(U // 2, U + 1, (N,), generator=g); tl[0] = U
+    go = torch.linspace(0.5, 2.0, N)
+    ol, og = oracle.rnnt(x.numpy(), tg.numpy(), il.numpy(), tl.numpy(), grad_out=go.numpy())
+    xd = x.to(dev()).requires_grad_(True)
+    loss = hb.transducer_forward_score(xd, tg.to(dev()), il.to(dev()), tl.to(dev()), from_logits=True)
+    (loss * go.to(dev())).sum().backward()
+    np.testing.assert_allclose(loss.detach().double().cpu().numpy(), ol, rtol=LOSS_RTOL)
+    err = np.abs(xd.grad.double().cpu().numpy() - og).max()
+    assert err < GRAD_ATOL, f"{err:.3e}"
+
+
+def test_permuted_view_and_strided_grad(hb, oracle):
+    """ha/recognizer.py:70: the loss sees logits.permute(1,0,2) of an (N,T,C) buffer; no copy is made
+    and the gradient comes back with the same strides."""
+    x, tg, il, tl = _rand_ctc(7, 120, 6, 48, 20)
+    base = x.permute(1, 0, 2).contiguous().to(dev()).requires_grad_(True)     # (N,T,C) leaf
+    view = base.permute(1, 0, 2)
+    assert not view.is_contiguous()
+    loss = hb.ctc_forward_score3(view, tg.to(dev()), il.to(dev()), tl.to(dev()), from_logits=True)
+    loss.sum().backward()
+    ol, og = oracle.ctc(x.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    np.testing.assert_allclose(loss.detach().double().cpu().numpy(), ol, rtol=LOSS_RTOL)
+    assert np.abs(base.grad.permute(1, 0, 2).double().cpu().numpy() - og).max() < GRAD_ATOL
+
+
+def test_edge_cases(hb, oracle):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(6, 4, 8, generator=g)
+    tg = torch.tensor([[1, 2, 3], [1, 1, 1], [2, 0, 0], [4, 5, 0]])
+    il = torch.tensor([6, 4, 5, 1]); tl = torch.tensor([3, 3, 0, 1])   # ok, infeasible, empty target, T=1
+    ol, og = oracle.ctc(x.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    xd = x.to(dev()).requires_grad_(True)
+    loss = hb.ctc_forward_score3(xd, tg.to(dev()), il.to(dev()), tl.to(dev()), from_logits=True)
+    loss.sum().backward()
+    lo = loss.detach().cpu().numpy()
+    assert np.isinf(lo[1]) and lo[1] > 0 and np.isinf(ol[1])
+    np.testing.assert_allclose(lo[[0, 2, 3]], ol[[0, 2, 3]], rtol=LOSS_RTOL)
+    assert not xd.grad[:, 1].any(), "infeasible utterance: zero gradient"
+    assert np.abs(xd.grad.double().cpu().numpy() - og).max() < GRAD_ATOL
+    # out-of-range label / length -> NaN loss, zero gradient, other utterances untouched
+    bad = tg.clone(); bad[0, 1] = 99
+    xd2 = x.to(dev()).requires_grad_(True)
+    l2 = hb.ctc_forward_score3(xd2, bad.to(dev()), il.to(dev()), tl.to(dev()), from_logits=True)
+    l2[2:].sum().backward()
+    assert torch.isnan(l2[0]) and not xd2.grad[:, 0].any()
+    np.testing.assert_allclose(l2[2:].detach().cpu().numpy(), ol[2:], rtol=LOSS_RTOL)
+
+
+def test_rnnt_live_call_site(hb):
+    """rnnt_loss wrapper (ha/recognizer.py:121-126) vs torchaudio on the same GPU."""
+    torchaudio = pytest.importorskip("torchaudio")
+    g = torch.Generator().manual_seed(9)
+    N, T, U, V = 4, 30, 8, 24
+    x = torch.randn(N, T, U + 1, V, generator=g).to(dev())
+    tg = torch.randint(1, V, (N, U), generator=g).to(dev())
+    il = torch.tensor([30, 21, 30, 17]).to(dev()); tl = torch.tensor([8, 8, 3, 5]).to(dev())
+    a = x.clone().requires_grad_(True)
+    la = hb.rnnt_loss(a, tg.int(), il.int(), tl.int(), blank=0, reduction="mean", fused_log_softmax=True)
+    la.backward()
+    b = x.clone().requires_grad_(True)
+    lb = torchaudio.functional.rnnt_loss(b, tg.int(), il.int(), tl.int(), blank=0, reduction="mean",
+                                         fused_log_softmax=True)
+    lb.backward()
+    assert abs(float(la) / float(lb) - 1) < 1e-5
+    assert (a.grad - b.grad).abs().max() < 1e-5
+
+
+def test_ctc_live_call_site(hb):
+    """ctc_loss wrapper (ha/recognizer.py:71) vs F.ctc_loss(reduction='mean') in float64 on the GPU."""
+    x, tg, il, tl = _rand_ctc(11, 150, 6, 40, 25)
+    a = x.to(dev()).requires_grad_(True)
+    la = hb.ctc_loss(a, tg.to(dev()), il.to(dev()), tl.to(dev()), from_logits=True)
+    la.backward()
+    b = x.double().to(dev()).requires_grad_(True)
+    lb = torch.nn.functional.ctc_loss(b.log_softmax(-1), tg.to(dev()), il.to(dev()), tl.to(dev()))
+    lb.backward()
+    assert abs(float(la) / float(lb) - 1) < 1e-5
+    assert (a.grad.double() - b.grad).abs().max() < 1e-6      # scaled by 1/(N*L): tighter in absolute terms
+
+
+def test_greedy_bit_exact(hb, oracle):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 300, 40, generator=g).log_softmax(-1)
+    x[0, 3] = x[0, 3, 2]                # a full tie: index 0 must win
+    x[1, 7, 5] = x[1, 7].max()          # a two-way tie
+    il = torch.tensor([300, 250, 1, 0, 299])
+    hyp, hl, ali, sc = hb.greedy_decode(x.to(dev()))
+    scores, alignments = x.max(dim=-1)
+    assert torch.equal(ali.cpu(), alignments) and torch.equal(sc.cpu(), scores)
+    for n in range(5):
+        ref = [int(i) for i in torch.unique_consecutive(alignments[n]) if i]
+        assert hyp[n, :hl[n]].tolist() == ref
+        assert (hyp[n, hl[n]:] == -1).all()
+    o_ali, o_sc, o_hyp, o_hl = oracle.greedy(x.numpy(), il.numpy())
+    hyp, hl, ali, sc = hb.greedy_decode(x.to(dev()), il.to(dev()))
+    assert np.array_equal(hyp.cpu().numpy(), o_hyp) and np.array_equal(hl.cpu().numpy(), o_hl)
+    assert np.array_equal(ali.cpu().numpy(), o_ali)
+
+
+def test_viterbi_bit_exact(hb, oracle):
+    x, tg, il, tl = _rand_ctc(21, 200, 6, 30, 40)
+    lp = x.log_softmax(-1)
+    ali, sc = hb.ctc_viterbi_align(lp.to(dev()), tg.to(dev()), il.to(dev()), tl.to(dev()))
+    o_ali, o_sc = oracle.ctc_viterbi(lp.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    assert np.array_equal(ali.cpu().numpy(), o_ali)
+    assert np.array_equal(sc.cpu().numpy().view(np.int32), o_sc.view(np.int32)), "scores must match bit for bit"
