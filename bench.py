@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — loss + logit-gradient throughput of the alignment-loss hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ctc|star|rnnt] [--impl b200|reference]
+
+A "step" is one pass of the hot path (forward loss + backward logit gradient, grad_output = 1/N)
+over one synthetic batch.  Workloads are BASELINE.json's configs: ctc = configs[1]
+(B=256 T=1500 V=1024 U=300, the headline), star = configs[2], rnnt = configs[3].  With N > 1 every
+rank owns a full batch of its own (utterances are independent: weak scaling, no data-path
+collective) and the only collective is the all-reduce of [sum loss, count] (configs[4]).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kind, B, T, V, U)
+    "ctc": ("ctc", 256, 1500, 1024, 300),
+    "star": ("star", 128, 1000, 512, 200),
+    "rnnt": ("rnnt", 32, 500, 1024, 100),
+    "ctc_c1": ("ctc", 8, 200, 256, 50),
+}
+
+
+def alg_bytes(kind, B, T, V, U):
+    """read the logits once + write the logit gradient once, fp32."""
+    return 8 * V * B * T * ((U + 1) if kind == "rnnt" else 1)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(kind, B, T, V, U, seed, device=None, pin=False):
+    """Synthetic batch, SURVEY.md §8(d): randn logits, labels in 1..V-1, full lengths."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    shape = (B, T, V) if kind != "rnnt" else (B, T, U + 1, V)
+    x = torch.empty(shape, dtype=torch.float32, pin_memory=pin)
+    # filled in chunks: one 6.6 GB randn call is slow and doubles peak host memory
+    flat = x.view(-1)
+    step = 1 << 26
+    for i in range(0, flat.numel(), step):
+        flat[i:i + step].normal_(generator=g)
+    tg = torch.randint(1, V, (B, U), generator=g)
+    il = torch.full((B,), T, dtype=torch.int64)
+    tl = torch.full((B,), U, dtype=torch.int64)
+    if device is not None:
+        x, tg, il, tl = x.to(device), tg.to(device), il.to(device), tl.to(device)
+    return x, tg, il, tl
+
+
+def cpu_reference_run(kind, B, T, V, U, seconds_target, threads):
+    """Time the CPU restatement (oracle, kind "port": the reference is pure Python + PyTorch autograd
+    and does not travel to the GPU box) on a bounded sample of the workload: same T, V, U, fewer
+    utterances.  Returns (frames_per_s, sample_description, B_cpu, seconds)."""
+    import numpy as np
+    from oracle import oracle
+    oracle.build()
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    rng = np.random.default_rng(0)
+
+    def run(b):
+        shape = (T, b, V) if kind != "rnnt" else (b, T, U + 1, V)
+        x = rng.standard_normal(shape, dtype=np.float32).astype(np.float64)
+        tg = rng.integers(1, V, (b, U)); il = np.full(b, T); tl = np.full(b, U)
+        t0 = time.perf_counter()
+        if kind == "ctc":
+            oracle.ctc(x, tg, il, tl)
+        elif kind == "star":
+            oracle.star(x, tg, il, tl, star_penalty=-0.5)
+        else:
+            oracle.rnnt(x, tg, il, tl)
+        return time.perf_counter() - t0
+
+    b0 = max(1, min(B, threads))
+    if kind == "rnnt":
+        b0 = max(1, min(B, threads // 2, 4))
+    t_probe = run(b0)
+    b = int(max(b0, min(B, b0 * seconds_target / max(t_probe, 1e-3))))
+    if kind == "rnnt":
+        b = min(b, 8)            # 0.8 GB of float64 joint per utterance
+    b = max(b0, (b // b0) * b0)
+    t = run(b) if b != b0 else t_probe
+    return b * T / t, f"B_cpu={b} of B={B}, same T={T} V={V} U={U}, float64, loss+grad", b, t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="ctc", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    kind, B, T, V, U = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "utterance-frames/sec (loss + logit gradient)"
+    config = {"workload": f"{args.workload}: {kind} B={B}/GPU T={T} V={V} U={U} fp32, full lengths, from logits",
+              "batch_per_gpu": B, "T": T, "V": V, "U": U, "sharding": f"batch x{max(world, args.gpus)} (utterances independent)",
+              "l2": "inputs larger than L2 (no flush needed)" if alg_bytes(kind, B, T, V, U) // 2 > 2 * 126e6
+              else "inputs rotate over 4 buffer sets larger than L2 in total"}
+    threads = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # the reference's CPU implementation of the path, all host threads, bounded sample per step
+        vals = []
+        per_step = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+        for i in range(args.warmup + args.steps):
+            fps, sample, b, t = cpu_reference_run(kind, B, T, V, U, per_step, threads)
+            if i >= args.warmup:
+                vals.append((fps, t))
+        v = sum(f for f, _ in vals) / len(vals)
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t for _, t in vals) / len(vals),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config,
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import haloop_b200 as hb
+    from haloop_b200 import ops
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # small workloads rotate over several input sets so that no step finds its logits in L2
+    nbytes_x = alg_bytes(kind, B, T, V, U) // 2
+    nsets = 1 if nbytes_x > 2 * 126e6 else max(2, int(4 * 126e6 // nbytes_x) + 1)
+    sets = [make_inputs(kind, B, T, V, U, seed=1000 * rank + s, device=dev) for s in range(nsets)]
+    gout = torch.full((B,), 1.0, device=dev)
+    red = torch.zeros(2, device=dev, dtype=torch.float64)
+
+    def view(x):
+        # the reference's call site hands the loss logits.permute(1,0,2) of an (N,T,C) buffer
+        return x.permute(1, 0, 2) if kind != "rnnt" else x
+
+    fwd_ev, bwd_ev = [], []
+
+    def step(i, timed=False):
+        x, tg, il, tl = sets[i % nsets]
+        xv = view(x)
+        if timed:
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+        if kind == "ctc":
+            loss, ws = ops.ctc_fwd(xv, tg, il, tl, True)
+        elif kind == "star":
+            loss, ws = ops.star_fwd(xv, tg, il, tl, -0.5, True)
+        else:
+            loss, ws = ops.rnnt_fwd(xv, tg, il, tl, True)
+        if timed:
+            e1.record()
+        if kind == "ctc":
+            gx = ops.ctc_bwd(xv, ws, gout, U, True)
+        elif kind == "star":
+            gx = ops.star_bwd(xv, ws, gout, U, True)
+        else:
+            gx = ops.rnnt_bwd(xv, ws, gout, True)
+        if timed:
+            e2.record()
+            fwd_ev.append((e0, e1)); bwd_ev.append((e1, e2))
+        red[0] = loss.sum(); red[1] = float(B)
+        if world > 1:
+            dist.all_reduce(red)            # the path's only collective: [sum loss, count]
+        return gx
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        step(i, timed=True)
+    t_end.record()
+    barrier()
+    ms_total = t_start.elapsed_time(t_end)
+    clocks = sampler.stop() if rank == 0 else None
+    mean_loss = float(red[0] / red[1])
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t) / args.steps
+    frames = B * T * world
+    value = frames / (ms_step * 1e-3)
+    fwd_ms = sum(a.elapsed_time(b) for a, b in fwd_ev) / len(fwd_ev)
+    bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_ev) / len(bwd_ev)
+
+    # ---- end to end: pinned host logits -> device, loss + gradient, loss back to the host, every step;
+    #      the copy of step k+1 overlaps the kernels of step k on a second stream
+    e2e = None
+    if not args.no_e2e:
+        hx, htg, hil, htl = make_inputs(kind, B, T, V, U, seed=77 + rank, pin=True)
+        htg, hil, htl = htg.pin_memory(), hil.pin_memory(), htl.pin_memory()
+        hloss = torch.empty(B, dtype=torch.float32).pin_memory()
+        dbuf = [torch.empty_like(sets[0][0]) for _ in range(2)]
+        dtg = [torch.empty_like(sets[0][1]) for _ in range(2)]
+        dil = [torch.empty_like(sets[0][2]) for _ in range(2)]
+        dtl = [torch.empty_like(sets[0][3]) for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        main_stream = torch.cuda.current_stream()
+
+        def upload(k):
+            s = k & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[s])
+                dbuf[s].copy_(hx, non_blocking=True); dtg[s].copy_(htg, non_blocking=True)
+                dil[s].copy_(hil, non_blocking=True); dtl[s].copy_(htl, non_blocking=True)
+                ready[s].record(copy_stream)
+
+        def compute(s):
+            main_stream.wait_event(ready[s])
+            xd = view(dbuf[s]).requires_grad_(True)
+            if kind == "ctc":
+                loss = hb.ctc_forward_score3(xd, dtg[s], dil[s], dtl[s], from_logits=True)
+            elif kind == "star":
+                loss = hb.star_ctc_forward_score(xd, dtg[s], dil[s], dtl[s], star_penalty=-0.5, from_logits=True)
+            else:
+                loss = hb.transducer_forward_score(xd, dtg[s], dil[s], dtl[s], from_logits=True)
+            loss.sum().backward()
+            hloss.copy_(loss.detach(), non_blocking=True)
+            freed[s].record(main_stream)
+            dbuf[s].requires_grad_(False)
+
+        for s in range(2):
+            freed[s].record(main_stream)
+        n_e2e = max(3, min(args.steps, 8))
+        upload(0)
+        compute(0)                              # warm-up step (untimed)
+        barrier()
+        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es.record()
+        upload(1)
+        for k in range(1, 1 + n_e2e):
+            if k < n_e2e:
+                upload(k + 1)                   # next step's copy overlaps this step's kernels
+            compute(k & 1)
+        ee.record()
+        barrier()
+        t2 = torch.tensor([es.elapsed_time(ee)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t2) / n_e2e
+        h2d = hx.numel() * 4 + htg.numel() * 8 + 16 * B
+        e2e = {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4 * B, "ms_per_step": e2e_ms, "steps": n_e2e,
+               "note": "pinned host logits -> device every step (double-buffered on a copy stream), loss read back"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    ab = alg_bytes(kind, B, T, V, U)
+    achieved = ab / (bwd_ms * 1e-3) / 1e9
+    launches_per_step = {"ctc": 4, "star": 4, "rnnt": 5}[kind]
+    out = {
+        "metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "mean_loss": mean_loss, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+        "roofline": {
+            "bound": "hbm", "kernel": f"{kind}_grad_kernel (the whole backward call: reads the logits, writes the gradient)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+            "step_achieved": ab / (ms_step * 1e-3) / 1e9, "step_frac": ab / (ms_step * 1e-3) / 1e9 / peak,
+        },
+    }
+    if e2e:
+        out["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        fps, sample, b, tcpu = cpu_reference_run(kind, B, T, V, U, args.cpu_seconds, threads)
+        out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                               "sample": sample, "seconds": tcpu}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -100,15 +100,25 @@ static int ctc_trellis_launch(const TrellisParams& tp, int nslot_max, int N, cud
         if ((rc = set_smem(ctc_trellis_kernel<JJ>, smem, "ctc_trellis"))) return rc; \
         ctc_trellis_kernel<JJ><<<grid, block, smem, st>>>(p);                         \
     } while (0)
-    if (nslot_max <= 1) HAB_LAUNCH_TRELLIS(1);
-    else if (nslot_max <= 2) HAB_LAUNCH_TRELLIS(2);
-    else if (nslot_max <= 4) HAB_LAUNCH_TRELLIS(4);
-    else if (nslot_max <= 8) HAB_LAUNCH_TRELLIS(8);
-    else if (nslot_max <= 12) HAB_LAUNCH_TRELLIS(12);
-    else if (nslot_max <= 16) HAB_LAUNCH_TRELLIS(16);
-    else if (nslot_max <= 24) HAB_LAUNCH_TRELLIS(24);
-    else if (nslot_max <= 32) HAB_LAUNCH_TRELLIS(32);
-    else return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length > 1023 is not supported");
+    // J = slots per warp = ceil((S+1)/32): every slot is computed (straight-line code), so J is exact
+    // for the common sizes
+    switch (nslot_max) {
+        case 1: HAB_LAUNCH_TRELLIS(1); break;
+        case 2: HAB_LAUNCH_TRELLIS(2); break;
+        case 3: HAB_LAUNCH_TRELLIS(3); break;
+        case 4: HAB_LAUNCH_TRELLIS(4); break;
+        case 5: HAB_LAUNCH_TRELLIS(5); break;
+        case 6: HAB_LAUNCH_TRELLIS(6); break;
+        case 7: HAB_LAUNCH_TRELLIS(7); break;
+        case 8: HAB_LAUNCH_TRELLIS(8); break;
+        case 9: case 10: HAB_LAUNCH_TRELLIS(10); break;
+        case 11: case 12: HAB_LAUNCH_TRELLIS(12); break;
+        case 13: case 14: case 15: case 16: HAB_LAUNCH_TRELLIS(16); break;
+        default:
+            if (nslot_max <= 24) HAB_LAUNCH_TRELLIS(24);
+            else if (nslot_max <= 32) HAB_LAUNCH_TRELLIS(32);
+            else return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length > 1023 is not supported");
+    }
 #undef HAB_LAUNCH_TRELLIS
     return check_launch("ctc_trellis_kernel");
 }
@@ -222,13 +232,20 @@ static int star_trellis_launch(const StarTrellisParams& tp, int nslot_max, int N
         if ((rc = set_smem(star_trellis_kernel<JJ>, smem, "star_trellis"))) return rc; \
         star_trellis_kernel<JJ><<<grid, block, smem, st>>>(p);                         \
     } while (0)
-    if (nslot_max <= 1) HAB_LAUNCH_STAR(1);
-    else if (nslot_max <= 2) HAB_LAUNCH_STAR(2);
-    else if (nslot_max <= 4) HAB_LAUNCH_STAR(4);
-    else if (nslot_max <= 8) HAB_LAUNCH_STAR(8);
-    else if (nslot_max <= 12) HAB_LAUNCH_STAR(12);
-    else if (nslot_max <= 16) HAB_LAUNCH_STAR(16);
-    else return fail(HA_ERR_UNSUPPORTED_SHAPE, "star-CTC target length > 511 is not supported");
+    switch (nslot_max) {
+        case 1: HAB_LAUNCH_STAR(1); break;
+        case 2: HAB_LAUNCH_STAR(2); break;
+        case 3: HAB_LAUNCH_STAR(3); break;
+        case 4: HAB_LAUNCH_STAR(4); break;
+        case 5: HAB_LAUNCH_STAR(5); break;
+        case 6: HAB_LAUNCH_STAR(6); break;
+        case 7: HAB_LAUNCH_STAR(7); break;
+        case 8: HAB_LAUNCH_STAR(8); break;
+        case 9: case 10: HAB_LAUNCH_STAR(10); break;
+        case 11: case 12: HAB_LAUNCH_STAR(12); break;
+        case 13: case 14: case 15: case 16: HAB_LAUNCH_STAR(16); break;
+        default: return fail(HA_ERR_UNSUPPORTED_SHAPE, "star-CTC target length > 511 is not supported");
+    }
 #undef HAB_LAUNCH_STAR
     return check_launch("star_trellis_kernel");
 }
@@ -376,9 +393,9 @@ int ha_rnnt_fwd(const float* joint, int N, int T, int U1, int V,
 
     RnntLatticeParams lp{};
     lp.N = N; lp.T = T; lp.U1 = U1; lp.D = w.D; lp.meta = pp.meta;
-    lp.bl = rp.bl; lp.lb = rp.lb; lp.alpha = (double*)(base + w.alpha); lp.occ = (float2*)(base + w.occ);
+    lp.bl = rp.bl; lp.lb = rp.lb; lp.alpha = (double*)(base + w.alpha); lp.beta = (double*)(base + w.beta); lp.occ = (float2*)(base + w.occ);
     lp.loss = loss; lp.loss_ws = (float*)(base + w.loss);
-    rnnt_lattice_kernel<<<N, round_up(U1, 32), 0, st>>>(lp);
+    rnnt_lattice_kernel<<<N, round_up(U1, 32) * (round_up(U1, 32) <= 512 ? 2 : 1), 0, st>>>(lp);
     return check_launch("rnnt_lattice_kernel");
 }
 

@@ -37,6 +37,33 @@ __device__ __forceinline__ float lae2(float a, float b) {
     return m + lg2f(1.0f + ex2f(d));
 }
 
+// ---- split log-domain numbers -------------------------------------------------------------------
+// A trellis value is kept as h + l with h an integer-valued float and |l| <~ 1, so every rounding
+// happens at magnitude ~1 (6e-8) however large the log-probability itself is: fp32 alpha/beta then
+// carry ~1e-7 of error instead of ulp(T * log V) (SURVEY.md finding 3).  All on the FP32 pipe.
+struct SF { float h, l; };
+constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: (x + kMagic) - kMagic == rint(x) for |x| < 2^22
+__device__ __forceinline__ float round_int(float x) { return __fsub_rn(__fadd_rn(x, kMagic), kMagic); }
+__device__ __forceinline__ SF sf_void() { SF r; r.h = kVoid; r.l = 0.0f; return r; }
+// log2(2^a + 2^b); the result's l is in [-0.5, 1.5] (not renormalised)
+__device__ __forceinline__ SF lae_sf(SF a, SF b) {
+    const float d = (a.h - b.h) + (a.l - b.l);
+    const bool p = d > 0.0f;
+    SF r;
+    r.h = p ? a.h : b.h;
+    r.l = (p ? a.l : b.l) + lg2f(1.0f + ex2f(-fabsf(d)));
+    return r;
+}
+// a + (K + f) with K integer-valued, renormalised so that |l| <= 0.5; void stays void
+__device__ __forceinline__ SF add_norm(SF a, float K, float f) {
+    const float l = a.l + f;
+    const float r = round_int(l);
+    SF o;
+    o.h = fmaxf((a.h + K) + r, kVoid);
+    o.l = l - r;
+    return o;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -26,7 +26,7 @@ struct CtcWs {                 // workspace layout (byte offsets), filled by ctc
 __host__ inline CtcWs ctc_ws_layout(int T, int N, int S) {
     CtcWs w;
     w.Sp = round_up(S > 0 ? S : 1, 4);
-    w.E = round_up(S + 1, 4);                       // blank + S labels per emission row
+    w.E = round_up(S + 4, 4);                       // row shift c_t, blank, 2 x void, S labels per emission row
     w.JWp = round_up((S + 1 + 31) / 32, 4);         // per-slot offsets stored in front of a trellis row
     w.SPX = w.JWp + round_up(2 * S + 2, 4);         // + (blank,label) pairs
     size_t o = 256;                                 // header
@@ -189,12 +189,19 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_rows_kernel(RowsParams 
             s = warp_sum(s);
             l2 = m2 + log2f(s);
         }
+        // Emissions are stored relative to an integer per-row shift c_t = rint(max gathered emission),
+        // so the likeliest state of every frame sits near 0.  The shifts cancel in every posterior
+        // (both sweeps see the same rows); only the loss needs their sum, which the trellis adds back.
+        const float eblank = fmaf(row[0], kLog2e, -l2);
+        float emax = eblank;
+        for (int k = lane; k < L; k += 32) emax = fmaxf(emax, fmaf(row[s_tgt[k]], kLog2e, -l2));
+        const float ct = round_int(warp_max(emax));
         float* erow = p.em + ((size_t)n * p.T + t) * p.E;
         if (lane == 0) {
             p.lse2[(size_t)n * p.T + t] = l2;
-            erow[0] = fmaf(row[0], kLog2e, -l2);
+            *(float4*)erow = make_float4(ct, eblank - ct, kVoid, kVoid);
         }
-        for (int k = lane; k < L; k += 32) erow[1 + k] = fmaf(row[s_tgt[k]], kLog2e, -l2);
+        for (int k = lane; k < L; k += 32) erow[4 + k] = fmaf(row[s_tgt[k]], kLog2e, -l2) - ct;
         __syncwarp();
         if (r + nstage < nrows) issue(r + nstage);
     }
@@ -204,8 +211,9 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_rows_kernel(RowsParams 
 struct TrellisParams {
     int T, N;
     const int4* meta; const int* order; const int* tgt; int Sp;
-    float* em; int E;          // emissions in, occupancies out (in place)
-    float* tr; int SPX, JWp;   // row = [JWp slot offsets (int)] [2*(L+1) floats: (blank,label) pairs]
+    float* em; int E;          // emission rows in: [0] row shift c_t  [1] blank  [2],[3] void  [4+k] label k
+                               // (log2, shifted); occupancy rows out, in place: [1] blank  [4+k] label k
+    float* tr; int SPX, JWp;   // stored trellis row = [JWp slot bases][2*(L+1) floats relative to them]
     float* loss; float* loss_ws;
     int nstage; int warp_bytes;
 };
@@ -214,13 +222,18 @@ __host__ __device__ inline int trellis_warp_bytes(int E, int SPX, int nstage) {
     return round_up((nstage * (E + SPX) + 2 * E) * 4 + 2 * nstage * 8, 128);
 }
 
-constexpr int kRenorm = 4;   // steps between per-slot renormalisations
+constexpr float kRebase = 24.0f;   // a slot is re-based when its states drift this far (log2 units) from the base
 
-// grid ceil(N/2), block 128: warps (2u, 2u+1) are the alpha and beta side of one utterance.
+// grid ceil(N/2), block 128: warps (2u, 2u+1) are the alpha and beta side of one utterance; each
+// warp is alone on its SM sub-partition, so the per-step code is straight-line and written
+// stage-major (every stage loops over the J slots) to keep J independent MUFU/FADD chains in flight.
+//
 // Side d walks time from its own end: step i is frame t = d ? T-1-i : i, on its own ordering of
-// the label pairs (beta = alpha on the reversed label sequence).  Phase 1 (first half of the
-// frames) stores every trellis row; phase 2 combines live rows with the rows the other side
-// stored, so posteriors need T sequential steps instead of 2T and nothing is recomputed.
+// the label pairs (beta = alpha on the reversed label sequence).  Lane l of slot j owns pair
+// q = 32 j + l = (blank state 2q, label state 2q+1), each a split number (common.cuh).  Phase 1
+// (first half of the frames) stores every row as floats relative to a per-slot base; phase 2
+// combines live rows with the rows the other side stored, so posteriors need T sequential steps
+// instead of 2T and nothing is recomputed.
 template <int J>
 __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -237,7 +250,6 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
         return;
     }
     const int P = L + 1;
-    const int nslot = (P + 31) >> 5;
     const int nstage = p.nstage, E = p.E, SPX = p.SPX, JWp = p.JWp;
 
     unsigned char* wb = smem_raw + (size_t)warp * p.warp_bytes;
@@ -251,13 +263,19 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
     mbar_init_fence();
     __syncwarp();
 
-    // skip transitions into my label states (ha/ctc.py:140-142), in my own direction
-    unsigned allowed = 0;
+    // per slot: where my label sits in an emission row (the void entry [2] when I have none), whether
+    // my pair / label exists, and whether the skip transition into my label is allowed
+    // (ha/ctc.py:140-142)
+    unsigned allowed = 0, hasp = 0, hasl = 0;
+    int eoff[J];
     {
         const int* y = p.tgt + (size_t)n * p.Sp;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int q = 32 * j + lane;
+            eoff[j] = (q < L) ? 4 + (dir ? L - 1 - q : q) : 2;
+            if (q < P) hasp |= 1u << j;
+            if (q < L) hasl |= 1u << j;
             if (q >= 1 && q < L) {
                 const int ycur = y[dir ? L - 1 - q : q] & kLabelMask;
                 const int yprv = y[dir ? L - q : q - 1] & kLabelMask;
@@ -267,17 +285,21 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
         }
     }
 
-    float a0[J], a1[J];
-    int off[J];
+    SF a0[J], a1[J];       // blank / label state of my pair in slot j
+    float base[J];         // storage base of slot j (integer valued)
 #pragma unroll
-    for (int j = 0; j < J; ++j) { a0[j] = kVoid; a1[j] = kVoid; off[j] = 0; }
+    for (int j = 0; j < J; ++j) { a0[j] = sf_void(); a1[j] = sf_void(); base[j] = 0.0f; }
 
     float* em_base = p.em + (size_t)n * p.T * E;
     float* tr_base = p.tr + (size_t)n * p.T * SPX;
-    const uint32_t em_bytes = (uint32_t)round_up(P, 4) * 4u;
+    const uint32_t em_bytes = (uint32_t)round_up(L + 4, 4) * 4u;
     const uint32_t tr_bytes = (uint32_t)(JWp + round_up(2 * P, 4)) * 4u;
     const int tm = Tn >> 1;
     const int steps1 = dir ? Tn - tm : tm;
+    // the other side's copy of my state s is its state 2L - s: my blank 2q <-> its R0 - 64 j, my label
+    // <-> one below, with R0 = 2 (L - lane); slot bases likewise shift by exactly j per slot
+    const int R0 = 2 * (L - lane);
+    const int B0 = R0 >> 6, B1 = (R0 - 1) >> 6;
 
     auto issue_em = [&](int i) {          // lane 0 only
         const int st = i % nstage, t = dir ? Tn - 1 - i : i;
@@ -302,134 +324,182 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
     if (lane == 0)
         for (int i = 0; i < min(nstage, Tn); ++i) issue_em(i);
 
-    int IZ = 0; float fZ = 0.0f; bool feasible = true;
+    float IZ = 0.0f, fZ = 0.0f, csum = 0.0f;
+    bool feasible = true;
+    int st = 0; uint32_t par = 0;          // emission ring position
+    int ts = 0; uint32_t tpar = 0;         // trellis ring position (phase 2)
 
     for (int i = 0; i < Tn; ++i) {
         if (i == steps1) phase_switch();
-        const int st = i % nstage;
         const int t = dir ? Tn - 1 - i : i;
-        mbar_wait(&bar_em[st], (uint32_t)(i / nstage) & 1u);
+        mbar_wait(&bar_em[st], par);
         const float* er = em_ring + st * E;
-        const float eb = er[0];
-        float el[J];
+        csum += er[0];
+        const float eb = er[1];
+        const float Kb = round_int(eb), fb = eb - Kb;
+        float Kl[J], fl[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const int q = 32 * j + lane;
-            el[j] = (q < L) ? er[1 + (dir ? L - 1 - q : q)] : kVoid;
+            const float e = er[eoff[j]];
+            Kl[j] = round_int(e);
+            fl[j] = e - Kl[j];
         }
         __syncwarp();
         if (lane == 0 && i + nstage < Tn) issue_em(i + nstage);
+        if (++st == nstage) { st = 0; par ^= 1u; }
 
         if (i == 0) {
-            if (lane == 0) { a0[0] = eb; a1[0] = el[0]; }     // ha/ctc.py:138 (el is void when L == 0)
+            if (lane == 0) {                                       // ha/ctc.py:138
+                SF z; z.h = 0.0f; z.l = 0.0f;
+                a0[0] = add_norm(z, Kb, fb);
+                a1[0] = add_norm(z, Kl[0], fl[0]);                 // void when L == 0
+            }
         } else {
-            float c[J];
+            // c = label state of the pair below (lane - 1; lane 0 takes lane 31 of the slot below)
+            float ch[J], cl[J];
+            {
+                float rh[J], rl[J];
 #pragma unroll
-            for (int j = 0; j < J; ++j)
-                if (j < nslot) c[j] = __shfl_sync(0xffffffffu, a1[j], (lane + 31) & 31);
-            if (lane == 0) {
+                for (int j = 0; j < J; ++j) {
+                    rh[j] = __shfl_sync(0xffffffffu, a1[j].h, (lane + 31) & 31);
+                    rl[j] = __shfl_sync(0xffffffffu, a1[j].l, (lane + 31) & 31);
+                }
 #pragma unroll
-                for (int j = J - 1; j >= 1; --j)
-                    if (j < nslot) c[j] = c[j - 1] + (float)(off[j - 1] - off[j]);
-                c[0] = kVoid;
-            }
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                if (j < nslot) {
-                    const float u = lae2(a0[j], c[j]);            // self (+) previous label -> blank
-                    const float sel = ((allowed >> j) & 1u) ? u : a0[j];
-                    a1[j] = fmaxf(lae2(sel, a1[j]) + el[j], kVoid);
-                    a0[j] = fmaxf(u + eb, kVoid);
+                for (int j = 0; j < J; ++j) {
+                    ch[j] = lane ? rh[j] : (j ? rh[j ? j - 1 : 0] : kVoid);
+                    cl[j] = lane ? rl[j] : (j ? rl[j ? j - 1 : 0] : 0.0f);
                 }
             }
-        }
-        if ((i % kRenorm) == kRenorm - 1) {
+            // u = blank (+) previous label;  v = label (+) (skip allowed ? u : blank)     [ha/ctc.py:155-167]
+            float d[J], tt[J], uh[J], ul[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) d[j] = (a0[j].h - ch[j]) + (a0[j].l - cl[j]);
+#pragma unroll
+            for (int j = 0; j < J; ++j) tt[j] = ex2f(-fabsf(d[j]));
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                if (j < nslot) {
-                    const float m = warp_max(fmaxf(a0[j], a1[j]));
-                    if (m > kVoidTest) {
-                        const float k = rintf(m);
-                        a0[j] -= k; a1[j] -= k; off[j] += (int)k;
-                    }
-                }
+                uh[j] = (d[j] > 0.0f) ? a0[j].h : ch[j];
+                ul[j] = (d[j] > 0.0f) ? a0[j].l : cl[j];
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) tt[j] = lg2f(1.0f + tt[j]);
+#pragma unroll
+            for (int j = 0; j < J; ++j) ul[j] += tt[j];
+            float sh[J], sl[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                sh[j] = ((allowed >> j) & 1u) ? uh[j] : a0[j].h;
+                sl[j] = ((allowed >> j) & 1u) ? ul[j] : a0[j].l;
+                d[j] = (sh[j] - a1[j].h) + (sl[j] - a1[j].l);
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) tt[j] = ex2f(-fabsf(d[j]));
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                sh[j] = (d[j] > 0.0f) ? sh[j] : a1[j].h;
+                sl[j] = (d[j] > 0.0f) ? sl[j] : a1[j].l;
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) tt[j] = lg2f(1.0f + tt[j]);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                SF u; u.h = uh[j]; u.l = ul[j];
+                SF v; v.h = sh[j]; v.l = sl[j] + tt[j];
+                a0[j] = add_norm(u, Kb, fb);
+                a1[j] = add_norm(v, Kl[j], fl[j]);
             }
         }
         if (i < steps1) {
-            float* row = tr_base + (size_t)t * SPX;
+            // Rows are stored relative to a per-slot integer base.  A live slot is re-based (one warp
+            // max) only when some state rose well above its base or none is left near it; the test
+            // itself is three warp-wide OR reductions for all slots together.
+            unsigned up = 0, near = 0, live = 0;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                if (j < nslot) {
-                    const int q = 32 * j + lane;
-                    if (q < P) ((float2*)(row + JWp))[q] = make_float2(a0[j], a1[j]);
-                    if (lane == j) ((int*)row)[j] = off[j];
-                }
+                const float m = fmaxf(a0[j].h, a1[j].h);
+                const float dd = m - base[j];
+                up |= (dd > kRebase) ? (1u << j) : 0u;             // voids give dd ~ -1e30
+                near |= (dd > -kRebase) ? (1u << j) : 0u;
+                live |= (m > kVoidTest) ? (1u << j) : 0u;
+            }
+            up = __reduce_or_sync(0xffffffffu, up);
+            near = __reduce_or_sync(0xffffffffu, near);
+            live = __reduce_or_sync(0xffffffffu, live);
+            const unsigned need = up | (live & ~near);
+            if (need) {
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    if ((need >> j) & 1u) base[j] = warp_max(fmaxf(a0[j].h, a1[j].h));
+            }
+            float* row = tr_base + (size_t)t * SPX;
+            float2* prow = (float2*)(row + JWp) + lane;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                if ((hasp >> j) & 1u)
+                    prow[32 * j] = make_float2((a0[j].h - base[j]) + a0[j].l, (a1[j].h - base[j]) + a1[j].l);
+                if (lane == j && 32 * j < P) row[j] = base[j];
             }
         } else {
             const int k = i - steps1;
-            const int ts = k % nstage;
-            mbar_wait(&bar_tr[ts], (uint32_t)(k / nstage) & 1u);
-            const float* orow = tr_ring + ts * SPX + JWp;
-            const int* ooff = (const int*)(tr_ring + ts * SPX);
-            // the other side's state for my state s is its state 2L - s
-            float v0[J], v1[J];
-            int i0[J], i1[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                v0[j] = kVoid; v1[j] = kVoid; i0[j] = 0; i1[j] = 0;
-                if (j < nslot) {
-                    const int q = 32 * j + lane;
-                    if (q < P) {
-                        const int r0 = 2 * (L - q);
-                        v0[j] = a0[j] + orow[r0] - eb;
-                        i0[j] = off[j] + ooff[r0 >> 6];
-                    }
-                    if (q < L) {
-                        const int r1 = 2 * (L - q) - 1;
-                        v1[j] = a1[j] + orow[r1] - el[j];
-                        i1[j] = off[j] + ooff[r1 >> 6];
-                    }
-                }
-            }
+            mbar_wait(&bar_tr[ts], tpar);
+            const float* orow = tr_ring + ts * SPX + JWp + R0;     // [-64 j] = other side's copy of my blank
+            const float* ob0 = tr_ring + ts * SPX + B0;            // [-j]    = its slot base
+            const float* ob1 = tr_ring + ts * SPX + B1;
+            // posterior exponent = [h + other base - K] (integers) + [l + other value - f] (small), minus log Z.
+            auto expo = [&](int jj, float& xi0, float& xf0, float& xi1, float& xf1) {
+                const bool vp = (hasp >> jj) & 1u, vl = (hasl >> jj) & 1u;
+                const float o0 = vp ? orow[-64 * jj] : 0.0f, o1 = vl ? orow[-64 * jj - 1] : 0.0f;
+                const float b0 = vp ? ob0[-jj] : 0.0f, b1 = vl ? ob1[-jj] : 0.0f;
+                xi0 = vp ? (a0[jj].h + b0) - Kb : kVoid;
+                xf0 = vp ? (a0[jj].l + o0) - fb : 0.0f;
+                xi1 = vl ? (a1[jj].h + b1) - Kl[jj] : kVoid;
+                xf1 = vl ? (a1[jj].l + o1) - fl[jj] : 0.0f;
+            };
             if (k == 0) {
                 double mx = -1.0e300;
 #pragma unroll
-                for (int j = 0; j < J; ++j)
-                    if (j < nslot) mx = fmax(mx, fmax((double)i0[j] + (double)v0[j], (double)i1[j] + (double)v1[j]));
+                for (int j = 0; j < J; ++j) {
+                    float xi0, xf0, xi1, xf1;
+                    expo(j, xi0, xf0, xi1, xf1);
+                    mx = fmax(mx, fmax((double)xi0 + (double)xf0, (double)xi1 + (double)xf1));
+                }
                 mx = warp_max_d(mx);
                 feasible = mx > (double)kVoidTest;
                 float s = 0.0f;
 #pragma unroll
-                for (int j = 0; j < J; ++j)
-                    if (j < nslot)
-                        s += ex2f((float)((double)i0[j] + (double)v0[j] - mx)) +
-                             ex2f((float)((double)i1[j] + (double)v1[j] - mx));
-                s = warp_sum(s);
-                const double logZ2 = mx + (double)log2f(s);
-                const double fl = floor(logZ2);
-                IZ = feasible ? (int)fl : 0;
-                fZ = feasible ? (float)(logZ2 - fl) : 0.0f;
-                if (dir == 0 && lane == 0) {
-                    const float v = feasible ? (float)(-logZ2 * kLn2) : CUDART_INF_F;
-                    p.loss[n] = v; p.loss_ws[n] = v;
+                for (int j = 0; j < J; ++j) {
+                    float xi0, xf0, xi1, xf1;
+                    expo(j, xi0, xf0, xi1, xf1);
+                    s += ex2f((float)((double)xi0 + (double)xf0 - mx)) +
+                         ex2f((float)((double)xi1 + (double)xf1 - mx));
                 }
+                s = warp_sum(s);
+                const double logZ2 = mx + (double)log2f(s);        // of the shifted emissions
+                const double fl2 = floor(logZ2);
+                IZ = feasible ? (float)fl2 : 0.0f;
+                fZ = feasible ? (float)(logZ2 - fl2) : 0.0f;
             }
             float* ob = occ_buf + (i & 1) * E;
             if (lane == 0) bulk_wait_read<1>();     // the store issued two steps ago has left this buffer
             __syncwarp();
+            float g0[J], g1[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                float xi0, xf0, xi1, xf1;
+                expo(j, xi0, xf0, xi1, xf1);
+                g0[j] = (xi0 - IZ) + (xf0 - fZ);
+                g1[j] = (xi1 - IZ) + (xf1 - fZ);
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) { g0[j] = ex2f(g0[j]); g1[j] = ex2f(g1[j]); }
             float bsum = 0.0f;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                if (j < nslot) {
-                    const int q = 32 * j + lane;
-                    const float g0 = feasible ? ex2f(v0[j] + (float)(i0[j] - IZ) - fZ) : 0.0f;
-                    const float g1 = feasible ? ex2f(v1[j] + (float)(i1[j] - IZ) - fZ) : 0.0f;
-                    bsum += g0;
-                    if (q < L) ob[1 + (dir ? L - 1 - q : q)] = g1;
-                }
+                bsum += feasible ? g0[j] : 0.0f;
+                if ((hasl >> j) & 1u) ob[eoff[j]] = feasible ? g1[j] : 0.0f;
             }
             bsum = warp_sum(bsum);
-            if (lane == 0) ob[0] = bsum;
+            if (lane == 0) ob[1] = bsum;
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -437,9 +507,15 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
                 bulk_commit();
                 if (k + nstage < Tn - steps1) issue_tr(k + nstage);
             }
+            if (++ts == nstage) { ts = 0; tpar ^= 1u; }
         }
     }
     if (steps1 == Tn) phase_switch();     // only T == 1, beta side: still owes the barrier
+    if (dir == 0 && lane == 0) {
+        // log Z of the true emissions = log Z of the shifted ones + the sum of all T row shifts
+        const float v = feasible ? (float)(-((double)IZ + (double)fZ + (double)csum) * kLn2) : CUDART_INF_F;
+        p.loss[n] = v; p.loss_ws[n] = v;
+    }
     if (lane == 0) bulk_wait_all<0>();
 }
 
@@ -499,7 +575,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_grad_kernel(GradParams 
     const float* xb = p.x + (long long)n * p.sx_n;
     float* gb = p.gx + (long long)n * p.sg_n;
     const float g = p.gout[n];
-    const uint32_t occ_bytes = (uint32_t)round_up(L + 1, 4) * 4u;
+    const uint32_t occ_bytes = (uint32_t)round_up(L + 4, 4) * 4u;
 
     auto issue = [&](int r) {
         const int stage = r % nstage;
@@ -518,7 +594,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_grad_kernel(GradParams 
                 const float* src = xb + (long long)t * p.sx_t;
                 for (int c = lane; c < V; c += 32) dst[c] = src[c];
             }
-            for (int c = lane; c <= L; c += 32) dst[V + c] = osrc[c];
+            for (int c = lane; c < L + 4; c += 32) dst[V + c] = osrc[c];
         }
     };
     for (int r = 0; r < min(nstage - 1, nreal); ++r) issue(r);
@@ -558,13 +634,13 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_grad_kernel(GradParams 
         for (int k = lane; k < L; k += 32) {
             const int w = s_tgt[k];
             if (!(w & kNotFirst)) {
-                float s = occ[1 + k];
-                for (int j = s_nxt[k]; j >= 0; j = s_nxt[j]) s += occ[1 + j];
+                float s = occ[4 + k];
+                for (int j = s_nxt[k]; j >= 0; j = s_nxt[j]) s += occ[4 + j];
                 row[w & kLabelMask] -= g * s;
             }
         }
         __syncwarp();
-        if (lane == 0) row[0] -= g * occ[0];
+        if (lane == 0) row[0] -= g * occ[1];
         float* dstg = gb + (long long)t * p.sg_t;
         if (p.use_bulk) {
             fence_async_smem();

@@ -18,7 +18,7 @@
 namespace hab {
 
 struct RnntWs {
-    size_t meta, tgt, loss, lse2, bl, lb, alpha, occ, total;
+    size_t meta, tgt, loss, lse2, bl, lb, alpha, beta, occ, total;
     int Up, D;   // padded target stride; diagonals per utterance
 };
 
@@ -35,6 +35,7 @@ __host__ inline RnntWs rnnt_ws_layout(int N, int T, int U1) {
     w.bl = take(sizeof(float) * (size_t)N * w.D * U1);          // skewed (t+u, u)
     w.lb = take(sizeof(float) * (size_t)N * w.D * U1);
     w.alpha = take(sizeof(double) * (size_t)N * w.D * U1);
+    w.beta = take(sizeof(double) * (size_t)N * w.D * U1);
     w.occ = take(sizeof(float2) * (size_t)N * w.D * U1);        // (occ_blank, occ_label), skewed
     w.total = o;
     return w;
@@ -169,7 +170,7 @@ struct RnntLatticeParams {
     int N, T, U1, D;
     const int4* meta;
     const float* bl; const float* lb;
-    double* alpha; float2* occ;
+    double* alpha; double* beta; float2* occ;
     float* loss; float* loss_ws;
 };
 
@@ -182,80 +183,108 @@ __device__ __forceinline__ double lae2_d(double a, double b) {
 
 constexpr double kVoidD = -1.0e30;
 
-// grid N, block round_up(U1, 32).  Thread u owns column u; on anti-diagonal d it is at t = d - u.
-// alpha[t,u] = (alpha[t-1,u] + blank[t-1,u]) (+) (alpha[t,u-1] + label[t,u-1])   ha/transducer.py:197-202
+// grid N, block sides * round_up(U1, 32).  Thread u of a side owns column u; on anti-diagonal d it is
+// at t = d - u.  With sides == 2 the alpha sweep (threads [0, half)) and the beta sweep (threads
+// [half, 2 half)) run concurrently, each behind its own named barrier; with sides == 1 (U+1 > 512)
+// the same threads run them one after the other.  Arc occupancies are then one parallel pass.
+//   alpha[t,u] = (alpha[t-1,u] + blank[t-1,u]) (+) (alpha[t,u-1] + label[t,u-1])   ha/transducer.py:197-202
 __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(RnntLatticeParams p) {
-    __shared__ double s_edge[2][32];
+    __shared__ double s_edge[2][2][32];     // [side][diagonal parity][warp]
     __shared__ double s_logz;
     const int n = blockIdx.x;
-    const int u = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int U1 = p.U1;
+    const int half = round_up(U1, 32);
+    const int sides = blockDim.x / half;
+    const int side = threadIdx.x / half;
+    const int u = threadIdx.x - side * half, lane = u & 31, warp = u >> 5, nwarp = half >> 5;
     const int4 mt = p.meta[n];
-    const int Tn = mt.x, Un = mt.y, U1 = p.U1;
-    if (mt.z) { if (u == 0) { p.loss[n] = CUDART_NAN_F; p.loss_ws[n] = CUDART_NAN_F; } return; }
+    const int Tn = mt.x, Un = mt.y;
+    if (mt.z) { if (threadIdx.x == 0) { p.loss[n] = CUDART_NAN_F; p.loss_ws[n] = CUDART_NAN_F; } return; }
     const float* bl = p.bl + (size_t)n * p.D * U1;
     const float* lb = p.lb + (size_t)n * p.D * U1;
     double* al = p.alpha + (size_t)n * p.D * U1;
+    double* be = p.beta + (size_t)n * p.D * U1;
     float2* occ = p.occ + (size_t)n * p.D * U1;
     const int nd = Tn + Un;                 // diagonals 0 .. nd-1
     const bool col = u <= Un;
 
-    // ---- alpha, forward over diagonals
-    double a = kVoidD;                      // alpha of my node on the previous diagonal
-    for (int d = 0; d < nd; ++d) {
-        const int t = d - u;
-        // neighbour u-1's previous-diagonal value = alpha[t, u-1]
-        double left = __shfl_up_sync(0xffffffffu, a, 1);
-        if (lane == 0) left = (warp > 0) ? s_edge[(d + 1) & 1][warp - 1] : kVoidD;
-        double cur = kVoidD;
-        if (col && t >= 0 && t < Tn) {
-            if (d == 0) cur = 0.0;          // alpha[0,0]
-            else {
-                const double up = (t >= 1) ? a + (double)bl[(size_t)(d - 1) * U1 + u] : kVoidD;
-                const double lf = (u >= 1) ? left + (double)lb[(size_t)(d - 1) * U1 + u - 1] : kVoidD;
-                cur = lae2_d(lf, up);
+    if (side == 0) {
+        // ---- alpha, forward over diagonals; emissions of the next diagonal are fetched a step ahead
+        double a = kVoidD;                  // alpha of my node on the previous diagonal
+        float nbl = 0.0f, nlb = 0.0f;       // blank[t-1,u], label[t,u-1] for the coming diagonal
+        for (int d = 0; d < nd; ++d) {
+            const int t = d - u;
+            const float cbl = nbl, clb = nlb;
+            if (d + 1 < nd && col) {
+                nbl = bl[(size_t)d * U1 + u];
+                nlb = (u >= 1) ? lb[(size_t)d * U1 + u - 1] : 0.0f;
             }
-            al[(size_t)d * U1 + u] = cur;
+            double left = __shfl_up_sync(0xffffffffu, a, 1);       // alpha[t, u-1]
+            if (lane == 0) left = (warp > 0) ? s_edge[0][(d + 1) & 1][warp - 1] : kVoidD;
+            double cur = kVoidD;
+            if (col && t >= 0 && t < Tn) {
+                if (d == 0) cur = 0.0;      // alpha[0,0]
+                else {
+                    const double up = (t >= 1) ? a + (double)cbl : kVoidD;
+                    const double lf = (u >= 1) ? left + (double)clb : kVoidD;
+                    cur = lae2_d(lf, up);
+                }
+                al[(size_t)d * U1 + u] = cur;
+            }
+            a = cur;
+            if (lane == 31) s_edge[0][d & 1][warp] = a;
+            named_bar_sync(1, half);
         }
-        a = cur;
-        if (lane == 31) s_edge[d & 1][warp] = a;
-        __syncthreads();
+        // log Z = alpha[T-1,U] + blank[T-1,U]                                  ha/transducer.py:204-205
+        if (u == Un) s_logz = a + (double)bl[(size_t)(nd - 1) * U1 + Un];
     }
-    // log Z = alpha[T-1,U] + blank[T-1,U]                                     ha/transducer.py:204-205
-    if (u == Un) s_logz = a + (double)bl[(size_t)(nd - 1) * U1 + Un];
+    if (side == sides - 1) {
+        // ---- beta, backward over diagonals
+        double b = kVoidD;                  // beta[t+1,u]: my node on the next diagonal
+        float nbl = 0.0f, nlb = 0.0f;
+        if (col && nd >= 1) { nbl = bl[(size_t)(nd - 1) * U1 + u]; nlb = lb[(size_t)(nd - 1) * U1 + u]; }
+        for (int d = nd - 1; d >= 0; --d) {
+            const int t = d - u;
+            const float cbl = nbl, clb = nlb;
+            if (d >= 1 && col) { nbl = bl[(size_t)(d - 1) * U1 + u]; nlb = lb[(size_t)(d - 1) * U1 + u]; }
+            double right = __shfl_down_sync(0xffffffffu, b, 1);    // beta[t, u+1]
+            if (lane == 31) right = (warp + 1 < nwarp) ? s_edge[1][(d + 1) & 1][warp + 1] : kVoidD;
+            double cur = kVoidD;
+            if (col && t >= 0 && t < Tn) {
+                double tb, tl;
+                if (t == Tn - 1) tb = (u == Un) ? (double)cbl : kVoidD;   // only the terminal blank leaves the last frame
+                else tb = b + (double)cbl;
+                tl = (u < Un) ? right + (double)clb : kVoidD;
+                cur = lae2_d(tb, tl);
+                be[(size_t)d * U1 + u] = cur;
+            }
+            b = cur;
+            if (lane == 0) s_edge[1][d & 1][warp] = b;
+            named_bar_sync(2, half);
+        }
+    }
     __syncthreads();
     const double logz = s_logz;
     const bool feasible = logz > -1.0e29;
-    if (u == 0) {
+    if (threadIdx.x == 0) {
         const float v = feasible ? (float)(-logz * kLn2) : CUDART_INF_F;
         p.loss[n] = v; p.loss_ws[n] = v;
     }
-
-    // ---- beta, backward over diagonals, arc occupancies on the fly
-    double b = kVoidD;                      // beta of my node on the next diagonal = beta[t+1,u]
-    for (int d = nd - 1; d >= 0; --d) {
-        const int t = d - u;
-        double right = __shfl_down_sync(0xffffffffu, b, 1);      // beta[t, u+1]
-        if (lane == 31) right = (warp + 1 < (int)(blockDim.x >> 5)) ? s_edge[(d + 1) & 1][warp + 1] : kVoidD;
-        double cur = kVoidD;
-        if (col && t >= 0 && t < Tn) {
-            const size_t k = (size_t)d * U1 + u;
-            const double vb = (double)bl[k], vl = (double)lb[k];
+    // ---- arc occupancies: occ_blank = alpha + blank + beta[t+1,u] - logZ, occ_label = alpha + label + beta[t,u+1] - logZ
+    for (int k = threadIdx.x; k < nd * U1; k += blockDim.x) {
+        const int d = k / U1, uu = k - d * U1, t = d - uu;
+        if (uu > Un || t < 0 || t >= Tn) continue;
+        float2 o = make_float2(0.0f, 0.0f);
+        if (feasible) {
+            const double base = al[k] - logz;
             double tb, tl;
-            if (t == Tn - 1) tb = (u == Un) ? vb : kVoidD;       // only the terminal blank leaves the last frame
-            else tb = b + vb;
-            tl = (u < Un) ? right + vl : kVoidD;
-            cur = lae2_d(tb, tl);
-            float2 o = make_float2(0.0f, 0.0f);
-            if (feasible) {
-                const double base = al[k] - logz;
-                o.x = ex2f((float)fmax(base + tb, -200.0));
-                o.y = ex2f((float)fmax(base + tl, -200.0));
-            }
-            occ[k] = o;
+            if (t == Tn - 1) tb = (uu == Un) ? (double)bl[k] : kVoidD;
+            else tb = be[(size_t)(d + 1) * U1 + uu] + (double)bl[k];
+            tl = (uu < Un) ? be[(size_t)(d + 1) * U1 + uu + 1] + (double)lb[k] : kVoidD;
+            o.x = ex2f((float)fmax(base + tb, -200.0));
+            o.y = ex2f((float)fmax(base + tl, -200.0));
         }
-        b = cur;
-        if (lane == 0) s_edge[d & 1][warp] = b;
-        __syncthreads();
+        occ[k] = o;
     }
 }
 

@@ -22,7 +22,7 @@ struct StarWs {
 __host__ inline StarWs star_ws_layout(int T, int N, int S) {
     StarWs w;
     w.Sp = round_up(S > 0 ? S : 1, 4);
-    w.E = round_up(2 + 2 * S, 4);                   // blank, all-star, S x (label, star\label)
+    w.E = round_up(4 + 2 * S, 4);                   // row shift, blank, all-star, pad, S x (label, star\label)
     w.JWp = round_up((S + 1 + 31) / 32, 4);
     w.SPX = w.JWp + 4 * (S + 1);
     size_t o = 256;
@@ -48,7 +48,8 @@ struct StarRowsParams {
     int from_logits, use_bulk, rows_per_warp, nstage, nwarps;
 };
 
-// emission row: [0] blank  [1] log2 P  [2+2k] label y_k  [3+2k] log2(P - p_{y_k}) (log2 P when y_k == 0)
+// emission row: [0] integer row shift c_t  [1] blank  [2] log2 P  [4+2k] label y_k  [5+2k] log2(P - p_{y_k})
+// (log2 P when y_k == 0), all relative to c_t = rint(max(blank, log2 P)),
 // for k < min(L_n + 1, S): the star in front of position L_n reads targets[n, L_n] (ha/star.py:46-47).
 template <bool VEC4>
 __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsParams p) {
@@ -124,11 +125,14 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
         const float e0 = ex2f(fmaf(row[0], kLog2e, -m2));
         const float l2 = p.from_logits ? m2 + log2f(s + e0) : 0.0f;
         const float lP = fmaxf(m2 + log2f(s) - l2, kVoid);        // log2 sum_{c>=1} p_c   (ha/star.py:30)
+        const float eblank = fmaf(row[0], kLog2e, -l2);
+        const float ct = round_int(fmaxf(eblank, lP));            // every other emission is <= log2 P
         float* erow = p.em + ((size_t)n * p.T + t) * p.E;
         if (lane == 0) {
             p.lse2[(size_t)n * p.T + t] = l2;
-            erow[0] = fmaf(row[0], kLog2e, -l2);
-            erow[1] = lP;
+            erow[0] = ct;
+            erow[1] = eblank - ct;
+            erow[2] = lP - ct;
         }
         for (int k = lane; k < Ks; k += 32) {
             const int y = s_tgt[k];
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
                 const float d = fminf(lab - lP, 0.0f);
                 sub = fmaxf(lP + log2f(-expm1f(d * (float)kLn2)), kVoid);
             }
-            ((float2*)(erow + 2))[k] = make_float2(lab, sub);
+            ((float2*)(erow + 4))[k] = make_float2(lab - ct, fmaxf(sub - ct, kVoid));
         }
         __syncwarp();
         if (r + nstage < nrows) issue(r + nstage);
@@ -151,18 +155,19 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
 struct StarTrellisParams {
     int T, N, S;
     const int4* meta; const int* order; const int* tgt; int Sp;
-    float* em; int E;          // emissions in; occupancy rows out (in place): [0] blank occupancy
-                               // [1] G = sum_k h_k   [2+2k] label occupancy   [3+2k] h_k (0 if y_k == 0)
-                               // with h_k = gamma(star k) / (P - p_{y_k})
-    float* tr; int SPX, JWp;   // row = [JWp slot offsets][4*(L+1) floats: quads]
+    float* em; int E;          // emission rows in (layout above); occupancy rows out, in place:
+                               // [1] blank occupancy  [2] G = sum_k h_k  [4+2k] label occupancy
+                               // [5+2k] h_k (0 if y_k == 0), with h_k = gamma(star k) / (P - p_{y_k})
+    float* tr; int SPX, JWp;   // stored row = [JWp slot bases][4*(L+1) floats relative to them: quads]
     float* loss; float* loss_ws;
     float pen2;                // star_penalty in log2 units
     int nstage; int warp_bytes;
 };
 
 // grid ceil(N/2), block 128: warps (2u, 2u+1) are the alpha and beta side of one utterance (see
-// ctc_trellis_kernel).  Both sides keep quad k in lane k%32 of slot k/32; beta is not a mirror image
-// of alpha here (labels have no self loop, stars have a back edge), so it has its own update.
+// ctc_trellis_kernel: same meet-in-the-middle schedule, same split numbers, straight-line slots).
+// Both sides keep quad k in lane k%32 of slot k/32; beta is not a mirror image of alpha here
+// (labels have no self loop, stars have a back edge), so it has its own update.
 template <int J>
 __global__ void __launch_bounds__(128, 1) star_trellis_kernel(StarTrellisParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -179,9 +184,8 @@ __global__ void __launch_bounds__(128, 1) star_trellis_kernel(StarTrellisParams 
         return;
     }
     const int Q = L + 1, Ks = min(L + 1, p.S);
-    const int nslot = (Q + 31) >> 5;
     const int nstage = p.nstage, E = p.E, SPX = p.SPX, JWp = p.JWp;
-    const float pen2 = p.pen2;
+    const float Kp = round_int(p.pen2), fp = p.pen2 - Kp;
 
     unsigned char* wb = smem_raw + (size_t)warp * p.warp_bytes;
     float* em_ring = (float*)wb;
@@ -210,14 +214,14 @@ __global__ void __launch_bounds__(128, 1) star_trellis_kernel(StarTrellisParams 
         }
     }
 
-    float b0[J], st[J], b1[J], lb[J];
-    int off[J];
+    SF b0[J], st[J], b1[J], lb[J];
+    float base[J];
 #pragma unroll
-    for (int j = 0; j < J; ++j) { b0[j] = st[j] = b1[j] = lb[j] = kVoid; off[j] = 0; }
+    for (int j = 0; j < J; ++j) { b0[j] = st[j] = b1[j] = lb[j] = sf_void(); base[j] = 0.0f; }
 
     float* em_base = p.em + (size_t)n * p.T * E;
     float* tr_base = p.tr + (size_t)n * p.T * SPX;
-    const uint32_t em_bytes = (uint32_t)round_up(2 + 2 * Ks, 4) * 4u;
+    const uint32_t em_bytes = (uint32_t)round_up(4 + 2 * Ks, 4) * 4u;
     const uint32_t tr_bytes = (uint32_t)(JWp + 4 * Q) * 4u;
     const int tm = Tn >> 1;
     const int steps1 = dir ? Tn - tm : tm;
@@ -244,171 +248,181 @@ __global__ void __launch_bounds__(128, 1) star_trellis_kernel(StarTrellisParams 
     if (lane == 0)
         for (int i = 0; i < min(nstage, Tn); ++i) issue_em(i);
 
-    int IZ = 0; float fZ = 0.0f; bool feasible = true;
+    float IZ = 0.0f, fZ = 0.0f, csum = 0.0f;
+    bool feasible = true;
+    int se = 0; uint32_t par = 0;
+    int ts = 0; uint32_t tpar = 0;
 
     for (int i = 0; i < Tn; ++i) {
         if (i == steps1) phase_switch();
-        const int s_em = i % nstage;
         const int t = dir ? Tn - 1 - i : i;
-        mbar_wait(&bar_em[s_em], (uint32_t)(i / nstage) & 1u);
-        const float* er = em_ring + s_em * E;
-        const float eb = er[0];
-        float el[J], es[J];
+        mbar_wait(&bar_em[se], par);
+        const float* er = em_ring + se * E;
+        const float ct = er[0];
+        csum += ct;
+        const float eb = er[1], eall = er[2];
+        const float Kb = round_int(eb), fb = eb - Kb;
+        float Kl[J], fl[J], Ks_[J], fs[J];       // label / star emissions of my quad, split; the star's
+                                                  // include the penalty paid on entering it
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int k = 32 * j + lane;
-            el[j] = kVoid; es[j] = kVoid;
+            float el = kVoid, es = kVoid;
             if (k < Ks) {
-                const float2 e = ((const float2*)(er + 2))[k];
-                el[j] = (k < L) ? e.x : kVoid;
-                es[j] = e.y;
+                const float2 e = ((const float2*)(er + 4))[k];
+                el = (k < L) ? e.x : kVoid;
+                es = e.y;
             } else if (k == L) {
-                es[j] = er[1];                 // L == S: the last star is the all-star (ha/star.py:47)
+                es = eall;                        // L == S: the last star is the all-star (ha/star.py:47)
             }
+            Kl[j] = round_int(el); fl[j] = el - Kl[j];
+            const float ks = round_int(es);
+            Ks_[j] = fmaxf(ks + Kp, kVoid); fs[j] = (es - ks) + fp;
         }
         __syncwarp();
         if (lane == 0 && i + nstage < Tn) issue_em(i + nstage);
+        if (++se == nstage) { se = 0; par ^= 1u; }
 
         if (dir == 0) {
             // previous label, from the lane below (virtual state -1 holds 0.0 before the first frame)
-            float c[J];
+            SF c[J];
+            float rh_prev = (i == 0) ? 0.0f : kVoid, rl_prev = 0.0f;
 #pragma unroll
-            for (int j = 0; j < J; ++j)
-                if (j < nslot) c[j] = __shfl_sync(0xffffffffu, lb[j], (lane + 31) & 31);
-            if (lane == 0) {
-#pragma unroll
-                for (int j = J - 1; j >= 1; --j)
-                    if (j < nslot) c[j] = c[j - 1] + (float)(off[j - 1] - off[j]);
-                c[0] = (i == 0) ? 0.0f : kVoid;
+            for (int j = 0; j < J; ++j) {
+                const float rh = __shfl_sync(0xffffffffu, lb[j].h, (lane + 31) & 31);
+                const float rl = __shfl_sync(0xffffffffu, lb[j].l, (lane + 31) & 31);
+                c[j].h = lane ? rh : rh_prev;
+                c[j].l = lane ? rl : rl_prev;
+                rh_prev = rh; rl_prev = rl;
             }
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                if (j < nslot) {
-                    const float u = lae2(st[j], b1[j]);
-                    const float v = lae2(u, b0[j]);
-                    const float w0 = lae2(c[j], b0[j]);
-                    const float vl = ((allowed >> j) & 1u) ? lae2(v, c[j]) : v;
-                    b1[j] = fmaxf(u + eb, kVoid);
-                    st[j] = fmaxf(v + pen2 + es[j], kVoid);
-                    lb[j] = fmaxf(vl + el[j], kVoid);
-                    b0[j] = fmaxf(w0 + eb, kVoid);
-                }
+                const SF u = lae_sf(st[j], b1[j]);
+                const SF v = lae_sf(u, b0[j]);
+                const SF w0 = lae_sf(c[j], b0[j]);
+                const SF vc = lae_sf(v, c[j]);
+                SF vl;
+                vl.h = ((allowed >> j) & 1u) ? vc.h : v.h;
+                vl.l = ((allowed >> j) & 1u) ? vc.l : v.l;
+                b1[j] = add_norm(u, Kb, fb);
+                st[j] = add_norm(v, Ks_[j], fs[j]);
+                lb[j] = add_norm(vl, Kl[j], fl[j]);
+                b0[j] = add_norm(w0, Kb, fb);
             }
         } else if (i == 0) {
             // beta at the last frame: the four final states (ha/star.py:156-163), emission included
+            SF z; z.h = 0.0f; z.l = 0.0f;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const int k = 32 * j + lane;
-                if (k == L) { b0[j] = eb; st[j] = fmaxf(pen2 + es[j], kVoid); b1[j] = eb; }
-                if (k == L - 1) lb[j] = el[j];
+                if (k == L) { b0[j] = add_norm(z, Kb, fb); st[j] = add_norm(z, Ks_[j], fs[j]); b1[j] = b0[j]; }
+                if (k == L - 1) lb[j] = add_norm(z, Kl[j], fl[j]);
             }
         } else {
-            // next quad's first blank and label, from the lane above
-            float n0[J], nl[J];
+            // next quad's first blank and label, from the lane above (lane 31 takes lane 0 of the slot above)
+            SF n0[J], nl[J];
+            float r0h[J], r0l[J], rlh[J], rll[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                if (j < nslot) {
-                    n0[j] = __shfl_sync(0xffffffffu, b0[j], (lane + 1) & 31);
-                    nl[j] = __shfl_sync(0xffffffffu, lb[j], (lane + 1) & 31);
-                }
-            }
-            if (lane == 31) {
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    if (j < nslot) {
-                        if (j + 1 < nslot && j + 1 < J) {
-                            const float dd = (float)(off[j + 1 < J ? j + 1 : j] - off[j]);
-                            n0[j] = n0[j + 1 < J ? j + 1 : j] + dd;
-                            nl[j] = nl[j + 1 < J ? j + 1 : j] + dd;
-                        } else {
-                            n0[j] = kVoid; nl[j] = kVoid;
-                        }
-                    }
-                }
+                r0h[j] = __shfl_sync(0xffffffffu, b0[j].h, (lane + 1) & 31);
+                r0l[j] = __shfl_sync(0xffffffffu, b0[j].l, (lane + 1) & 31);
+                rlh[j] = __shfl_sync(0xffffffffu, lb[j].h, (lane + 1) & 31);
+                rll[j] = __shfl_sync(0xffffffffu, lb[j].l, (lane + 1) & 31);
             }
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                if (j < nslot) {
-                    const float x = lae2(st[j], lb[j]);
-                    const float z = lae2(b1[j], x);
-                    const float w0 = lae2(b0[j], x);
-                    const float vl = ((allowed >> j) & 1u) ? lae2(n0[j], nl[j]) : n0[j];
-                    b0[j] = fmaxf(w0 + eb, kVoid);
-                    st[j] = fmaxf(z + pen2 + es[j], kVoid);
-                    b1[j] = fmaxf(z + eb, kVoid);
-                    lb[j] = fmaxf(vl + el[j], kVoid);
-                }
+                const bool edge = lane == 31;
+                n0[j].h = edge ? ((j + 1 < J) ? r0h[(j + 1 < J) ? j + 1 : j] : kVoid) : r0h[j];
+                n0[j].l = edge ? ((j + 1 < J) ? r0l[(j + 1 < J) ? j + 1 : j] : 0.0f) : r0l[j];
+                nl[j].h = edge ? ((j + 1 < J) ? rlh[(j + 1 < J) ? j + 1 : j] : kVoid) : rlh[j];
+                nl[j].l = edge ? ((j + 1 < J) ? rll[(j + 1 < J) ? j + 1 : j] : 0.0f) : rll[j];
             }
-        }
-        if ((i % kRenorm) == kRenorm - 1) {
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                if (j < nslot) {
-                    const float m = warp_max(fmaxf(fmaxf(b0[j], st[j]), fmaxf(b1[j], lb[j])));
-                    if (m > kVoidTest) {
-                        const float k = rintf(m);
-                        b0[j] -= k; st[j] -= k; b1[j] -= k; lb[j] -= k; off[j] += (int)k;
-                    }
-                }
+                const SF x = lae_sf(st[j], lb[j]);
+                const SF z = lae_sf(b1[j], x);
+                const SF w0 = lae_sf(b0[j], x);
+                const SF nn = lae_sf(n0[j], nl[j]);
+                SF vl;
+                vl.h = ((allowed >> j) & 1u) ? nn.h : n0[j].h;
+                vl.l = ((allowed >> j) & 1u) ? nn.l : n0[j].l;
+                b0[j] = add_norm(w0, Kb, fb);
+                st[j] = add_norm(z, Ks_[j], fs[j]);
+                b1[j] = add_norm(z, Kb, fb);
+                lb[j] = add_norm(vl, Kl[j], fl[j]);
             }
         }
         if (i < steps1) {
+            unsigned up = 0, near = 0, live = 0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const float m = fmaxf(fmaxf(b0[j].h, st[j].h), fmaxf(b1[j].h, lb[j].h));
+                const float d = m - base[j];
+                up |= (d > kRebase) ? (1u << j) : 0u;
+                near |= (d > -kRebase) ? (1u << j) : 0u;
+                live |= (m > kVoidTest) ? (1u << j) : 0u;
+            }
+            up = __reduce_or_sync(0xffffffffu, up);
+            near = __reduce_or_sync(0xffffffffu, near);
+            live = __reduce_or_sync(0xffffffffu, live);
+            const unsigned need = up | (live & ~near);
+            if (need) {
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    if ((need >> j) & 1u)
+                        base[j] = warp_max(fmaxf(fmaxf(b0[j].h, st[j].h), fmaxf(b1[j].h, lb[j].h)));
+            }
             float* row = tr_base + (size_t)t * SPX;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                if (j < nslot) {
-                    const int k = 32 * j + lane;
-                    if (k < Q) ((float4*)(row + JWp))[k] = make_float4(b0[j], st[j], b1[j], lb[j]);
-                    if (lane == j) ((int*)row)[j] = off[j];
-                }
+                const int k = 32 * j + lane;
+                if (k < Q)
+                    ((float4*)(row + JWp))[k] = make_float4((b0[j].h - base[j]) + b0[j].l, (st[j].h - base[j]) + st[j].l,
+                                                            (b1[j].h - base[j]) + b1[j].l, (lb[j].h - base[j]) + lb[j].l);
+                if (lane == j && 32 * j < Q) row[j] = base[j];
             }
         } else {
             const int k2 = i - steps1;
-            const int ts = k2 % nstage;
-            mbar_wait(&bar_tr[ts], (uint32_t)(k2 / nstage) & 1u);
+            mbar_wait(&bar_tr[ts], tpar);
             const float4* orow = (const float4*)(tr_ring + ts * SPX + JWp);
-            const int* ooff = (const int*)(tr_ring + ts * SPX);
-            float v0[J], vs[J], v1[J], vl[J];
-            int ii[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                v0[j] = vs[j] = v1[j] = vl[j] = kVoid; ii[j] = 0;
-                if (j < nslot) {
-                    const int k = 32 * j + lane;
-                    if (k < Q) {
-                        const float4 o = orow[k];
-                        v0[j] = b0[j] + o.x - eb;
-                        vs[j] = st[j] + o.y - (pen2 + es[j]);
-                        v1[j] = b1[j] + o.z - eb;
-                        vl[j] = (k < L) ? lb[j] + o.w - el[j] : kVoid;
-                        ii[j] = off[j] + ooff[j];
-                    }
-                }
-            }
+            const float* obase = tr_ring + ts * SPX;
+            // posterior exponent of a state = [h + other base - K] + [l + other value - f] - log Z
+            auto expo = [&](int jj, float& xi0, float& xf0, float& xis, float& xfs, float& xi1, float& xf1,
+                            float& xil, float& xfl) {
+                const int k = 32 * jj + lane;
+                const bool in = k < Q;
+                const float4 o = in ? orow[k] : make_float4(kVoid, kVoid, kVoid, kVoid);
+                const float ob = in ? obase[jj] : 0.0f;
+                xi0 = (b0[jj].h + ob) - Kb;      xf0 = (b0[jj].l + o.x) - fb;
+                xis = (st[jj].h + ob) - Ks_[jj]; xfs = (st[jj].l + o.y) - fs[jj];
+                xi1 = (b1[jj].h + ob) - Kb;      xf1 = (b1[jj].l + o.z) - fb;
+                xil = (k < L) ? (lb[jj].h + ob) - Kl[jj] : kVoid;
+                xfl = (lb[jj].l + o.w) - fl[jj];
+            };
             if (k2 == 0) {
                 double mx = -1.0e300;
 #pragma unroll
-                for (int j = 0; j < J; ++j)
-                    if (j < nslot)
-                        mx = fmax(mx, (double)ii[j] + (double)fmaxf(fmaxf(v0[j], vs[j]), fmaxf(v1[j], vl[j])));
+                for (int j = 0; j < J; ++j) {
+                    float a, b, c, d, e, f, g, h;
+                    expo(j, a, b, c, d, e, f, g, h);
+                    mx = fmax(mx, fmax(fmax((double)a + (double)b, (double)c + (double)d),
+                                       fmax((double)e + (double)f, (double)g + (double)h)));
+                }
                 mx = warp_max_d(mx);
                 feasible = mx > (double)kVoidTest;
                 float s = 0.0f;
 #pragma unroll
-                for (int j = 0; j < J; ++j)
-                    if (j < nslot) {
-                        const float d = (float)((double)ii[j] - mx);
-                        s += ex2f(v0[j] + d) + ex2f(vs[j] + d) + ex2f(v1[j] + d) + ex2f(vl[j] + d);
-                    }
+                for (int j = 0; j < J; ++j) {
+                    float a, b, c, d, e, f, g, h;
+                    expo(j, a, b, c, d, e, f, g, h);
+                    s += ex2f((float)((double)a + (double)b - mx)) + ex2f((float)((double)c + (double)d - mx)) +
+                         ex2f((float)((double)e + (double)f - mx)) + ex2f((float)((double)g + (double)h - mx));
+                }
                 s = warp_sum(s);
                 const double logZ2 = mx + (double)log2f(s);
-                const double fl = floor(logZ2);
-                IZ = feasible ? (int)fl : 0;
-                fZ = feasible ? (float)(logZ2 - fl) : 0.0f;
-                if (dir == 0 && lane == 0) {
-                    const float v = feasible ? (float)(-logZ2 * kLn2) : CUDART_INF_F;
-                    p.loss[n] = v; p.loss_ws[n] = v;
-                }
+                const double fl2 = floor(logZ2);
+                IZ = feasible ? (float)fl2 : 0.0f;
+                fZ = feasible ? (float)(logZ2 - fl2) : 0.0f;
             }
             float* ob = occ_buf + (i & 1) * E;
             if (lane == 0) bulk_wait_read<1>();
@@ -416,22 +430,23 @@ __global__ void __launch_bounds__(128, 1) star_trellis_kernel(StarTrellisParams 
             float bsum = 0.0f, gsum = 0.0f;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                if (j < nslot) {
-                    const int k = 32 * j + lane;
-                    const float d = (float)(ii[j] - IZ) - fZ;
-                    const float g0 = feasible ? ex2f(v0[j] + d) : 0.0f;
-                    const float g1 = feasible ? ex2f(v1[j] + d) : 0.0f;
-                    const float gl = feasible ? ex2f(vl[j] + d) : 0.0f;
-                    // h = gamma(star) / (P - p_y) = 2^(log2 gamma - es)
-                    const float h = (feasible && k < Q) ? ex2f(vs[j] + d - es[j]) : 0.0f;
-                    bsum += g0 + g1;
-                    gsum += h;
-                    if (k < Ks) ((float2*)(ob + 2))[k] = make_float2(gl, ((exclude >> j) & 1u) ? h : 0.0f);
-                }
+                const int k = 32 * j + lane;
+                float xi0, xf0, xis, xfs, xi1, xf1, xil, xfl;
+                expo(j, xi0, xf0, xis, xfs, xi1, xf1, xil, xfl);
+                const float g0 = feasible ? ex2f((xi0 - IZ) + (xf0 - fZ)) : 0.0f;
+                const float g1 = feasible ? ex2f((xi1 - IZ) + (xf1 - fZ)) : 0.0f;
+                const float gl = feasible ? ex2f((xil - IZ) + (xfl - fZ)) : 0.0f;
+                // h = gamma(star) / (P - p_y) = 2^(log2 gamma - es), es = the star's TRUE emission: without the
+                // penalty and with the row shift added back (the shift cancels in gamma, not in P - p_y)
+                const float h = (feasible && k < Q)
+                                    ? ex2f(((xis - IZ) - ((Ks_[j] - Kp) + ct)) + ((xfs - fZ) - (fs[j] - fp))) : 0.0f;
+                bsum += g0 + g1;
+                gsum += h;
+                if (k < Ks) ((float2*)(ob + 4))[k] = make_float2(gl, ((exclude >> j) & 1u) ? h : 0.0f);
             }
             bsum = warp_sum(bsum);
             gsum = warp_sum(gsum);
-            if (lane == 0) { ob[0] = bsum; ob[1] = gsum; }
+            if (lane == 0) { ob[1] = bsum; ob[2] = gsum; }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -439,9 +454,14 @@ __global__ void __launch_bounds__(128, 1) star_trellis_kernel(StarTrellisParams 
                 bulk_commit();
                 if (k2 + nstage < Tn - steps1) issue_tr(k2 + nstage);
             }
+            if (++ts == nstage) { ts = 0; tpar ^= 1u; }
         }
     }
     if (steps1 == Tn) phase_switch();
+    if (dir == 0 && lane == 0) {
+        const float v = feasible ? (float)(-((double)IZ + (double)fZ + (double)csum) * kLn2) : CUDART_INF_F;
+        p.loss[n] = v; p.loss_ws[n] = v;
+    }
     if (lane == 0) bulk_wait_all<0>();
 }
 
@@ -497,7 +517,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
     float* gb = p.gx + (long long)n * p.sg_n;
     const float g = p.gout[n];
     const float delta = p.from_logits ? 1.0f : 0.0f;
-    const uint32_t occ_bytes = (uint32_t)round_up(2 + 2 * Ks, 4) * 4u;
+    const uint32_t occ_bytes = (uint32_t)round_up(4 + 2 * Ks, 4) * 4u;
 
     auto issue = [&](int r) {
         const int stage = r % nstage;
@@ -513,7 +533,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
             }
         } else {
             for (int c = lane; c < V; c += 32) dst[c] = src[c];
-            for (int c = lane; c < 2 + 2 * Ks; c += 32) dst[V + c] = osrc[c];
+            for (int c = lane; c < 4 + 2 * Ks; c += 32) dst[V + c] = osrc[c];
         }
     };
     for (int r = 0; r < min(nstage - 1, nreal); ++r) issue(r);
@@ -531,17 +551,17 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
         float* occ = row + V;
         const int t = t0 + warp + nw * r;
         const float l2 = p.lse2[(size_t)n * p.T + t];
-        const float occ_blank = occ[0], G = occ[1];
+        const float occ_blank = occ[1], G = occ[2];
         const float p0 = ex2f(fmaf(row[0], kLog2e, -l2));
         // per-class corrections, computed from the untouched logits by the first position of each
         // label chain and parked in that position's occupancy slot
         for (int k = lane; k < Ks; k += 32) {
             const int w = s_tgt[k];
             if (!(w & kNotFirst)) {
-                float sl = (k < L) ? occ[2 + 2 * k] : 0.0f, sh = occ[3 + 2 * k];
-                for (int j = s_nxt[k]; j >= 0; j = s_nxt[j]) { sl += (j < L) ? occ[2 + 2 * j] : 0.0f; sh += occ[3 + 2 * j]; }
+                float sl = (k < L) ? occ[4 + 2 * k] : 0.0f, sh = occ[5 + 2 * k];
+                for (int j = s_nxt[k]; j >= 0; j = s_nxt[j]) { sl += (j < L) ? occ[4 + 2 * j] : 0.0f; sh += occ[5 + 2 * j]; }
                 const float pc = ex2f(fmaf(row[w & kLabelMask], kLog2e, -l2));
-                occ[2 + 2 * k] = g * (pc * sh - sl);
+                occ[4 + 2 * k] = g * (pc * sh - sl);
             }
         }
         __syncwarp();
@@ -562,7 +582,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
         __syncwarp();
         for (int k = lane; k < Ks; k += 32) {
             const int w = s_tgt[k];
-            if (!(w & kNotFirst)) row[w & kLabelMask] += occ[2 + 2 * k];
+            if (!(w & kNotFirst)) row[w & kLabelMask] += occ[4 + 2 * k];
         }
         float* dstg = gb + (long long)t * p.sg_t;
         if (p.use_bulk) {
