@@ -2,6 +2,7 @@
 // kernel selection and launches.  No allocation, no synchronisation, no global state.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/ha_b200.h"
@@ -84,40 +85,39 @@ size_t ha_ctc_workspace_bytes(int T, int N, int V, int S) {
     return ctc_ws_layout(T, N, S).total;
 }
 
-static int ctc_trellis_launch(const TrellisParams& tp, int nslot_max, int N, cudaStream_t st) {
+static int ctc_trellis_launch(const TrellisParams& tp, int nslot, int N, cudaStream_t st) {
     TrellisParams p = tp;
-    // ring depth: as deep as shared memory allows, at most 8
+    // One CTA per utterance; W warps per sweep direction, each owning J slots of 32 label pairs.
+    // Few warps with many slots keep the per-step bookkeeping (ring waits, barrier, mailbox) small
+    // next to the log-add chains; W = 2 still gives every SM sub-partition two or more warps.
+    if (nslot > 32) return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length > 1023 is not supported");
+    int env_w = 0;
+    if (const char* e = getenv("HA_B200_TRELLIS_W")) env_w = atoi(e);
+    int W = nslot < 4 ? 1 : (nslot <= 16 ? 2 : 4);
+    if (env_w >= 1 && env_w <= 4) W = env_w;
+    int J = (nslot + W - 1) / W;
+    const int Js[] = {1, 2, 3, 4, 5, 6, 8};
+    int Jt = 8;
+    for (int c : Js) if (c >= J) { Jt = c; break; }
+    if (J > 8) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: J=%d", J);
+    p.W = (nslot + Jt - 1) / Jt;
     int ns = 8;
-    while (ns >= 2 && (size_t)4 * trellis_warp_bytes(p.E, p.SPX, ns) > 200 * 1024) --ns;
+    while (ns >= 2 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, p.Sp, ns, p.W) > 110 * 1024) --ns;
     if (ns < 2) return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length too large for the trellis kernel");
     p.nstage = ns;
-    p.warp_bytes = trellis_warp_bytes(p.E, p.SPX, ns);
-    const size_t smem = (size_t)4 * p.warp_bytes;
-    const dim3 grid((N + 1) / 2), block(128);
+    p.dir_bytes = trellis_dir_bytes(p.E, p.SPX, p.Sp, ns, p.W);
+    const size_t smem = (size_t)2 * p.dir_bytes;
+    const dim3 grid(N), block(64 * p.W);
     int rc;
-#define HAB_LAUNCH_TRELLIS(JJ)                                                        \
-    do {                                                                              \
-        if ((rc = set_smem(ctc_trellis_kernel<JJ>, smem, "ctc_trellis"))) return rc; \
-        ctc_trellis_kernel<JJ><<<grid, block, smem, st>>>(p);                         \
-    } while (0)
-    // J = slots per warp = ceil((S+1)/32): every slot is computed (straight-line code), so J is exact
-    // for the common sizes
-    switch (nslot_max) {
-        case 1: HAB_LAUNCH_TRELLIS(1); break;
-        case 2: HAB_LAUNCH_TRELLIS(2); break;
-        case 3: HAB_LAUNCH_TRELLIS(3); break;
-        case 4: HAB_LAUNCH_TRELLIS(4); break;
-        case 5: HAB_LAUNCH_TRELLIS(5); break;
-        case 6: HAB_LAUNCH_TRELLIS(6); break;
-        case 7: HAB_LAUNCH_TRELLIS(7); break;
-        case 8: HAB_LAUNCH_TRELLIS(8); break;
-        case 9: case 10: HAB_LAUNCH_TRELLIS(10); break;
-        case 11: case 12: HAB_LAUNCH_TRELLIS(12); break;
-        case 13: case 14: case 15: case 16: HAB_LAUNCH_TRELLIS(16); break;
-        default:
-            if (nslot_max <= 24) HAB_LAUNCH_TRELLIS(24);
-            else if (nslot_max <= 32) HAB_LAUNCH_TRELLIS(32);
-            else return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length > 1023 is not supported");
+#define HAB_LAUNCH_TRELLIS(JJ)                                                              \
+    case JJ:                                                                                \
+        if ((rc = set_smem(ctc_trellis_kernel<JJ, 256>, smem, "ctc_trellis"))) return rc;  \
+        ctc_trellis_kernel<JJ, 256><<<grid, block, smem, st>>>(p);                         \
+        break
+    switch (Jt) {
+        HAB_LAUNCH_TRELLIS(1); HAB_LAUNCH_TRELLIS(2); HAB_LAUNCH_TRELLIS(3); HAB_LAUNCH_TRELLIS(4);
+        HAB_LAUNCH_TRELLIS(5); HAB_LAUNCH_TRELLIS(6); HAB_LAUNCH_TRELLIS(8);
+        default: return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: J=%d", Jt);
     }
 #undef HAB_LAUNCH_TRELLIS
     return check_launch("ctc_trellis_kernel");
@@ -170,6 +170,7 @@ int ha_ctc_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
     tp.T = T; tp.N = N; tp.meta = pp.meta; tp.order = pp.order; tp.tgt = pp.tgt; tp.Sp = w.Sp;
     tp.em = rp.em; tp.E = w.E; tp.tr = (float*)(base + w.tr); tp.SPX = w.SPX; tp.JWp = w.JWp;
     tp.loss = loss; tp.loss_ws = (float*)(base + w.loss);
+    tp.probe = (long long*)base;   // first 256 workspace bytes are reserved
     if ((rc = ctc_trellis_launch(tp, (S + 1 + 31) / 32, N, st))) return rc;
 
     return HA_OK;

@@ -13,6 +13,7 @@ constexpr float kVoid = -1.0e30f;       // "void" (ha/ctc.py:135 uses finfo.min)
 constexpr float kVoidTest = -1.0e29f;   // anything below this is void
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr double kLn2 = 0.6931471805599453094;
+constexpr double kLog2e_d = 1.4426950408889634074;
 
 constexpr int kLabelMask = 0x3fffffff;  // tgt words: label | kNotFirst
 constexpr int kNotFirst = 0x40000000;   // an earlier position of the same utterance holds the same label
@@ -44,6 +45,8 @@ __device__ __forceinline__ float lae2(float a, float b) {
 struct SF { float h, l; };
 constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: (x + kMagic) - kMagic == rint(x) for |x| < 2^22
 __device__ __forceinline__ float round_int(float x) { return __fsub_rn(__fadd_rn(x, kMagic), kMagic); }
+// small integer -> float without a conversion instruction
+__device__ __forceinline__ float small_int_to_float(int k) { return __int_as_float(0x4B400000 + k) - kMagic; }
 __device__ __forceinline__ SF sf_void() { SF r; r.h = kVoid; r.l = 0.0f; return r; }
 // log2(2^a + 2^b); the result's l is in [-0.5, 1.5] (not renormalised)
 __device__ __forceinline__ SF lae_sf(SF a, SF b) {

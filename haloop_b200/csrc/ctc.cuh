@@ -4,15 +4,17 @@
 //   ctc_prep_kernel     targets/lengths -> int32 metadata, duplicate-label chains, work order
 //   ctc_rows_kernel     one warp per (b,t) row: log-softmax statistics + gather of the blank and
 //                       label emissions (rows staged in shared memory by bulk async copies)
-//   ctc_trellis_kernel  alpha and beta recursions as two warps per utterance that meet in the
-//                       middle; extended-label states live in registers as (blank,label) pairs
-//                       interleaved across the 32 lanes; emission rows and the other side's stored
-//                       trellis rows are prefetched through a TMA (cp.async.bulk) ring; posterior
-//                       occupancies overwrite the emission buffer in place
+//   ctc_trellis_kernel  one CTA per utterance: W warps sweep alpha forward and W warps sweep beta
+//                       backward until they meet in the middle; extended-label states live in
+//                       registers as (blank,label) pairs across the lanes, neighbours exchanged by
+//                       warp shuffles (and a 2-float mailbox between warps); emission rows and the
+//                       other side's stored trellis rows are prefetched through a TMA
+//                       (cp.async.bulk) ring; posterior occupancies overwrite the emission buffer
 //   ctc_grad_kernel     one warp per row: softmax - occupancy, times grad_out, written once
 //
-// All log-domain values are log2.  alpha/beta are kept relative to per-slot (64-state) integer
-// offsets so fp32 state stays O(100) in magnitude whatever T is (SURVEY.md finding 3).
+// All log-domain values are log2.  alpha/beta are split numbers (integer part + fraction, common.cuh)
+// and gathered emissions are stored as int8 integer part + fp32 fraction, so every fp32 rounding in the
+// recursions happens at magnitude ~1 whatever T and log V are (SURVEY.md finding 3).
 #pragma once
 #include "common.cuh"
 
@@ -20,13 +22,18 @@ namespace hab {
 
 struct CtcWs {                 // workspace layout (byte offsets), filled by ctc_ws_layout()
     size_t meta, order, tgt, dupnext, loss, lse2, em, tr, total;
-    int Sp, E, JWp, SPX;
+    int Sp, E, JWp, SPX;       // E: floats per emission row (header + fractions + packed int8 parts)
 };
+
+// emission row (bytes): [0,16) float ct, Kb, fb, 0   [16, 16+4 Sp) float f[k]   then int8 K[k]:
+// log2 p(label k) - ct = K[k] + f[k], blank = Kb + fb, ct = integer row shift.  The occupancy row
+// written in place reuses the float part: [1] blank occupancy, [4+k] label occupancy.
+__host__ __device__ inline int ctc_em_floats(int Sp) { return 4 + Sp + round_up(Sp, 16) / 4; }
 
 __host__ inline CtcWs ctc_ws_layout(int T, int N, int S) {
     CtcWs w;
     w.Sp = round_up(S > 0 ? S : 1, 4);
-    w.E = round_up(S + 4, 4);                       // row shift c_t, blank, 2 x void, S labels per emission row
+    w.E = ctc_em_floats(w.Sp);
     w.JWp = round_up((S + 1 + 31) / 32, 4);         // per-slot offsets stored in front of a trellis row
     w.SPX = w.JWp + round_up(2 * S + 2, 4);         // + (blank,label) pairs
     size_t o = 256;                                 // header
@@ -192,16 +199,27 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_rows_kernel(RowsParams 
         // Emissions are stored relative to an integer per-row shift c_t = rint(max gathered emission),
         // so the likeliest state of every frame sits near 0.  The shifts cancel in every posterior
         // (both sweeps see the same rows); only the loss needs their sum, which the trellis adds back.
+        // Each emission is evaluated in float64 from the fp32 logit and split into an int8 integer
+        // part and an fp32 fraction: its quantisation error is ~3e-8 instead of ulp(log2 p)/2.
         const float eblank = fmaf(row[0], kLog2e, -l2);
         float emax = eblank;
         for (int k = lane; k < L; k += 32) emax = fmaxf(emax, fmaf(row[s_tgt[k]], kLog2e, -l2));
         const float ct = round_int(warp_max(emax));
+        const double shift = (double)l2 + (double)ct;
         float* erow = p.em + ((size_t)n * p.T + t) * p.E;
+        signed char* krow = (signed char*)(erow + 4 + p.Sp);
         if (lane == 0) {
             p.lse2[(size_t)n * p.T + t] = l2;
-            *(float4*)erow = make_float4(ct, eblank - ct, kVoid, kVoid);
+            const double e = fma((double)row[0], kLog2e_d, -shift);
+            const double K = fmax(rint(e), -127.0);
+            *(float4*)erow = make_float4(ct, (float)K, (float)(e - K), 0.0f);
         }
-        for (int k = lane; k < L; k += 32) erow[4 + k] = fmaf(row[s_tgt[k]], kLog2e, -l2) - ct;
+        for (int k = lane; k < L; k += 32) {
+            const double e = fma((double)row[s_tgt[k]], kLog2e_d, -shift);
+            const double K = fmax(rint(e), -127.0);
+            erow[4 + k] = (float)(e - K);
+            krow[k] = (signed char)(int)K;
+        }
         __syncwarp();
         if (r + nstage < nrows) issue(r + nstage);
     }
@@ -211,69 +229,74 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_rows_kernel(RowsParams 
 struct TrellisParams {
     int T, N;
     const int4* meta; const int* order; const int* tgt; int Sp;
-    float* em; int E;          // emission rows in: [0] row shift c_t  [1] blank  [2],[3] void  [4+k] label k
-                               // (log2, shifted); occupancy rows out, in place: [1] blank  [4+k] label k
+    float* em; int E;          // emission rows in / occupancy rows out, in place (layout: ctc_em_floats)
     float* tr; int SPX, JWp;   // stored trellis row = [JWp slot bases][2*(L+1) floats relative to them]
     float* loss; float* loss_ws;
-    int nstage; int warp_bytes;
+    int nstage, W;             // ring depth; warps per sweep direction
+    int dir_bytes;             // shared memory per direction
+    long long* probe;          // HAB_PROBE builds only: cycle stamps of one warp
 };
 
-__host__ __device__ inline int trellis_warp_bytes(int E, int SPX, int nstage) {
-    return round_up((nstage * (E + SPX) + 2 * E) * 4 + 2 * nstage * 8, 128);
+// per-direction shared memory: [em ring][trellis ring][2 occupancy rows][mailboxes][partials][mbarriers]
+__host__ __device__ inline int trellis_dir_bytes(int E, int SPX, int Sp, int nstage, int W) {
+    return round_up(nstage * (E + SPX) * 4 + 2 * (4 + Sp) * 4 + 2 * W * 8 + 2 * W * 4 + W * 16 + 2 * nstage * 8, 128);
 }
 
 constexpr float kRebase = 24.0f;   // a slot is re-based when its states drift this far (log2 units) from the base
 
-// grid ceil(N/2), block 128: warps (2u, 2u+1) are the alpha and beta side of one utterance; each
-// warp is alone on its SM sub-partition, so the per-step code is straight-line and written
-// stage-major (every stage loops over the J slots) to keep J independent MUFU/FADD chains in flight.
-//
-// Side d walks time from its own end: step i is frame t = d ? T-1-i : i, on its own ordering of
-// the label pairs (beta = alpha on the reversed label sequence).  Lane l of slot j owns pair
-// q = 32 j + l = (blank state 2q, label state 2q+1), each a split number (common.cuh).  Phase 1
-// (first half of the frames) stores every row as floats relative to a per-slot base; phase 2
-// combines live rows with the rows the other side stored, so posteriors need T sequential steps
-// instead of 2T and nothing is recomputed.
-template <int J>
-__global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
+// grid N (one CTA per utterance, longest first), block 64*W: warps [0,W) sweep alpha forward in time,
+// warps [W,2W) sweep beta backward; the two sides meet in the middle.  Side d's step i is frame
+// t = d ? T-1-i : i and it orders the label pairs its own way (beta = alpha on the reversed label
+// sequence).  Warp w of a side owns J slots of 32 pairs: pair q = 32 (w J + j) + lane =
+// (blank state 2q, label state 2q+1), each a split number (common.cuh).  The only value crossing a
+// lane boundary per step is the label state of pair q-1: a shuffle inside a warp, a two-float mailbox
+// between warps, with one named barrier per step per side.  Phase 1 (first half of the frames)
+// stores every row as floats relative to a per-slot base; phase 2 combines live rows with the rows the
+// other side stored, so posteriors need T sequential steps instead of 2T and nothing is recomputed.
+template <int J, int MAXT>
+__global__ void __launch_bounds__(MAXT) ctc_trellis_kernel(TrellisParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int W = p.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int usel = warp >> 1, dir = warp & 1;
-    const int idx = blockIdx.x * 2 + usel;
-    if (idx >= p.N) return;
-    const int n = p.order[idx];
+    const int dir = warp >= W, w = warp - dir * W;
+    const int n = p.order[blockIdx.x];
     const int4 mt = p.meta[n];
     const int Tn = mt.x, L = mt.y;
     if (mt.z || Tn == 0) {
         const float v = mt.z ? CUDART_NAN_F : ((L == 0) ? 0.0f : CUDART_INF_F);
-        if (dir == 0 && lane == 0) { p.loss[n] = v; p.loss_ws[n] = v; }
+        if (threadIdx.x == 0) { p.loss[n] = v; p.loss_ws[n] = v; }
         return;
     }
     const int P = L + 1;
-    const int nstage = p.nstage, E = p.E, SPX = p.SPX, JWp = p.JWp;
+    const int nstage = p.nstage, E = p.E, SPX = p.SPX, JWp = p.JWp, Sp = p.Sp;
+    const bool leader = (w == 0 && lane == 0);
+    const int nthr = 32 * W;                      // threads of my side
+    const int barid = 1 + dir;
 
-    unsigned char* wb = smem_raw + (size_t)warp * p.warp_bytes;
-    float* em_ring = (float*)wb;
+    unsigned char* db = smem_raw + (size_t)dir * p.dir_bytes;
+    float* em_ring = (float*)db;
     float* tr_ring = em_ring + nstage * E;
-    float* occ_buf = tr_ring + nstage * SPX;
-    uint64_t* bar_em = (uint64_t*)(occ_buf + 2 * E);
+    float* occ_buf = tr_ring + nstage * SPX;      // 2 x (4 + Sp)
+    float2* mail = (float2*)(occ_buf + 2 * (4 + Sp));        // [2][W] label state of a warp's last pair
+    float* psum = (float*)(mail + 2 * W);                    // [2][W] blank occupancy partial sums
+    double* redm = (double*)(psum + 2 * W);                  // [W] log Z partial maxima
+    float* reds = (float*)(redm + W);                        // [W] log Z partial sums
+    uint64_t* bar_em = (uint64_t*)(reds + 2 * W);
     uint64_t* bar_tr = bar_em + nstage;
-    if (lane == 0)
+    if (leader)
         for (int s = 0; s < nstage; ++s) { mbar_init(&bar_em[s], 1); mbar_init(&bar_tr[s], 1); }
     mbar_init_fence();
-    __syncwarp();
+    __syncthreads();
 
-    // per slot: where my label sits in an emission row (the void entry [2] when I have none), whether
-    // my pair / label exists, and whether the skip transition into my label is allowed
-    // (ha/ctc.py:140-142)
+    // per slot: do my pair / my label exist, and is the skip transition into my label allowed
+    // (ha/ctc.py:140-142)?
+    const int q0 = 32 * (w * J) + lane;           // my pair in slot 0
     unsigned allowed = 0, hasp = 0, hasl = 0;
-    int eoff[J];
     {
         const int* y = p.tgt + (size_t)n * p.Sp;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const int q = 32 * j + lane;
-            eoff[j] = (q < L) ? 4 + (dir ? L - 1 - q : q) : 2;
+            const int q = q0 + 32 * j;
             if (q < P) hasp |= 1u << j;
             if (q < L) hasl |= 1u << j;
             if (q >= 1 && q < L) {
@@ -284,6 +307,12 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
             }
         }
     }
+    // my label of slot j sits at position pos0 +- 32 j of an emission row (reversed for beta)
+    const int pos0 = dir ? L - 1 - q0 : q0;
+    const int pstep = dir ? -32 : 32;
+    // the other side's copy of my blank 2q is its state 2 (L - q) = R0 - 64 j, my label one below
+    const int R0 = 2 * (L - q0);
+    const int B0 = R0 >> 6, B1 = (R0 - 1) >> 6;   // slots of those states: exactly j lower per slot
 
     SF a0[J], a1[J];       // blank / label state of my pair in slot j
     float base[J];         // storage base of slot j (integer valued)
@@ -292,36 +321,37 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
 
     float* em_base = p.em + (size_t)n * p.T * E;
     float* tr_base = p.tr + (size_t)n * p.T * SPX;
-    const uint32_t em_bytes = (uint32_t)round_up(L + 4, 4) * 4u;
+    const uint32_t emf_bytes = (uint32_t)(4 + round_up(L, 4)) * 4u;       // header + fractions
+    const uint32_t emk_bytes = (uint32_t)round_up(L, 16);                  // int8 integer parts
     const uint32_t tr_bytes = (uint32_t)(JWp + round_up(2 * P, 4)) * 4u;
     const int tm = Tn >> 1;
     const int steps1 = dir ? Tn - tm : tm;
-    // the other side's copy of my state s is its state 2L - s: my blank 2q <-> its R0 - 64 j, my label
-    // <-> one below, with R0 = 2 (L - lane); slot bases likewise shift by exactly j per slot
-    const int R0 = 2 * (L - lane);
-    const int B0 = R0 >> 6, B1 = (R0 - 1) >> 6;
+    // my pairs are all unreachable before step `first` (pair q needs q frames to be reached)
+    const int first = 32 * (w * J);
 
-    auto issue_em = [&](int i) {          // lane 0 only
+    auto issue_em = [&](int i) {          // leader only
         const int st = i % nstage, t = dir ? Tn - 1 - i : i;
-        mbar_expect_tx(&bar_em[st], em_bytes);
-        bulk_g2s(em_ring + st * E, em_base + (size_t)t * E, em_bytes, &bar_em[st]);
+        const float* src = em_base + (size_t)t * E;
+        mbar_expect_tx(&bar_em[st], emf_bytes + emk_bytes);
+        bulk_g2s(em_ring + st * E, src, emf_bytes, &bar_em[st]);
+        if (emk_bytes) bulk_g2s(em_ring + st * E + 4 + Sp, src + 4 + Sp, emk_bytes, &bar_em[st]);
     };
-    auto issue_tr = [&](int k) {          // lane 0 only; k-th phase-2 step
+    auto issue_tr = [&](int k) {          // leader only; k-th phase-2 step
         const int st = k % nstage, i = steps1 + k, t = dir ? Tn - 1 - i : i;
         mbar_expect_tx(&bar_tr[st], tr_bytes);
         bulk_g2s(tr_ring + st * SPX, tr_base + (size_t)t * SPX, tr_bytes, &bar_tr[st]);
     };
     auto phase_switch = [&]() {
-        // my stored rows -> visible to the sibling warp's bulk (async-proxy) loads, and vice versa
+        // my stored rows -> visible to the other side's bulk (async-proxy) loads, and vice versa
         __threadfence();
         fence_async_all();
-        named_bar_sync(1 + usel, 64);
+        __syncthreads();
         fence_async_all();
-        if (lane == 0)
+        if (leader)
             for (int k = 0; k < min(nstage, Tn - steps1); ++k) issue_tr(k);
     };
 
-    if (lane == 0)
+    if (leader)
         for (int i = 0; i < min(nstage, Tn); ++i) issue_em(i);
 
     float IZ = 0.0f, fZ = 0.0f, csum = 0.0f;
@@ -332,30 +362,41 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
     for (int i = 0; i < Tn; ++i) {
         if (i == steps1) phase_switch();
         const int t = dir ? Tn - 1 - i : i;
+        const bool phase2 = i >= steps1;
+#ifdef HAB_PROBE
+        const bool pr = (blockIdx.x == 0 && warp == 0 && lane == 0 && (i == 100 || i == 101 || i == Tn - 50));
+        const int pb = (i == 100) ? 0 : (i == 101 ? 8 : 16);
+        if (pr) p.probe[pb + 0] = clock64();
+#endif
         mbar_wait(&bar_em[st], par);
+#ifdef HAB_PROBE
+        if (pr) p.probe[pb + 1] = clock64();
+#endif
         const float* er = em_ring + st * E;
+        const signed char* kr = (const signed char*)(er + 4 + Sp);
+        const float Kb = er[1], fb = er[2];
         csum += er[0];
-        const float eb = er[1];
-        const float Kb = round_int(eb), fb = eb - Kb;
         float Kl[J], fl[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const float e = er[eoff[j]];
-            Kl[j] = round_int(e);
-            fl[j] = e - Kl[j];
+            const bool v = (hasl >> j) & 1u;
+            const int pos = v ? pos0 + pstep * j : 0;
+            Kl[j] = v ? small_int_to_float((int)kr[pos]) : kVoid;
+            fl[j] = v ? er[4 + pos] : 0.0f;
         }
-        __syncwarp();
-        if (lane == 0 && i + nstage < Tn) issue_em(i + nstage);
-        if (++st == nstage) { st = 0; par ^= 1u; }
 
+#ifdef HAB_PROBE
+        if (pr) p.probe[pb + 2] = clock64();
+#endif
         if (i == 0) {
-            if (lane == 0) {                                       // ha/ctc.py:138
+            if (q0 == 0) {                                         // ha/ctc.py:138
                 SF z; z.h = 0.0f; z.l = 0.0f;
                 a0[0] = add_norm(z, Kb, fb);
                 a1[0] = add_norm(z, Kl[0], fl[0]);                 // void when L == 0
             }
-        } else {
-            // c = label state of the pair below (lane - 1; lane 0 takes lane 31 of the slot below)
+        } else if (i >= first) {
+            // c = label state of the pair below: lane - 1; lane 0 takes lane 31 of the slot below, or the
+            // mailbox the warp below filled in the previous step
             float ch[J], cl[J];
             {
                 float rh[J], rl[J];
@@ -364,10 +405,12 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
                     rh[j] = __shfl_sync(0xffffffffu, a1[j].h, (lane + 31) & 31);
                     rl[j] = __shfl_sync(0xffffffffu, a1[j].l, (lane + 31) & 31);
                 }
+                float2 in = make_float2(kVoid, 0.0f);
+                if (w > 0) in = mail[((i - 1) & 1) * W + w - 1];
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    ch[j] = lane ? rh[j] : (j ? rh[j ? j - 1 : 0] : kVoid);
-                    cl[j] = lane ? rl[j] : (j ? rl[j ? j - 1 : 0] : 0.0f);
+                    ch[j] = lane ? rh[j] : (j ? rh[j ? j - 1 : 0] : in.x);
+                    cl[j] = lane ? rl[j] : (j ? rl[j ? j - 1 : 0] : in.y);
                 }
             }
             // u = blank (+) previous label;  v = label (+) (skip allowed ? u : blank)     [ha/ctc.py:155-167]
@@ -409,7 +452,13 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
                 a1[j] = add_norm(v, Kl[j], fl[j]);
             }
         }
-        if (i < steps1) {
+#ifdef HAB_PROBE
+        if (pr) p.probe[pb + 3] = clock64();
+#endif
+        // my last pair's label state for the warp above (read in its next step)
+        if (lane == 31 && w + 1 < W) mail[(i & 1) * W + w] = make_float2(a1[J - 1].h, a1[J - 1].l);
+
+        if (!phase2) {
             // Rows are stored relative to a per-slot integer base.  A live slot is re-based (one warp
             // max) only when some state rose well above its base or none is left near it; the test
             // itself is three warp-wide OR reductions for all slots together.
@@ -432,12 +481,12 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
                     if ((need >> j) & 1u) base[j] = warp_max(fmaxf(a0[j].h, a1[j].h));
             }
             float* row = tr_base + (size_t)t * SPX;
-            float2* prow = (float2*)(row + JWp) + lane;
+            float2* prow = (float2*)(row + JWp) + q0;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 if ((hasp >> j) & 1u)
                     prow[32 * j] = make_float2((a0[j].h - base[j]) + a0[j].l, (a1[j].h - base[j]) + a1[j].l);
-                if (lane == j && 32 * j < P) row[j] = base[j];
+                if (lane == j && 32 * (w * J + j) < P) row[w * J + j] = base[j];
             }
         } else {
             const int k = i - steps1;
@@ -445,7 +494,7 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
             const float* orow = tr_ring + ts * SPX + JWp + R0;     // [-64 j] = other side's copy of my blank
             const float* ob0 = tr_ring + ts * SPX + B0;            // [-j]    = its slot base
             const float* ob1 = tr_ring + ts * SPX + B1;
-            // posterior exponent = [h + other base - K] (integers) + [l + other value - f] (small), minus log Z.
+            // posterior exponent = [h + other base - K] (integers) + [l + other value - f] (small), minus log Z
             auto expo = [&](int jj, float& xi0, float& xf0, float& xi1, float& xf1) {
                 const bool vp = (hasp >> jj) & 1u, vl = (hasl >> jj) & 1u;
                 const float o0 = vp ? orow[-64 * jj] : 0.0f, o1 = vl ? orow[-64 * jj - 1] : 0.0f;
@@ -456,6 +505,7 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
                 xf1 = vl ? (a1[jj].l + o1) - fl[jj] : 0.0f;
             };
             if (k == 0) {
+                // log Z over all my side's states at the meeting frame: two-pass max / sum across the W warps
                 double mx = -1.0e300;
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
@@ -464,6 +514,9 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
                     mx = fmax(mx, fmax((double)xi0 + (double)xf0, (double)xi1 + (double)xf1));
                 }
                 mx = warp_max_d(mx);
+                if (lane == 0) redm[w] = mx;
+                named_bar_sync(barid, nthr);
+                for (int x = 0; x < W; ++x) mx = fmax(mx, redm[x]);
                 feasible = mx > (double)kVoidTest;
                 float s = 0.0f;
 #pragma unroll
@@ -474,14 +527,16 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
                          ex2f((float)((double)xi1 + (double)xf1 - mx));
                 }
                 s = warp_sum(s);
+                if (lane == 0) reds[w] = s;
+                named_bar_sync(barid, nthr);
+                s = 0.0f;
+                for (int x = 0; x < W; ++x) s += reds[x];
                 const double logZ2 = mx + (double)log2f(s);        // of the shifted emissions
                 const double fl2 = floor(logZ2);
                 IZ = feasible ? (float)fl2 : 0.0f;
                 fZ = feasible ? (float)(logZ2 - fl2) : 0.0f;
             }
-            float* ob = occ_buf + (i & 1) * E;
-            if (lane == 0) bulk_wait_read<1>();     // the store issued two steps ago has left this buffer
-            __syncwarp();
+            float* ob = occ_buf + (i & 1) * (4 + Sp);
             float g0[J], g1[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) {
@@ -496,27 +551,48 @@ __global__ void __launch_bounds__(128, 1) ctc_trellis_kernel(TrellisParams p) {
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 bsum += feasible ? g0[j] : 0.0f;
-                if ((hasl >> j) & 1u) ob[eoff[j]] = feasible ? g1[j] : 0.0f;
+                if ((hasl >> j) & 1u) ob[4 + pos0 + pstep * j] = feasible ? g1[j] : 0.0f;
             }
             bsum = warp_sum(bsum);
-            if (lane == 0) ob[1] = bsum;
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                bulk_s2g(em_base + (size_t)t * E, ob, em_bytes);
+            if (lane == 0) psum[(i & 1) * W + w] = bsum;
+            fence_async_smem();                     // my occupancy writes -> visible to the leader's bulk store
+            if (leader) bulk_wait_read<0>();        // the previous row's store has left the other buffer... and this one
+        }
+#ifdef HAB_PROBE
+        if (pr) p.probe[pb + 4] = clock64();
+#endif
+        // ---- one barrier per step per side: mailboxes, occupancy row and ring stages change hands
+        named_bar_sync(barid, nthr);
+#ifdef HAB_PROBE
+        if (pr) p.probe[pb + 5] = clock64();
+#endif
+        if (leader) {
+            if (i + nstage < Tn) issue_em(i + nstage);
+            if (phase2) {
+                const int k = i - steps1;
+                float* ob = occ_buf + (i & 1) * (4 + Sp);
+                float b = 0.0f;
+                for (int x = 0; x < W; ++x) b += psum[(i & 1) * W + x];
+                ob[1] = b;
+                fence_async_smem();
+                bulk_s2g(em_base + (size_t)t * E, ob, emf_bytes);
                 bulk_commit();
                 if (k + nstage < Tn - steps1) issue_tr(k + nstage);
             }
-            if (++ts == nstage) { ts = 0; tpar ^= 1u; }
         }
+        if (++st == nstage) { st = 0; par ^= 1u; }
+        if (phase2 && ++ts == nstage) { ts = 0; tpar ^= 1u; }
+#ifdef HAB_PROBE
+        if (pr) p.probe[pb + 6] = clock64();
+#endif
     }
     if (steps1 == Tn) phase_switch();     // only T == 1, beta side: still owes the barrier
-    if (dir == 0 && lane == 0) {
+    if (dir == 0 && leader) {
         // log Z of the true emissions = log Z of the shifted ones + the sum of all T row shifts
         const float v = feasible ? (float)(-((double)IZ + (double)fZ + (double)csum) * kLn2) : CUDART_INF_F;
         p.loss[n] = v; p.loss_ws[n] = v;
     }
-    if (lane == 0) bulk_wait_all<0>();
+    if (leader) bulk_wait_all<0>();
 }
 
 // ------------------------------------------------------------------------------------ grad ---
@@ -575,7 +651,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_grad_kernel(GradParams 
     const float* xb = p.x + (long long)n * p.sx_n;
     float* gb = p.gx + (long long)n * p.sg_n;
     const float g = p.gout[n];
-    const uint32_t occ_bytes = (uint32_t)round_up(L + 4, 4) * 4u;
+    const uint32_t occ_bytes = (uint32_t)(4 + round_up(L, 4)) * 4u;
 
     auto issue = [&](int r) {
         const int stage = r % nstage;

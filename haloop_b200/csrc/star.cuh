@@ -152,6 +152,10 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
 }
 
 // --------------------------------------------------------------------------------- trellis ---
+__host__ __device__ inline int trellis_warp_bytes(int E, int SPX, int nstage) {
+    return round_up((nstage * (E + SPX) + 2 * E) * 4 + 2 * nstage * 8, 128);
+}
+
 struct StarTrellisParams {
     int T, N, S;
     const int4* meta; const int* order; const int* tgt; int Sp;

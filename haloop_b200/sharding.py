@@ -1,0 +1,87 @@
+"""Length bucketing and batch sharding for multi-GPU runs (BASELINE.json configs[4]).
+
+Utterances are independent in all three losses, so the path shards by whole
+utterances with no data-path collective: logits and gradients never leave the rank that owns them.
+The only exchange is one all-reduce of [sum_b loss_b * w_b, sum_b w_b] per step.
+
+bucket_by_length mirrors the reference's DurationBatchSampler (ha/sampler.py:7-29: grow a batch until
+(len(batch)+1) * max_duration would exceed the budget), with padded bytes instead of seconds, after
+sorting by length so that padding inside a bucket stays small.
+"""
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import torch
+
+
+@dataclass
+class Bucket:
+    indices: List[int]      # utterance ids
+    t_max: int
+    u_max: int
+    cost: int               # padded logit bytes
+
+
+def padded_cost(n, t_max, u_max, vocab, kind):
+    """Bytes of the padded fp32 logits of a bucket: B*T*V (ctc/star) or B*T*(U+1)*V (rnnt)."""
+    per = t_max * vocab * 4 * ((u_max + 1) if kind == "rnnt" else 1)
+    return n * per
+
+
+def bucket_by_length(in_lens: Sequence[int], tgt_lens: Sequence[int], vocab: int, budget_bytes: int,
+                     kind: str = "ctc") -> List[Bucket]:
+    """Sort by input length, then cut greedily: a bucket closes when adding the next utterance would
+    push its padded cost past `budget_bytes` (the DurationBatchSampler rule, ha/sampler.py:13-29)."""
+    order = sorted(range(len(in_lens)), key=lambda i: (in_lens[i], tgt_lens[i]))
+    buckets, cur, t_max, u_max = [], [], 0, 0
+    for i in order:
+        nt, nu = max(t_max, in_lens[i]), max(u_max, tgt_lens[i])
+        if cur and padded_cost(len(cur) + 1, nt, nu, vocab, kind) > budget_bytes:
+            buckets.append(Bucket(cur, t_max, u_max, padded_cost(len(cur), t_max, u_max, vocab, kind)))
+            cur, nt, nu = [], in_lens[i], tgt_lens[i]
+        cur.append(i)
+        t_max, u_max = nt, nu
+    if cur:
+        buckets.append(Bucket(cur, t_max, u_max, padded_cost(len(cur), t_max, u_max, vocab, kind)))
+    return buckets
+
+
+def deal_buckets(buckets: Sequence[Bucket], world_size: int) -> List[List[int]]:
+    """Greedy cost balancing: heaviest bucket first, each to the currently lightest rank.
+    Returns, per rank, the list of bucket indices it owns (deterministic on every rank)."""
+    loads = [0] * world_size
+    owned = [[] for _ in range(world_size)]
+    for b in sorted(range(len(buckets)), key=lambda k: (-buckets[k].cost, k)):
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        owned[r].append(b)
+        loads[r] += buckets[b].cost
+    for o in owned:
+        o.sort()
+    return owned
+
+
+def shard_batch(n_utts: int, rank: int, world_size: int) -> range:
+    """Contiguous split of one already-formed batch: utterances [lo, hi) belong to `rank`."""
+    per, rem = divmod(n_utts, world_size)
+    lo = rank * per + min(rank, rem)
+    return range(lo, lo + per + (1 if rank < rem else 0))
+
+
+def reduce_loss(local_losses: torch.Tensor, weights: torch.Tensor = None, group=None):
+    """Global weighted mean of per-utterance losses across ranks with ONE all-reduce of two numbers.
+
+    weights = 1/target_length reproduces ctc_reduce_mean (ha/ctc.py:177-178) over the global batch;
+    weights = None is the plain batch mean torchaudio's rnnt_loss 'mean' uses (ha/recognizer.py:125).
+    Works on any backend (nccl on GPUs, gloo in the CPU tests); without an initialised process group
+    it is the local mean.  Differentiable w.r.t. local_losses.
+    """
+    import torch.distributed as dist
+    w = torch.ones_like(local_losses) if weights is None else weights.to(local_losses.dtype)
+    num = (local_losses * w).sum() if weights is not None else local_losses.sum()
+    cnt = torch.tensor(float(local_losses.numel()), device=local_losses.device, dtype=local_losses.dtype)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return num / cnt
+    buf = torch.stack([num.detach(), cnt])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    # value = global mean; gradient flows only through this rank's own numerator
+    return (num - num.detach() + buf[0]) / buf[1]

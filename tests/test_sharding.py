@@ -1,0 +1,97 @@
+"""Host-side logic of the multi-GPU path: bucketing, dealing, and the loss
+all-reduce on a world_size-2 gloo group (CPU)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from haloop_b200 import sharding
+
+
+def test_bucket_rule_matches_duration_batch_sampler():
+    """Same growth rule as ha/sampler.py:13-29 with bytes for seconds, on length-sorted input."""
+    g = torch.Generator().manual_seed(0)
+    T = torch.randint(20, 150, (200,), generator=g).mul(10).tolist()
+    U = [max(1, min(t // 5, (t - 1) // 2)) for t in T]
+    budget = 8 * 1500 * 1024 * 4
+    buckets = sharding.bucket_by_length(T, U, 1024, budget, "ctc")
+    seen = sorted(i for b in buckets for i in b.indices)
+    assert seen == list(range(200)), "every utterance lands in exactly one bucket"
+    for b in buckets:
+        assert b.t_max == max(T[i] for i in b.indices) and b.u_max == max(U[i] for i in b.indices)
+        assert b.cost <= budget or len(b.indices) == 1
+        assert b.cost == len(b.indices) * b.t_max * 1024 * 4
+    # sorted by length: buckets are contiguous in T, so padding waste is small
+    waste = sum(b.cost for b in buckets) / (sum(T) * 1024 * 4)
+    assert waste < 1.15
+    rn = sharding.bucket_by_length(T, U, 1024, 32 * 500 * 101 * 1024 * 4, "rnnt")
+    assert all(b.cost == len(b.indices) * b.t_max * (b.u_max + 1) * 1024 * 4 for b in rn)
+
+
+def test_deal_is_balanced_and_deterministic():
+    g = torch.Generator().manual_seed(1)
+    T = torch.randint(200, 1500, (4096,), generator=g).tolist()
+    U = [max(1, t // 6) for t in T]
+    buckets = sharding.bucket_by_length(T, U, 1024, 256 * 1500 * 1024 * 4 // 8, "ctc")
+    for world in (2, 4, 8):
+        owned = sharding.deal_buckets(buckets, world)
+        assert sorted(b for o in owned for b in o) == list(range(len(buckets)))
+        loads = [sum(buckets[b].cost for b in o) for o in owned]
+        assert max(loads) / (sum(loads) / world) < 1.10, "greedy deal keeps ranks within 10% (75 buckets)"
+        assert owned == sharding.deal_buckets(buckets, world)
+
+
+def test_shard_batch_partitions():
+    for n, world in ((256, 8), (13, 4), (3, 8)):
+        parts = [list(sharding.shard_batch(n, r, world)) for r in range(world)]
+        assert sum(parts, []) == list(range(n))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(7)
+        losses = torch.rand(10, generator=g, dtype=torch.float64) * 100
+        tl = torch.randint(1, 30, (10,), generator=g).double()
+        mine = sharding.shard_batch(10, rank, world)
+        loc = losses[mine.start:mine.stop].clone().requires_grad_(True)
+        tot = sharding.reduce_loss(loc, 1.0 / tl[mine.start:mine.stop])
+        tot.backward()
+        ref = (losses / tl).mean()                      # ctc_reduce_mean over the global batch, ha/ctc.py:177-178
+        plain = sharding.reduce_loss(losses[mine.start:mine.stop])
+        ok = (abs(float(tot) - float(ref)) < 1e-12 and
+              torch.allclose(loc.grad, (1.0 / tl[mine.start:mine.stop]) / 10) and
+              abs(float(plain) - float(losses.mean())) < 1e-12)
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_loss_allreduce_world2_gloo():
+    """The path's one collective: [sum loss*w, count] all-reduced; every rank gets the global mean and
+    the gradient of its own utterances only."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(out) == {0: True, 1: True}
+
+
+def test_reduce_loss_without_process_group():
+    l = torch.tensor([2.0, 4.0], requires_grad=True)
+    assert float(sharding.reduce_loss(l)) == 3.0
+    assert abs(float(sharding.reduce_loss(l, torch.tensor([0.5, 0.25]))) - 1.0) < 1e-7
