@@ -87,9 +87,9 @@ size_t ha_ctc_workspace_bytes(int T, int N, int V, int S) {
 
 static int ctc_trellis_launch(const TrellisParams& tp, int nslot, int N, cudaStream_t st) {
     TrellisParams p = tp;
-    // One CTA per utterance; W warps per sweep direction, each owning J slots of 32 label pairs.
-    // Few warps with many slots keep the per-step bookkeeping (ring waits, barrier, mailbox) small
-    // next to the log-add chains; W = 2 still gives every SM sub-partition two or more warps.
+    // One CTA per utterance: W compute warps per sweep direction, each owning J slots of 32 label
+    // pairs, plus one producer warp per direction.  Few compute warps with many slots keep the per-step
+    // bookkeeping small next to the log-add chains.
     if (nslot > 32) return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length > 1023 is not supported");
     int env_w = 0;
     if (const char* e = getenv("HA_B200_TRELLIS_W")) env_w = atoi(e);
@@ -97,22 +97,26 @@ static int ctc_trellis_launch(const TrellisParams& tp, int nslot, int N, cudaStr
     if (env_w >= 1 && env_w <= 4) W = env_w;
     int J = (nslot + W - 1) / W;
     const int Js[] = {1, 2, 3, 4, 5, 6, 8};
-    int Jt = 8;
+    int Jt = 0;
     for (int c : Js) if (c >= J) { Jt = c; break; }
-    if (J > 8) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: J=%d", J);
+    if (!Jt) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: J=%d", J);
     p.W = (nslot + Jt - 1) / Jt;
-    int ns = 8;
-    while (ns >= 2 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, p.Sp, ns, p.W) > 110 * 1024) --ns;
-    if (ns < 2) return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length too large for the trellis kernel");
+    p.G = kMaxG;
+    int ns = 4;
+    while (ns >= 2 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, p.Sp, ns, p.G, p.W) > 100 * 1024) --ns;
+    if (ns < 2) {
+        ns = 2;
+        while (p.G > 1 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, p.Sp, ns, p.G, p.W) > 220 * 1024) p.G >>= 1;
+    }
     p.nstage = ns;
-    p.dir_bytes = trellis_dir_bytes(p.E, p.SPX, p.Sp, ns, p.W);
+    p.dir_bytes = trellis_dir_bytes(p.E, p.SPX, p.Sp, ns, p.G, p.W);
     const size_t smem = (size_t)2 * p.dir_bytes;
-    const dim3 grid(N), block(64 * p.W);
+    const dim3 grid(N), block(32 * (2 * p.W + 2));
     int rc;
-#define HAB_LAUNCH_TRELLIS(JJ)                                                              \
-    case JJ:                                                                                \
-        if ((rc = set_smem(ctc_trellis_kernel<JJ, 256>, smem, "ctc_trellis"))) return rc;  \
-        ctc_trellis_kernel<JJ, 256><<<grid, block, smem, st>>>(p);                         \
+#define HAB_LAUNCH_TRELLIS(JJ)                                                         \
+    case JJ:                                                                           \
+        if ((rc = set_smem(ctc_trellis_kernel<JJ>, smem, "ctc_trellis"))) return rc;  \
+        ctc_trellis_kernel<JJ><<<grid, block, smem, st>>>(p);                         \
         break
     switch (Jt) {
         HAB_LAUNCH_TRELLIS(1); HAB_LAUNCH_TRELLIS(2); HAB_LAUNCH_TRELLIS(3); HAB_LAUNCH_TRELLIS(4);
@@ -170,7 +174,7 @@ int ha_ctc_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
     tp.T = T; tp.N = N; tp.meta = pp.meta; tp.order = pp.order; tp.tgt = pp.tgt; tp.Sp = w.Sp;
     tp.em = rp.em; tp.E = w.E; tp.tr = (float*)(base + w.tr); tp.SPX = w.SPX; tp.JWp = w.JWp;
     tp.loss = loss; tp.loss_ws = (float*)(base + w.loss);
-    tp.probe = (long long*)base;   // first 256 workspace bytes are reserved
+    tp.probe = (long long*)base;   // first 256 workspace bytes are reserved (HAB_PROBE builds)
     if ((rc = ctc_trellis_launch(tp, (S + 1 + 31) / 32, N, st))) return rc;
 
     return HA_OK;

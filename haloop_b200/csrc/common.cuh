@@ -47,6 +47,24 @@ constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: (x + kMagic) - kMagic == 
 __device__ __forceinline__ float round_int(float x) { return __fsub_rn(__fadd_rn(x, kMagic), kMagic); }
 // small integer -> float without a conversion instruction
 __device__ __forceinline__ float small_int_to_float(int k) { return __int_as_float(0x4B400000 + k) - kMagic; }
+// ---- stored trellis values: Q11.20 fixed point relative to a per-slot integer base -----------------
+// A split number (h, l) is stored as round((h - base + l) * 2^20) in one int32: absolute precision
+// 5e-7 at any distance up to 2047 log2 units below the base (the state that matters for a posterior
+// can sit hundreds of units below its slot's maximum when posteriors are peaky); void -> INT_MIN.
+constexpr int kFixVoid = (int)0x80000000;
+__device__ __forceinline__ int sf_to_fix(SF a, float base) {
+    const float d = a.h - base;                                   // integer valued
+    const int id = __float_as_int(fmaxf(d, -2047.0f) + kMagic) - 0x4B400000;
+    const int il = __float_as_int(fmaf(a.l, 1048576.0f, kMagic)) - 0x4B400000;
+    return (d < kVoidTest) ? kFixVoid : id * 1048576 + il;
+}
+// fixed -> (integer part, fraction in [0,1)) as floats; void -> (kVoid, 0)
+__device__ __forceinline__ void fix_to_parts(int v, float& hi, float& lo) {
+    const int ih = v >> 20;
+    const int il = v - (ih << 20);
+    hi = (v == kFixVoid) ? kVoid : small_int_to_float(ih);
+    lo = small_int_to_float(il) * (1.0f / 1048576.0f);
+}
 __device__ __forceinline__ SF sf_void() { SF r; r.h = kVoid; r.l = 0.0f; return r; }
 // log2(2^a + 2^b); the result's l is in [-0.5, 1.5] (not renormalised)
 __device__ __forceinline__ SF lae_sf(SF a, SF b) {
@@ -96,6 +114,9 @@ __device__ __forceinline__ void mbar_init_fence() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;

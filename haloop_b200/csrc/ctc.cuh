@@ -232,33 +232,45 @@ struct TrellisParams {
     float* em; int E;          // emission rows in / occupancy rows out, in place (layout: ctc_em_floats)
     float* tr; int SPX, JWp;   // stored trellis row = [JWp slot bases][2*(L+1) floats relative to them]
     float* loss; float* loss_ws;
-    int nstage, W;             // ring depth; warps per sweep direction
+    int nstage, G, W;          // ring stages; frames per stage; compute warps per sweep direction
     int dir_bytes;             // shared memory per direction
-    long long* probe;          // HAB_PROBE builds only: cycle stamps of one warp
+    long long* probe;          // HAB_PROBE builds only
 };
 
-// per-direction shared memory: [em ring][trellis ring][2 occupancy rows][mailboxes][partials][mbarriers]
-__host__ __device__ inline int trellis_dir_bytes(int E, int SPX, int Sp, int nstage, int W) {
-    return round_up(nstage * (E + SPX) * 4 + 2 * (4 + Sp) * 4 + 2 * W * 8 + 2 * W * 4 + W * 16 + 2 * nstage * 8, 128);
+constexpr int kMaxG = 4;
+
+// per-direction shared memory: nstage x [G emission rows | G trellis rows | G occupancy rows | G x W partials]
+// then mailboxes, log Z partials and the full/empty mbarriers
+__host__ __device__ inline int trellis_stage_floats(int E, int SPX, int Sp, int G, int W) {
+    return G * (E + SPX + (4 + Sp)) + round_up(G * W, 4);
+}
+__host__ __device__ inline int trellis_dir_bytes(int E, int SPX, int Sp, int nstage, int G, int W) {
+    return round_up(nstage * trellis_stage_floats(E, SPX, Sp, G, W) * 4 + 2 * W * 8 + W * 16 + 2 * nstage * 8, 128);
 }
 
 constexpr float kRebase = 24.0f;   // a slot is re-based when its states drift this far (log2 units) from the base
 
-// grid N (one CTA per utterance, longest first), block 64*W: warps [0,W) sweep alpha forward in time,
-// warps [W,2W) sweep beta backward; the two sides meet in the middle.  Side d's step i is frame
-// t = d ? T-1-i : i and it orders the label pairs its own way (beta = alpha on the reversed label
-// sequence).  Warp w of a side owns J slots of 32 pairs: pair q = 32 (w J + j) + lane =
-// (blank state 2q, label state 2q+1), each a split number (common.cuh).  The only value crossing a
-// lane boundary per step is the label state of pair q-1: a shuffle inside a warp, a two-float mailbox
-// between warps, with one named barrier per step per side.  Phase 1 (first half of the frames)
-// stores every row as floats relative to a per-slot base; phase 2 combines live rows with the rows the
-// other side stored, so posteriors need T sequential steps instead of 2T and nothing is recomputed.
-template <int J, int MAXT>
-__global__ void __launch_bounds__(MAXT) ctc_trellis_kernel(TrellisParams p) {
+// grid N (one CTA per utterance, longest first), block 32*(2W+2).  Warps [0,W) sweep alpha forward in
+// time, warps [W,2W) sweep beta backward, and the two sides meet in the middle; warps 2W and 2W+1 are
+// the sides' producers: one elected lane each issues every bulk (TMA) copy, so the compute warps never
+// touch the copy engine.  A ring stage holds G consecutive frames: emission rows in, (phase 2) the
+// other side's stored trellis rows in, occupancy rows out; full/empty mbarriers hand stages over.
+//
+// Side d's step i is frame t = d ? T-1-i : i and it orders the label pairs its own way (beta = alpha
+// on the reversed label sequence).  Warp w of a side owns J slots of 32 pairs: pair
+// q = 32 (w J + j) + lane = (blank state 2q, label state 2q+1), each a split number (common.cuh).  The
+// only value crossing a lane boundary per step is the label state of pair q-1: a shuffle inside a
+// warp, a two-float mailbox between warps, with one named barrier per step per side.  Phase 1 (first
+// half of the frames) stores every row as floats relative to a per-slot base; phase 2 combines live
+// rows with the rows the other side stored, so posteriors need T sequential steps, not 2T.
+template <int J>
+__global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int W = p.W;
+    const int W = p.W, G = p.G, nstage = p.nstage;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int dir = warp >= W, w = warp - dir * W;
+    const bool producer = warp >= 2 * W;
+    const int dir = producer ? warp - 2 * W : (warp >= W);
+    const int w = producer ? 0 : warp - dir * W;
     const int n = p.order[blockIdx.x];
     const int4 mt = p.meta[n];
     const int Tn = mt.x, L = mt.y;
@@ -268,26 +280,95 @@ __global__ void __launch_bounds__(MAXT) ctc_trellis_kernel(TrellisParams p) {
         return;
     }
     const int P = L + 1;
-    const int nstage = p.nstage, E = p.E, SPX = p.SPX, JWp = p.JWp, Sp = p.Sp;
-    const bool leader = (w == 0 && lane == 0);
-    const int nthr = 32 * W;                      // threads of my side
-    const int barid = 1 + dir;
+    const int E = p.E, SPX = p.SPX, JWp = p.JWp, Sp = p.Sp, OC = 4 + p.Sp;
+    const int SF_ = trellis_stage_floats(E, SPX, Sp, G, W);
 
     unsigned char* db = smem_raw + (size_t)dir * p.dir_bytes;
-    float* em_ring = (float*)db;
-    float* tr_ring = em_ring + nstage * E;
-    float* occ_buf = tr_ring + nstage * SPX;      // 2 x (4 + Sp)
-    float2* mail = (float2*)(occ_buf + 2 * (4 + Sp));        // [2][W] label state of a warp's last pair
-    float* psum = (float*)(mail + 2 * W);                    // [2][W] blank occupancy partial sums
-    double* redm = (double*)(psum + 2 * W);                  // [W] log Z partial maxima
-    float* reds = (float*)(redm + W);                        // [W] log Z partial sums
-    uint64_t* bar_em = (uint64_t*)(reds + 2 * W);
-    uint64_t* bar_tr = bar_em + nstage;
-    if (leader)
-        for (int s = 0; s < nstage; ++s) { mbar_init(&bar_em[s], 1); mbar_init(&bar_tr[s], 1); }
+    float* stages = (float*)db;                                   // stage s: + s * SF_
+    float2* mail = (float2*)(stages + nstage * SF_);              // [2][W] label state of a warp's last pair
+    double* redm = (double*)(mail + 2 * W);                       // [W] log Z partial maxima
+    float* reds = (float*)(redm + W);                             // [W] log Z partial sums
+    uint64_t* full = (uint64_t*)(reds + 2 * W);
+    uint64_t* empty = full + nstage;
+    if (producer && lane == 0)
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init_fence();
     __syncthreads();
 
+    float* em_base = p.em + (size_t)n * p.T * E;
+    float* tr_base = p.tr + (size_t)n * p.T * SPX;
+    const uint32_t occ_bytes = (uint32_t)(4 + round_up(L, 4)) * 4u;        // header + label occupancies
+    const int tm = Tn >> 1;
+    const int steps1 = dir ? Tn - tm : tm;         // phase-1 steps of my side
+    const int steps2 = Tn - steps1;
+    const int ng1 = (steps1 + G - 1) / G, ng2 = (steps2 + G - 1) / G;
+
+    if (producer) {
+        // ---------------------------------------------------------------- producer (one lane) ---
+        // group k (global count over both phases) lives in stage k % nstage; frames of a group are
+        // contiguous in memory whichever way the side walks time
+        auto group_rows = [&](int phase, int k, int& t_lo, int& cnt) {
+            const int i0 = (phase ? steps1 : 0) + k * G;                       // first step of the group
+            cnt = min(G, (phase ? Tn : steps1) - i0);
+            t_lo = dir ? Tn - i0 - cnt : i0;
+        };
+        auto drain = [&](int s, int k2) {       // write back the occupancy rows of phase-2 group k2
+            int t_lo, cnt;
+            group_rows(1, k2, t_lo, cnt);
+            float* st = stages + s * SF_;
+            float* occ = st + G * (E + SPX);
+            const float* ps = occ + G * OC;
+            for (int r = 0; r < cnt; ++r) {
+                float b = 0.0f;
+                for (int x = 0; x < W; ++x) b += ps[r * W + x];
+                occ[r * OC + 1] = b;
+            }
+            fence_async_smem();
+            for (int r = 0; r < cnt; ++r) bulk_s2g(em_base + (size_t)(t_lo + r) * E, occ + r * OC, occ_bytes);
+            bulk_commit();
+            bulk_wait_read<0>();
+        };
+        if (lane == 0) {
+            for (int k = 0; k < ng1; ++k) {
+                const int s = k % nstage, use = k / nstage;
+                if (use > 0) mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);
+                int t_lo, cnt;
+                group_rows(0, k, t_lo, cnt);
+                mbar_expect_tx(&full[s], (uint32_t)cnt * E * 4u);
+                bulk_g2s(stages + s * SF_, em_base + (size_t)t_lo * E, (uint32_t)cnt * E * 4u, &full[s]);
+            }
+        }
+        __threadfence();
+        fence_async_all();
+        __syncthreads();                           // phase switch: both sides' stored rows are complete
+        fence_async_all();
+        if (lane == 0) {
+            for (int k2 = 0; k2 < ng2 + nstage; ++k2) {
+                const int k = ng1 + k2;
+                const int s = k % nstage, use = k / nstage;
+                if (use > 0) {
+                    const int kprev = k - nstage;            // group that used this stage before
+                    if (k2 < ng2 || kprev >= ng1) mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);
+                    if (kprev >= ng1) drain(s, kprev - ng1);
+                }
+                if (k2 < ng2) {
+                    int t_lo, cnt;
+                    group_rows(1, k2, t_lo, cnt);
+                    float* st = stages + s * SF_;
+                    mbar_expect_tx(&full[s], (uint32_t)cnt * (E + SPX) * 4u);
+                    bulk_g2s(st, em_base + (size_t)t_lo * E, (uint32_t)cnt * E * 4u, &full[s]);
+                    bulk_g2s(st + G * E, tr_base + (size_t)t_lo * SPX, (uint32_t)cnt * SPX * 4u, &full[s]);
+                }
+            }
+            bulk_wait_all<0>();
+        }
+        return;
+    }
+
+    // ------------------------------------------------------------------------ compute warps ---
+    const bool leader = (w == 0 && lane == 0);
+    const int nthr = 32 * W;                      // compute threads of my side
+    const int barid = 1 + dir;
     // per slot: do my pair / my label exist, and is the skip transition into my label allowed
     // (ha/ctc.py:140-142)?
     const int q0 = 32 * (w * J) + lane;           // my pair in slot 0
@@ -313,70 +394,34 @@ __global__ void __launch_bounds__(MAXT) ctc_trellis_kernel(TrellisParams p) {
     // the other side's copy of my blank 2q is its state 2 (L - q) = R0 - 64 j, my label one below
     const int R0 = 2 * (L - q0);
     const int B0 = R0 >> 6, B1 = (R0 - 1) >> 6;   // slots of those states: exactly j lower per slot
+    // my pairs are all unreachable before step `first` (pair q needs q frames to be reached)
+    const int first = 32 * (w * J);
 
     SF a0[J], a1[J];       // blank / label state of my pair in slot j
     float base[J];         // storage base of slot j (integer valued)
 #pragma unroll
     for (int j = 0; j < J; ++j) { a0[j] = sf_void(); a1[j] = sf_void(); base[j] = 0.0f; }
 
-    float* em_base = p.em + (size_t)n * p.T * E;
-    float* tr_base = p.tr + (size_t)n * p.T * SPX;
-    const uint32_t emf_bytes = (uint32_t)(4 + round_up(L, 4)) * 4u;       // header + fractions
-    const uint32_t emk_bytes = (uint32_t)round_up(L, 16);                  // int8 integer parts
-    const uint32_t tr_bytes = (uint32_t)(JWp + round_up(2 * P, 4)) * 4u;
-    const int tm = Tn >> 1;
-    const int steps1 = dir ? Tn - tm : tm;
-    // my pairs are all unreachable before step `first` (pair q needs q frames to be reached)
-    const int first = 32 * (w * J);
-
-    auto issue_em = [&](int i) {          // leader only
-        const int st = i % nstage, t = dir ? Tn - 1 - i : i;
-        const float* src = em_base + (size_t)t * E;
-        mbar_expect_tx(&bar_em[st], emf_bytes + emk_bytes);
-        bulk_g2s(em_ring + st * E, src, emf_bytes, &bar_em[st]);
-        if (emk_bytes) bulk_g2s(em_ring + st * E + 4 + Sp, src + 4 + Sp, emk_bytes, &bar_em[st]);
-    };
-    auto issue_tr = [&](int k) {          // leader only; k-th phase-2 step
-        const int st = k % nstage, i = steps1 + k, t = dir ? Tn - 1 - i : i;
-        mbar_expect_tx(&bar_tr[st], tr_bytes);
-        bulk_g2s(tr_ring + st * SPX, tr_base + (size_t)t * SPX, tr_bytes, &bar_tr[st]);
-    };
-    auto phase_switch = [&]() {
-        // my stored rows -> visible to the other side's bulk (async-proxy) loads, and vice versa
-        __threadfence();
-        fence_async_all();
-        __syncthreads();
-        fence_async_all();
-        if (leader)
-            for (int k = 0; k < min(nstage, Tn - steps1); ++k) issue_tr(k);
-    };
-
-    if (leader)
-        for (int i = 0; i < min(nstage, Tn); ++i) issue_em(i);
-
     float IZ = 0.0f, fZ = 0.0f, csum = 0.0f;
     bool feasible = true;
-    int st = 0; uint32_t par = 0;          // emission ring position
-    int ts = 0; uint32_t tpar = 0;         // trellis ring position (phase 2)
+    float Kb, fb, Kl[J], fl[J];
 
-    for (int i = 0; i < Tn; ++i) {
-        if (i == steps1) phase_switch();
-        const int t = dir ? Tn - 1 - i : i;
-        const bool phase2 = i >= steps1;
-#ifdef HAB_PROBE
-        const bool pr = (blockIdx.x == 0 && warp == 0 && lane == 0 && (i == 100 || i == 101 || i == Tn - 50));
-        const int pb = (i == 100) ? 0 : (i == 101 ? 8 : 16);
-        if (pr) p.probe[pb + 0] = clock64();
-#endif
-        mbar_wait(&bar_em[st], par);
-#ifdef HAB_PROBE
-        if (pr) p.probe[pb + 1] = clock64();
-#endif
-        const float* er = em_ring + st * E;
+    // ring cursor: stage, parity of its full barrier, frame within the group, frames in the group
+    int s = 0, g = 0, cnt = 0; uint32_t fpar = 0;
+    const float* stg = stages;
+
+    auto fetch = [&](int i, int phase_end) {
+        // emission row of step i: wait for the stage at the start of a group, then decode my entries
+        if (g == 0) {
+            cnt = min(G, phase_end - i);
+            stg = stages + s * SF_;
+            mbar_wait(&full[s], fpar);
+        }
+        const int ridx = dir ? cnt - 1 - g : g;
+        const float* er = stg + ridx * E;
         const signed char* kr = (const signed char*)(er + 4 + Sp);
-        const float Kb = er[1], fb = er[2];
+        Kb = er[1]; fb = er[2];
         csum += er[0];
-        float Kl[J], fl[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const bool v = (hasl >> j) & 1u;
@@ -384,10 +429,9 @@ __global__ void __launch_bounds__(MAXT) ctc_trellis_kernel(TrellisParams p) {
             Kl[j] = v ? small_int_to_float((int)kr[pos]) : kVoid;
             fl[j] = v ? er[4 + pos] : 0.0f;
         }
-
-#ifdef HAB_PROBE
-        if (pr) p.probe[pb + 2] = clock64();
-#endif
+        return ridx;
+    };
+    auto advance = [&](int i) {
         if (i == 0) {
             if (q0 == 0) {                                         // ha/ctc.py:138
                 SF z; z.h = 0.0f; z.l = 0.0f;
@@ -452,147 +496,179 @@ __global__ void __launch_bounds__(MAXT) ctc_trellis_kernel(TrellisParams p) {
                 a1[j] = add_norm(v, Kl[j], fl[j]);
             }
         }
-#ifdef HAB_PROBE
-        if (pr) p.probe[pb + 3] = clock64();
-#endif
         // my last pair's label state for the warp above (read in its next step)
         if (lane == 31 && w + 1 < W) mail[(i & 1) * W + w] = make_float2(a1[J - 1].h, a1[J - 1].l);
+    };
+    auto step_end = [&]() {
+        // one barrier per step per side (mailboxes change hands); the stage goes back to the producer
+        // after its last frame
+        named_bar_sync(barid, nthr);
+        if (++g == cnt) {
+            if (leader) mbar_arrive(&empty[s]);
+            g = 0;
+            if (++s == nstage) { s = 0; fpar ^= 1u; }
+        }
+    };
 
-        if (!phase2) {
+    // ---------------------------------------------------------------------------- phase 1 ---
+    {
+        int2* prow = (int2*)(tr_base + (size_t)(dir ? Tn - 1 : 0) * SPX + JWp) + q0;
+        float* hrow = tr_base + (size_t)(dir ? Tn - 1 : 0) * SPX + w * J;
+        const long long rstep = dir ? -(long long)SPX : (long long)SPX;
+        for (int i = 0; i < steps1; ++i) {
+#ifdef HAB_PROBE
+            const bool pr = (blockIdx.x == 0 && warp == 0 && lane == 0 && (i == 101 || i == 102));
+            const int pb = (i == 101) ? 0 : 8;
+            if (pr) p.probe[pb + 0] = clock64();
+#endif
+            fetch(i, steps1);
+#ifdef HAB_PROBE
+            if (pr) p.probe[pb + 1] = clock64();
+#endif
+            advance(i);
+#ifdef HAB_PROBE
+            if (pr) p.probe[pb + 2] = clock64();
+#endif
             // Rows are stored relative to a per-slot integer base.  A live slot is re-based (one warp
-            // max) only when some state rose well above its base or none is left near it; the test
-            // itself is three warp-wide OR reductions for all slots together.
-            unsigned up = 0, near = 0, live = 0;
+            // max) only when some state rose well above its base or none is left near it; the test is
+            // one warp-wide OR reduction for all slots together.
+            unsigned bits = 0;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const float m = fmaxf(a0[j].h, a1[j].h);
                 const float dd = m - base[j];
-                up |= (dd > kRebase) ? (1u << j) : 0u;             // voids give dd ~ -1e30
-                near |= (dd > -kRebase) ? (1u << j) : 0u;
-                live |= (m > kVoidTest) ? (1u << j) : 0u;
+                bits |= (dd > kRebase) ? (1u << j) : 0u;               // voids give dd ~ -1e30
+                bits |= (dd > -kRebase) ? (0x100u << j) : 0u;
+                bits |= (m > kVoidTest) ? (0x10000u << j) : 0u;
             }
-            up = __reduce_or_sync(0xffffffffu, up);
-            near = __reduce_or_sync(0xffffffffu, near);
-            live = __reduce_or_sync(0xffffffffu, live);
-            const unsigned need = up | (live & ~near);
+            bits = __reduce_or_sync(0xffffffffu, bits);
+            const unsigned need = (bits | ((bits >> 16) & ~(bits >> 8))) & 0xffu;
             if (need) {
 #pragma unroll
                 for (int j = 0; j < J; ++j)
                     if ((need >> j) & 1u) base[j] = warp_max(fmaxf(a0[j].h, a1[j].h));
             }
-            float* row = tr_base + (size_t)t * SPX;
-            float2* prow = (float2*)(row + JWp) + q0;
+            float bsel = base[0];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                if ((hasp >> j) & 1u)
-                    prow[32 * j] = make_float2((a0[j].h - base[j]) + a0[j].l, (a1[j].h - base[j]) + a1[j].l);
-                if (lane == j && 32 * (w * J + j) < P) row[w * J + j] = base[j];
-            }
-        } else {
-            const int k = i - steps1;
-            mbar_wait(&bar_tr[ts], tpar);
-            const float* orow = tr_ring + ts * SPX + JWp + R0;     // [-64 j] = other side's copy of my blank
-            const float* ob0 = tr_ring + ts * SPX + B0;            // [-j]    = its slot base
-            const float* ob1 = tr_ring + ts * SPX + B1;
-            // posterior exponent = [h + other base - K] (integers) + [l + other value - f] (small), minus log Z
-            auto expo = [&](int jj, float& xi0, float& xf0, float& xi1, float& xf1) {
-                const bool vp = (hasp >> jj) & 1u, vl = (hasl >> jj) & 1u;
-                const float o0 = vp ? orow[-64 * jj] : 0.0f, o1 = vl ? orow[-64 * jj - 1] : 0.0f;
-                const float b0 = vp ? ob0[-jj] : 0.0f, b1 = vl ? ob1[-jj] : 0.0f;
-                xi0 = vp ? (a0[jj].h + b0) - Kb : kVoid;
-                xf0 = vp ? (a0[jj].l + o0) - fb : 0.0f;
-                xi1 = vl ? (a1[jj].h + b1) - Kl[jj] : kVoid;
-                xf1 = vl ? (a1[jj].l + o1) - fl[jj] : 0.0f;
-            };
-            if (k == 0) {
-                // log Z over all my side's states at the meeting frame: two-pass max / sum across the W warps
-                double mx = -1.0e300;
+            for (int j = 1; j < J; ++j) bsel = (lane == j) ? base[j] : bsel;
 #pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    float xi0, xf0, xi1, xf1;
-                    expo(j, xi0, xf0, xi1, xf1);
-                    mx = fmax(mx, fmax((double)xi0 + (double)xf0, (double)xi1 + (double)xf1));
-                }
-                mx = warp_max_d(mx);
-                if (lane == 0) redm[w] = mx;
-                named_bar_sync(barid, nthr);
-                for (int x = 0; x < W; ++x) mx = fmax(mx, redm[x]);
-                feasible = mx > (double)kVoidTest;
-                float s = 0.0f;
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    float xi0, xf0, xi1, xf1;
-                    expo(j, xi0, xf0, xi1, xf1);
-                    s += ex2f((float)((double)xi0 + (double)xf0 - mx)) +
-                         ex2f((float)((double)xi1 + (double)xf1 - mx));
-                }
-                s = warp_sum(s);
-                if (lane == 0) reds[w] = s;
-                named_bar_sync(barid, nthr);
-                s = 0.0f;
-                for (int x = 0; x < W; ++x) s += reds[x];
-                const double logZ2 = mx + (double)log2f(s);        // of the shifted emissions
-                const double fl2 = floor(logZ2);
-                IZ = feasible ? (float)fl2 : 0.0f;
-                fZ = feasible ? (float)(logZ2 - fl2) : 0.0f;
-            }
-            float* ob = occ_buf + (i & 1) * (4 + Sp);
-            float g0[J], g1[J];
+            for (int j = 0; j < J; ++j)
+                if ((hasp >> j) & 1u) prow[32 * j] = make_int2(sf_to_fix(a0[j], base[j]), sf_to_fix(a1[j], base[j]));
+            if (lane < J && 32 * (w * J + lane) < P) hrow[lane] = bsel;
+            prow = (int2*)((float*)prow + rstep);
+            hrow += rstep;
+#ifdef HAB_PROBE
+            if (pr) p.probe[pb + 3] = clock64();
+#endif
+            step_end();
+#ifdef HAB_PROBE
+            if (pr) p.probe[pb + 4] = clock64();
+#endif
+        }
+    }
+    // my stored rows -> visible to the other side's bulk (async-proxy) loads, and vice versa
+    __threadfence();
+    fence_async_all();
+    __syncthreads();
+
+    // ---------------------------------------------------------------------------- phase 2 ---
+    for (int i = steps1; i < Tn; ++i) {
+#ifdef HAB_PROBE
+        const bool pr = (blockIdx.x == 0 && warp == 0 && lane == 0 && (i == steps1 + 101 || i == steps1 + 102));
+        const int pb = (i == steps1 + 101) ? 16 : 24;
+        if (pr) p.probe[pb + 0] = clock64();
+#endif
+        const int ridx = fetch(i, Tn);
+#ifdef HAB_PROBE
+        if (pr) p.probe[pb + 1] = clock64();
+#endif
+        advance(i);
+#ifdef HAB_PROBE
+        if (pr) p.probe[pb + 2] = clock64();
+#endif
+        const float* trow = stg + G * E + ridx * SPX;
+        const int* orow = (const int*)(trow + JWp) + R0;      // [-64 j] = other side's copy of my blank (Q11.20)
+        const float* ob0 = trow + B0;                         // [-j]    = its slot base
+        const float* ob1 = trow + B1;
+        // posterior exponent = [h + other base + other integer part - K] + [l + other fraction - f], minus log Z
+        auto expo = [&](int jj, float& xi0, float& xf0, float& xi1, float& xf1) {
+            const bool vp = (hasp >> jj) & 1u, vl = (hasl >> jj) & 1u;
+            const int o0 = vp ? orow[-64 * jj] : kFixVoid, o1 = vl ? orow[-64 * jj - 1] : kFixVoid;
+            const float b0 = vp ? ob0[-jj] : 0.0f, b1 = vl ? ob1[-jj] : 0.0f;
+            float h0, l0, h1, l1;
+            fix_to_parts(o0, h0, l0);
+            fix_to_parts(o1, h1, l1);
+            xi0 = ((a0[jj].h + b0) + h0) - Kb;
+            xf0 = (a0[jj].l + l0) - fb;
+            xi1 = ((a1[jj].h + b1) + h1) - Kl[jj];
+            xf1 = (a1[jj].l + l1) - fl[jj];
+        };
+        if (i == steps1) {
+            // log Z over all my side's states at the meeting frame: two-pass max / sum across the W warps
+            double mx = -1.0e300;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 float xi0, xf0, xi1, xf1;
                 expo(j, xi0, xf0, xi1, xf1);
-                g0[j] = (xi0 - IZ) + (xf0 - fZ);
-                g1[j] = (xi1 - IZ) + (xf1 - fZ);
+                mx = fmax(mx, fmax((double)xi0 + (double)xf0, (double)xi1 + (double)xf1));
             }
-#pragma unroll
-            for (int j = 0; j < J; ++j) { g0[j] = ex2f(g0[j]); g1[j] = ex2f(g1[j]); }
-            float bsum = 0.0f;
+            mx = warp_max_d(mx);
+            if (lane == 0) redm[w] = mx;
+            named_bar_sync(barid, nthr);
+            for (int x = 0; x < W; ++x) mx = fmax(mx, redm[x]);
+            feasible = mx > (double)kVoidTest;
+            float sm = 0.0f;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                bsum += feasible ? g0[j] : 0.0f;
-                if ((hasl >> j) & 1u) ob[4 + pos0 + pstep * j] = feasible ? g1[j] : 0.0f;
+                float xi0, xf0, xi1, xf1;
+                expo(j, xi0, xf0, xi1, xf1);
+                sm += ex2f((float)((double)xi0 + (double)xf0 - mx)) +
+                      ex2f((float)((double)xi1 + (double)xf1 - mx));
             }
-            bsum = warp_sum(bsum);
-            if (lane == 0) psum[(i & 1) * W + w] = bsum;
-            fence_async_smem();                     // my occupancy writes -> visible to the leader's bulk store
-            if (leader) bulk_wait_read<0>();        // the previous row's store has left the other buffer... and this one
+            sm = warp_sum(sm);
+            if (lane == 0) reds[w] = sm;
+            named_bar_sync(barid, nthr);
+            sm = 0.0f;
+            for (int x = 0; x < W; ++x) sm += reds[x];
+            const double logZ2 = mx + (double)log2f(sm);        // of the shifted emissions
+            const double fl2 = floor(logZ2);
+            IZ = feasible ? (float)fl2 : 0.0f;
+            fZ = feasible ? (float)(logZ2 - fl2) : 0.0f;
         }
+        float* ob = (float*)stg + G * (E + SPX) + ridx * OC;       // occupancy row of this frame
+        float* ps = (float*)stg + G * (E + SPX) + G * OC;
+        float g0[J], g1[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            float xi0, xf0, xi1, xf1;
+            expo(j, xi0, xf0, xi1, xf1);
+            g0[j] = (xi0 - IZ) + (xf0 - fZ);
+            g1[j] = (xi1 - IZ) + (xf1 - fZ);
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) { g0[j] = ex2f(g0[j]); g1[j] = ex2f(g1[j]); }
+        float bsum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            bsum += feasible ? g0[j] : 0.0f;
+            if ((hasl >> j) & 1u) ob[4 + pos0 + pstep * j] = feasible ? g1[j] : 0.0f;
+        }
+        bsum = warp_sum(bsum);
+        if (lane == 0) ps[ridx * W + w] = bsum;
+        if (g == cnt - 1) fence_async_smem();       // this group's occupancy writes -> the producer's bulk stores
+#ifdef HAB_PROBE
+        if (pr) p.probe[pb + 3] = clock64();
+#endif
+        step_end();
 #ifdef HAB_PROBE
         if (pr) p.probe[pb + 4] = clock64();
 #endif
-        // ---- one barrier per step per side: mailboxes, occupancy row and ring stages change hands
-        named_bar_sync(barid, nthr);
-#ifdef HAB_PROBE
-        if (pr) p.probe[pb + 5] = clock64();
-#endif
-        if (leader) {
-            if (i + nstage < Tn) issue_em(i + nstage);
-            if (phase2) {
-                const int k = i - steps1;
-                float* ob = occ_buf + (i & 1) * (4 + Sp);
-                float b = 0.0f;
-                for (int x = 0; x < W; ++x) b += psum[(i & 1) * W + x];
-                ob[1] = b;
-                fence_async_smem();
-                bulk_s2g(em_base + (size_t)t * E, ob, emf_bytes);
-                bulk_commit();
-                if (k + nstage < Tn - steps1) issue_tr(k + nstage);
-            }
-        }
-        if (++st == nstage) { st = 0; par ^= 1u; }
-        if (phase2 && ++ts == nstage) { ts = 0; tpar ^= 1u; }
-#ifdef HAB_PROBE
-        if (pr) p.probe[pb + 6] = clock64();
-#endif
     }
-    if (steps1 == Tn) phase_switch();     // only T == 1, beta side: still owes the barrier
     if (dir == 0 && leader) {
         // log Z of the true emissions = log Z of the shifted ones + the sum of all T row shifts
         const float v = feasible ? (float)(-((double)IZ + (double)fZ + (double)csum) * kLn2) : CUDART_INF_F;
         p.loss[n] = v; p.loss_ws[n] = v;
     }
-    if (leader) bulk_wait_all<0>();
 }
 
 // ------------------------------------------------------------------------------------ grad ---

@@ -13,9 +13,9 @@ def run(B, T, V, U):
         loss, ws = ops.ctc_fwd(x.permute(1, 0, 2), tg, il, tl, True)
     torch.cuda.synchronize()
     pr = ws[:256].view(torch.int64).cpu().tolist()
-    for name, o in (("step100", 0), ("step101", 8), ("stepT-50(phase2)", 16)):
-        a = pr[o:o + 7]
-        print(f"B={B} T={T} U={U} {name}: wait_em {a[1]-a[0]}, decode {a[2]-a[1]}, update {a[3]-a[2]}, store/gamma {a[4]-a[3]}, barrier {a[5]-a[4]}, leader {a[6]-a[5]}, total {a[6]-a[0]}")
-    print("  step100 start -> step101 start:", pr[8] - pr[0])
+    for name, o in (("ph1 s101", 0), ("ph1 s102", 8), ("ph2 s101", 16), ("ph2 s102", 24)):
+        a = pr[o:o + 5]
+        print(f"B={B} T={T} U={U} {name}: fetch {a[1]-a[0]}, advance {a[2]-a[1]}, store/gamma {a[3]-a[2]}, step_end {a[4]-a[3]}, total {a[4]-a[0]}")
+    print("  ph1 s101->s102:", pr[8] - pr[0], " ph2 s101->s102:", pr[24] - pr[16])
 run(16, 1500, 64, 30)
 run(256, 1500, 1024, 300)
