@@ -103,13 +103,13 @@ static int ctc_trellis_launch(const TrellisParams& tp, int nslot, int N, cudaStr
     p.W = (nslot + Jt - 1) / Jt;
     p.G = kMaxG;
     int ns = 4;
-    while (ns >= 2 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, p.Sp, ns, p.G, p.W) > 100 * 1024) --ns;
+    while (ns >= 2 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, 4 + p.Sp, ns, p.G, p.W, 1) > 100 * 1024) --ns;
     if (ns < 2) {
         ns = 2;
-        while (p.G > 1 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, p.Sp, ns, p.G, p.W) > 220 * 1024) p.G >>= 1;
+        while (p.G > 1 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, 4 + p.Sp, ns, p.G, p.W, 1) > 220 * 1024) p.G >>= 1;
     }
     p.nstage = ns;
-    p.dir_bytes = trellis_dir_bytes(p.E, p.SPX, p.Sp, ns, p.G, p.W);
+    p.dir_bytes = trellis_dir_bytes(p.E, p.SPX, 4 + p.Sp, ns, p.G, p.W, 1);
     const size_t smem = (size_t)2 * p.dir_bytes;
     const dim3 grid(N), block(32 * (2 * p.W + 2));
     int rc;
@@ -222,34 +222,37 @@ size_t ha_star_workspace_bytes(int T, int N, int V, int S) {
     return star_ws_layout(T, N, S).total;
 }
 
-static int star_trellis_launch(const StarTrellisParams& tp, int nslot_max, int N, cudaStream_t st) {
+static int star_trellis_launch(const StarTrellisParams& tp, int nslot, int N, cudaStream_t st) {
     StarTrellisParams p = tp;
-    int ns = 8;
-    while (ns >= 2 && (size_t)4 * trellis_warp_bytes(p.E, p.SPX, ns) > 200 * 1024) --ns;
-    if (ns < 2) return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length too large for the star trellis kernel");
+    if (nslot > 16) return fail(HA_ERR_UNSUPPORTED_SHAPE, "star-CTC target length > 511 is not supported");
+    int env_w = 0;
+    if (const char* e = getenv("HA_B200_TRELLIS_W")) env_w = atoi(e);
+    int W = nslot < 3 ? 1 : (nslot <= 8 ? 2 : 4);
+    if (env_w >= 1 && env_w <= 4) W = env_w;
+    const int J = (nslot + W - 1) / W;
+    if (J > 4) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: star J=%d", J);
+    p.W = (nslot + J - 1) / J;
+    p.G = kMaxG;
+    const int OC = 8 + 2 * p.Sp;
+    int ns = 4;
+    while (ns >= 2 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, OC, ns, p.G, p.W, 2) > 100 * 1024) --ns;
+    if (ns < 2) {
+        ns = 2;
+        while (p.G > 1 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, OC, ns, p.G, p.W, 2) > 220 * 1024) p.G >>= 1;
+    }
     p.nstage = ns;
-    p.warp_bytes = trellis_warp_bytes(p.E, p.SPX, ns);
-    const size_t smem = (size_t)4 * p.warp_bytes;
-    const dim3 grid((N + 1) / 2), block(128);
+    p.dir_bytes = trellis_dir_bytes(p.E, p.SPX, OC, ns, p.G, p.W, 2);
+    const size_t smem = (size_t)2 * p.dir_bytes;
+    const dim3 grid(N), block(32 * (2 * p.W + 2));
     int rc;
 #define HAB_LAUNCH_STAR(JJ)                                                            \
-    do {                                                                               \
+    case JJ:                                                                           \
         if ((rc = set_smem(star_trellis_kernel<JJ>, smem, "star_trellis"))) return rc; \
         star_trellis_kernel<JJ><<<grid, block, smem, st>>>(p);                         \
-    } while (0)
-    switch (nslot_max) {
-        case 1: HAB_LAUNCH_STAR(1); break;
-        case 2: HAB_LAUNCH_STAR(2); break;
-        case 3: HAB_LAUNCH_STAR(3); break;
-        case 4: HAB_LAUNCH_STAR(4); break;
-        case 5: HAB_LAUNCH_STAR(5); break;
-        case 6: HAB_LAUNCH_STAR(6); break;
-        case 7: HAB_LAUNCH_STAR(7); break;
-        case 8: HAB_LAUNCH_STAR(8); break;
-        case 9: case 10: HAB_LAUNCH_STAR(10); break;
-        case 11: case 12: HAB_LAUNCH_STAR(12); break;
-        case 13: case 14: case 15: case 16: HAB_LAUNCH_STAR(16); break;
-        default: return fail(HA_ERR_UNSUPPORTED_SHAPE, "star-CTC target length > 511 is not supported");
+        break
+    switch (J) {
+        HAB_LAUNCH_STAR(1); HAB_LAUNCH_STAR(2); HAB_LAUNCH_STAR(3); HAB_LAUNCH_STAR(4);
+        default: return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: star J=%d", J);
     }
 #undef HAB_LAUNCH_STAR
     return check_launch("star_trellis_kernel");

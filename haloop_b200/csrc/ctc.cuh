@@ -241,14 +241,88 @@ constexpr int kMaxG = 4;
 
 // per-direction shared memory: nstage x [G emission rows | G trellis rows | G occupancy rows | G x W partials]
 // then mailboxes, log Z partials and the full/empty mbarriers
-__host__ __device__ inline int trellis_stage_floats(int E, int SPX, int Sp, int G, int W) {
-    return G * (E + SPX + (4 + Sp)) + round_up(G * W, 4);
+// (OC = floats of one occupancy row, NP = partial sums per row and warp)
+__host__ __device__ inline int trellis_stage_floats(int E, int SPX, int OC, int G, int W, int NP) {
+    return G * (E + SPX + OC) + round_up(G * W * NP, 4);
 }
-__host__ __device__ inline int trellis_dir_bytes(int E, int SPX, int Sp, int nstage, int G, int W) {
-    return round_up(nstage * trellis_stage_floats(E, SPX, Sp, G, W) * 4 + 2 * W * 8 + W * 16 + 2 * nstage * 8, 128);
+__host__ __device__ inline int trellis_dir_bytes(int E, int SPX, int OC, int nstage, int G, int W, int NP) {
+    return round_up(nstage * trellis_stage_floats(E, SPX, OC, G, W, NP) * 4 + 2 * W * 16 + W * 16 + 2 * nstage * 8, 128);
 }
 
 constexpr float kRebase = 24.0f;   // a slot is re-based when its states drift this far (log2 units) from the base
+
+// The producer warp of one sweep side (shared by the CTC and star-CTC trellis kernels): one lane issues
+// every bulk copy.  Group k (counted over both phases) lives in stage k % nstage and holds up to G
+// consecutive frames, which are contiguous in memory whichever way the side walks time.
+//   phase 1: emission rows in.   phase 2: emission rows + the other side's stored trellis rows in,
+//   occupancy rows (with the NP per-row partial sums of the W compute warps folded into floats
+//   [1, 1+NP)) written back over the emission rows once the compute warps release the stage.
+template <int NP>
+__device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_t* full, uint64_t* empty,
+                                                 int nstage, int G, int W, int E, int SPX, int OC,
+                                                 float* em_base, float* tr_base, uint32_t occ_bytes,
+                                                 int Tn, int steps1, int dir, int lane) {
+    const int steps2 = Tn - steps1;
+    const int ng1 = (steps1 + G - 1) / G, ng2 = (steps2 + G - 1) / G;
+    auto group_rows = [&](int phase, int k, int& t_lo, int& cnt) {
+        const int i0 = (phase ? steps1 : 0) + k * G;                       // first step of the group
+        cnt = min(G, (phase ? Tn : steps1) - i0);
+        t_lo = dir ? Tn - i0 - cnt : i0;
+    };
+    auto drain = [&](int s, int k2) {       // write back the occupancy rows of phase-2 group k2
+        int t_lo, cnt;
+        group_rows(1, k2, t_lo, cnt);
+        float* st = stages + s * SF_;
+        float* occ = st + G * (E + SPX);
+        const float* ps = occ + G * OC;
+        for (int r = 0; r < cnt; ++r) {
+#pragma unroll
+            for (int c = 0; c < NP; ++c) {
+                float b = 0.0f;
+                for (int x = 0; x < W; ++x) b += ps[(r * W + x) * NP + c];
+                occ[r * OC + 1 + c] = b;
+            }
+        }
+        fence_async_smem();
+        for (int r = 0; r < cnt; ++r) bulk_s2g(em_base + (size_t)(t_lo + r) * E, occ + r * OC, occ_bytes);
+        bulk_commit();
+        bulk_wait_read<0>();
+    };
+    if (lane == 0) {
+        for (int k = 0; k < ng1; ++k) {
+            const int s = k % nstage, use = k / nstage;
+            if (use > 0) mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);
+            int t_lo, cnt;
+            group_rows(0, k, t_lo, cnt);
+            mbar_expect_tx(&full[s], (uint32_t)cnt * E * 4u);
+            bulk_g2s(stages + s * SF_, em_base + (size_t)t_lo * E, (uint32_t)cnt * E * 4u, &full[s]);
+        }
+    }
+    __threadfence();
+    fence_async_all();
+    __syncthreads();                           // phase switch: both sides' stored rows are complete
+    fence_async_all();
+    if (lane == 0) {
+        for (int k2 = 0; k2 < ng2 + nstage; ++k2) {
+            const int k = ng1 + k2;
+            const int s = k % nstage, use = k / nstage;
+            if (use > 0) {
+                const int kprev = k - nstage;            // group that used this stage before
+                if (k2 < ng2 || kprev >= ng1) mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);
+                if (kprev >= ng1) drain(s, kprev - ng1);
+            }
+            if (k2 < ng2) {
+                int t_lo, cnt;
+                group_rows(1, k2, t_lo, cnt);
+                float* st = stages + s * SF_;
+                mbar_expect_tx(&full[s], (uint32_t)cnt * (E + SPX) * 4u);
+                bulk_g2s(st, em_base + (size_t)t_lo * E, (uint32_t)cnt * E * 4u, &full[s]);
+                bulk_g2s(st + G * E, tr_base + (size_t)t_lo * SPX, (uint32_t)cnt * SPX * 4u, &full[s]);
+            }
+        }
+        bulk_wait_all<0>();
+    }
+}
 
 // grid N (one CTA per utterance, longest first), block 32*(2W+2).  Warps [0,W) sweep alpha forward in
 // time, warps [W,2W) sweep beta backward, and the two sides meet in the middle; warps 2W and 2W+1 are
@@ -281,7 +355,7 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
     }
     const int P = L + 1;
     const int E = p.E, SPX = p.SPX, JWp = p.JWp, Sp = p.Sp, OC = 4 + p.Sp;
-    const int SF_ = trellis_stage_floats(E, SPX, Sp, G, W);
+    const int SF_ = trellis_stage_floats(E, SPX, OC, G, W, 1);
 
     unsigned char* db = smem_raw + (size_t)dir * p.dir_bytes;
     float* stages = (float*)db;                                   // stage s: + s * SF_
@@ -300,68 +374,10 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
     const uint32_t occ_bytes = (uint32_t)(4 + round_up(L, 4)) * 4u;        // header + label occupancies
     const int tm = Tn >> 1;
     const int steps1 = dir ? Tn - tm : tm;         // phase-1 steps of my side
-    const int steps2 = Tn - steps1;
-    const int ng1 = (steps1 + G - 1) / G, ng2 = (steps2 + G - 1) / G;
 
     if (producer) {
-        // ---------------------------------------------------------------- producer (one lane) ---
-        // group k (global count over both phases) lives in stage k % nstage; frames of a group are
-        // contiguous in memory whichever way the side walks time
-        auto group_rows = [&](int phase, int k, int& t_lo, int& cnt) {
-            const int i0 = (phase ? steps1 : 0) + k * G;                       // first step of the group
-            cnt = min(G, (phase ? Tn : steps1) - i0);
-            t_lo = dir ? Tn - i0 - cnt : i0;
-        };
-        auto drain = [&](int s, int k2) {       // write back the occupancy rows of phase-2 group k2
-            int t_lo, cnt;
-            group_rows(1, k2, t_lo, cnt);
-            float* st = stages + s * SF_;
-            float* occ = st + G * (E + SPX);
-            const float* ps = occ + G * OC;
-            for (int r = 0; r < cnt; ++r) {
-                float b = 0.0f;
-                for (int x = 0; x < W; ++x) b += ps[r * W + x];
-                occ[r * OC + 1] = b;
-            }
-            fence_async_smem();
-            for (int r = 0; r < cnt; ++r) bulk_s2g(em_base + (size_t)(t_lo + r) * E, occ + r * OC, occ_bytes);
-            bulk_commit();
-            bulk_wait_read<0>();
-        };
-        if (lane == 0) {
-            for (int k = 0; k < ng1; ++k) {
-                const int s = k % nstage, use = k / nstage;
-                if (use > 0) mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);
-                int t_lo, cnt;
-                group_rows(0, k, t_lo, cnt);
-                mbar_expect_tx(&full[s], (uint32_t)cnt * E * 4u);
-                bulk_g2s(stages + s * SF_, em_base + (size_t)t_lo * E, (uint32_t)cnt * E * 4u, &full[s]);
-            }
-        }
-        __threadfence();
-        fence_async_all();
-        __syncthreads();                           // phase switch: both sides' stored rows are complete
-        fence_async_all();
-        if (lane == 0) {
-            for (int k2 = 0; k2 < ng2 + nstage; ++k2) {
-                const int k = ng1 + k2;
-                const int s = k % nstage, use = k / nstage;
-                if (use > 0) {
-                    const int kprev = k - nstage;            // group that used this stage before
-                    if (k2 < ng2 || kprev >= ng1) mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);
-                    if (kprev >= ng1) drain(s, kprev - ng1);
-                }
-                if (k2 < ng2) {
-                    int t_lo, cnt;
-                    group_rows(1, k2, t_lo, cnt);
-                    float* st = stages + s * SF_;
-                    mbar_expect_tx(&full[s], (uint32_t)cnt * (E + SPX) * 4u);
-                    bulk_g2s(st, em_base + (size_t)t_lo * E, (uint32_t)cnt * E * 4u, &full[s]);
-                    bulk_g2s(st + G * E, tr_base + (size_t)t_lo * SPX, (uint32_t)cnt * SPX * 4u, &full[s]);
-                }
-            }
-            bulk_wait_all<0>();
-        }
+        trellis_producer<1>(stages, SF_, full, empty, nstage, G, W, E, SPX, OC, em_base, tr_base, occ_bytes,
+                            Tn, steps1, dir, lane);
         return;
     }
 
@@ -654,7 +670,7 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
             if ((hasl >> j) & 1u) ob[4 + pos0 + pstep * j] = feasible ? g1[j] : 0.0f;
         }
         bsum = warp_sum(bsum);
-        if (lane == 0) ps[ridx * W + w] = bsum;
+        if (lane == 0) ps[ridx * W + w] = bsum;      // folded into occupancy float [1] by the producer
         if (g == cnt - 1) fence_async_smem();       // this group's occupancy writes -> the producer's bulk stores
 #ifdef HAB_PROBE
         if (pr) p.probe[pb + 3] = clock64();

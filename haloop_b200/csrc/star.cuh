@@ -19,10 +19,17 @@ struct StarWs {
     int Sp, E, JWp, SPX;
 };
 
+// emission row (floats): [0] ct  [1] Kb [2] fb (blank)  [4] Ka [5] fa (all-star = log2 P)
+// [8+2k] f_label[k]  [9+2k] f_star[k]   then char2 (K_label[k], K_star[k]):  every emission is
+// ct + K + f with ct the integer row shift, K an int8 integer part and f an fp32 fraction.
+// The occupancy row written in place reuses the float part: [1] blank occupancy  [2] G = sum_k h_k
+// [8+2k] label occupancy  [9+2k] h_k (0 if y_k == 0), with h_k = gamma(star k) / (P - p_{y_k}).
+__host__ __device__ inline int star_em_floats(int Sp) { return 8 + 2 * Sp + round_up(2 * Sp, 16) / 4; }
+
 __host__ inline StarWs star_ws_layout(int T, int N, int S) {
     StarWs w;
     w.Sp = round_up(S > 0 ? S : 1, 4);
-    w.E = round_up(4 + 2 * S, 4);                   // row shift, blank, all-star, pad, S x (label, star\label)
+    w.E = star_em_floats(w.Sp);
     w.JWp = round_up((S + 1 + 31) / 32, 4);
     w.SPX = w.JWp + 4 * (S + 1);
     size_t o = 256;
@@ -48,9 +55,10 @@ struct StarRowsParams {
     int from_logits, use_bulk, rows_per_warp, nstage, nwarps;
 };
 
-// emission row: [0] integer row shift c_t  [1] blank  [2] log2 P  [4+2k] label y_k  [5+2k] log2(P - p_{y_k})
-// (log2 P when y_k == 0), all relative to c_t = rint(max(blank, log2 P)),
-// for k < min(L_n + 1, S): the star in front of position L_n reads targets[n, L_n] (ha/star.py:46-47).
+// One warp per (b,t) row: log-softmax statistics, log2 P = log2 sum_{c>=1} p_c, and for every target
+// position k < min(L_n + 1, S) the label emission and the star emission log2(P - p_{y_k}) (log2 P when
+// y_k == 0); the star in front of position L_n reads targets[n, L_n] (ha/star.py:46-47).  All
+// relative to the integer row shift c_t = rint(max(blank, log2 P)).  Row layout: star_em_floats().
 template <bool VEC4>
 __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -127,24 +135,38 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
         const float lP = fmaxf(m2 + log2f(s) - l2, kVoid);        // log2 sum_{c>=1} p_c   (ha/star.py:30)
         const float eblank = fmaf(row[0], kLog2e, -l2);
         const float ct = round_int(fmaxf(eblank, lP));            // every other emission is <= log2 P
+        // emissions in float64 from the fp32 logits, split into int8 integer part + fp32 fraction
+        const double shift = (double)l2 + (double)ct;
+        const double lPd = ((double)m2 + (double)log2f(s)) - (double)l2;      // log2 P, unshifted
         float* erow = p.em + ((size_t)n * p.T + t) * p.E;
+        char2* krow = (char2*)(erow + 8 + 2 * p.Sp);
+        auto split = [](double e, float& K, float& f) {
+            const double k = fmax(rint(e), -127.0);
+            K = (float)k; f = (float)(e - k);
+        };
         if (lane == 0) {
             p.lse2[(size_t)n * p.T + t] = l2;
-            erow[0] = ct;
-            erow[1] = eblank - ct;
-            erow[2] = lP - ct;
+            float Kb, fb, Ka, fa;
+            split(fma((double)row[0], kLog2e_d, -shift), Kb, fb);
+            split(fmax(lPd - (double)ct, -1.0e29), Ka, fa);
+            *(float4*)erow = make_float4(ct, Kb, fb, 0.0f);
+            *(float4*)(erow + 4) = make_float4(Ka, fa, 0.0f, 0.0f);
         }
         for (int k = lane; k < Ks; k += 32) {
             const int y = s_tgt[k];
-            const float lab = fmaf(row[y], kLog2e, -l2);
-            float sub = lP;
+            const double lab = fma((double)row[y], kLog2e_d, -shift);         // shifted
+            double sub = lPd - (double)ct;
             if (y != 0) {
                 // logsubexp (ha/star.py:4-5): log2 P + log2(1 - 2^(lab - log2 P)), via expm1 so that a
                 // label holding almost all of P does not cancel
-                const float d = fminf(lab - lP, 0.0f);
-                sub = fmaxf(lP + log2f(-expm1f(d * (float)kLn2)), kVoid);
+                const float d = fminf((float)(lab - sub), 0.0f);
+                sub += (double)log2f(-expm1f(d * (float)kLn2));
             }
-            ((float2*)(erow + 4))[k] = make_float2(lab - ct, fmaxf(sub - ct, kVoid));
+            float Kl, fl, Ks2, fs2;
+            split(lab, Kl, fl);
+            split(fmax(sub, -1.0e29), Ks2, fs2);
+            ((float2*)(erow + 8))[k] = make_float2(fl, fs2);
+            krow[k] = make_char2((signed char)(int)Kl, (signed char)(int)Ks2);
         }
         __syncwarp();
         if (r + nstage < nrows) issue(r + nstage);
@@ -152,63 +174,80 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
 }
 
 // --------------------------------------------------------------------------------- trellis ---
-__host__ __device__ inline int trellis_warp_bytes(int E, int SPX, int nstage) {
-    return round_up((nstage * (E + SPX) + 2 * E) * 4 + 2 * nstage * 8, 128);
-}
-
 struct StarTrellisParams {
     int T, N, S;
     const int4* meta; const int* order; const int* tgt; int Sp;
-    float* em; int E;          // emission rows in (layout above); occupancy rows out, in place:
-                               // [1] blank occupancy  [2] G = sum_k h_k  [4+2k] label occupancy
-                               // [5+2k] h_k (0 if y_k == 0), with h_k = gamma(star k) / (P - p_{y_k})
-    float* tr; int SPX, JWp;   // stored row = [JWp slot bases][4*(L+1) floats relative to them: quads]
+    float* em; int E;          // emission rows in / occupancy rows out, in place (layout: star_em_floats)
+    float* tr; int SPX, JWp;   // stored row = [JWp slot bases][4*(L+1) Q11.20 ints: quads]
     float* loss; float* loss_ws;
     float pen2;                // star_penalty in log2 units
-    int nstage; int warp_bytes;
+    int nstage, G, W;          // ring stages; frames per stage; compute warps per sweep direction
+    int dir_bytes;
 };
 
-// grid ceil(N/2), block 128: warps (2u, 2u+1) are the alpha and beta side of one utterance (see
-// ctc_trellis_kernel: same meet-in-the-middle schedule, same split numbers, straight-line slots).
-// Both sides keep quad k in lane k%32 of slot k/32; beta is not a mirror image of alpha here
-// (labels have no self loop, stars have a back edge), so it has its own update.
+// Same CTA shape and ring protocol as ctc_trellis_kernel (one CTA per utterance, W compute warps +
+// one producer warp per sweep side, meet in the middle).  Both sides keep quad k in lane k%32 of slot
+// k/32 of warp k/(32 J); beta is not a mirror image of alpha here (labels have no self loop, stars have
+// a back edge), so it has its own update and its mailbox runs downwards.
 template <int J>
-__global__ void __launch_bounds__(128, 1) star_trellis_kernel(StarTrellisParams p) {
+__global__ void __launch_bounds__(320) star_trellis_kernel(StarTrellisParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int W = p.W, G = p.G, nstage = p.nstage;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int usel = warp >> 1, dir = warp & 1;
-    const int idx = blockIdx.x * 2 + usel;
-    if (idx >= p.N) return;
-    const int n = p.order[idx];
+    const bool producer = warp >= 2 * W;
+    const int dir = producer ? warp - 2 * W : (warp >= W);
+    const int w = producer ? 0 : warp - dir * W;
+    const int n = p.order[blockIdx.x];
     const int4 mt = p.meta[n];
     const int Tn = mt.x, L = mt.y;
     if (mt.z || Tn == 0) {
         const float v = mt.z ? CUDART_NAN_F : CUDART_INF_F;
-        if (dir == 0 && lane == 0) { p.loss[n] = v; p.loss_ws[n] = v; }
+        if (threadIdx.x == 0) { p.loss[n] = v; p.loss_ws[n] = v; }
         return;
     }
     const int Q = L + 1, Ks = min(L + 1, p.S);
-    const int nstage = p.nstage, E = p.E, SPX = p.SPX, JWp = p.JWp;
+    const int E = p.E, SPX = p.SPX, JWp = p.JWp, Sp = p.Sp, OC = 8 + 2 * p.Sp;
+    const int SF_ = trellis_stage_floats(E, SPX, OC, G, W, 2);
     const float Kp = round_int(p.pen2), fp = p.pen2 - Kp;
 
-    unsigned char* wb = smem_raw + (size_t)warp * p.warp_bytes;
-    float* em_ring = (float*)wb;
-    float* tr_ring = em_ring + nstage * E;
-    float* occ_buf = tr_ring + nstage * SPX;
-    uint64_t* bar_em = (uint64_t*)(occ_buf + 2 * E);
-    uint64_t* bar_tr = bar_em + nstage;
-    if (lane == 0)
-        for (int s = 0; s < nstage; ++s) { mbar_init(&bar_em[s], 1); mbar_init(&bar_tr[s], 1); }
+    unsigned char* db = smem_raw + (size_t)dir * p.dir_bytes;
+    float* stages = (float*)db;
+    float4* mail = (float4*)(stages + nstage * SF_);              // [2][W]
+    double* redm = (double*)(mail + 2 * W);
+    float* reds = (float*)(redm + W);
+    uint64_t* full = (uint64_t*)(reds + 2 * W);
+    uint64_t* empty = full + nstage;
+    if (producer && lane == 0)
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init_fence();
-    __syncwarp();
+    __syncthreads();
 
+    float* em_base = p.em + (size_t)n * p.T * E;
+    float* tr_base = p.tr + (size_t)n * p.T * SPX;
+    const uint32_t occ_bytes = (uint32_t)(8 + round_up(2 * Ks, 4)) * 4u;
+    const int tm = Tn >> 1;
+    const int steps1 = dir ? Tn - tm : tm;
+
+    if (producer) {
+        trellis_producer<2>(stages, SF_, full, empty, nstage, G, W, E, SPX, OC, em_base, tr_base, occ_bytes,
+                            Tn, steps1, dir, lane);
+        return;
+    }
+
+    const bool leader = (w == 0 && lane == 0);
+    const int nthr = 32 * W;
+    const int barid = 1 + dir;
+    const int k0 = 32 * (w * J) + lane;           // my quad in slot 0
     // alpha: may label k be entered from label k-1?   beta: may label k be left for label k+1?
-    unsigned allowed = 0, exclude = 0;   // exclude: star k excludes a class (y_k != 0)
+    unsigned allowed = 0, exclude = 0, hasq = 0, hasl = 0, hase = 0;   // exclude: star k excludes a class
     {
         const int* y = p.tgt + (size_t)n * p.Sp;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const int k = 32 * j + lane;
+            const int k = k0 + 32 * j;
+            if (k < Q) hasq |= 1u << j;
+            if (k < L) hasl |= 1u << j;
+            if (k < Ks) hase |= 1u << j;
             if (k < Ks && (y[k] & kLabelMask) != 0) exclude |= 1u << j;
             if (dir == 0) {
                 if (k < L && (k == 0 || (y[k] & kLabelMask) != (y[k - 1] & kLabelMask))) allowed |= 1u << j;
@@ -217,256 +256,275 @@ __global__ void __launch_bounds__(128, 1) star_trellis_kernel(StarTrellisParams 
             }
         }
     }
+    // my quads cannot be reached before this step (alpha spreads upwards one quad per frame from
+    // quad 0, beta downwards from quad L)
+    const int first = dir ? L - (32 * (w + 1) * J - 1) - 2 : 32 * (w * J) - 2;
 
     SF b0[J], st[J], b1[J], lb[J];
     float base[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) { b0[j] = st[j] = b1[j] = lb[j] = sf_void(); base[j] = 0.0f; }
 
-    float* em_base = p.em + (size_t)n * p.T * E;
-    float* tr_base = p.tr + (size_t)n * p.T * SPX;
-    const uint32_t em_bytes = (uint32_t)round_up(4 + 2 * Ks, 4) * 4u;
-    const uint32_t tr_bytes = (uint32_t)(JWp + 4 * Q) * 4u;
-    const int tm = Tn >> 1;
-    const int steps1 = dir ? Tn - tm : tm;
-
-    auto issue_em = [&](int i) {
-        const int s = i % nstage, t = dir ? Tn - 1 - i : i;
-        mbar_expect_tx(&bar_em[s], em_bytes);
-        bulk_g2s(em_ring + s * E, em_base + (size_t)t * E, em_bytes, &bar_em[s]);
-    };
-    auto issue_tr = [&](int k) {
-        const int s = k % nstage, i = steps1 + k, t = dir ? Tn - 1 - i : i;
-        mbar_expect_tx(&bar_tr[s], tr_bytes);
-        bulk_g2s(tr_ring + s * SPX, tr_base + (size_t)t * SPX, tr_bytes, &bar_tr[s]);
-    };
-    auto phase_switch = [&]() {
-        __threadfence();
-        fence_async_all();
-        named_bar_sync(1 + usel, 64);
-        fence_async_all();
-        if (lane == 0)
-            for (int k = 0; k < min(nstage, Tn - steps1); ++k) issue_tr(k);
-    };
-
-    if (lane == 0)
-        for (int i = 0; i < min(nstage, Tn); ++i) issue_em(i);
-
-    float IZ = 0.0f, fZ = 0.0f, csum = 0.0f;
+    float IZ = 0.0f, fZ = 0.0f, csum = 0.0f, ct = 0.0f;
     bool feasible = true;
-    int se = 0; uint32_t par = 0;
-    int ts = 0; uint32_t tpar = 0;
+    float Kb, fb, Kl[J], fl[J], Ks_[J], fs[J];   // blank / label / star emissions of my quad, split; the
+                                                  // star's include the penalty paid on entering it
+    int s = 0, g = 0, cnt = 0; uint32_t fpar = 0;
+    const float* stg = stages;
 
-    for (int i = 0; i < Tn; ++i) {
-        if (i == steps1) phase_switch();
-        const int t = dir ? Tn - 1 - i : i;
-        mbar_wait(&bar_em[se], par);
-        const float* er = em_ring + se * E;
-        const float ct = er[0];
+    auto fetch = [&](int i, int phase_end) {
+        if (g == 0) {
+            cnt = min(G, phase_end - i);
+            stg = stages + s * SF_;
+            mbar_wait(&full[s], fpar);
+        }
+        const int ridx = dir ? cnt - 1 - g : g;
+        const float* er = stg + ridx * E;
+        const char2* kr = (const char2*)(er + 8 + 2 * Sp);
+        ct = er[0]; Kb = er[1]; fb = er[2];
+        const float Ka = er[4], fa = er[5];
         csum += ct;
-        const float eb = er[1], eall = er[2];
-        const float Kb = round_int(eb), fb = eb - Kb;
-        float Kl[J], fl[J], Ks_[J], fs[J];       // label / star emissions of my quad, split; the star's
-                                                  // include the penalty paid on entering it
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const int k = 32 * j + lane;
-            float el = kVoid, es = kVoid;
-            if (k < Ks) {
-                const float2 e = ((const float2*)(er + 4))[k];
-                el = (k < L) ? e.x : kVoid;
-                es = e.y;
-            } else if (k == L) {
-                es = eall;                        // L == S: the last star is the all-star (ha/star.py:47)
-            }
-            Kl[j] = round_int(el); fl[j] = el - Kl[j];
-            const float ks = round_int(es);
-            Ks_[j] = fmaxf(ks + Kp, kVoid); fs[j] = (es - ks) + fp;
+            const int k = k0 + 32 * j;
+            const bool ve = (hase >> j) & 1u, vl = (hasl >> j) & 1u;
+            const float2 f = ve ? ((const float2*)(er + 8))[k] : make_float2(0.0f, 0.0f);
+            const char2 kk = ve ? kr[k] : make_char2(0, 0);
+            Kl[j] = vl ? small_int_to_float((int)kk.x) : kVoid;
+            fl[j] = vl ? f.x : 0.0f;
+            // the star of quad k: its own entry, or the all-star when k == L == S (ha/star.py:47)
+            const float ks = ve ? small_int_to_float((int)kk.y) : ((k == L) ? Ka : kVoid);
+            const float fs0 = ve ? f.y : ((k == L) ? fa : 0.0f);
+            Ks_[j] = fmaxf(ks + Kp, kVoid);
+            fs[j] = fs0 + fp;
         }
-        __syncwarp();
-        if (lane == 0 && i + nstage < Tn) issue_em(i + nstage);
-        if (++se == nstage) { se = 0; par ^= 1u; }
-
+        return ridx;
+    };
+    auto advance = [&](int i) {
         if (dir == 0) {
-            // previous label, from the lane below (virtual state -1 holds 0.0 before the first frame)
-            SF c[J];
-            float rh_prev = (i == 0) ? 0.0f : kVoid, rl_prev = 0.0f;
+            if (i >= first) {
+                // previous label, from the lane below (virtual state -1 holds 0.0 before the first frame)
+                float ch[J], cl[J];
+                {
+                    float rh[J], rl[J];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const float rh = __shfl_sync(0xffffffffu, lb[j].h, (lane + 31) & 31);
-                const float rl = __shfl_sync(0xffffffffu, lb[j].l, (lane + 31) & 31);
-                c[j].h = lane ? rh : rh_prev;
-                c[j].l = lane ? rl : rl_prev;
-                rh_prev = rh; rl_prev = rl;
-            }
+                    for (int j = 0; j < J; ++j) {
+                        rh[j] = __shfl_sync(0xffffffffu, lb[j].h, (lane + 31) & 31);
+                        rl[j] = __shfl_sync(0xffffffffu, lb[j].l, (lane + 31) & 31);
+                    }
+                    float4 in = make_float4((i == 0) ? 0.0f : kVoid, 0.0f, 0.0f, 0.0f);
+                    if (w > 0) in = mail[((i - 1) & 1) * W + w - 1];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const SF u = lae_sf(st[j], b1[j]);
-                const SF v = lae_sf(u, b0[j]);
-                const SF w0 = lae_sf(c[j], b0[j]);
-                const SF vc = lae_sf(v, c[j]);
-                SF vl;
-                vl.h = ((allowed >> j) & 1u) ? vc.h : v.h;
-                vl.l = ((allowed >> j) & 1u) ? vc.l : v.l;
-                b1[j] = add_norm(u, Kb, fb);
-                st[j] = add_norm(v, Ks_[j], fs[j]);
-                lb[j] = add_norm(vl, Kl[j], fl[j]);
-                b0[j] = add_norm(w0, Kb, fb);
-            }
-        } else if (i == 0) {
-            // beta at the last frame: the four final states (ha/star.py:156-163), emission included
-            SF z; z.h = 0.0f; z.l = 0.0f;
+                    for (int j = 0; j < J; ++j) {
+                        ch[j] = lane ? rh[j] : (j ? rh[j ? j - 1 : 0] : in.x);
+                        cl[j] = lane ? rl[j] : (j ? rl[j ? j - 1 : 0] : in.y);
+                    }
+                }
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int k = 32 * j + lane;
-                if (k == L) { b0[j] = add_norm(z, Kb, fb); st[j] = add_norm(z, Ks_[j], fs[j]); b1[j] = b0[j]; }
-                if (k == L - 1) lb[j] = add_norm(z, Kl[j], fl[j]);
+                for (int j = 0; j < J; ++j) {
+                    SF c; c.h = ch[j]; c.l = cl[j];
+                    const SF u = lae_sf(st[j], b1[j]);
+                    const SF v = lae_sf(u, b0[j]);
+                    const SF w0 = lae_sf(c, b0[j]);
+                    const SF vc = lae_sf(v, c);
+                    SF vl;
+                    vl.h = ((allowed >> j) & 1u) ? vc.h : v.h;
+                    vl.l = ((allowed >> j) & 1u) ? vc.l : v.l;
+                    b1[j] = add_norm(u, Kb, fb);
+                    st[j] = add_norm(v, Ks_[j], fs[j]);
+                    lb[j] = add_norm(vl, Kl[j], fl[j]);
+                    b0[j] = add_norm(w0, Kb, fb);
+                }
             }
+            if (lane == 31 && w + 1 < W) mail[(i & 1) * W + w] = make_float4(lb[J - 1].h, lb[J - 1].l, 0.0f, 0.0f);
         } else {
-            // next quad's first blank and label, from the lane above (lane 31 takes lane 0 of the slot above)
-            SF n0[J], nl[J];
-            float r0h[J], r0l[J], rlh[J], rll[J];
+            if (i == 0) {
+                // beta at the last frame: the four final states (ha/star.py:156-163), emission included
+                SF z; z.h = 0.0f; z.l = 0.0f;
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                r0h[j] = __shfl_sync(0xffffffffu, b0[j].h, (lane + 1) & 31);
-                r0l[j] = __shfl_sync(0xffffffffu, b0[j].l, (lane + 1) & 31);
-                rlh[j] = __shfl_sync(0xffffffffu, lb[j].h, (lane + 1) & 31);
-                rll[j] = __shfl_sync(0xffffffffu, lb[j].l, (lane + 1) & 31);
-            }
+                for (int j = 0; j < J; ++j) {
+                    const int k = k0 + 32 * j;
+                    if (k == L) { b0[j] = add_norm(z, Kb, fb); st[j] = add_norm(z, Ks_[j], fs[j]); b1[j] = b0[j]; }
+                    if (k == L - 1) lb[j] = add_norm(z, Kl[j], fl[j]);
+                }
+            } else if (i >= first) {
+                // next quad's first blank and label, from the lane above (lane 31 takes lane 0 of the slot
+                // above, or the mailbox of the warp above)
+                float n0h[J], n0l[J], nlh[J], nll[J];
+                {
+                    float r0h[J], r0l[J], rlh[J], rll[J];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const bool edge = lane == 31;
-                n0[j].h = edge ? ((j + 1 < J) ? r0h[(j + 1 < J) ? j + 1 : j] : kVoid) : r0h[j];
-                n0[j].l = edge ? ((j + 1 < J) ? r0l[(j + 1 < J) ? j + 1 : j] : 0.0f) : r0l[j];
-                nl[j].h = edge ? ((j + 1 < J) ? rlh[(j + 1 < J) ? j + 1 : j] : kVoid) : rlh[j];
-                nl[j].l = edge ? ((j + 1 < J) ? rll[(j + 1 < J) ? j + 1 : j] : 0.0f) : rll[j];
-            }
+                    for (int j = 0; j < J; ++j) {
+                        r0h[j] = __shfl_sync(0xffffffffu, b0[j].h, (lane + 1) & 31);
+                        r0l[j] = __shfl_sync(0xffffffffu, b0[j].l, (lane + 1) & 31);
+                        rlh[j] = __shfl_sync(0xffffffffu, lb[j].h, (lane + 1) & 31);
+                        rll[j] = __shfl_sync(0xffffffffu, lb[j].l, (lane + 1) & 31);
+                    }
+                    float4 in = make_float4(kVoid, 0.0f, kVoid, 0.0f);
+                    if (w + 1 < W) in = mail[((i - 1) & 1) * W + w + 1];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const SF x = lae_sf(st[j], lb[j]);
-                const SF z = lae_sf(b1[j], x);
-                const SF w0 = lae_sf(b0[j], x);
-                const SF nn = lae_sf(n0[j], nl[j]);
-                SF vl;
-                vl.h = ((allowed >> j) & 1u) ? nn.h : n0[j].h;
-                vl.l = ((allowed >> j) & 1u) ? nn.l : n0[j].l;
-                b0[j] = add_norm(w0, Kb, fb);
-                st[j] = add_norm(z, Ks_[j], fs[j]);
-                b1[j] = add_norm(z, Kb, fb);
-                lb[j] = add_norm(vl, Kl[j], fl[j]);
+                    for (int j = 0; j < J; ++j) {
+                        const bool edge = lane == 31;
+                        const int jn = (j + 1 < J) ? j + 1 : j;
+                        n0h[j] = edge ? ((j + 1 < J) ? r0h[jn] : in.x) : r0h[j];
+                        n0l[j] = edge ? ((j + 1 < J) ? r0l[jn] : in.y) : r0l[j];
+                        nlh[j] = edge ? ((j + 1 < J) ? rlh[jn] : in.z) : rlh[j];
+                        nll[j] = edge ? ((j + 1 < J) ? rll[jn] : in.w) : rll[j];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    SF n0; n0.h = n0h[j]; n0.l = n0l[j];
+                    SF nl; nl.h = nlh[j]; nl.l = nll[j];
+                    const SF x = lae_sf(st[j], lb[j]);
+                    const SF z = lae_sf(b1[j], x);
+                    const SF w0 = lae_sf(b0[j], x);
+                    const SF nn = lae_sf(n0, nl);
+                    SF vl;
+                    vl.h = ((allowed >> j) & 1u) ? nn.h : n0.h;
+                    vl.l = ((allowed >> j) & 1u) ? nn.l : n0.l;
+                    b0[j] = add_norm(w0, Kb, fb);
+                    st[j] = add_norm(z, Ks_[j], fs[j]);
+                    b1[j] = add_norm(z, Kb, fb);
+                    lb[j] = add_norm(vl, Kl[j], fl[j]);
+                }
             }
+            if (lane == 0 && w > 0) mail[(i & 1) * W + w] = make_float4(b0[0].h, b0[0].l, lb[0].h, lb[0].l);
         }
-        if (i < steps1) {
-            unsigned up = 0, near = 0, live = 0;
+    };
+    auto step_end = [&]() {
+        named_bar_sync(barid, nthr);
+        if (++g == cnt) {
+            if (leader) mbar_arrive(&empty[s]);
+            g = 0;
+            if (++s == nstage) { s = 0; fpar ^= 1u; }
+        }
+    };
+    auto smax = [&](int j) { return fmaxf(fmaxf(b0[j].h, st[j].h), fmaxf(b1[j].h, lb[j].h)); };
+
+    // ---------------------------------------------------------------------------- phase 1 ---
+    {
+        int4* prow = (int4*)(tr_base + (size_t)(dir ? Tn - 1 : 0) * SPX + JWp) + k0;
+        float* hrow = tr_base + (size_t)(dir ? Tn - 1 : 0) * SPX + w * J;
+        const long long rstep = dir ? -(long long)SPX : (long long)SPX;
+        for (int i = 0; i < steps1; ++i) {
+            fetch(i, steps1);
+            advance(i);
+            unsigned bits = 0;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                const float m = fmaxf(fmaxf(b0[j].h, st[j].h), fmaxf(b1[j].h, lb[j].h));
-                const float d = m - base[j];
-                up |= (d > kRebase) ? (1u << j) : 0u;
-                near |= (d > -kRebase) ? (1u << j) : 0u;
-                live |= (m > kVoidTest) ? (1u << j) : 0u;
+                const float m = smax(j);
+                const float dd = m - base[j];
+                bits |= (dd > kRebase) ? (1u << j) : 0u;
+                bits |= (dd > -kRebase) ? (0x100u << j) : 0u;
+                bits |= (m > kVoidTest) ? (0x10000u << j) : 0u;
             }
-            up = __reduce_or_sync(0xffffffffu, up);
-            near = __reduce_or_sync(0xffffffffu, near);
-            live = __reduce_or_sync(0xffffffffu, live);
-            const unsigned need = up | (live & ~near);
+            bits = __reduce_or_sync(0xffffffffu, bits);
+            const unsigned need = (bits | ((bits >> 16) & ~(bits >> 8))) & 0xffu;
             if (need) {
 #pragma unroll
                 for (int j = 0; j < J; ++j)
-                    if ((need >> j) & 1u)
-                        base[j] = warp_max(fmaxf(fmaxf(b0[j].h, st[j].h), fmaxf(b1[j].h, lb[j].h)));
+                    if ((need >> j) & 1u) base[j] = warp_max(smax(j));
             }
-            float* row = tr_base + (size_t)t * SPX;
+            float bsel = base[0];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int k = 32 * j + lane;
-                if (k < Q)
-                    ((float4*)(row + JWp))[k] = make_float4((b0[j].h - base[j]) + b0[j].l, (st[j].h - base[j]) + st[j].l,
-                                                            (b1[j].h - base[j]) + b1[j].l, (lb[j].h - base[j]) + lb[j].l);
-                if (lane == j && 32 * j < Q) row[j] = base[j];
-            }
-        } else {
-            const int k2 = i - steps1;
-            mbar_wait(&bar_tr[ts], tpar);
-            const float4* orow = (const float4*)(tr_ring + ts * SPX + JWp);
-            const float* obase = tr_ring + ts * SPX;
-            // posterior exponent of a state = [h + other base - K] + [l + other value - f] - log Z
-            auto expo = [&](int jj, float& xi0, float& xf0, float& xis, float& xfs, float& xi1, float& xf1,
-                            float& xil, float& xfl) {
-                const int k = 32 * jj + lane;
-                const bool in = k < Q;
-                const float4 o = in ? orow[k] : make_float4(kVoid, kVoid, kVoid, kVoid);
-                const float ob = in ? obase[jj] : 0.0f;
-                xi0 = (b0[jj].h + ob) - Kb;      xf0 = (b0[jj].l + o.x) - fb;
-                xis = (st[jj].h + ob) - Ks_[jj]; xfs = (st[jj].l + o.y) - fs[jj];
-                xi1 = (b1[jj].h + ob) - Kb;      xf1 = (b1[jj].l + o.z) - fb;
-                xil = (k < L) ? (lb[jj].h + ob) - Kl[jj] : kVoid;
-                xfl = (lb[jj].l + o.w) - fl[jj];
-            };
-            if (k2 == 0) {
-                double mx = -1.0e300;
+            for (int j = 1; j < J; ++j) bsel = (lane == j) ? base[j] : bsel;
 #pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    float a, b, c, d, e, f, g, h;
-                    expo(j, a, b, c, d, e, f, g, h);
-                    mx = fmax(mx, fmax(fmax((double)a + (double)b, (double)c + (double)d),
-                                       fmax((double)e + (double)f, (double)g + (double)h)));
-                }
-                mx = warp_max_d(mx);
-                feasible = mx > (double)kVoidTest;
-                float s = 0.0f;
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    float a, b, c, d, e, f, g, h;
-                    expo(j, a, b, c, d, e, f, g, h);
-                    s += ex2f((float)((double)a + (double)b - mx)) + ex2f((float)((double)c + (double)d - mx)) +
-                         ex2f((float)((double)e + (double)f - mx)) + ex2f((float)((double)g + (double)h - mx));
-                }
-                s = warp_sum(s);
-                const double logZ2 = mx + (double)log2f(s);
-                const double fl2 = floor(logZ2);
-                IZ = feasible ? (float)fl2 : 0.0f;
-                fZ = feasible ? (float)(logZ2 - fl2) : 0.0f;
-            }
-            float* ob = occ_buf + (i & 1) * E;
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
-            float bsum = 0.0f, gsum = 0.0f;
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int k = 32 * j + lane;
-                float xi0, xf0, xis, xfs, xi1, xf1, xil, xfl;
-                expo(j, xi0, xf0, xis, xfs, xi1, xf1, xil, xfl);
-                const float g0 = feasible ? ex2f((xi0 - IZ) + (xf0 - fZ)) : 0.0f;
-                const float g1 = feasible ? ex2f((xi1 - IZ) + (xf1 - fZ)) : 0.0f;
-                const float gl = feasible ? ex2f((xil - IZ) + (xfl - fZ)) : 0.0f;
-                // h = gamma(star) / (P - p_y) = 2^(log2 gamma - es), es = the star's TRUE emission: without the
-                // penalty and with the row shift added back (the shift cancels in gamma, not in P - p_y)
-                const float h = (feasible && k < Q)
-                                    ? ex2f(((xis - IZ) - ((Ks_[j] - Kp) + ct)) + ((xfs - fZ) - (fs[j] - fp))) : 0.0f;
-                bsum += g0 + g1;
-                gsum += h;
-                if (k < Ks) ((float2*)(ob + 4))[k] = make_float2(gl, ((exclude >> j) & 1u) ? h : 0.0f);
-            }
-            bsum = warp_sum(bsum);
-            gsum = warp_sum(gsum);
-            if (lane == 0) { ob[1] = bsum; ob[2] = gsum; }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                bulk_s2g(em_base + (size_t)t * E, ob, em_bytes);
-                bulk_commit();
-                if (k2 + nstage < Tn - steps1) issue_tr(k2 + nstage);
-            }
-            if (++ts == nstage) { ts = 0; tpar ^= 1u; }
+            for (int j = 0; j < J; ++j)
+                if ((hasq >> j) & 1u)
+                    prow[32 * j] = make_int4(sf_to_fix(b0[j], base[j]), sf_to_fix(st[j], base[j]),
+                                             sf_to_fix(b1[j], base[j]), sf_to_fix(lb[j], base[j]));
+            if (lane < J && 32 * (w * J + lane) < Q) hrow[lane] = bsel;
+            prow = (int4*)((float*)prow + rstep);
+            hrow += rstep;
+            step_end();
         }
     }
-    if (steps1 == Tn) phase_switch();
-    if (dir == 0 && lane == 0) {
+    __threadfence();
+    fence_async_all();
+    __syncthreads();
+
+    // ---------------------------------------------------------------------------- phase 2 ---
+    for (int i = steps1; i < Tn; ++i) {
+        const int ridx = fetch(i, Tn);
+        advance(i);
+        const float* trow = stg + G * E + ridx * SPX;
+        const int4* orow = (const int4*)(trow + JWp) + k0;       // [32 j] = other side's copy of my quad
+        const float* obase = trow + w * J;                        // [j] = its slot base
+        // posterior exponent of a state = [h + other base + other integer part - K] + [l + other fraction - f] - log Z
+        auto expo = [&](int jj, float& xi0, float& xf0, float& xis, float& xfs, float& xi1, float& xf1,
+                        float& xil, float& xfl) {
+            const bool in = (hasq >> jj) & 1u;
+            const int4 o = in ? orow[32 * jj] : make_int4(kFixVoid, kFixVoid, kFixVoid, kFixVoid);
+            const float ob = in ? obase[jj] : 0.0f;
+            float h, l;
+            fix_to_parts(o.x, h, l); xi0 = ((b0[jj].h + ob) + h) - Kb;      xf0 = (b0[jj].l + l) - fb;
+            fix_to_parts(o.y, h, l); xis = ((st[jj].h + ob) + h) - Ks_[jj]; xfs = (st[jj].l + l) - fs[jj];
+            fix_to_parts(o.z, h, l); xi1 = ((b1[jj].h + ob) + h) - Kb;      xf1 = (b1[jj].l + l) - fb;
+            fix_to_parts(o.w, h, l); xil = ((lb[jj].h + ob) + h) - Kl[jj];  xfl = (lb[jj].l + l) - fl[jj];
+            if (!((hasl >> jj) & 1u)) xil = kVoid;
+        };
+        if (i == steps1) {
+            double mx = -1.0e300;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                float a, b, c, d, e, f, gg, h;
+                expo(j, a, b, c, d, e, f, gg, h);
+                mx = fmax(mx, fmax(fmax((double)a + (double)b, (double)c + (double)d),
+                                   fmax((double)e + (double)f, (double)gg + (double)h)));
+            }
+            mx = warp_max_d(mx);
+            if (lane == 0) redm[w] = mx;
+            named_bar_sync(barid, nthr);
+            for (int x = 0; x < W; ++x) mx = fmax(mx, redm[x]);
+            feasible = mx > (double)kVoidTest;
+            float sm = 0.0f;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                float a, b, c, d, e, f, gg, h;
+                expo(j, a, b, c, d, e, f, gg, h);
+                sm += ex2f((float)((double)a + (double)b - mx)) + ex2f((float)((double)c + (double)d - mx)) +
+                      ex2f((float)((double)e + (double)f - mx)) + ex2f((float)((double)gg + (double)h - mx));
+            }
+            sm = warp_sum(sm);
+            if (lane == 0) reds[w] = sm;
+            named_bar_sync(barid, nthr);
+            sm = 0.0f;
+            for (int x = 0; x < W; ++x) sm += reds[x];
+            const double logZ2 = mx + (double)log2f(sm);
+            const double fl2 = floor(logZ2);
+            IZ = feasible ? (float)fl2 : 0.0f;
+            fZ = feasible ? (float)(logZ2 - fl2) : 0.0f;
+        }
+        float* ob = (float*)stg + G * (E + SPX) + ridx * OC;
+        float* ps = (float*)stg + G * (E + SPX) + G * OC;
+        float bsum = 0.0f, gsum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int k = k0 + 32 * j;
+            float xi0, xf0, xis, xfs, xi1, xf1, xil, xfl;
+            expo(j, xi0, xf0, xis, xfs, xi1, xf1, xil, xfl);
+            const float g0 = feasible ? ex2f((xi0 - IZ) + (xf0 - fZ)) : 0.0f;
+            const float g1 = feasible ? ex2f((xi1 - IZ) + (xf1 - fZ)) : 0.0f;
+            const float gl = feasible ? ex2f((xil - IZ) + (xfl - fZ)) : 0.0f;
+            // h = gamma(star) / (P - p_y) = 2^(log2 gamma - es), es = the star's TRUE emission: without the
+            // penalty and with the row shift added back (the shift cancels in gamma, not in P - p_y)
+            const float h = (feasible && ((hasq >> j) & 1u))
+                                ? ex2f(((xis - IZ) - ((Ks_[j] - Kp) + ct)) + ((xfs - fZ) - (fs[j] - fp))) : 0.0f;
+            bsum += g0 + g1;
+            gsum += h;
+            if (k < Ks) ((float2*)(ob + 8))[k] = make_float2(gl, ((exclude >> j) & 1u) ? h : 0.0f);
+        }
+        bsum = warp_sum(bsum);
+        gsum = warp_sum(gsum);
+        if (lane == 0) { ps[(ridx * W + w) * 2] = bsum; ps[(ridx * W + w) * 2 + 1] = gsum; }
+        if (g == cnt - 1) fence_async_smem();
+        step_end();
+    }
+    if (dir == 0 && leader) {
         const float v = feasible ? (float)(-((double)IZ + (double)fZ + (double)csum) * kLn2) : CUDART_INF_F;
         p.loss[n] = v; p.loss_ws[n] = v;
     }
-    if (lane == 0) bulk_wait_all<0>();
 }
 
 // ------------------------------------------------------------------------------------ grad ---
@@ -521,7 +579,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
     float* gb = p.gx + (long long)n * p.sg_n;
     const float g = p.gout[n];
     const float delta = p.from_logits ? 1.0f : 0.0f;
-    const uint32_t occ_bytes = (uint32_t)round_up(4 + 2 * Ks, 4) * 4u;
+    const uint32_t occ_bytes = (uint32_t)(8 + round_up(2 * Ks, 4)) * 4u;
 
     auto issue = [&](int r) {
         const int stage = r % nstage;
@@ -537,7 +595,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
             }
         } else {
             for (int c = lane; c < V; c += 32) dst[c] = src[c];
-            for (int c = lane; c < 4 + 2 * Ks; c += 32) dst[V + c] = osrc[c];
+            for (int c = lane; c < 8 + 2 * Ks; c += 32) dst[V + c] = osrc[c];
         }
     };
     for (int r = 0; r < min(nstage - 1, nreal); ++r) issue(r);
@@ -562,10 +620,10 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
         for (int k = lane; k < Ks; k += 32) {
             const int w = s_tgt[k];
             if (!(w & kNotFirst)) {
-                float sl = (k < L) ? occ[4 + 2 * k] : 0.0f, sh = occ[5 + 2 * k];
-                for (int j = s_nxt[k]; j >= 0; j = s_nxt[j]) { sl += (j < L) ? occ[4 + 2 * j] : 0.0f; sh += occ[5 + 2 * j]; }
+                float sl = (k < L) ? occ[8 + 2 * k] : 0.0f, sh = occ[9 + 2 * k];
+                for (int j = s_nxt[k]; j >= 0; j = s_nxt[j]) { sl += (j < L) ? occ[8 + 2 * j] : 0.0f; sh += occ[9 + 2 * j]; }
                 const float pc = ex2f(fmaf(row[w & kLabelMask], kLog2e, -l2));
-                occ[4 + 2 * k] = g * (pc * sh - sl);
+                occ[8 + 2 * k] = g * (pc * sh - sl);
             }
         }
         __syncwarp();
@@ -586,7 +644,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
         __syncwarp();
         for (int k = lane; k < Ks; k += 32) {
             const int w = s_tgt[k];
-            if (!(w & kNotFirst)) row[w & kLabelMask] += occ[4 + 2 * k];
+            if (!(w & kNotFirst)) row[w & kLabelMask] += occ[8 + 2 * k];
         }
         float* dstg = gb + (long long)t * p.sg_t;
         if (p.use_bulk) {
