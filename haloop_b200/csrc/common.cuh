@@ -47,6 +47,23 @@ constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: (x + kMagic) - kMagic == 
 __device__ __forceinline__ float round_int(float x) { return __fsub_rn(__fadd_rn(x, kMagic), kMagic); }
 // small integer -> float without a conversion instruction
 __device__ __forceinline__ float small_int_to_float(int k) { return __int_as_float(0x4B400000 + k) - kMagic; }
+// ---- emissions in float-float arithmetic ----------------------------------------------------------
+// e = x * log2(e) - l2 - ct for an fp32 logit x, split into an integer part K (clamped to int8 range)
+// and a fraction f with |error| ~1e-8: two-product and two-sum error-free transformations on the FP32
+// pipe (float64 conversions run at 1/16 rate and made the row kernels compute bound).
+constexpr float kLog2eHi = 1.4426950216293335f;             // fl(log2 e)
+constexpr float kLog2eLo = 1.9259629911266175e-8f;          // log2 e - fl(log2 e)
+__device__ __forceinline__ void emission_split(float x, float l2, float ct, float& K, float& f) {
+    const float ph = x * kLog2eHi;
+    const float pl = fmaf(x, kLog2eLo, fmaf(x, kLog2eHi, -ph));        // x*log2e = ph + pl
+    const float s = ph - l2;                                             // two-sum of ph + (-l2)
+    const float bb = s - ph;
+    const float err = (ph - (s - bb)) + (-l2 - bb);
+    const float Kt = fmaxf(round_int(s - ct) + ct, ct - 127.0f);         // integer part of the unshifted value
+    K = Kt - ct;
+    f = (s - Kt) + (err + pl);
+}
+
 // ---- stored trellis values: Q11.20 fixed point relative to a per-slot integer base -----------------
 // A split number (h, l) is stored as round((h - base + l) * 2^20) in one int32: absolute precision
 // 5e-7 at any distance up to 2047 log2 units below the base (the state that matters for a posterior

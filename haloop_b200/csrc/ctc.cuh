@@ -199,26 +199,25 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_rows_kernel(RowsParams 
         // Emissions are stored relative to an integer per-row shift c_t = rint(max gathered emission),
         // so the likeliest state of every frame sits near 0.  The shifts cancel in every posterior
         // (both sweeps see the same rows); only the loss needs their sum, which the trellis adds back.
-        // Each emission is evaluated in float64 from the fp32 logit and split into an int8 integer
-        // part and an fp32 fraction: its quantisation error is ~3e-8 instead of ulp(log2 p)/2.
+        // Each emission is evaluated in float-float arithmetic from the fp32 logit and split into an int8
+        // integer part and an fp32 fraction: its quantisation error is ~1e-8 instead of ulp(log2 p)/2.
         const float eblank = fmaf(row[0], kLog2e, -l2);
         float emax = eblank;
         for (int k = lane; k < L; k += 32) emax = fmaxf(emax, fmaf(row[s_tgt[k]], kLog2e, -l2));
         const float ct = round_int(warp_max(emax));
-        const double shift = (double)l2 + (double)ct;
         float* erow = p.em + ((size_t)n * p.T + t) * p.E;
         signed char* krow = (signed char*)(erow + 4 + p.Sp);
         if (lane == 0) {
             p.lse2[(size_t)n * p.T + t] = l2;
-            const double e = fma((double)row[0], kLog2e_d, -shift);
-            const double K = fmax(rint(e), -127.0);
-            *(float4*)erow = make_float4(ct, (float)K, (float)(e - K), 0.0f);
+            float K, f;
+            emission_split(row[0], l2, ct, K, f);
+            *(float4*)erow = make_float4(ct, K, f, 0.0f);
         }
         for (int k = lane; k < L; k += 32) {
-            const double e = fma((double)row[s_tgt[k]], kLog2e_d, -shift);
-            const double K = fmax(rint(e), -127.0);
-            erow[4 + k] = (float)(e - K);
-            krow[k] = (signed char)(int)K;
+            float K, f;
+            emission_split(row[s_tgt[k]], l2, ct, K, f);
+            erow[4 + k] = f;
+            krow[k] = (signed char)__float2int_rn(K);
         }
         __syncwarp();
         if (r + nstage < nrows) issue(r + nstage);

@@ -135,38 +135,49 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
         const float lP = fmaxf(m2 + log2f(s) - l2, kVoid);        // log2 sum_{c>=1} p_c   (ha/star.py:30)
         const float eblank = fmaf(row[0], kLog2e, -l2);
         const float ct = round_int(fmaxf(eblank, lP));            // every other emission is <= log2 P
-        // emissions in float64 from the fp32 logits, split into int8 integer part + fp32 fraction
-        const double shift = (double)l2 + (double)ct;
-        const double lPd = ((double)m2 + (double)log2f(s)) - (double)l2;      // log2 P, unshifted
+        // emissions in float-float arithmetic from the fp32 logits, split into int8 integer part + fp32
+        // fraction (emission_split, common.cuh).  log2 P and the star terms are (hi, lo) float pairs too.
+        const float lgs = log2f(s);
+        const float lPh = m2 + lgs;                                        // log2 P + l2, rounded ...
+        const float lbb = lPh - m2;
+        const float lPl = (m2 - (lPh - lbb)) + (lgs - lbb);                // ... and the rounding error (two-sum)
         float* erow = p.em + ((size_t)n * p.T + t) * p.E;
         char2* krow = (char2*)(erow + 8 + 2 * p.Sp);
-        auto split = [](double e, float& K, float& f) {
-            const double k = fmax(rint(e), -127.0);
-            K = (float)k; f = (float)(e - k);
+        // (vh + vl) - l2 - ct  ->  int8 K + fraction f
+        auto split2 = [&](float vh, float vl, float& K, float& f) {
+            const float s1 = vh - l2;
+            const float bb = s1 - vh;
+            const float err = (vh - (s1 - bb)) + (-l2 - bb);
+            const float Kt = fmaxf(round_int(s1 - ct) + ct, ct - 127.0f);
+            K = Kt - ct;
+            f = (s1 - Kt) + (err + vl);
         };
         if (lane == 0) {
             p.lse2[(size_t)n * p.T + t] = l2;
             float Kb, fb, Ka, fa;
-            split(fma((double)row[0], kLog2e_d, -shift), Kb, fb);
-            split(fmax(lPd - (double)ct, -1.0e29), Ka, fa);
+            emission_split(row[0], l2, ct, Kb, fb);
+            split2(fmaxf(lPh, kVoid), lPl, Ka, fa);
             *(float4*)erow = make_float4(ct, Kb, fb, 0.0f);
             *(float4*)(erow + 4) = make_float4(Ka, fa, 0.0f, 0.0f);
         }
         for (int k = lane; k < Ks; k += 32) {
             const int y = s_tgt[k];
-            const double lab = fma((double)row[y], kLog2e_d, -shift);         // shifted
-            double sub = lPd - (double)ct;
+            float Kl, fl, Ks2, fs2;
+            emission_split(row[y], l2, ct, Kl, fl);
+            float add = 0.0f;
             if (y != 0) {
                 // logsubexp (ha/star.py:4-5): log2 P + log2(1 - 2^(lab - log2 P)), via expm1 so that a
                 // label holding almost all of P does not cancel
-                const float d = fminf((float)(lab - sub), 0.0f);
-                sub += (double)log2f(-expm1f(d * (float)kLn2));
+                const float d = fminf(fmaf(row[y], kLog2e, -lPh), 0.0f);   // lab - log2 P (l2 cancels)
+                add = fmaxf(log2f(-expm1f(d * (float)kLn2)), kVoid);
             }
-            float Kl, fl, Ks2, fs2;
-            split(lab, Kl, fl);
-            split(fmax(sub, -1.0e29), Ks2, fs2);
+            // star emission = log2 P + add: fold `add` into the low word (|add| is small unless the label
+            // holds nearly all of P, where its own relative error dominates anyway)
+            const float sh = lPh + add;
+            const float sl = lPl + ((lPh - sh) + add);
+            split2(fmaxf(sh, kVoid), sl, Ks2, fs2);
             ((float2*)(erow + 8))[k] = make_float2(fl, fs2);
-            krow[k] = make_char2((signed char)(int)Kl, (signed char)(int)Ks2);
+            krow[k] = make_char2((signed char)__float2int_rn(Kl), (signed char)__float2int_rn(Ks2));
         }
         __syncwarp();
         if (r + nstage < nrows) issue(r + nstage);

@@ -1,0 +1,45 @@
+"""Summarise an .ncu-rep (read here, no GPU needed) into a small text table for profiles/.
+usage: python tools/ncu_summary.py gpurun_out/prof_ctc_r01.ncu-rep > profiles/ncu_ctc_r01.txt"""
+import csv, subprocess, sys, io
+rep = sys.argv[1]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units = rows[0], rows[1]
+want = [
+    ("Kernel Name", "kernel"), ("gpu__time_duration.sum", "time"),
+    ("dram__bytes_read.sum", "dram_read"), ("dram__bytes_write.sum", "dram_write"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_pct"),
+    ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+    ("launch__shared_mem_per_block_dynamic", "dyn_smem"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu_pct"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma_pct"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu_pct"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu_pct"),
+    ("smsp__inst_executed.sum", "warp_insts"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall_barrier"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_sb"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_sb"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall_wait"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall_math"),
+]
+idx = {n: hdr.index(n) for n, _ in want if n in hdr}
+print(f"# {rep}: ncu --set full --clock-control none (per-launch values; cold cache, serialised replays)")
+for r in rows[2:]:
+    print("-" * 100)
+    for n, short in want:
+        if n in idx:
+            u = units[idx[n]]
+            print(f"{short:18s} {r[idx[n]]} {u}")
+    try:
+        rd = float(r[idx["dram__bytes_read.sum"]]); wr = float(r[idx["dram__bytes_write.sum"]])
+        ur, uw = units[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_write.sum"]]
+        f = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = rd * f[ur] + wr * f[uw]
+        t = float(r[idx["gpu__time_duration.sum"]]); tu = units[idx["gpu__time_duration.sum"]]
+        tf = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}[tu]
+        print(f"{'dram_total':18s} {tot/1e9:.4f} GB  -> {tot/1e9/(t*tf):.0f} GB/s under the profiler")
+    except Exception as e:
+        print("dram_total n/a", e)
