@@ -35,6 +35,19 @@ def alg_bytes(kind, B, T, V, U):
     return 8 * V * B * T * ((U + 1) if kind == "rnnt" else 1)
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the latest committed ncu --set full summary
+    (profiles/traffic_rNN.json, BASELINE-size workloads only); None if there is none."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")))
+    if not files:
+        return None
+    try:
+        return json.load(open(files[-1])).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -348,9 +361,13 @@ def main():
         "clocks": clocks,
         "roofline": {
             "bound": "hbm", "kernel": f"{kind}_grad_kernel (the whole backward call: reads the logits, writes the gradient)",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic(f"{kind}_grad_kernel") if args.workload in ("ctc", "star", "rnnt") else None,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
             "step_achieved": ab / (ms_step * 1e-3) / 1e9, "step_frac": ab / (ms_step * 1e-3) / 1e9 / peak,
+            "note": "HBM-bound streaming kernel of the step (the only one whose algorithmic bytes are defined: it reads the "
+                    "logits and writes the gradient); bwd_ms/ms_per_step is its live share of the step. The trellis kernel "
+                    "is instruction-issue bound, see profiles/ and DESIGN.md.",
         },
     }
     if e2e:
