@@ -127,9 +127,14 @@ def cpu_reference_run(kind, B, T, V, U, seconds_target, threads):
     and does not travel to the GPU box) on a bounded sample of the workload: same T, V, U, fewer
     utterances.  Returns (frames_per_s, sample_description, B_cpu, seconds)."""
     import numpy as np
+    os.environ["OMP_NUM_THREADS"] = str(threads)      # must be set before libgomp initialises
     from oracle import oracle
     oracle.build()
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    try:                                               # torchrun pins OMP_NUM_THREADS=1; the CPU arm uses every core
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
+    except Exception:
+        pass
     rng = np.random.default_rng(0)
 
     def run(b):
@@ -372,7 +377,7 @@ def main():
     }
     if e2e:
         out["e2e"] = e2e
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         fps, sample, b, tcpu = cpu_reference_run(kind, B, T, V, U, args.cpu_seconds, threads)
         out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                                "sample": sample, "seconds": tcpu}
