@@ -45,8 +45,9 @@ __device__ __forceinline__ float lae2(float a, float b) {
 struct SF { float h, l; };
 constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: (x + kMagic) - kMagic == rint(x) for |x| < 2^22
 __device__ __forceinline__ float round_int(float x) { return __fsub_rn(__fadd_rn(x, kMagic), kMagic); }
-// small integer -> float without a conversion instruction
-__device__ __forceinline__ float small_int_to_float(int k) { return __int_as_float(0x4B400000 + k) - kMagic; }
+// integer -> float: I2FP.F32.S32 is a fast ALU-class instruction on sm_100 (F2I is not: float -> int goes
+// through the magic constant instead)
+__device__ __forceinline__ float small_int_to_float(int k) { return (float)k; }
 // ---- emissions in float-float arithmetic ----------------------------------------------------------
 // e = x * log2(e) - l2 - ct for an fp32 logit x, split into an integer part K (clamped to int8 range)
 // and a fraction f with |error| ~1e-8: two-product and two-sum error-free transformations on the FP32
@@ -148,8 +149,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (the launch fails) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 26); ++spin)
         if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+// Producer-side wait: back off between polls so a spinning producer lane does not take issue slots
+// from the compute warps of its scheduler.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        if (mbar_try_wait(bar, parity)) return;
+        __nanosleep(200);
+    }
     __trap();
 }
 // global -> shared, completion counted on an mbarrier. bytes % 16 == 0, both addresses 16B aligned.

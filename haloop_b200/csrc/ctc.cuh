@@ -169,18 +169,18 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_rows_kernel(RowsParams 
         const float* row = wrows + (size_t)stage * V;
         const int t = t0 + warp + kRowWarps * r;
         float l2 = 0.0f;                       // log2-sum-exp2 of the row; 0 when x already holds log-probs
-        if (p.from_logits) {
-            float mx = -CUDART_INF_F;
-            if (VEC4) {
-                const float4* r4 = (const float4*)row;
-                for (int c = lane; c < (V >> 2); c += 32) {
-                    float4 v = r4[c];
-                    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-                }
-            } else {
-                for (int c = lane; c < V; c += 32) mx = fmaxf(mx, row[c]);
+        float mx = -CUDART_INF_F;
+        if (VEC4) {
+            const float4* r4 = (const float4*)row;
+            for (int c = lane; c < (V >> 2); c += 32) {
+                float4 v = r4[c];
+                mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
             }
-            mx = warp_max(mx);
+        } else {
+            for (int c = lane; c < V; c += 32) mx = fmaxf(mx, row[c]);
+        }
+        mx = warp_max(mx);
+        if (p.from_logits) {
             const float m2 = mx * kLog2e;
             float s = 0.0f;
             if (VEC4) {
@@ -196,15 +196,12 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_rows_kernel(RowsParams 
             s = warp_sum(s);
             l2 = m2 + log2f(s);
         }
-        // Emissions are stored relative to an integer per-row shift c_t = rint(max gathered emission),
-        // so the likeliest state of every frame sits near 0.  The shifts cancel in every posterior
+        // Emissions are stored relative to an integer per-row shift c_t = rint(log2 p of the row's likeliest
+        // class), so the likeliest state of every frame sits near 0 and the integer parts fit an int8.  The shifts cancel in every posterior
         // (both sweeps see the same rows); only the loss needs their sum, which the trellis adds back.
         // Each emission is evaluated in float-float arithmetic from the fp32 logit and split into an int8
         // integer part and an fp32 fraction: its quantisation error is ~1e-8 instead of ulp(log2 p)/2.
-        const float eblank = fmaf(row[0], kLog2e, -l2);
-        float emax = eblank;
-        for (int k = lane; k < L; k += 32) emax = fmaxf(emax, fmaf(row[s_tgt[k]], kLog2e, -l2));
-        const float ct = round_int(warp_max(emax));
+        const float ct = round_int(fmaf(mx, kLog2e, -l2));       // emission of the row's likeliest class
         float* erow = p.em + ((size_t)n * p.T + t) * p.E;
         signed char* krow = (signed char*)(erow + 4 + p.Sp);
         if (lane == 0) {
@@ -290,7 +287,7 @@ __device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_
     if (lane == 0) {
         for (int k = 0; k < ng1; ++k) {
             const int s = k % nstage, use = k / nstage;
-            if (use > 0) mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);
+            if (use > 0) mbar_wait_backoff(&empty[s], (uint32_t)(use - 1) & 1u);
             int t_lo, cnt;
             group_rows(0, k, t_lo, cnt);
             mbar_expect_tx(&full[s], (uint32_t)cnt * E * 4u);
@@ -307,7 +304,7 @@ __device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_
             const int s = k % nstage, use = k / nstage;
             if (use > 0) {
                 const int kprev = k - nstage;            // group that used this stage before
-                if (k2 < ng2 || kprev >= ng1) mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);
+                if (k2 < ng2 || kprev >= ng1) mbar_wait_backoff(&empty[s], (uint32_t)(use - 1) & 1u);
                 if (kprev >= ng1) drain(s, kprev - ng1);
             }
             if (k2 < ng2) {
@@ -343,7 +340,9 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool producer = warp >= 2 * W;
     const int dir = producer ? warp - 2 * W : (warp >= W);
-    const int w = producer ? 0 : warp - dir * W;
+    // the beta side takes its warps in reverse order, so each SM sub-partition hosts an alpha warp that is
+    // busy early (low label pairs are reached first) next to a beta warp that is busy late
+    const int w = producer ? 0 : (dir ? 2 * W - 1 - warp : warp);
     const int n = p.order[blockIdx.x];
     const int4 mt = p.meta[n];
     const int Tn = mt.x, L = mt.y;
@@ -409,8 +408,11 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
     // the other side's copy of my blank 2q is its state 2 (L - q) = R0 - 64 j, my label one below
     const int R0 = 2 * (L - q0);
     const int B0 = R0 >> 6, B1 = (R0 - 1) >> 6;   // slots of those states: exactly j lower per slot
-    // my pairs are all unreachable before step `first` (pair q needs q frames to be reached)
+    // my pairs are all unreachable before step `first` (pair q needs q frames to be reached) and none of
+    // them can still reach the end after step `last` (one pair per remaining frame at most): outside
+    // [first, last] the warp only keeps the barriers, mailboxes and stores going
     const int first = 32 * (w * J);
+    const int last = Tn - L + (32 * (w + 1) * J - 1) + 1;
 
     SF a0[J], a1[J];       // blank / label state of my pair in slot j
     float base[J];         // storage base of slot j (integer valued)
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
                 a0[0] = add_norm(z, Kb, fb);
                 a1[0] = add_norm(z, Kl[0], fl[0]);                 // void when L == 0
             }
-        } else if (i >= first) {
+        } else if (i >= first && i <= last) {
             // c = label state of the pair below: lane - 1; lane 0 takes lane 31 of the slot below, or the
             // mailbox the warp below filled in the previous step
             float ch[J], cl[J];
@@ -652,23 +654,30 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
         }
         float* ob = (float*)stg + G * (E + SPX) + ridx * OC;       // occupancy row of this frame
         float* ps = (float*)stg + G * (E + SPX) + G * OC;
-        float g0[J], g1[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            float xi0, xf0, xi1, xf1;
-            expo(j, xi0, xf0, xi1, xf1);
-            g0[j] = (xi0 - IZ) + (xf0 - fZ);
-            g1[j] = (xi1 - IZ) + (xf1 - fZ);
-        }
-#pragma unroll
-        for (int j = 0; j < J; ++j) { g0[j] = ex2f(g0[j]); g1[j] = ex2f(g1[j]); }
         float bsum = 0.0f;
+        if (i >= first && i <= last) {
+            float g0[J], g1[J];
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            bsum += feasible ? g0[j] : 0.0f;
-            if ((hasl >> j) & 1u) ob[4 + pos0 + pstep * j] = feasible ? g1[j] : 0.0f;
+            for (int j = 0; j < J; ++j) {
+                float xi0, xf0, xi1, xf1;
+                expo(j, xi0, xf0, xi1, xf1);
+                g0[j] = (xi0 - IZ) + (xf0 - fZ);
+                g1[j] = (xi1 - IZ) + (xf1 - fZ);
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) { g0[j] = ex2f(g0[j]); g1[j] = ex2f(g1[j]); }
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                bsum += feasible ? g0[j] : 0.0f;
+                if ((hasl >> j) & 1u) ob[4 + pos0 + pstep * j] = feasible ? g1[j] : 0.0f;
+            }
+            bsum = warp_sum(bsum);
+        } else {
+            // none of my states is on any complete path at this frame: their posteriors are exactly zero
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+                if ((hasl >> j) & 1u) ob[4 + pos0 + pstep * j] = 0.0f;
         }
-        bsum = warp_sum(bsum);
         if (lane == 0) ps[ridx * W + w] = bsum;      // folded into occupancy float [1] by the producer
         if (g == cnt - 1) fence_async_smem();       // this group's occupancy writes -> the producer's bulk stores
 #ifdef HAB_PROBE

@@ -207,7 +207,9 @@ __global__ void __launch_bounds__(320) star_trellis_kernel(StarTrellisParams p) 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool producer = warp >= 2 * W;
     const int dir = producer ? warp - 2 * W : (warp >= W);
-    const int w = producer ? 0 : warp - dir * W;
+    // the beta side takes its warps in reverse order, so each SM sub-partition hosts an alpha warp that is
+    // busy early (low label pairs are reached first) next to a beta warp that is busy late
+    const int w = producer ? 0 : (dir ? 2 * W - 1 - warp : warp);
     const int n = p.order[blockIdx.x];
     const int4 mt = p.meta[n];
     const int Tn = mt.x, L = mt.y;
