@@ -25,10 +25,19 @@ struct CtcWs {                 // workspace layout (byte offsets), filled by ctc
     int Sp, E, JWp, SPX;       // E: floats per emission row (header + fractions + packed int8 parts)
 };
 
-// emission row (bytes): [0,16) float ct, Kb, fb, 0   [16, 16+4 Sp) float f[k]   then int8 K[k]:
-// log2 p(label k) - ct = K[k] + f[k], blank = Kb + fb, ct = integer row shift.  The occupancy row
-// written in place reuses the float part: [1] blank occupancy, [4+k] label occupancy.
-__host__ __device__ inline int ctc_em_floats(int Sp) { return 4 + Sp + round_up(Sp, 16) / 4; }
+// emission row (32-bit words): [0] float ct (integer row shift)  [1] blank  [4+k] label k, where an
+// emission is the Q8.24 fixed-point value of log2 p - ct (integer part in [-128, 1], fraction resolved
+// to 6e-8: one word, one shared-memory load, two I2FP to decode).  The occupancy row written in place:
+// [1] blank occupancy, [4+k] label occupancy (floats).
+__host__ __device__ inline int ctc_em_floats(int Sp) { return 4 + Sp; }
+__device__ __forceinline__ int emission_word(float K, float f) {
+    const int fi = __float2int_rn(fmaxf(f, -0.5f) * 16777216.0f);
+    return (int)(((unsigned)__float2int_rn(K) << 24) + (unsigned)fi);
+}
+__device__ __forceinline__ void emission_decode(int v, float& K, float& f) {
+    K = (float)(v >> 24);
+    f = (float)(v & 0xffffff) * (1.0f / 16777216.0f);
+}
 
 __host__ inline CtcWs ctc_ws_layout(int T, int N, int S) {
     CtcWs w;
@@ -203,18 +212,16 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_rows_kernel(RowsParams 
         // integer part and an fp32 fraction: its quantisation error is ~1e-8 instead of ulp(log2 p)/2.
         const float ct = round_int(fmaf(mx, kLog2e, -l2));       // emission of the row's likeliest class
         float* erow = p.em + ((size_t)n * p.T + t) * p.E;
-        signed char* krow = (signed char*)(erow + 4 + p.Sp);
         if (lane == 0) {
             p.lse2[(size_t)n * p.T + t] = l2;
             float K, f;
             emission_split(row[0], l2, ct, K, f);
-            *(float4*)erow = make_float4(ct, K, f, 0.0f);
+            *(float4*)erow = make_float4(ct, __int_as_float(emission_word(K, f)), 0.0f, 0.0f);
         }
         for (int k = lane; k < L; k += 32) {
             float K, f;
             emission_split(row[s_tgt[k]], l2, ct, K, f);
-            erow[4 + k] = f;
-            krow[k] = (signed char)__float2int_rn(K);
+            ((int*)erow)[4 + k] = emission_word(K, f);
         }
         __syncwarp();
         if (r + nstage < nrows) issue(r + nstage);
@@ -245,7 +252,7 @@ __host__ __device__ inline int trellis_dir_bytes(int E, int SPX, int OC, int nst
     return round_up(nstage * trellis_stage_floats(E, SPX, OC, G, W, NP) * 4 + 2 * W * 16 + W * 16 + 2 * nstage * 8, 128);
 }
 
-constexpr float kRebase = 24.0f;   // a slot is re-based when its states drift this far (log2 units) from the base
+constexpr float kRebase = 24.0f;   // (star-CTC) a slot is re-based when its states drift this far from the base
 
 // The producer warp of one sweep side (shared by the CTC and star-CTC trellis kernels): one lane issues
 // every bulk copy.  Group k (counted over both phases) lives in stage k % nstage and holds up to G
@@ -352,7 +359,7 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
         return;
     }
     const int P = L + 1;
-    const int E = p.E, SPX = p.SPX, JWp = p.JWp, Sp = p.Sp, OC = 4 + p.Sp;
+    const int E = p.E, SPX = p.SPX, JWp = p.JWp, OC = 4 + p.Sp;
     const int SF_ = trellis_stage_floats(E, SPX, OC, G, W, 1);
 
     unsigned char* db = smem_raw + (size_t)dir * p.dir_bytes;
@@ -402,9 +409,14 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
             }
         }
     }
-    // my label of slot j sits at position pos0 +- 32 j of an emission row (reversed for beta)
+    // my label of slot j sits at position pos0 +- 32 j of an emission row (reversed for beta).  Slots
+    // without a label read a clamped in-range word instead: their states carry finite garbage that never
+    // flows back into real states (transitions only go up) and is masked out of every output.
     const int pos0 = dir ? L - 1 - q0 : q0;
     const int pstep = dir ? -32 : 32;
+    int poff[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) poff[j] = 4 + max(0, min(pos0 + pstep * j, max(L - 1, 0)));
     // the other side's copy of my blank 2q is its state 2 (L - q) = R0 - 64 j, my label one below
     const int R0 = 2 * (L - q0);
     const int B0 = R0 >> 6, B1 = (R0 - 1) >> 6;   // slots of those states: exactly j lower per slot
@@ -419,7 +431,7 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
 #pragma unroll
     for (int j = 0; j < J; ++j) { a0[j] = sf_void(); a1[j] = sf_void(); base[j] = 0.0f; }
 
-    float IZ = 0.0f, fZ = 0.0f, csum = 0.0f;
+    float IZ = 0.0f, fZ = 0.0f, csum = 0.0f, cin_h = kVoid;
     bool feasible = true;
     float Kb, fb, Kl[J], fl[J];
 
@@ -436,16 +448,11 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
         }
         const int ridx = dir ? cnt - 1 - g : g;
         const float* er = stg + ridx * E;
-        const signed char* kr = (const signed char*)(er + 4 + Sp);
-        Kb = er[1]; fb = er[2];
+        const int* ew = (const int*)er;
         csum += er[0];
+        emission_decode(ew[1], Kb, fb);
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const bool v = (hasl >> j) & 1u;
-            const int pos = v ? pos0 + pstep * j : 0;
-            Kl[j] = v ? small_int_to_float((int)kr[pos]) : kVoid;
-            fl[j] = v ? er[4 + pos] : 0.0f;
-        }
+        for (int j = 0; j < J; ++j) emission_decode(ew[poff[j]], Kl[j], fl[j]);
         return ridx;
     };
     auto advance = [&](int i) {
@@ -453,7 +460,7 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
             if (q0 == 0) {                                         // ha/ctc.py:138
                 SF z; z.h = 0.0f; z.l = 0.0f;
                 a0[0] = add_norm(z, Kb, fb);
-                a1[0] = add_norm(z, Kl[0], fl[0]);                 // void when L == 0
+                if (L > 0) a1[0] = add_norm(z, Kl[0], fl[0]);
             }
         } else if (i >= first && i <= last) {
             // c = label state of the pair below: lane - 1; lane 0 takes lane 31 of the slot below, or the
@@ -473,6 +480,7 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
                     ch[j] = lane ? rh[j] : (j ? rh[j ? j - 1 : 0] : in.x);
                     cl[j] = lane ? rl[j] : (j ? rl[j ? j - 1 : 0] : in.y);
                 }
+                cin_h = in.x;
             }
             // u = blank (+) previous label;  v = label (+) (skip allowed ? u : blank)     [ha/ctc.py:155-167]
             float d[J], tt[J], uh[J], ul[J];
@@ -546,24 +554,18 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
 #ifdef HAB_PROBE
             if (pr) p.probe[pb + 2] = clock64();
 #endif
-            // Rows are stored relative to a per-slot integer base.  A live slot is re-based (one warp
-            // max) only when some state rose well above its base or none is left near it; the test is
-            // one warp-wide OR reduction for all slots together.
-            unsigned bits = 0;
+            // Rows are stored in Q11.20 fixed point relative to a per-slot integer base: absolute precision,
+            // so the base only has to stay within ~2000 log2 units of the states that matter.  Every 8th
+            // step it is reset to the slot maximum; a slot nobody has reached yet inherits its neighbour's.
+            if ((i & 7) == 0) {
+                float inherit = __shfl_sync(0xffffffffu, cin_h, 0);
+                inherit = (inherit > kVoidTest) ? inherit : base[0];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const float m = fmaxf(a0[j].h, a1[j].h);
-                const float dd = m - base[j];
-                bits |= (dd > kRebase) ? (1u << j) : 0u;               // voids give dd ~ -1e30
-                bits |= (dd > -kRebase) ? (0x100u << j) : 0u;
-                bits |= (m > kVoidTest) ? (0x10000u << j) : 0u;
-            }
-            bits = __reduce_or_sync(0xffffffffu, bits);
-            const unsigned need = (bits | ((bits >> 16) & ~(bits >> 8))) & 0xffu;
-            if (need) {
-#pragma unroll
-                for (int j = 0; j < J; ++j)
-                    if ((need >> j) & 1u) base[j] = warp_max(fmaxf(a0[j].h, a1[j].h));
+                for (int j = 0; j < J; ++j) {
+                    const float m = warp_max(fmaxf(a0[j].h, a1[j].h));
+                    base[j] = (m > kVoidTest) ? m : inherit;
+                    inherit = base[j];
+                }
             }
             float bsel = base[0];
 #pragma unroll
