@@ -93,8 +93,8 @@ static int ctc_trellis_launch(const TrellisParams& tp, int nslot, int N, cudaStr
     if (nslot > 32) return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length > 1023 is not supported");
     int env_w = 0;
     if (const char* e = getenv("HA_B200_TRELLIS_W")) env_w = atoi(e);
-    int W = nslot < 2 ? 1 : (nslot < 4 ? 2 : 4);     // measured on B200: W=4 beats W=2 from 4 slots up
-    if (env_w >= 1 && env_w <= 4) W = env_w;
+    int W = nslot < 2 ? 1 : ((nslot + 1) / 2 < 5 ? (nslot + 1) / 2 : 5);   // two slots per warp up to 5 warps (measured)
+    if (env_w >= 1 && env_w <= 6) W = env_w;
     int J = (nslot + W - 1) / W;
     const int Js[] = {1, 2, 3, 4, 5, 6, 8};
     int Jt = 0;
@@ -228,7 +228,7 @@ static int star_trellis_launch(const StarTrellisParams& tp, int nslot, int N, cu
     int env_w = 0;
     if (const char* e = getenv("HA_B200_TRELLIS_W")) env_w = atoi(e);
     int W = nslot < 2 ? 1 : (nslot < 4 ? 2 : 4);
-    if (env_w >= 1 && env_w <= 4) W = env_w;
+    if (env_w >= 1 && env_w <= 6) W = env_w;
     const int J = (nslot + W - 1) / W;
     if (J > 4) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: star J=%d", J);
     p.W = (nslot + J - 1) / J;

@@ -65,6 +65,35 @@ __device__ __forceinline__ void emission_split(float x, float l2, float ct, floa
     f = (s - Kt) + (err + pl);
 }
 
+// ---- packed FP32x2 arithmetic (sm_100: FADD2 / FFMA2 issue two fp32 operations per instruction) -------
+// The trellis kernels are bound by instruction issue and half of their instructions are fp32 adds, so
+// per-slot quantities are kept as float2 over pairs of slots and added two at a time.
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long ra, rb, rc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+    float2 c;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(rc));
+    return c;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    unsigned long long ra, rb, rc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+    float2 c;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(rc));
+    return c;
+}
+// J per-slot floats stored as float2 over slot pairs; [j] with a compile-time j resolves to one register
+template <int J>
+struct SlotVec {
+    float2 v[(J + 1) / 2];
+    __device__ __forceinline__ float& operator[](int j) { return (j & 1) ? v[j >> 1].y : v[j >> 1].x; }
+    __device__ __forceinline__ float operator[](int j) const { return (j & 1) ? v[j >> 1].y : v[j >> 1].x; }
+};
+
 // ---- stored trellis values: Q11.20 fixed point relative to a per-slot integer base -----------------
 // A split number (h, l) is stored as round((h - base + l) * 2^20) in one int32: absolute precision
 // 5e-7 at any distance up to 2047 log2 units below the base (the state that matters for a posterior

@@ -341,7 +341,7 @@ __device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_
 // half of the frames) stores every row as floats relative to a per-slot base; phase 2 combines live
 // rows with the rows the other side stored, so posteriors need T sequential steps, not 2T.
 template <int J>
-__global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
+__global__ void __launch_bounds__(448) ctc_trellis_kernel(TrellisParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = p.W, G = p.G, nstage = p.nstage;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -426,14 +426,23 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
     const int first = 32 * (w * J);
     const int last = Tn - L + (32 * (w + 1) * J - 1) + 1;
 
-    SF a0[J], a1[J];       // blank / label state of my pair in slot j
+    // blank / label state of my pair in slot j as split numbers (h + l), kept as float2 over slot pairs so
+    // that the adds of two slots issue as one FADD2
+    constexpr int JP = (J + 1) / 2;
+    SlotVec<J> a0h, a0l, a1h, a1l;
     float base[J];         // storage base of slot j (integer valued)
 #pragma unroll
-    for (int j = 0; j < J; ++j) { a0[j] = sf_void(); a1[j] = sf_void(); base[j] = 0.0f; }
+    for (int jp = 0; jp < JP; ++jp) {
+        a0h.v[jp] = a1h.v[jp] = make_float2(kVoid, kVoid);
+        a0l.v[jp] = a1l.v[jp] = make_float2(0.0f, 0.0f);
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) base[j] = 0.0f;
 
     float IZ = 0.0f, fZ = 0.0f, csum = 0.0f, cin_h = kVoid;
     bool feasible = true;
-    float Kb, fb, Kl[J], fl[J];
+    float Kb, fb;
+    SlotVec<J> Kl, fl;
 
     // ring cursor: stage, parity of its full barrier, frame within the group, frames in the group
     int s = 0, g = 0, cnt = 0; uint32_t fpar = 0;
@@ -452,26 +461,38 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
         csum += er[0];
         emission_decode(ew[1], Kb, fb);
 #pragma unroll
-        for (int j = 0; j < J; ++j) emission_decode(ew[poff[j]], Kl[j], fl[j]);
+        for (int j = 0; j < J; ++j) { float K, f; emission_decode(ew[poff[j]], K, f); Kl[j] = K; fl[j] = f; }
+        if (J & 1) { Kl[J] = kVoid; fl[J] = 0.0f; }          // padding half of the last slot pair
         return ridx;
+    };
+    // (h, l) + (K, f), renormalised so that |l| <= 0.5, for two slots at once; void stays void
+    auto add_norm2 = [&](float2 h, float2 l, float2 K, float2 f, float2& oh, float2& ol) {
+        const float2 m2 = make_float2(kMagic, kMagic);
+        const float2 ll = add2(l, f);
+        const float2 r = sub2(add2(ll, m2), m2);
+        float2 hh = add2(add2(h, K), r);
+        hh.x = fmaxf(hh.x, kVoid); hh.y = fmaxf(hh.y, kVoid);
+        oh = hh;
+        ol = sub2(ll, r);
     };
     auto advance = [&](int i) {
         if (i == 0) {
             if (q0 == 0) {                                         // ha/ctc.py:138
                 SF z; z.h = 0.0f; z.l = 0.0f;
-                a0[0] = add_norm(z, Kb, fb);
-                if (L > 0) a1[0] = add_norm(z, Kl[0], fl[0]);
+                const SF b = add_norm(z, Kb, fb);
+                a0h[0] = b.h; a0l[0] = b.l;
+                if (L > 0) { const SF c = add_norm(z, Kl[0], fl[0]); a1h[0] = c.h; a1l[0] = c.l; }
             }
         } else if (i >= first && i <= last) {
             // c = label state of the pair below: lane - 1; lane 0 takes lane 31 of the slot below, or the
             // mailbox the warp below filled in the previous step
-            float ch[J], cl[J];
+            SlotVec<J> ch, cl;
             {
                 float rh[J], rl[J];
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    rh[j] = __shfl_sync(0xffffffffu, a1[j].h, (lane + 31) & 31);
-                    rl[j] = __shfl_sync(0xffffffffu, a1[j].l, (lane + 31) & 31);
+                    rh[j] = __shfl_sync(0xffffffffu, a1h[j], (lane + 31) & 31);
+                    rl[j] = __shfl_sync(0xffffffffu, a1l[j], (lane + 31) & 31);
                 }
                 float2 in = make_float2(kVoid, 0.0f);
                 if (w > 0) in = mail[((i - 1) & 1) * W + w - 1];
@@ -480,49 +501,56 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
                     ch[j] = lane ? rh[j] : (j ? rh[j ? j - 1 : 0] : in.x);
                     cl[j] = lane ? rl[j] : (j ? rl[j ? j - 1 : 0] : in.y);
                 }
+                if (J & 1) { ch[J] = kVoid; cl[J] = 0.0f; }      // padding half of the last pair
                 cin_h = in.x;
             }
             // u = blank (+) previous label;  v = label (+) (skip allowed ? u : blank)     [ha/ctc.py:155-167]
-            float d[J], tt[J], uh[J], ul[J];
+            const float2 one2 = make_float2(1.0f, 1.0f);
+            SlotVec<J> d, tt, uh, ul, sh, sl;
 #pragma unroll
-            for (int j = 0; j < J; ++j) d[j] = (a0[j].h - ch[j]) + (a0[j].l - cl[j]);
+            for (int jp = 0; jp < JP; ++jp)
+                d.v[jp] = add2(sub2(a0h.v[jp], ch.v[jp]), sub2(a0l.v[jp], cl.v[jp]));
 #pragma unroll
-            for (int j = 0; j < J; ++j) tt[j] = ex2f(-fabsf(d[j]));
+            for (int j = 0; j < 2 * JP; ++j) tt[j] = ex2f(-fabsf(d[j]));
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                uh[j] = (d[j] > 0.0f) ? a0[j].h : ch[j];
-                ul[j] = (d[j] > 0.0f) ? a0[j].l : cl[j];
+            for (int j = 0; j < 2 * JP; ++j) {
+                uh[j] = (d[j] > 0.0f) ? a0h[j] : ch[j];
+                ul[j] = (d[j] > 0.0f) ? a0l[j] : cl[j];
             }
 #pragma unroll
-            for (int j = 0; j < J; ++j) tt[j] = lg2f(1.0f + tt[j]);
+            for (int jp = 0; jp < JP; ++jp) tt.v[jp] = add2(tt.v[jp], one2);
 #pragma unroll
-            for (int j = 0; j < J; ++j) ul[j] += tt[j];
-            float sh[J], sl[J];
+            for (int j = 0; j < 2 * JP; ++j) tt[j] = lg2f(tt[j]);
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                sh[j] = ((allowed >> j) & 1u) ? uh[j] : a0[j].h;
-                sl[j] = ((allowed >> j) & 1u) ? ul[j] : a0[j].l;
-                d[j] = (sh[j] - a1[j].h) + (sl[j] - a1[j].l);
+            for (int jp = 0; jp < JP; ++jp) ul.v[jp] = add2(ul.v[jp], tt.v[jp]);
+#pragma unroll
+            for (int j = 0; j < 2 * JP; ++j) {
+                sh[j] = ((allowed >> j) & 1u) ? uh[j] : a0h[j];
+                sl[j] = ((allowed >> j) & 1u) ? ul[j] : a0l[j];
             }
 #pragma unroll
-            for (int j = 0; j < J; ++j) tt[j] = ex2f(-fabsf(d[j]));
+            for (int jp = 0; jp < JP; ++jp)
+                d.v[jp] = add2(sub2(sh.v[jp], a1h.v[jp]), sub2(sl.v[jp], a1l.v[jp]));
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                sh[j] = (d[j] > 0.0f) ? sh[j] : a1[j].h;
-                sl[j] = (d[j] > 0.0f) ? sl[j] : a1[j].l;
+            for (int j = 0; j < 2 * JP; ++j) tt[j] = ex2f(-fabsf(d[j]));
+#pragma unroll
+            for (int j = 0; j < 2 * JP; ++j) {
+                sh[j] = (d[j] > 0.0f) ? sh[j] : a1h[j];
+                sl[j] = (d[j] > 0.0f) ? sl[j] : a1l[j];
             }
 #pragma unroll
-            for (int j = 0; j < J; ++j) tt[j] = lg2f(1.0f + tt[j]);
+            for (int jp = 0; jp < JP; ++jp) tt.v[jp] = add2(tt.v[jp], one2);
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                SF u; u.h = uh[j]; u.l = ul[j];
-                SF v; v.h = sh[j]; v.l = sl[j] + tt[j];
-                a0[j] = add_norm(u, Kb, fb);
-                a1[j] = add_norm(v, Kl[j], fl[j]);
+            for (int j = 0; j < 2 * JP; ++j) tt[j] = lg2f(tt[j]);
+            const float2 Kb2 = make_float2(Kb, Kb), fb2 = make_float2(fb, fb);
+#pragma unroll
+            for (int jp = 0; jp < JP; ++jp) {
+                add_norm2(uh.v[jp], ul.v[jp], Kb2, fb2, a0h.v[jp], a0l.v[jp]);
+                add_norm2(sh.v[jp], add2(sl.v[jp], tt.v[jp]), Kl.v[jp], fl.v[jp], a1h.v[jp], a1l.v[jp]);
             }
         }
         // my last pair's label state for the warp above (read in its next step)
-        if (lane == 31 && w + 1 < W) mail[(i & 1) * W + w] = make_float2(a1[J - 1].h, a1[J - 1].l);
+        if (lane == 31 && w + 1 < W) mail[(i & 1) * W + w] = make_float2(a1h[J - 1], a1l[J - 1]);
     };
     auto step_end = [&]() {
         // one barrier per step per side (mailboxes change hands); the stage goes back to the producer
@@ -562,7 +590,7 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
                 inherit = (inherit > kVoidTest) ? inherit : base[0];
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    const float m = warp_max(fmaxf(a0[j].h, a1[j].h));
+                    const float m = warp_max(fmaxf(a0h[j], a1h[j]));
                     base[j] = (m > kVoidTest) ? m : inherit;
                     inherit = base[j];
                 }
@@ -572,7 +600,11 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
             for (int j = 1; j < J; ++j) bsel = (lane == j) ? base[j] : bsel;
 #pragma unroll
             for (int j = 0; j < J; ++j)
-                if ((hasp >> j) & 1u) prow[32 * j] = make_int2(sf_to_fix(a0[j], base[j]), sf_to_fix(a1[j], base[j]));
+                if ((hasp >> j) & 1u) {
+                    SF x0; x0.h = a0h[j]; x0.l = a0l[j];
+                    SF x1; x1.h = a1h[j]; x1.l = a1l[j];
+                    prow[32 * j] = make_int2(sf_to_fix(x0, base[j]), sf_to_fix(x1, base[j]));
+                }
             if (lane < J && 32 * (w * J + lane) < P) hrow[lane] = bsel;
             prow = (int2*)((float*)prow + rstep);
             hrow += rstep;
@@ -617,10 +649,10 @@ __global__ void __launch_bounds__(320) ctc_trellis_kernel(TrellisParams p) {
             float h0, l0, h1, l1;
             fix_to_parts(o0, h0, l0);
             fix_to_parts(o1, h1, l1);
-            xi0 = ((a0[jj].h + b0) + h0) - Kb;
-            xf0 = (a0[jj].l + l0) - fb;
-            xi1 = ((a1[jj].h + b1) + h1) - Kl[jj];
-            xf1 = (a1[jj].l + l1) - fl[jj];
+            xi0 = ((a0h[jj] + b0) + h0) - Kb;
+            xf0 = (a0l[jj] + l0) - fb;
+            xi1 = ((a1h[jj] + b1) + h1) - Kl[jj];
+            xf1 = (a1l[jj] + l1) - fl[jj];
         };
         if (i == steps1) {
             // log Z over all my side's states at the meeting frame: two-pass max / sum across the W warps

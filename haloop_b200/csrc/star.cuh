@@ -201,7 +201,7 @@ struct StarTrellisParams {
 // k/32 of warp k/(32 J); beta is not a mirror image of alpha here (labels have no self loop, stars have
 // a back edge), so it has its own update and its mailbox runs downwards.
 template <int J>
-__global__ void __launch_bounds__(320) star_trellis_kernel(StarTrellisParams p) {
+__global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = p.W, G = p.G, nstage = p.nstage;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
