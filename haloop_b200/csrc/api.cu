@@ -233,7 +233,7 @@ static int star_trellis_launch(const StarTrellisParams& tp, int nslot, int N, cu
     if (J > 4) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: star J=%d", J);
     p.W = (nslot + J - 1) / J;
     p.G = kMaxG;
-    const int OC = 8 + 2 * p.Sp;
+    const int OC = 4 + 2 * p.Sp;
     int ns = 4;
     while (ns >= 2 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, OC, ns, p.G, p.W, 2) > 100 * 1024) --ns;
     if (ns < 2) {

@@ -19,12 +19,11 @@ struct StarWs {
     int Sp, E, JWp, SPX;
 };
 
-// emission row (floats): [0] ct  [1] Kb [2] fb (blank)  [4] Ka [5] fa (all-star = log2 P)
-// [8+2k] f_label[k]  [9+2k] f_star[k]   then char2 (K_label[k], K_star[k]):  every emission is
-// ct + K + f with ct the integer row shift, K an int8 integer part and f an fp32 fraction.
-// The occupancy row written in place reuses the float part: [1] blank occupancy  [2] G = sum_k h_k
-// [8+2k] label occupancy  [9+2k] h_k (0 if y_k == 0), with h_k = gamma(star k) / (P - p_{y_k}).
-__host__ __device__ inline int star_em_floats(int Sp) { return 8 + 2 * Sp + round_up(2 * Sp, 16) / 4; }
+// emission row (32-bit words): [0] float ct (integer row shift)  [1] blank  [2] all-star (log2 P)
+// [4+2k] label y_k  [5+2k] star "anything but y_k", each a Q8.24 fixed-point value of log2 p - ct
+// (emission_word, ctc.cuh).  The occupancy row written in place (floats): [1] blank occupancy
+// [2] G = sum_k h_k  [4+2k] label occupancy  [5+2k] h_k (0 if y_k == 0), h_k = gamma(star k) / (P - p_{y_k}).
+__host__ __device__ inline int star_em_floats(int Sp) { return 4 + 2 * Sp; }
 
 __host__ inline StarWs star_ws_layout(int T, int N, int S) {
     StarWs w;
@@ -142,8 +141,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
         const float lbb = lPh - m2;
         const float lPl = (m2 - (lPh - lbb)) + (lgs - lbb);                // ... and the rounding error (two-sum)
         float* erow = p.em + ((size_t)n * p.T + t) * p.E;
-        char2* krow = (char2*)(erow + 8 + 2 * p.Sp);
-        // (vh + vl) - l2 - ct  ->  int8 K + fraction f
+        // (vh + vl) - l2 - ct  ->  integer part K + fraction f
         auto split2 = [&](float vh, float vl, float& K, float& f) {
             const float s1 = vh - l2;
             const float bb = s1 - vh;
@@ -157,8 +155,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
             float Kb, fb, Ka, fa;
             emission_split(row[0], l2, ct, Kb, fb);
             split2(fmaxf(lPh, kVoid), lPl, Ka, fa);
-            *(float4*)erow = make_float4(ct, Kb, fb, 0.0f);
-            *(float4*)(erow + 4) = make_float4(Ka, fa, 0.0f, 0.0f);
+            *(float4*)erow = make_float4(ct, __int_as_float(emission_word(Kb, fb)), __int_as_float(emission_word(Ka, fa)), 0.0f);
         }
         for (int k = lane; k < Ks; k += 32) {
             const int y = s_tgt[k];
@@ -176,8 +173,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
             const float sh = lPh + add;
             const float sl = lPl + ((lPh - sh) + add);
             split2(fmaxf(sh, kVoid), sl, Ks2, fs2);
-            ((float2*)(erow + 8))[k] = make_float2(fl, fs2);
-            krow[k] = make_char2((signed char)__float2int_rn(Kl), (signed char)__float2int_rn(Ks2));
+            ((int2*)(erow + 4))[k] = make_int2(emission_word(Kl, fl), emission_word(Ks2, fs2));
         }
         __syncwarp();
         if (r + nstage < nrows) issue(r + nstage);
@@ -219,7 +215,7 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
         return;
     }
     const int Q = L + 1, Ks = min(L + 1, p.S);
-    const int E = p.E, SPX = p.SPX, JWp = p.JWp, Sp = p.Sp, OC = 8 + 2 * p.Sp;
+    const int E = p.E, SPX = p.SPX, JWp = p.JWp, OC = 4 + 2 * p.Sp;
     const int SF_ = trellis_stage_floats(E, SPX, OC, G, W, 2);
     const float Kp = round_int(p.pen2), fp = p.pen2 - Kp;
 
@@ -237,7 +233,7 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
 
     float* em_base = p.em + (size_t)n * p.T * E;
     float* tr_base = p.tr + (size_t)n * p.T * SPX;
-    const uint32_t occ_bytes = (uint32_t)(8 + round_up(2 * Ks, 4)) * 4u;
+    const uint32_t occ_bytes = (uint32_t)(4 + round_up(2 * Ks, 4)) * 4u;
     const int tm = Tn >> 1;
     const int steps1 = dir ? Tn - tm : tm;
 
@@ -272,13 +268,15 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
     // my quads cannot be reached before this step (alpha spreads upwards one quad per frame from
     // quad 0, beta downwards from quad L)
     const int first = dir ? L - (32 * (w + 1) * J - 1) - 2 : 32 * (w * J) - 2;
+    // ... and none of them can still be on a complete path after this step (one quad per remaining frame)
+    const int last = dir ? Tn - 32 * (w * J) + 1 : Tn - L + (32 * (w + 1) * J - 1) + 1;
 
     SF b0[J], st[J], b1[J], lb[J];
     float base[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) { b0[j] = st[j] = b1[j] = lb[j] = sf_void(); base[j] = 0.0f; }
 
-    float IZ = 0.0f, fZ = 0.0f, csum = 0.0f, ct = 0.0f;
+    float IZ = 0.0f, fZ = 0.0f, csum = 0.0f, ct = 0.0f, cin_h = kVoid;
     bool feasible = true;
     float Kb, fb, Kl[J], fl[J], Ks_[J], fs[J];   // blank / label / star emissions of my quad, split; the
                                                   // star's include the penalty paid on entering it
@@ -293,21 +291,25 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
         }
         const int ridx = dir ? cnt - 1 - g : g;
         const float* er = stg + ridx * E;
-        const char2* kr = (const char2*)(er + 8 + 2 * Sp);
-        ct = er[0]; Kb = er[1]; fb = er[2];
-        const float Ka = er[4], fa = er[5];
+        const int* ew = (const int*)er;
+        ct = er[0];
         csum += ct;
+        emission_decode(ew[1], Kb, fb);
+        float Ka, fa;
+        emission_decode(ew[2], Ka, fa);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int k = k0 + 32 * j;
             const bool ve = (hase >> j) & 1u, vl = (hasl >> j) & 1u;
-            const float2 f = ve ? ((const float2*)(er + 8))[k] : make_float2(0.0f, 0.0f);
-            const char2 kk = ve ? kr[k] : make_char2(0, 0);
-            Kl[j] = vl ? small_int_to_float((int)kk.x) : kVoid;
-            fl[j] = vl ? f.x : 0.0f;
+            const int2 wv = ve ? ((const int2*)(ew + 4))[k] : make_int2(0, 0);
+            float K1, f1, K2, f2;
+            emission_decode(wv.x, K1, f1);
+            emission_decode(wv.y, K2, f2);
+            Kl[j] = vl ? K1 : kVoid;
+            fl[j] = vl ? f1 : 0.0f;
             // the star of quad k: its own entry, or the all-star when k == L == S (ha/star.py:47)
-            const float ks = ve ? small_int_to_float((int)kk.y) : ((k == L) ? Ka : kVoid);
-            const float fs0 = ve ? f.y : ((k == L) ? fa : 0.0f);
+            const float ks = ve ? K2 : ((k == L) ? Ka : kVoid);
+            const float fs0 = ve ? f2 : ((k == L) ? fa : 0.0f);
             Ks_[j] = fmaxf(ks + Kp, kVoid);
             fs[j] = fs0 + fp;
         }
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
     };
     auto advance = [&](int i) {
         if (dir == 0) {
-            if (i >= first) {
+            if (i >= first && i <= last) {
                 // previous label, from the lane below (virtual state -1 holds 0.0 before the first frame)
                 float ch[J], cl[J];
                 {
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
                     }
                     float4 in = make_float4((i == 0) ? 0.0f : kVoid, 0.0f, 0.0f, 0.0f);
                     if (w > 0) in = mail[((i - 1) & 1) * W + w - 1];
+                    cin_h = in.x;
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
                         ch[j] = lane ? rh[j] : (j ? rh[j ? j - 1 : 0] : in.x);
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
                     if (k == L) { b0[j] = add_norm(z, Kb, fb); st[j] = add_norm(z, Ks_[j], fs[j]); b1[j] = b0[j]; }
                     if (k == L - 1) lb[j] = add_norm(z, Kl[j], fl[j]);
                 }
-            } else if (i >= first) {
+            } else if (i >= first && i <= last) {
                 // next quad's first blank and label, from the lane above (lane 31 takes lane 0 of the slot
                 // above, or the mailbox of the warp above)
                 float n0h[J], n0l[J], nlh[J], nll[J];
@@ -375,6 +378,7 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
                     }
                     float4 in = make_float4(kVoid, 0.0f, kVoid, 0.0f);
                     if (w + 1 < W) in = mail[((i - 1) & 1) * W + w + 1];
+                    cin_h = fmaxf(in.x, in.z);
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
                         const bool edge = lane == 31;
@@ -423,21 +427,18 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
         for (int i = 0; i < steps1; ++i) {
             fetch(i, steps1);
             advance(i);
-            unsigned bits = 0;
+            // Q11.20 storage is absolute in precision, so the per-slot base only has to stay within ~2000
+            // log2 units of the states that matter: reset to the slot maximum every 8th step; slots nobody
+            // has reached yet take the warp's maximum
+            if ((i & 7) == 0) {
+                float m[J], wm = kVoid;
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const float m = smax(j);
-                const float dd = m - base[j];
-                bits |= (dd > kRebase) ? (1u << j) : 0u;
-                bits |= (dd > -kRebase) ? (0x100u << j) : 0u;
-                bits |= (m > kVoidTest) ? (0x10000u << j) : 0u;
-            }
-            bits = __reduce_or_sync(0xffffffffu, bits);
-            const unsigned need = (bits | ((bits >> 16) & ~(bits >> 8))) & 0xffu;
-            if (need) {
+                for (int j = 0; j < J; ++j) { m[j] = warp_max(smax(j)); wm = fmaxf(wm, m[j]); }
+                if (!(wm > kVoidTest)) wm = cin_h;          // nobody here yet: what the neighbouring warp sends
+                if (wm > kVoidTest) {
 #pragma unroll
-                for (int j = 0; j < J; ++j)
-                    if ((need >> j) & 1u) base[j] = warp_max(smax(j));
+                    for (int j = 0; j < J; ++j) base[j] = (m[j] > kVoidTest) ? m[j] : wm;
+                }
             }
             float bsel = base[0];
 #pragma unroll
@@ -526,7 +527,7 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
                                 ? ex2f(((xis - IZ) - ((Ks_[j] - Kp) + ct)) + ((xfs - fZ) - (fs[j] - fp))) : 0.0f;
             bsum += g0 + g1;
             gsum += h;
-            if (k < Ks) ((float2*)(ob + 8))[k] = make_float2(gl, ((exclude >> j) & 1u) ? h : 0.0f);
+            if (k < Ks) ((float2*)(ob + 4))[k] = make_float2(gl, ((exclude >> j) & 1u) ? h : 0.0f);
         }
         bsum = warp_sum(bsum);
         gsum = warp_sum(gsum);
@@ -592,7 +593,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
     float* gb = p.gx + (long long)n * p.sg_n;
     const float g = p.gout[n];
     const float delta = p.from_logits ? 1.0f : 0.0f;
-    const uint32_t occ_bytes = (uint32_t)(8 + round_up(2 * Ks, 4)) * 4u;
+    const uint32_t occ_bytes = (uint32_t)(4 + round_up(2 * Ks, 4)) * 4u;
 
     auto issue = [&](int r) {
         const int stage = r % nstage;
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
             }
         } else {
             for (int c = lane; c < V; c += 32) dst[c] = src[c];
-            for (int c = lane; c < 8 + 2 * Ks; c += 32) dst[V + c] = osrc[c];
+            for (int c = lane; c < 4 + 2 * Ks; c += 32) dst[V + c] = osrc[c];
         }
     };
     for (int r = 0; r < min(nstage - 1, nreal); ++r) issue(r);
@@ -633,10 +634,10 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
         for (int k = lane; k < Ks; k += 32) {
             const int w = s_tgt[k];
             if (!(w & kNotFirst)) {
-                float sl = (k < L) ? occ[8 + 2 * k] : 0.0f, sh = occ[9 + 2 * k];
-                for (int j = s_nxt[k]; j >= 0; j = s_nxt[j]) { sl += (j < L) ? occ[8 + 2 * j] : 0.0f; sh += occ[9 + 2 * j]; }
+                float sl = (k < L) ? occ[4 + 2 * k] : 0.0f, sh = occ[5 + 2 * k];
+                for (int j = s_nxt[k]; j >= 0; j = s_nxt[j]) { sl += (j < L) ? occ[4 + 2 * j] : 0.0f; sh += occ[5 + 2 * j]; }
                 const float pc = ex2f(fmaf(row[w & kLabelMask], kLog2e, -l2));
-                occ[8 + 2 * k] = g * (pc * sh - sl);
+                occ[4 + 2 * k] = g * (pc * sh - sl);
             }
         }
         __syncwarp();
@@ -657,7 +658,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
         __syncwarp();
         for (int k = lane; k < Ks; k += 32) {
             const int w = s_tgt[k];
-            if (!(w & kNotFirst)) row[w & kLabelMask] += occ[8 + 2 * k];
+            if (!(w & kNotFirst)) row[w & kLabelMask] += occ[4 + 2 * k];
         }
         float* dstg = gb + (long long)t * p.sg_t;
         if (p.use_bulk) {
