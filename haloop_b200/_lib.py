@@ -9,7 +9,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(_HERE, "libha_b200.so")
+SO_PATH = os.environ.get("HA_B200_SO") or os.path.join(_HERE, "libha_b200.so")   # override: A/B builds
 HEADER = os.path.join(ROOT, "include", "ha_b200.h")
 
 NVCC_FLAGS = [

@@ -224,6 +224,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// The phase-switch barrier of the trellis kernels: producer and compute warps come from different code
+// paths, so the barrier instruction lives in one non-inlined function and every thread of the CTA
+// executes the same instruction (bar.sync on a named barrier with an explicit thread count).
+__device__ __noinline__ void cta_phase_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // index loads for int32 / int64 targets and lengths (the reference passes LongTensors from
 // Collator, ha/loop.py:29-41, and int32 in its own tests, ha/transducer.py:217-218)
 __device__ __forceinline__ long long load_idx(const void* p, long long i, int is64) {

@@ -241,6 +241,9 @@ struct TrellisParams {
 };
 
 constexpr int kMaxG = 4;
+constexpr int kPhaseBarrier = 3;   // named barrier all warps of the CTA (compute + producers) meet at between the phases;
+                                   // producers and compute warps arrive from different call sites, which bar.sync
+                                   // with an explicit id and thread count permits (__syncthreads would not)
 
 // per-direction shared memory: nstage x [G emission rows | G trellis rows | G occupancy rows | G x W partials]
 // then mailboxes, log Z partials and the full/empty mbarriers
@@ -303,7 +306,8 @@ __device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_
     }
     __threadfence();
     fence_async_all();
-    __syncthreads();                           // phase switch: both sides' stored rows are complete
+    __syncwarp();
+    cta_phase_barrier(kPhaseBarrier, (int)blockDim.x);   // phase switch: both sides' stored rows are complete
     fence_async_all();
     if (lane == 0) {
         for (int k2 = 0; k2 < ng2 + nstage; ++k2) {
@@ -620,7 +624,7 @@ __global__ void __launch_bounds__(448) ctc_trellis_kernel(TrellisParams p) {
     // my stored rows -> visible to the other side's bulk (async-proxy) loads, and vice versa
     __threadfence();
     fence_async_all();
-    __syncthreads();
+    cta_phase_barrier(kPhaseBarrier, (int)blockDim.x);
 
     // ---------------------------------------------------------------------------- phase 2 ---
     for (int i = steps1; i < Tn; ++i) {

@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
     }
     __threadfence();
     fence_async_all();
-    __syncthreads();
+    cta_phase_barrier(kPhaseBarrier, (int)blockDim.x);
 
     // ---------------------------------------------------------------------------- phase 2 ---
     for (int i = steps1; i < Tn; ++i) {

@@ -1,0 +1,23 @@
+"""A few small loss+grad calls of every kind, for compute-sanitizer runs."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import haloop_b200 as hb
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(0)
+for (T, N, V, S) in [(40, 3, 32, 9), (150, 2, 24, 70), (33, 2, 37, 5)]:
+    x = torch.randn(T, N, V, generator=g).to(dev).requires_grad_(True)
+    tg = torch.randint(1, V, (N, S), generator=g).to(dev)
+    il = torch.tensor([T, T - 7][:N] + [T // 2] * max(0, N - 2)).to(dev); tl = torch.tensor([S, S // 2][:N] + [1] * max(0, N - 2)).to(dev)
+    hb.ctc_forward_score3(x, tg, il, tl, from_logits=True).sum().backward()
+    x.grad = None
+    hb.star_ctc_forward_score(x, tg, il, tl, from_logits=True).sum().backward()
+for (N, T, U, V) in [(2, 17, 6, 16), (2, 12, 40, 37)]:
+    j = torch.randn(N, T, U + 1, V, generator=g).to(dev).requires_grad_(True)
+    tg = torch.randint(1, V, (N, U), generator=g).to(dev)
+    il = torch.tensor([T, T - 3]).to(dev); tl = torch.tensor([U, U // 2]).to(dev)
+    hb.transducer_forward_score(j, tg, il, tl, from_logits=True).sum().backward()
+lp = torch.randn(3, 50, 20, generator=g).log_softmax(-1).to(dev)
+hb.greedy_decode(lp, torch.tensor([50, 40, 3]).to(dev))
+hb.ctc_viterbi_align(lp.permute(1, 0, 2), torch.randint(1, 20, (3, 8), generator=g).to(dev), torch.tensor([50, 40, 30]).to(dev), torch.tensor([8, 5, 2]).to(dev))
+torch.cuda.synchronize()
+print("done")
