@@ -88,42 +88,42 @@ size_t ha_ctc_workspace_bytes(int T, int N, int V, int S) {
 static int ctc_trellis_launch(const TrellisParams& tp, int nslot, int N, cudaStream_t st) {
     TrellisParams p = tp;
     // One CTA per utterance: W compute warps per sweep direction, each owning J slots of 32 label
-    // pairs, plus one producer warp per direction.  Few compute warps with many slots keep the per-step
-    // bookkeeping small next to the log-add chains.
+    // pairs, plus one producer warp per direction.  (J, W) are template parameters (the per-step
+    // barriers and mailbox indices become immediates); two slots per warp up to 5 warps measured best.
     if (nslot > 32) return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length > 1023 is not supported");
     int env_w = 0;
     if (const char* e = getenv("HA_B200_TRELLIS_W")) env_w = atoi(e);
-    int W = nslot < 2 ? 1 : ((nslot + 1) / 2 < 5 ? (nslot + 1) / 2 : 5);   // two slots per warp up to 5 warps (measured)
-    if (env_w >= 1 && env_w <= 6) W = env_w;
+    int W = nslot < 2 ? 1 : ((nslot + 1) / 2 < 5 ? (nslot + 1) / 2 : 5);
+    if (env_w >= 1 && env_w <= 5) W = env_w < nslot ? env_w : nslot;
     int J = (nslot + W - 1) / W;
-    const int Js[] = {1, 2, 3, 4, 5, 6, 8};
-    int Jt = 0;
-    for (int c : Js) if (c >= J) { Jt = c; break; }
-    if (!Jt) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: J=%d", J);
-    p.W = (nslot + Jt - 1) / Jt;
+    if (J == 7) J = 8;
+    if (J > 8) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: J=%d", J);
+    W = (nslot + J - 1) / J;
+    p.W = W;
     p.G = kMaxG;
     int ns = 4;
-    while (ns >= 2 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, 4 + p.Sp, ns, p.G, p.W, 1) > 100 * 1024) --ns;
+    while (ns >= 2 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, 4 + p.Sp, ns, p.G, p.W, 32) > 100 * 1024) --ns;
     if (ns < 2) {
         ns = 2;
-        while (p.G > 1 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, 4 + p.Sp, ns, p.G, p.W, 1) > 220 * 1024) p.G >>= 1;
+        while (p.G > 1 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, 4 + p.Sp, ns, p.G, p.W, 32) > 218 * 1024) p.G >>= 1;
     }
     p.nstage = ns;
-    p.dir_bytes = trellis_dir_bytes(p.E, p.SPX, 4 + p.Sp, ns, p.G, p.W, 1);
-    const size_t smem = (size_t)2 * p.dir_bytes;
+    p.dir_bytes = trellis_dir_bytes(p.E, p.SPX, 4 + p.Sp, ns, p.G, p.W, 32);
+    const size_t smem = (size_t)2 * p.dir_bytes + kTrellisGuard;
     const dim3 grid(N), block(32 * (2 * p.W + 2));
-    int rc;
-#define HAB_LAUNCH_TRELLIS(JJ)                                                         \
-    case JJ:                                                                           \
-        if ((rc = set_smem(ctc_trellis_kernel<JJ>, smem, "ctc_trellis"))) return rc;  \
-        ctc_trellis_kernel<JJ><<<grid, block, smem, st>>>(p);                         \
-        break
-    switch (Jt) {
-        HAB_LAUNCH_TRELLIS(1); HAB_LAUNCH_TRELLIS(2); HAB_LAUNCH_TRELLIS(3); HAB_LAUNCH_TRELLIS(4);
-        HAB_LAUNCH_TRELLIS(5); HAB_LAUNCH_TRELLIS(6); HAB_LAUNCH_TRELLIS(8);
-        default: return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: J=%d", Jt);
+    int rc = HA_ERR_UNSUPPORTED_SHAPE;
+    bool hit = false;
+#define HAB_TRY(JJ, WW)                                                                        \
+    if (!hit && J == JJ && W == WW) {                                                          \
+        hit = true;                                                                            \
+        if ((rc = set_smem(ctc_trellis_kernel<JJ, WW>, smem, "ctc_trellis"))) return rc;       \
+        ctc_trellis_kernel<JJ, WW><<<grid, block, smem, st>>>(p);                              \
     }
-#undef HAB_LAUNCH_TRELLIS
+#define HAB_TRY_J(JJ) HAB_TRY(JJ, 1) HAB_TRY(JJ, 2) HAB_TRY(JJ, 3) HAB_TRY(JJ, 4) HAB_TRY(JJ, 5)
+    HAB_TRY_J(1) HAB_TRY_J(2) HAB_TRY_J(3) HAB_TRY_J(4) HAB_TRY_J(5) HAB_TRY_J(6) HAB_TRY_J(8)
+#undef HAB_TRY_J
+#undef HAB_TRY
+    if (!hit) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: J=%d W=%d", J, W);
     return check_launch("ctc_trellis_kernel");
 }
 

@@ -132,6 +132,43 @@ __device__ __forceinline__ SF add_norm(SF a, float K, float f) {
     return o;
 }
 
+// ---- extended-range linear numbers ----------------------------------------------------------------
+// value = m * 2^e with m an fp32 in [1, 2) (or a small multiple of it between a sum and the next
+// normalisation) and e an int32.  The CTC trellis runs in this representation: the sum-product
+// recursion costs integer exponent alignment + one FADD + one FMUL per transition instead of a
+// log-add-exp (2 MUFU + ~15 FP32 on split numbers), keeps 24 significant bits whatever the magnitude, and
+// has no range limit (the exponent is a full int).  "void" (probability 0) is m = 1, e = kVoidE: it
+// aligns to +0 against anything real, and adding voids keeps the exponent far below kVoidETest.
+struct XF { float m; int e; };
+constexpr int kVoidE = -(1 << 28);
+constexpr int kVoidETest = -(1 << 27);
+__device__ __forceinline__ XF xf_make(float m, int e) { XF r; r.m = m; r.e = e; return r; }
+__device__ __forceinline__ float xf_scale(float m, int d) {      // m * 2^d by exponent-field arithmetic
+    return __int_as_float(__float_as_int(m) + (int)((unsigned)d << 23));
+}
+// a + b, not normalised: mantissa < 2 max(ma, mb) at exponent max(ea, eb).  A term more than 2^127 below
+// the other one drops to (at most) a denormal.  Mantissas must be >= 1.
+__device__ __forceinline__ XF xf_add(XF a, XF b) {
+    const int ex = max(a.e, b.e);
+    const float xa = xf_scale(a.m, max(a.e - ex, -127));
+    const float xb = xf_scale(b.m, max(b.e - ex, -127));
+    return xf_make(xa + xb, ex);
+}
+// (s * p), mantissa back in [1, 2).  s.m * p must be a positive normal float.
+__device__ __forceinline__ XF xf_mul_norm(XF s, float p) {
+    const int rb = __float_as_int(s.m * p);
+    return xf_make(__int_as_float((rb & 0x007fffff) | 0x3f800000), s.e + (rb >> 23) - 127);
+}
+// stored trellis word: [12 bits: exponent distance below the slot base, saturating][20 mantissa bits]
+constexpr unsigned kPackVoid = 0xfff00000u;
+__device__ __forceinline__ int xf_pack(float m, int below) {     // m in [1,2), below >= 0
+    return (int)__funnelshift_r((unsigned)__float_as_int(m) << 9, (unsigned)min(below, 4095), 12);
+}
+__device__ __forceinline__ float xf_unpack_m(int w) {            // mantissa, truncation re-centred
+    return __int_as_float((int)((((unsigned)w << 3) & 0x007ffff8u) | 0x3f800004u));
+}
+__device__ __forceinline__ int xf_unpack_below(int w) { return (int)((unsigned)w >> 20); }
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -169,10 +206,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)     // suspend-time hint: the wait sleeps in hardware
         : "memory");
     return ok != 0;
 }
@@ -189,7 +226,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
 #pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
         if (mbar_try_wait(bar, parity)) return;
-        __nanosleep(200);
+        __nanosleep(1000);
     }
     __trap();
 }

@@ -25,11 +25,26 @@ struct CtcWs {                 // workspace layout (byte offsets), filled by ctc
     int Sp, E, JWp, SPX;       // E: floats per emission row (header + fractions + packed int8 parts)
 };
 
-// emission row (32-bit words): [0] float ct (integer row shift)  [1] blank  [4+k] label k, where an
-// emission is the Q8.24 fixed-point value of log2 p - ct (integer part in [-128, 1], fraction resolved
-// to 6e-8: one word, one shared-memory load, two I2FP to decode).  The occupancy row written in place:
-// [1] blank occupancy, [4+k] label occupancy (floats).
+// CTC emission row (floats): [0] ct (integer row shift)  [1] blank  [4+k] label k, where an emission is
+// the probability 2^(log2 p - ct) as a plain fp32 (<= 2^0.5, clamped below at 2^-126): the trellis runs in
+// the linear domain on extended-range numbers (common.cuh, XF).  The occupancy row written in place:
+// [1] blank occupancy, [4+k] label occupancy.
 __host__ __device__ inline int ctc_em_floats(int Sp) { return 4 + Sp; }
+// 2^(K + f) for an integer-valued K in [-127, 1] and |f| <= 0.5: degree-7 polynomial (relative error
+// ~1e-7, no MUFU), exponent added into the bit pattern
+__device__ __forceinline__ float emission_linear(float K, float f) {
+    float r = 1.5252733804059841e-05f;
+    r = fmaf(r, f, 1.5403530393381608e-04f);
+    r = fmaf(r, f, 1.3333558146428443e-03f);
+    r = fmaf(r, f, 9.618129107628477e-03f);
+    r = fmaf(r, f, 5.550410866482158e-02f);
+    r = fmaf(r, f, 2.402265069591007e-01f);
+    r = fmaf(r, f, 6.931471805599453e-01f);
+    r = fmaf(r, f, 1.0f);
+    const int k = __float2int_rn(K);
+    return (k < -125) ? 1.1754943508222875e-38f : xf_scale(r, k);
+}
+// star-CTC emission words (star.cuh): Q8.24 fixed-point value of log2 p - ct
 __device__ __forceinline__ int emission_word(float K, float f) {
     const int fi = __float2int_rn(fmaxf(f, -0.5f) * 16777216.0f);
     return (int)(((unsigned)__float2int_rn(K) << 24) + (unsigned)fi);
@@ -68,13 +83,13 @@ struct PrepParams {
     int star;   // duplicate chains also cover position L_n (< S): star-CTC's last star reads targets[n, L_n]
 };
 
-// grid N, block 128.  meta[n] = {T_n, L_n, invalid, 0}.
+// grid N, block 128.  meta[n] = {T_n, L_n, invalid, number of adjacent equal labels}.
 __global__ void __launch_bounds__(128) ctc_prep_kernel(PrepParams p) {
     extern __shared__ int s_y[];
-    __shared__ int s_bad, s_rank;
+    __shared__ int s_bad, s_rank, s_rep;
     const int n = blockIdx.x;
     long long Tn = load_idx(p.in_len, n, p.len64), Ln = load_idx(p.tgt_len, n, p.len64);
-    if (threadIdx.x == 0) { s_bad = (Tn < 0 || Tn > p.T || Ln < 0 || Ln > p.S) ? 1 : 0; s_rank = 0; }
+    if (threadIdx.x == 0) { s_bad = (Tn < 0 || Tn > p.T || Ln < 0 || Ln > p.S) ? 1 : 0; s_rank = 0; s_rep = 0; }
     __syncthreads();
     const int L = s_bad ? 0 : (int)Ln;
     for (int k = threadIdx.x; k < p.S; k += blockDim.x) {
@@ -93,6 +108,7 @@ __global__ void __launch_bounds__(128) ctc_prep_kernel(PrepParams p) {
         }
         p.tgt[(size_t)n * p.Sp + k] = y | (notfirst ? kNotFirst : 0);
         p.dupnext[(size_t)n * p.Sp + k] = nxt;
+        if (k >= 1 && k < L && s_y[k - 1] == y) atomicAdd(&s_rep, 1);
     }
     __syncthreads();
     {   // longest-first work order (rank by counting; N is a batch size)
@@ -108,7 +124,7 @@ __global__ void __launch_bounds__(128) ctc_prep_kernel(PrepParams p) {
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        p.meta[n] = make_int4(s_bad ? 0 : (int)Tn, L, s_bad, 0);
+        p.meta[n] = make_int4(s_bad ? 0 : (int)Tn, L, s_bad, s_rep);
         p.order[s_rank] = n;
     }
 }
@@ -206,22 +222,22 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_rows_kernel(RowsParams 
             l2 = m2 + log2f(s);
         }
         // Emissions are stored relative to an integer per-row shift c_t = rint(log2 p of the row's likeliest
-        // class), so the likeliest state of every frame sits near 0 and the integer parts fit an int8.  The shifts cancel in every posterior
-        // (both sweeps see the same rows); only the loss needs their sum, which the trellis adds back.
-        // Each emission is evaluated in float-float arithmetic from the fp32 logit and split into an int8
-        // integer part and an fp32 fraction: its quantisation error is ~1e-8 instead of ulp(log2 p)/2.
+        // class), so every stored probability is <= 2^0.5 and anything within 2^-126 of the row maximum is a
+        // normal fp32.  The shifts cancel in every posterior (both sweeps see the same rows); only the loss
+        // needs their sum, which the trellis adds back.  The exponent is evaluated in float-float arithmetic
+        // from the fp32 logit, so the stored probability is good to ~1e-7 relative whatever |log p| is.
         const float ct = round_int(fmaf(mx, kLog2e, -l2));       // emission of the row's likeliest class
         float* erow = p.em + ((size_t)n * p.T + t) * p.E;
         if (lane == 0) {
             p.lse2[(size_t)n * p.T + t] = l2;
             float K, f;
             emission_split(row[0], l2, ct, K, f);
-            *(float4*)erow = make_float4(ct, __int_as_float(emission_word(K, f)), 0.0f, 0.0f);
+            *(float4*)erow = make_float4(ct, emission_linear(K, f), 0.0f, 0.0f);
         }
         for (int k = lane; k < L; k += 32) {
             float K, f;
             emission_split(row[s_tgt[k]], l2, ct, K, f);
-            ((int*)erow)[4 + k] = emission_word(K, f);
+            erow[4 + k] = emission_linear(K, f);
         }
         __syncwarp();
         if (r + nstage < nrows) issue(r + nstage);
@@ -241,6 +257,8 @@ struct TrellisParams {
 };
 
 constexpr int kMaxG = 4;
+constexpr int kTrellisGuard = 2048;   // (CTC) bytes in front of the first stage: label pairs that do not exist read
+                                      // up to 2 KB below their stage in phase 2 instead of being predicated off
 constexpr int kPhaseBarrier = 3;   // named barrier all warps of the CTA (compute + producers) meet at between the phases;
                                    // producers and compute warps arrive from different call sites, which bar.sync
                                    // with an explicit id and thread count permits (__syncthreads would not)
@@ -257,13 +275,15 @@ __host__ __device__ inline int trellis_dir_bytes(int E, int SPX, int OC, int nst
 
 constexpr float kRebase = 24.0f;   // (star-CTC) a slot is re-based when its states drift this far from the base
 
-// The producer warp of one sweep side (shared by the CTC and star-CTC trellis kernels): one lane issues
+// The producer warp of one sweep side (shared by the CTC and star-CTC trellis kernels): lane 0 issues
 // every bulk copy.  Group k (counted over both phases) lives in stage k % nstage and holds up to G
 // consecutive frames, which are contiguous in memory whichever way the side walks time.
 //   phase 1: emission rows in.   phase 2: emission rows + the other side's stored trellis rows in,
 //   occupancy rows (with the NP per-row partial sums of the W compute warps folded into floats
 //   [1, 1+NP)) written back over the emission rows once the compute warps release the stage.
-template <int NP>
+// PER_LANE: the compute warps leave their partial sums un-reduced (32 lanes each) and this otherwise
+// idle warp does the reduction, off the compute warps' critical path.
+template <int NP, bool PER_LANE>
 __device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_t* full, uint64_t* empty,
                                                  int nstage, int G, int W, int E, int SPX, int OC,
                                                  float* em_base, float* tr_base, uint32_t occ_bytes,
@@ -281,23 +301,40 @@ __device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_
         float* st = stages + s * SF_;
         float* occ = st + G * (E + SPX);
         const float* ps = occ + G * OC;
-        for (int r = 0; r < cnt; ++r) {
+        if (PER_LANE) {
+            for (int r = 0; r < cnt; ++r) {
 #pragma unroll
-            for (int c = 0; c < NP; ++c) {
-                float b = 0.0f;
-                for (int x = 0; x < W; ++x) b += ps[(r * W + x) * NP + c];
-                occ[r * OC + 1 + c] = b;
+                for (int c = 0; c < NP; ++c) {
+                    float b = 0.0f;
+                    for (int x = 0; x < W; ++x) b += ps[((r * W + x) * NP + c) * 32 + lane];
+                    b = warp_sum(b);
+                    if (lane == 0) occ[r * OC + 1 + c] = b;
+                }
             }
+            __syncwarp();
         }
-        fence_async_smem();
-        for (int r = 0; r < cnt; ++r) bulk_s2g(em_base + (size_t)(t_lo + r) * E, occ + r * OC, occ_bytes);
-        bulk_commit();
-        bulk_wait_read<0>();
+        if (lane == 0) {
+            if (!PER_LANE) {
+                for (int r = 0; r < cnt; ++r) {
+#pragma unroll
+                    for (int c = 0; c < NP; ++c) {
+                        float b = 0.0f;
+                        for (int x = 0; x < W; ++x) b += ps[(r * W + x) * NP + c];
+                        occ[r * OC + 1 + c] = b;
+                    }
+                }
+            }
+            fence_async_smem();
+            for (int r = 0; r < cnt; ++r) bulk_s2g(em_base + (size_t)(t_lo + r) * E, occ + r * OC, occ_bytes);
+            bulk_commit();
+            bulk_wait_read<0>();
+        }
+        __syncwarp();
     };
-    if (lane == 0) {
-        for (int k = 0; k < ng1; ++k) {
-            const int s = k % nstage, use = k / nstage;
-            if (use > 0) mbar_wait_backoff(&empty[s], (uint32_t)(use - 1) & 1u);
+    for (int k = 0; k < ng1; ++k) {
+        const int s = k % nstage, use = k / nstage;
+        if (use > 0) mbar_wait_backoff(&empty[s], (uint32_t)(use - 1) & 1u);
+        if (lane == 0) {
             int t_lo, cnt;
             group_rows(0, k, t_lo, cnt);
             mbar_expect_tx(&full[s], (uint32_t)cnt * E * 4u);
@@ -309,26 +346,24 @@ __device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_
     __syncwarp();
     cta_phase_barrier(kPhaseBarrier, (int)blockDim.x);   // phase switch: both sides' stored rows are complete
     fence_async_all();
-    if (lane == 0) {
-        for (int k2 = 0; k2 < ng2 + nstage; ++k2) {
-            const int k = ng1 + k2;
-            const int s = k % nstage, use = k / nstage;
-            if (use > 0) {
-                const int kprev = k - nstage;            // group that used this stage before
-                if (k2 < ng2 || kprev >= ng1) mbar_wait_backoff(&empty[s], (uint32_t)(use - 1) & 1u);
-                if (kprev >= ng1) drain(s, kprev - ng1);
-            }
-            if (k2 < ng2) {
-                int t_lo, cnt;
-                group_rows(1, k2, t_lo, cnt);
-                float* st = stages + s * SF_;
-                mbar_expect_tx(&full[s], (uint32_t)cnt * (E + SPX) * 4u);
-                bulk_g2s(st, em_base + (size_t)t_lo * E, (uint32_t)cnt * E * 4u, &full[s]);
-                bulk_g2s(st + G * E, tr_base + (size_t)t_lo * SPX, (uint32_t)cnt * SPX * 4u, &full[s]);
-            }
+    for (int k2 = 0; k2 < ng2 + nstage; ++k2) {
+        const int k = ng1 + k2;
+        const int s = k % nstage, use = k / nstage;
+        if (use > 0) {
+            const int kprev = k - nstage;            // group that used this stage before
+            if (k2 < ng2 || kprev >= ng1) mbar_wait_backoff(&empty[s], (uint32_t)(use - 1) & 1u);
+            if (kprev >= ng1) drain(s, kprev - ng1);
         }
-        bulk_wait_all<0>();
+        if (k2 < ng2 && lane == 0) {
+            int t_lo, cnt;
+            group_rows(1, k2, t_lo, cnt);
+            float* st = stages + s * SF_;
+            mbar_expect_tx(&full[s], (uint32_t)cnt * (E + SPX) * 4u);
+            bulk_g2s(st, em_base + (size_t)t_lo * E, (uint32_t)cnt * E * 4u, &full[s]);
+            bulk_g2s(st + G * E, tr_base + (size_t)t_lo * SPX, (uint32_t)cnt * SPX * 4u, &full[s]);
+        }
     }
+    if (lane == 0) bulk_wait_all<0>();
 }
 
 // grid N (one CTA per utterance, longest first), block 32*(2W+2).  Warps [0,W) sweep alpha forward in
@@ -339,15 +374,20 @@ __device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_
 //
 // Side d's step i is frame t = d ? T-1-i : i and it orders the label pairs its own way (beta = alpha
 // on the reversed label sequence).  Warp w of a side owns J slots of 32 pairs: pair
-// q = 32 (w J + j) + lane = (blank state 2q, label state 2q+1), each a split number (common.cuh).  The
-// only value crossing a lane boundary per step is the label state of pair q-1: a shuffle inside a
-// warp, a two-float mailbox between warps, with one named barrier per step per side.  Phase 1 (first
-// half of the frames) stores every row as floats relative to a per-slot base; phase 2 combines live
-// rows with the rows the other side stored, so posteriors need T sequential steps, not 2T.
-template <int J>
-__global__ void __launch_bounds__(448) ctc_trellis_kernel(TrellisParams p) {
+// q = 32 (w J + j) + lane = (blank state 2q, label state 2q+1), each an extended-range linear number
+// (common.cuh, XF: fp32 mantissa + int32 exponent).  A step is   [ha/ctc.py:155-167]
+//     u = blank + label of pair q-1          blank' = u * p_t(blank)
+//     v = label + (skip allowed ? u : blank) label' = v * p_t(label)
+// The only value crossing a lane boundary is the label state of pair q-1: a shuffle inside a warp, an
+// 8-byte mailbox between warps, with one named barrier per step per side.  Phase 1 (first half of the
+// frames) stores every row as 32-bit words (20 mantissa bits + 12 bits of exponent distance below the
+// slot's maximum, refreshed every step); phase 2 multiplies the live pre-emission sums u, v with the row
+// the other side stored for the same frame: occupancy = u * beta / Z needs no division and posteriors
+// take T sequential steps, not 2T.
+template <int J, int W>
+__global__ void __launch_bounds__(32 * (2 * W + 2)) ctc_trellis_kernel(TrellisParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int W = p.W, G = p.G, nstage = p.nstage;
+    const int G = p.G, nstage = p.nstage;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool producer = warp >= 2 * W;
     const int dir = producer ? warp - 2 * W : (warp >= W);
@@ -357,21 +397,24 @@ __global__ void __launch_bounds__(448) ctc_trellis_kernel(TrellisParams p) {
     const int n = p.order[blockIdx.x];
     const int4 mt = p.meta[n];
     const int Tn = mt.x, L = mt.y;
-    if (mt.z || Tn == 0) {
+    // An alignment exists iff there is a frame per label plus a blank between equal neighbours (every
+    // stored emission is a positive number): decided here, because in the linear domain a void state next to
+    // a real one picks up 2^-127 of it instead of staying exactly void.
+    if (mt.z || Tn == 0 || Tn < L + mt.w) {
         const float v = mt.z ? CUDART_NAN_F : ((L == 0) ? 0.0f : CUDART_INF_F);
         if (threadIdx.x == 0) { p.loss[n] = v; p.loss_ws[n] = v; }
         return;
     }
     const int P = L + 1;
     const int E = p.E, SPX = p.SPX, JWp = p.JWp, OC = 4 + p.Sp;
-    const int SF_ = trellis_stage_floats(E, SPX, OC, G, W, 1);
+    const int SF_ = trellis_stage_floats(E, SPX, OC, G, W, 32);
 
-    unsigned char* db = smem_raw + (size_t)dir * p.dir_bytes;
+    unsigned char* db = smem_raw + kTrellisGuard + (size_t)dir * p.dir_bytes;
     float* stages = (float*)db;                                   // stage s: + s * SF_
-    float2* mail = (float2*)(stages + nstage * SF_);              // [2][W] label state of a warp's last pair
-    double* redm = (double*)(mail + 2 * W);                       // [W] log Z partial maxima
-    float* reds = (float*)(redm + W);                             // [W] log Z partial sums
-    uint64_t* full = (uint64_t*)(reds + 2 * W);
+    int2* mail = (int2*)(stages + nstage * SF_);                  // [2][W] label state of a warp's last pair
+    double* redd = (double*)(mail + 2 * W);                       // [W] Z partial sums
+    int* redi = (int*)(redd + W);                                 // [W] Z partial exponent maxima
+    uint64_t* full = (uint64_t*)(redi + 2 * W);
     uint64_t* empty = full + nstage;
     if (producer && lane == 0)
         for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -385,15 +428,19 @@ __global__ void __launch_bounds__(448) ctc_trellis_kernel(TrellisParams p) {
     const int steps1 = dir ? Tn - tm : tm;         // phase-1 steps of my side
 
     if (producer) {
-        trellis_producer<1>(stages, SF_, full, empty, nstage, G, W, E, SPX, OC, em_base, tr_base, occ_bytes,
+        trellis_producer<1, true>(stages, SF_, full, empty, nstage, G, W, E, SPX, OC, em_base, tr_base, occ_bytes,
                             Tn, steps1, dir, lane);
         return;
     }
 
     // ------------------------------------------------------------------------ compute warps ---
     const bool leader = (w == 0 && lane == 0);
-    const int nthr = 32 * W;                      // compute threads of my side
-    const int barid = 1 + dir;
+    constexpr int nthr = 32 * W;                  // compute threads of my side
+    // one named barrier per step per side (mailboxes change hands); immediate operands
+    auto side_barrier = [&]() {
+        if (dir) asm volatile("bar.sync 2, %0;" ::"n"(nthr) : "memory");
+        else asm volatile("bar.sync 1, %0;" ::"n"(nthr) : "memory");
+    };
     // per slot: do my pair / my label exist, and is the skip transition into my label allowed
     // (ha/ctc.py:140-142)?
     const int q0 = 32 * (w * J) + lane;           // my pair in slot 0
@@ -414,13 +461,14 @@ __global__ void __launch_bounds__(448) ctc_trellis_kernel(TrellisParams p) {
         }
     }
     // my label of slot j sits at position pos0 +- 32 j of an emission row (reversed for beta).  Slots
-    // without a label read a clamped in-range word instead: their states carry finite garbage that never
-    // flows back into real states (transitions only go up) and is masked out of every output.
+    // without a label read a clamped in-range emission instead (the blank when there is no label at all):
+    // their states are phantoms of real magnitude that never flow back into real states (transitions only
+    // go up) and are masked out of every output.
     const int pos0 = dir ? L - 1 - q0 : q0;
     const int pstep = dir ? -32 : 32;
     int poff[J];
 #pragma unroll
-    for (int j = 0; j < J; ++j) poff[j] = 4 + max(0, min(pos0 + pstep * j, max(L - 1, 0)));
+    for (int j = 0; j < J; ++j) poff[j] = (L > 0) ? 4 + max(0, min(pos0 + pstep * j, L - 1)) : 1;
     // the other side's copy of my blank 2q is its state 2 (L - q) = R0 - 64 j, my label one below
     const int R0 = 2 * (L - q0);
     const int B0 = R0 >> 6, B1 = (R0 - 1) >> 6;   // slots of those states: exactly j lower per slot
@@ -428,197 +476,105 @@ __global__ void __launch_bounds__(448) ctc_trellis_kernel(TrellisParams p) {
     // them can still reach the end after step `last` (one pair per remaining frame at most): outside
     // [first, last] the warp only keeps the barriers, mailboxes and stores going
     const int first = 32 * (w * J);
+    const int first1 = max(first, 1);             // step 0 initialises instead
     const int last = Tn - L + (32 * (w + 1) * J - 1) + 1;
 
-    // blank / label state of my pair in slot j as split numbers (h + l), kept as float2 over slot pairs so
-    // that the adds of two slots issue as one FADD2
-    constexpr int JP = (J + 1) / 2;
-    SlotVec<J> a0h, a0l, a1h, a1l;
-    float base[J];         // storage base of slot j (integer valued)
+    // blank / label state of my pair in slot j, and the sums u, v they were made from (the occupancy of
+    // a state is its pre-emission sum times the other side's stored value)
+    float mb[J], ml[J], su[J], sv[J];
+    int eb[J], el[J], eu[J], ev[J];
 #pragma unroll
-    for (int jp = 0; jp < JP; ++jp) {
-        a0h.v[jp] = a1h.v[jp] = make_float2(kVoid, kVoid);
-        a0l.v[jp] = a1l.v[jp] = make_float2(0.0f, 0.0f);
+    for (int j = 0; j < J; ++j) {
+        mb[j] = ml[j] = su[j] = sv[j] = 1.0f;
+        eb[j] = el[j] = eu[j] = ev[j] = kVoidE;
     }
-#pragma unroll
-    for (int j = 0; j < J; ++j) base[j] = 0.0f;
-
-    float IZ = 0.0f, fZ = 0.0f, csum = 0.0f, cin_h = kVoid;
+    float csum = 0.0f, rZ = 1.0f;
+    double logZ2 = 0.0;            // log2 Z of the shifted emissions
+    int eZ = 0;
     bool feasible = true;
-    float Kb, fb;
-    SlotVec<J> Kl, fl;
 
-    // ring cursor: stage, parity of its full barrier, frame within the group, frames in the group
-    int s = 0, g = 0, cnt = 0; uint32_t fpar = 0;
-    const float* stg = stages;
+    // ring cursor: stage and the parity of its full barrier
+    int s = 0; uint32_t fpar = 0;
 
-    auto fetch = [&](int i, int phase_end) {
-        // emission row of step i: wait for the stage at the start of a group, then decode my entries
-        if (g == 0) {
-            cnt = min(G, phase_end - i);
-            stg = stages + s * SF_;
-            mbar_wait(&full[s], fpar);
-        }
-        const int ridx = dir ? cnt - 1 - g : g;
-        const float* er = stg + ridx * E;
-        const int* ew = (const int*)er;
-        csum += er[0];
-        emission_decode(ew[1], Kb, fb);
+    // one step of the recursion on the emission row `er`
+    auto advance = [&](const float* er, int i) {
+        const float pb = er[1];
+        float pl[J];
 #pragma unroll
-        for (int j = 0; j < J; ++j) { float K, f; emission_decode(ew[poff[j]], K, f); Kl[j] = K; fl[j] = f; }
-        if (J & 1) { Kl[J] = kVoid; fl[J] = 0.0f; }          // padding half of the last slot pair
-        return ridx;
-    };
-    // (h, l) + (K, f), renormalised so that |l| <= 0.5, for two slots at once; void stays void
-    auto add_norm2 = [&](float2 h, float2 l, float2 K, float2 f, float2& oh, float2& ol) {
-        const float2 m2 = make_float2(kMagic, kMagic);
-        const float2 ll = add2(l, f);
-        const float2 r = sub2(add2(ll, m2), m2);
-        float2 hh = add2(add2(h, K), r);
-        hh.x = fmaxf(hh.x, kVoid); hh.y = fmaxf(hh.y, kVoid);
-        oh = hh;
-        ol = sub2(ll, r);
-    };
-    auto advance = [&](int i) {
-        if (i == 0) {
-            if (q0 == 0) {                                         // ha/ctc.py:138
-                SF z; z.h = 0.0f; z.l = 0.0f;
-                const SF b = add_norm(z, Kb, fb);
-                a0h[0] = b.h; a0l[0] = b.l;
-                if (L > 0) { const SF c = add_norm(z, Kl[0], fl[0]); a1h[0] = c.h; a1l[0] = c.l; }
-            }
-        } else if (i >= first && i <= last) {
+        for (int j = 0; j < J; ++j) pl[j] = er[poff[j]];
+        if (i >= first1 && i <= last) {
             // c = label state of the pair below: lane - 1; lane 0 takes lane 31 of the slot below, or the
             // mailbox the warp below filled in the previous step
-            SlotVec<J> ch, cl;
+            float cm[J]; int ce[J];
             {
-                float rh[J], rl[J];
+                float rm[J]; int re[J];
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    rh[j] = __shfl_sync(0xffffffffu, a1h[j], (lane + 31) & 31);
-                    rl[j] = __shfl_sync(0xffffffffu, a1l[j], (lane + 31) & 31);
+                    rm[j] = __shfl_sync(0xffffffffu, ml[j], (lane + 31) & 31);
+                    re[j] = __shfl_sync(0xffffffffu, el[j], (lane + 31) & 31);
                 }
-                float2 in = make_float2(kVoid, 0.0f);
+                int2 in = make_int2(__float_as_int(1.0f), kVoidE);
                 if (w > 0) in = mail[((i - 1) & 1) * W + w - 1];
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    ch[j] = lane ? rh[j] : (j ? rh[j ? j - 1 : 0] : in.x);
-                    cl[j] = lane ? rl[j] : (j ? rl[j ? j - 1 : 0] : in.y);
+                    cm[j] = lane ? rm[j] : (j ? rm[j ? j - 1 : 0] : __int_as_float(in.x));
+                    ce[j] = lane ? re[j] : (j ? re[j ? j - 1 : 0] : in.y);
                 }
-                if (J & 1) { ch[J] = kVoid; cl[J] = 0.0f; }      // padding half of the last pair
-                cin_h = in.x;
-            }
-            // u = blank (+) previous label;  v = label (+) (skip allowed ? u : blank)     [ha/ctc.py:155-167]
-            const float2 one2 = make_float2(1.0f, 1.0f);
-            SlotVec<J> d, tt, uh, ul, sh, sl;
-#pragma unroll
-            for (int jp = 0; jp < JP; ++jp)
-                d.v[jp] = add2(sub2(a0h.v[jp], ch.v[jp]), sub2(a0l.v[jp], cl.v[jp]));
-#pragma unroll
-            for (int j = 0; j < 2 * JP; ++j) tt[j] = ex2f(-fabsf(d[j]));
-#pragma unroll
-            for (int j = 0; j < 2 * JP; ++j) {
-                uh[j] = (d[j] > 0.0f) ? a0h[j] : ch[j];
-                ul[j] = (d[j] > 0.0f) ? a0l[j] : cl[j];
             }
 #pragma unroll
-            for (int jp = 0; jp < JP; ++jp) tt.v[jp] = add2(tt.v[jp], one2);
-#pragma unroll
-            for (int j = 0; j < 2 * JP; ++j) tt[j] = lg2f(tt[j]);
-#pragma unroll
-            for (int jp = 0; jp < JP; ++jp) ul.v[jp] = add2(ul.v[jp], tt.v[jp]);
-#pragma unroll
-            for (int j = 0; j < 2 * JP; ++j) {
-                sh[j] = ((allowed >> j) & 1u) ? uh[j] : a0h[j];
-                sl[j] = ((allowed >> j) & 1u) ? ul[j] : a0l[j];
+            for (int j = 0; j < J; ++j) {
+                const XF b = xf_make(mb[j], eb[j]);
+                const XF u = xf_add(b, xf_make(cm[j], ce[j]));
+                const bool al = (allowed >> j) & 1u;
+                const XF v = xf_add(xf_make(ml[j], el[j]), xf_make(al ? u.m : b.m, al ? u.e : b.e));
+                su[j] = u.m; eu[j] = u.e; sv[j] = v.m; ev[j] = v.e;
+                const XF nb = xf_mul_norm(u, pb), nl = xf_mul_norm(v, pl[j]);
+                mb[j] = nb.m; eb[j] = nb.e; ml[j] = nl.m; el[j] = nl.e;
             }
-#pragma unroll
-            for (int jp = 0; jp < JP; ++jp)
-                d.v[jp] = add2(sub2(sh.v[jp], a1h.v[jp]), sub2(sl.v[jp], a1l.v[jp]));
-#pragma unroll
-            for (int j = 0; j < 2 * JP; ++j) tt[j] = ex2f(-fabsf(d[j]));
-#pragma unroll
-            for (int j = 0; j < 2 * JP; ++j) {
-                sh[j] = (d[j] > 0.0f) ? sh[j] : a1h[j];
-                sl[j] = (d[j] > 0.0f) ? sl[j] : a1l[j];
-            }
-#pragma unroll
-            for (int jp = 0; jp < JP; ++jp) tt.v[jp] = add2(tt.v[jp], one2);
-#pragma unroll
-            for (int j = 0; j < 2 * JP; ++j) tt[j] = lg2f(tt[j]);
-            const float2 Kb2 = make_float2(Kb, Kb), fb2 = make_float2(fb, fb);
-#pragma unroll
-            for (int jp = 0; jp < JP; ++jp) {
-                add_norm2(uh.v[jp], ul.v[jp], Kb2, fb2, a0h.v[jp], a0l.v[jp]);
-                add_norm2(sh.v[jp], add2(sl.v[jp], tt.v[jp]), Kl.v[jp], fl.v[jp], a1h.v[jp], a1l.v[jp]);
-            }
+        } else if (i == 0 && q0 == 0) {                            // ha/ctc.py:138 (first > 0 for every other warp)
+            const XF one = xf_make(1.0f, 0);
+            const XF b = xf_mul_norm(one, pb);
+            mb[0] = b.m; eb[0] = b.e; eu[0] = 0;
+            if (L > 0) { const XF c = xf_mul_norm(one, pl[0]); ml[0] = c.m; el[0] = c.e; ev[0] = 0; }
         }
         // my last pair's label state for the warp above (read in its next step)
-        if (lane == 31 && w + 1 < W) mail[(i & 1) * W + w] = make_float2(a1h[J - 1], a1l[J - 1]);
+        if (lane == 31 && w + 1 < W) mail[(i & 1) * W + w] = make_int2(__float_as_int(ml[J - 1]), el[J - 1]);
     };
-    auto step_end = [&]() {
-        // one barrier per step per side (mailboxes change hands); the stage goes back to the producer
-        // after its last frame
-        named_bar_sync(barid, nthr);
-        if (++g == cnt) {
-            if (leader) mbar_arrive(&empty[s]);
-            g = 0;
-            if (++s == nstage) { s = 0; fpar ^= 1u; }
-        }
-    };
-
+    // A phase walks its frames one ring stage (<= G consecutive frames) at a time; the stage goes back to
+    // the producer after its last frame.  Row pointers advance by one row per step (backwards for beta).
+    const int rsgn = dir ? -1 : 1;
+    const bool mailer = (lane == 31 && w + 1 < W);
     // ---------------------------------------------------------------------------- phase 1 ---
     {
         int2* prow = (int2*)(tr_base + (size_t)(dir ? Tn - 1 : 0) * SPX + JWp) + q0;
-        float* hrow = tr_base + (size_t)(dir ? Tn - 1 : 0) * SPX + w * J;
+        int* hrow = (int*)(tr_base + (size_t)(dir ? Tn - 1 : 0) * SPX) + w * J + lane;
         const long long rstep = dir ? -(long long)SPX : (long long)SPX;
-        for (int i = 0; i < steps1; ++i) {
-#ifdef HAB_PROBE
-            const bool pr = (blockIdx.x == 0 && warp == 0 && lane == 0 && (i == 101 || i == 102));
-            const int pb = (i == 101) ? 0 : 8;
-            if (pr) p.probe[pb + 0] = clock64();
-#endif
-            fetch(i, steps1);
-#ifdef HAB_PROBE
-            if (pr) p.probe[pb + 1] = clock64();
-#endif
-            advance(i);
-#ifdef HAB_PROBE
-            if (pr) p.probe[pb + 2] = clock64();
-#endif
-            // Rows are stored in Q11.20 fixed point relative to a per-slot integer base: absolute precision,
-            // so the base only has to stay within ~2000 log2 units of the states that matter.  Every 8th
-            // step it is reset to the slot maximum; a slot nobody has reached yet inherits its neighbour's.
-            if ((i & 7) == 0) {
-                float inherit = __shfl_sync(0xffffffffu, cin_h, 0);
-                inherit = (inherit > kVoidTest) ? inherit : base[0];
+        const bool hstore = lane < J && 32 * (w * J + lane) < P;
+        for (int i0 = 0; i0 < steps1; i0 += G) {
+            const int cnt = min(G, steps1 - i0);
+            const float* er = stages + s * SF_ + (dir ? cnt - 1 : 0) * E;
+            mbar_wait(&full[s], fpar);
+            for (int i = i0; i < i0 + cnt; ++i, er += rsgn * E) {
+                csum += er[0];
+                if (i == 0 || (i >= first && i <= last)) advance(er, i);
+                else if (mailer) mail[(i & 1) * W + w] = make_int2(__float_as_int(ml[J - 1]), el[J - 1]);
+                // the row is stored relative to each slot's largest exponent of this very step: every word's
+                // distance is >= 0 and saturates 4095 binary orders below it
+                int bsel = 0;
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    const float m = warp_max(fmaxf(a0h[j], a1h[j]));
-                    base[j] = (m > kVoidTest) ? m : inherit;
-                    inherit = base[j];
+                    const int mx = __reduce_max_sync(0xffffffffu, max(eb[j], el[j]));
+                    if ((hasp >> j) & 1u)
+                        prow[32 * j] = make_int2(xf_pack(mb[j], mx - eb[j]), xf_pack(ml[j], mx - el[j]));
+                    bsel = (lane == j) ? mx : bsel;
                 }
+                if (hstore) *hrow = bsel;
+                prow = (int2*)((int*)prow + rstep);
+                hrow += rstep;
+                side_barrier();
             }
-            float bsel = base[0];
-#pragma unroll
-            for (int j = 1; j < J; ++j) bsel = (lane == j) ? base[j] : bsel;
-#pragma unroll
-            for (int j = 0; j < J; ++j)
-                if ((hasp >> j) & 1u) {
-                    SF x0; x0.h = a0h[j]; x0.l = a0l[j];
-                    SF x1; x1.h = a1h[j]; x1.l = a1l[j];
-                    prow[32 * j] = make_int2(sf_to_fix(x0, base[j]), sf_to_fix(x1, base[j]));
-                }
-            if (lane < J && 32 * (w * J + lane) < P) hrow[lane] = bsel;
-            prow = (int2*)((float*)prow + rstep);
-            hrow += rstep;
-#ifdef HAB_PROBE
-            if (pr) p.probe[pb + 3] = clock64();
-#endif
-            step_end();
-#ifdef HAB_PROBE
-            if (pr) p.probe[pb + 4] = clock64();
-#endif
+            if (leader) mbar_arrive(&empty[s]);
+            if (++s == nstage) { s = 0; fpar ^= 1u; }
         }
     }
     // my stored rows -> visible to the other side's bulk (async-proxy) loads, and vice versa
@@ -627,108 +583,91 @@ __global__ void __launch_bounds__(448) ctc_trellis_kernel(TrellisParams p) {
     cta_phase_barrier(kPhaseBarrier, (int)blockDim.x);
 
     // ---------------------------------------------------------------------------- phase 2 ---
-    for (int i = steps1; i < Tn; ++i) {
-#ifdef HAB_PROBE
-        const bool pr = (blockIdx.x == 0 && warp == 0 && lane == 0 && (i == steps1 + 101 || i == steps1 + 102));
-        const int pb = (i == steps1 + 101) ? 16 : 24;
-        if (pr) p.probe[pb + 0] = clock64();
-#endif
-        const int ridx = fetch(i, Tn);
-#ifdef HAB_PROBE
-        if (pr) p.probe[pb + 1] = clock64();
-#endif
-        advance(i);
-#ifdef HAB_PROBE
-        if (pr) p.probe[pb + 2] = clock64();
-#endif
-        const float* trow = stg + G * E + ridx * SPX;
-        const int* orow = (const int*)(trow + JWp) + R0;      // [-64 j] = other side's copy of my blank (Q11.20)
-        const float* ob0 = trow + B0;                         // [-j]    = its slot base
-        const float* ob1 = trow + B1;
-        // posterior exponent = [h + other base + other integer part - K] + [l + other fraction - f], minus log Z
-        auto expo = [&](int jj, float& xi0, float& xf0, float& xi1, float& xf1) {
-            const bool vp = (hasp >> jj) & 1u, vl = (hasl >> jj) & 1u;
-            const int o0 = vp ? orow[-64 * jj] : kFixVoid, o1 = vl ? orow[-64 * jj - 1] : kFixVoid;
-            const float b0 = vp ? ob0[-jj] : 0.0f, b1 = vl ? ob1[-jj] : 0.0f;
-            float h0, l0, h1, l1;
-            fix_to_parts(o0, h0, l0);
-            fix_to_parts(o1, h1, l1);
-            xi0 = ((a0h[jj] + b0) + h0) - Kb;
-            xf0 = (a0l[jj] + l0) - fb;
-            xi1 = ((a1h[jj] + b1) + h1) - Kl[jj];
-            xf1 = (a1l[jj] + l1) - fl[jj];
-        };
-        if (i == steps1) {
-            // log Z over all my side's states at the meeting frame: two-pass max / sum across the W warps
-            double mx = -1.0e300;
+    // the other side's words for my pair in slot j: [ooff - 64 j] my blank, one below my label; their slot
+    // bases at [B0 - j], [B1 - j].  Pairs that do not exist read harmless words inside the guard / stage
+    // and are masked out of the outputs.
+    const int ooff = JWp + R0;
+    // mantissa product and exponent of (my pre-emission sum) x (other side's stored value)
+    auto prod = [&](const int* trow, int jj, float& g0, int& x0, float& g1, int& x1) {
+        const int o0 = trow[ooff - 64 * jj], o1 = trow[ooff - 64 * jj - 1];
+        const int b0 = trow[B0 - jj], b1 = trow[B1 - jj];
+        g0 = su[jj] * xf_unpack_m(o0);
+        g1 = sv[jj] * xf_unpack_m(o1);
+        x0 = eu[jj] + b0 - xf_unpack_below(o0);
+        x1 = ev[jj] + b1 - xf_unpack_below(o1);
+    };
+    for (int i0 = steps1; i0 < Tn; i0 += G) {
+        const int cnt = min(G, Tn - i0);
+        const float* stg = stages + s * SF_;
+        const int r0 = dir ? cnt - 1 : 0;
+        const float* er = stg + r0 * E;
+        const int* trow = (const int*)(stg + G * E + r0 * SPX);
+        float* ob = (float*)stg + G * (E + SPX) + r0 * OC + 4 + pos0;          // my label of slot 0 in the occupancy row
+        float* ps = (float*)stg + G * (E + SPX) + G * OC + (r0 * W + w) * 32 + lane;
+        mbar_wait(&full[s], fpar);
+        for (int i = i0; i < i0 + cnt; ++i, er += rsgn * E, trow += rsgn * SPX, ob += rsgn * OC, ps += rsgn * (W * 32)) {
+            csum += er[0];
+            const bool active = (i == 0) || (i >= first && i <= last);
+            if (active) advance(er, i);
+            else if (mailer) mail[(i & 1) * W + w] = make_int2(__float_as_int(ml[J - 1]), el[J - 1]);
+            if (i == steps1) {
+                // Z = sum over my side's states at the meeting frame: exponent maximum, then a scaled sum
+                int pm = 4 * kVoidE;
+                float zg[2 * J]; int zx[2 * J];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                float xi0, xf0, xi1, xf1;
-                expo(j, xi0, xf0, xi1, xf1);
-                mx = fmax(mx, fmax((double)xi0 + (double)xf0, (double)xi1 + (double)xf1));
-            }
-            mx = warp_max_d(mx);
-            if (lane == 0) redm[w] = mx;
-            named_bar_sync(barid, nthr);
-            for (int x = 0; x < W; ++x) mx = fmax(mx, redm[x]);
-            feasible = mx > (double)kVoidTest;
-            float sm = 0.0f;
+                for (int j = 0; j < J; ++j) {
+                    prod(trow, j, zg[2 * j], zx[2 * j], zg[2 * j + 1], zx[2 * j + 1]);
+                    if (!(active && ((hasp >> j) & 1u))) zx[2 * j] = 4 * kVoidE;
+                    if (!(active && ((hasl >> j) & 1u))) zx[2 * j + 1] = 4 * kVoidE;
+                    pm = max(pm, max(zx[2 * j], zx[2 * j + 1]));
+                }
+                pm = __reduce_max_sync(0xffffffffu, pm);
+                if (lane == 0) redi[w] = pm;
+                side_barrier();
+                for (int x = 0; x < W; ++x) pm = max(pm, redi[x]);
+                feasible = pm > kVoidETest;
+                double sm = 0.0;
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                float xi0, xf0, xi1, xf1;
-                expo(j, xi0, xf0, xi1, xf1);
-                sm += ex2f((float)((double)xi0 + (double)xf0 - mx)) +
-                      ex2f((float)((double)xi1 + (double)xf1 - mx));
+                for (int j = 0; j < 2 * J; ++j) sm += (double)xf_scale(zg[j], max(zx[j] - pm, -126));
+#pragma unroll
+                for (int o = 16; o; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                if (lane == 0) redd[w] = sm;
+                side_barrier();
+                sm = 0.0;
+                for (int x = 0; x < W; ++x) sm += redd[x];
+                // Z = sm * 2^pm = mZ * 2^eZ with mZ in [1, 2)
+                const int ex = feasible ? ilogb(sm) : 0;
+                rZ = feasible ? (float)(1.0 / scalbn(sm, -ex)) : 1.0f;
+                eZ = feasible ? pm + ex : (1 << 29);          // infeasible: every occupancy underflows to ~0
+                logZ2 = feasible ? (double)pm + log2(sm) : 0.0;
             }
-            sm = warp_sum(sm);
-            if (lane == 0) reds[w] = sm;
-            named_bar_sync(barid, nthr);
-            sm = 0.0f;
-            for (int x = 0; x < W; ++x) sm += reds[x];
-            const double logZ2 = mx + (double)log2f(sm);        // of the shifted emissions
-            const double fl2 = floor(logZ2);
-            IZ = feasible ? (float)fl2 : 0.0f;
-            fZ = feasible ? (float)(logZ2 - fl2) : 0.0f;
+            float bsum = 0.0f;
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    float g0, g1; int x0, x1;
+                    prod(trow, j, g0, x0, g1, x1);
+                    g0 = xf_scale(g0 * rZ, max(x0 - eZ, -126));
+                    g1 = xf_scale(g1 * rZ, max(x1 - eZ, -126));
+                    bsum += ((hasp >> j) & 1u) ? g0 : 0.0f;
+                    if ((hasl >> j) & 1u) ob[pstep * j] = g1;
+                }
+            } else {
+                // none of my states is on any complete path at this frame: their posteriors are exactly zero
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    if ((hasl >> j) & 1u) ob[pstep * j] = 0.0f;
+            }
+            *ps = bsum;         // per-lane blank occupancy; the producer warp sums the 32 W of a row into float [1]
+            if (i == i0 + cnt - 1) fence_async_smem();   // this group's occupancy writes -> the producer's bulk stores
+            side_barrier();
         }
-        float* ob = (float*)stg + G * (E + SPX) + ridx * OC;       // occupancy row of this frame
-        float* ps = (float*)stg + G * (E + SPX) + G * OC;
-        float bsum = 0.0f;
-        if (i >= first && i <= last) {
-            float g0[J], g1[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                float xi0, xf0, xi1, xf1;
-                expo(j, xi0, xf0, xi1, xf1);
-                g0[j] = (xi0 - IZ) + (xf0 - fZ);
-                g1[j] = (xi1 - IZ) + (xf1 - fZ);
-            }
-#pragma unroll
-            for (int j = 0; j < J; ++j) { g0[j] = ex2f(g0[j]); g1[j] = ex2f(g1[j]); }
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                bsum += feasible ? g0[j] : 0.0f;
-                if ((hasl >> j) & 1u) ob[4 + pos0 + pstep * j] = feasible ? g1[j] : 0.0f;
-            }
-            bsum = warp_sum(bsum);
-        } else {
-            // none of my states is on any complete path at this frame: their posteriors are exactly zero
-#pragma unroll
-            for (int j = 0; j < J; ++j)
-                if ((hasl >> j) & 1u) ob[4 + pos0 + pstep * j] = 0.0f;
-        }
-        if (lane == 0) ps[ridx * W + w] = bsum;      // folded into occupancy float [1] by the producer
-        if (g == cnt - 1) fence_async_smem();       // this group's occupancy writes -> the producer's bulk stores
-#ifdef HAB_PROBE
-        if (pr) p.probe[pb + 3] = clock64();
-#endif
-        step_end();
-#ifdef HAB_PROBE
-        if (pr) p.probe[pb + 4] = clock64();
-#endif
+        if (leader) mbar_arrive(&empty[s]);
+        if (++s == nstage) { s = 0; fpar ^= 1u; }
     }
     if (dir == 0 && leader) {
         // log Z of the true emissions = log Z of the shifted ones + the sum of all T row shifts
-        const float v = feasible ? (float)(-((double)IZ + (double)fZ + (double)csum) * kLn2) : CUDART_INF_F;
+        const float v = feasible ? (float)(-(logZ2 + (double)csum) * kLn2) : CUDART_INF_F;
         p.loss[n] = v; p.loss_ws[n] = v;
     }
 }

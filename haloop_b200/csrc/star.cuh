@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
     const int steps1 = dir ? Tn - tm : tm;
 
     if (producer) {
-        trellis_producer<2>(stages, SF_, full, empty, nstage, G, W, E, SPX, OC, em_base, tr_base, occ_bytes,
+        trellis_producer<2, false>(stages, SF_, full, empty, nstage, G, W, E, SPX, OC, em_base, tr_base, occ_bytes,
                             Tn, steps1, dir, lane);
         return;
     }
