@@ -259,6 +259,8 @@ struct TrellisParams {
 constexpr int kMaxG = 4;
 constexpr int kTrellisGuard = 2048;   // (CTC) bytes in front of the first stage: label pairs that do not exist read
                                       // up to 2 KB below their stage in phase 2 instead of being predicated off
+constexpr int kEmptyBarrier = 4;   // + 4 dir + stage: "stage released" hand-over from a side's compute warps (bar.arrive,
+                                   // never blocking) to its producer warp (bar.sync: sleeps in hardware, no polling)
 constexpr int kPhaseBarrier = 3;   // named barrier all warps of the CTA (compute + producers) meet at between the phases;
                                    // producers and compute warps arrive from different call sites, which bar.sync
                                    // with an explicit id and thread count permits (__syncthreads would not)
@@ -284,7 +286,7 @@ constexpr float kRebase = 24.0f;   // (star-CTC) a slot is re-based when its sta
 // PER_LANE: the compute warps leave their partial sums un-reduced (32 lanes each) and this otherwise
 // idle warp does the reduction, off the compute warps' critical path.
 template <int NP, bool PER_LANE>
-__device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_t* full, uint64_t* empty,
+__device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_t* full,
                                                  int nstage, int G, int W, int E, int SPX, int OC,
                                                  float* em_base, float* tr_base, uint32_t occ_bytes,
                                                  int Tn, int steps1, int dir, int lane) {
@@ -333,7 +335,7 @@ __device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_
     };
     for (int k = 0; k < ng1; ++k) {
         const int s = k % nstage, use = k / nstage;
-        if (use > 0) mbar_wait_backoff(&empty[s], (uint32_t)(use - 1) & 1u);
+        if (use > 0) named_bar_sync(kEmptyBarrier + 4 * dir + s, 32 * W + 32);
         if (lane == 0) {
             int t_lo, cnt;
             group_rows(0, k, t_lo, cnt);
@@ -351,7 +353,7 @@ __device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_
         const int s = k % nstage, use = k / nstage;
         if (use > 0) {
             const int kprev = k - nstage;            // group that used this stage before
-            if (k2 < ng2 || kprev >= ng1) mbar_wait_backoff(&empty[s], (uint32_t)(use - 1) & 1u);
+            if (k2 < ng2 || kprev >= ng1) named_bar_sync(kEmptyBarrier + 4 * dir + s, 32 * W + 32);
             if (kprev >= ng1) drain(s, kprev - ng1);
         }
         if (k2 < ng2 && lane == 0) {
@@ -370,7 +372,8 @@ __device__ __forceinline__ void trellis_producer(float* stages, int SF_, uint64_
 // time, warps [W,2W) sweep beta backward, and the two sides meet in the middle; warps 2W and 2W+1 are
 // the sides' producers: one elected lane each issues every bulk (TMA) copy, so the compute warps never
 // touch the copy engine.  A ring stage holds G consecutive frames: emission rows in, (phase 2) the
-// other side's stored trellis rows in, occupancy rows out; full/empty mbarriers hand stages over.
+// other side's stored trellis rows in, occupancy rows out; a full mbarrier (TMA completion) and a named
+// "released" barrier per stage hand stages over.
 //
 // Side d's step i is frame t = d ? T-1-i : i and it orders the label pairs its own way (beta = alpha
 // on the reversed label sequence).  Warp w of a side owns J slots of 32 pairs: pair
@@ -415,9 +418,8 @@ __global__ void __launch_bounds__(32 * (2 * W + 2)) ctc_trellis_kernel(TrellisPa
     double* redd = (double*)(mail + 2 * W);                       // [W] Z partial sums
     int* redi = (int*)(redd + W);                                 // [W] Z partial exponent maxima
     uint64_t* full = (uint64_t*)(redi + 2 * W);
-    uint64_t* empty = full + nstage;
     if (producer && lane == 0)
-        for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < nstage; ++s) mbar_init(&full[s], 1);
     mbar_init_fence();
     __syncthreads();
 
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(32 * (2 * W + 2)) ctc_trellis_kernel(TrellisPa
     const int steps1 = dir ? Tn - tm : tm;         // phase-1 steps of my side
 
     if (producer) {
-        trellis_producer<1, true>(stages, SF_, full, empty, nstage, G, W, E, SPX, OC, em_base, tr_base, occ_bytes,
+        trellis_producer<1, true>(stages, SF_, full, nstage, G, W, E, SPX, OC, em_base, tr_base, occ_bytes,
                             Tn, steps1, dir, lane);
         return;
     }
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(32 * (2 * W + 2)) ctc_trellis_kernel(TrellisPa
                 hrow += rstep;
                 side_barrier();
             }
-            if (leader) mbar_arrive(&empty[s]);
+            named_bar_arrive(kEmptyBarrier + 4 * dir + s, nthr + 32);
             if (++s == nstage) { s = 0; fpar ^= 1u; }
         }
     }
@@ -662,7 +664,7 @@ __global__ void __launch_bounds__(32 * (2 * W + 2)) ctc_trellis_kernel(TrellisPa
             if (i == i0 + cnt - 1) fence_async_smem();   // this group's occupancy writes -> the producer's bulk stores
             side_barrier();
         }
-        if (leader) mbar_arrive(&empty[s]);
+        named_bar_arrive(kEmptyBarrier + 4 * dir + s, nthr + 32);
         if (++s == nstage) { s = 0; fpar ^= 1u; }
     }
     if (dir == 0 && leader) {

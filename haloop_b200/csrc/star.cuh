@@ -225,9 +225,8 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
     double* redm = (double*)(mail + 2 * W);
     float* reds = (float*)(redm + W);
     uint64_t* full = (uint64_t*)(reds + 2 * W);
-    uint64_t* empty = full + nstage;
     if (producer && lane == 0)
-        for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < nstage; ++s) mbar_init(&full[s], 1);
     mbar_init_fence();
     __syncthreads();
 
@@ -238,7 +237,7 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
     const int steps1 = dir ? Tn - tm : tm;
 
     if (producer) {
-        trellis_producer<2, false>(stages, SF_, full, empty, nstage, G, W, E, SPX, OC, em_base, tr_base, occ_bytes,
+        trellis_producer<2, false>(stages, SF_, full, nstage, G, W, E, SPX, OC, em_base, tr_base, occ_bytes,
                             Tn, steps1, dir, lane);
         return;
     }
@@ -412,7 +411,7 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
     auto step_end = [&]() {
         named_bar_sync(barid, nthr);
         if (++g == cnt) {
-            if (leader) mbar_arrive(&empty[s]);
+            named_bar_arrive(kEmptyBarrier + 4 * dir + s, nthr + 32);
             g = 0;
             if (++s == nstage) { s = 0; fpar ^= 1u; }
         }
