@@ -228,33 +228,36 @@ static int star_trellis_launch(const StarTrellisParams& tp, int nslot, int N, cu
     int env_w = 0;
     if (const char* e = getenv("HA_B200_TRELLIS_W")) env_w = atoi(e);
     int W = nslot < 2 ? 1 : (nslot < 4 ? 2 : 4);
-    if (env_w >= 1 && env_w <= 6) W = env_w;
+    if (env_w >= 1 && env_w <= 5) W = env_w < nslot ? env_w : nslot;
     const int J = (nslot + W - 1) / W;
     if (J > 4) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: star J=%d", J);
-    p.W = (nslot + J - 1) / J;
+    W = (nslot + J - 1) / J;
+    p.W = W;
     p.G = kMaxG;
     const int OC = 4 + 2 * p.Sp;
     int ns = 4;
-    while (ns >= 2 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, OC, ns, p.G, p.W, 2) > 100 * 1024) --ns;
+    while (ns >= 2 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, OC, ns, p.G, p.W, 64) > 100 * 1024) --ns;
     if (ns < 2) {
         ns = 2;
-        while (p.G > 1 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, OC, ns, p.G, p.W, 2) > 220 * 1024) p.G >>= 1;
+        while (p.G > 1 && (size_t)2 * trellis_dir_bytes(p.E, p.SPX, OC, ns, p.G, p.W, 64) > 220 * 1024) p.G >>= 1;
     }
     p.nstage = ns;
-    p.dir_bytes = trellis_dir_bytes(p.E, p.SPX, OC, ns, p.G, p.W, 2);
+    p.dir_bytes = trellis_dir_bytes(p.E, p.SPX, OC, ns, p.G, p.W, 64);
     const size_t smem = (size_t)2 * p.dir_bytes;
     const dim3 grid(N), block(32 * (2 * p.W + 2));
-    int rc;
-#define HAB_LAUNCH_STAR(JJ)                                                            \
-    case JJ:                                                                           \
-        if ((rc = set_smem(star_trellis_kernel<JJ>, smem, "star_trellis"))) return rc; \
-        star_trellis_kernel<JJ><<<grid, block, smem, st>>>(p);                         \
-        break
-    switch (J) {
-        HAB_LAUNCH_STAR(1); HAB_LAUNCH_STAR(2); HAB_LAUNCH_STAR(3); HAB_LAUNCH_STAR(4);
-        default: return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: star J=%d", J);
+    int rc = HA_ERR_UNSUPPORTED_SHAPE;
+    bool hit = false;
+#define HAB_TRY(JJ, WW)                                                                         \
+    if (!hit && J == JJ && W == WW) {                                                           \
+        hit = true;                                                                             \
+        if ((rc = set_smem(star_trellis_kernel<JJ, WW>, smem, "star_trellis"))) return rc;      \
+        star_trellis_kernel<JJ, WW><<<grid, block, smem, st>>>(p);                              \
     }
-#undef HAB_LAUNCH_STAR
+#define HAB_TRY_J(JJ) HAB_TRY(JJ, 1) HAB_TRY(JJ, 2) HAB_TRY(JJ, 3) HAB_TRY(JJ, 4) HAB_TRY(JJ, 5)
+    HAB_TRY_J(1) HAB_TRY_J(2) HAB_TRY_J(3) HAB_TRY_J(4)
+#undef HAB_TRY_J
+#undef HAB_TRY
+    if (!hit) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: star J=%d W=%d", J, W);
     return check_launch("star_trellis_kernel");
 }
 

@@ -261,6 +261,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// non-blocking arrival on a named barrier (the waiting side uses named_bar_sync with the same count)
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // The phase-switch barrier of the trellis kernels: producer and compute warps come from different code
 // paths, so the barrier instruction lives in one non-inlined function and every thread of the CTA
 // executes the same instruction (bar.sync on a named barrier with an explicit thread count).

@@ -19,9 +19,9 @@ struct StarWs {
     int Sp, E, JWp, SPX;
 };
 
-// emission row (32-bit words): [0] float ct (integer row shift)  [1] blank  [2] all-star (log2 P)
-// [4+2k] label y_k  [5+2k] star "anything but y_k", each a Q8.24 fixed-point value of log2 p - ct
-// (emission_word, ctc.cuh).  The occupancy row written in place (floats): [1] blank occupancy
+// emission row (floats): [0] ct (integer row shift)  [1] blank  [2] all-star P  [3] ct as an int
+// [4+2k] label y_k  [5+2k] star "anything but y_k", each the probability 2^(log2 p - ct) as a plain fp32
+// (emission_linear, ctc.cuh).  The occupancy row written in place (floats): [1] blank occupancy
 // [2] G = sum_k h_k  [4+2k] label occupancy  [5+2k] h_k (0 if y_k == 0), h_k = gamma(star k) / (P - p_{y_k}).
 __host__ __device__ inline int star_em_floats(int Sp) { return 4 + 2 * Sp; }
 
@@ -134,8 +134,9 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
         const float lP = fmaxf(m2 + log2f(s) - l2, kVoid);        // log2 sum_{c>=1} p_c   (ha/star.py:30)
         const float eblank = fmaf(row[0], kLog2e, -l2);
         const float ct = round_int(fmaxf(eblank, lP));            // every other emission is <= log2 P
-        // emissions in float-float arithmetic from the fp32 logits, split into int8 integer part + fp32
-        // fraction (emission_split, common.cuh).  log2 P and the star terms are (hi, lo) float pairs too.
+        // emission exponents in float-float arithmetic from the fp32 logits, split into an integer part and a
+        // fraction (emission_split, common.cuh) and stored as linear probabilities.  log2 P and the star
+        // terms are (hi, lo) float pairs too.
         const float lgs = log2f(s);
         const float lPh = m2 + lgs;                                        // log2 P + l2, rounded ...
         const float lbb = lPh - m2;
@@ -155,7 +156,8 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
             float Kb, fb, Ka, fa;
             emission_split(row[0], l2, ct, Kb, fb);
             split2(fmaxf(lPh, kVoid), lPl, Ka, fa);
-            *(float4*)erow = make_float4(ct, __int_as_float(emission_word(Kb, fb)), __int_as_float(emission_word(Ka, fa)), 0.0f);
+            *(float4*)erow = make_float4(ct, emission_linear(Kb, fb), emission_linear(Ka, fa),
+                                         __int_as_float(__float2int_rn(ct)));
         }
         for (int k = lane; k < Ks; k += 32) {
             const int y = s_tgt[k];
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
             const float sh = lPh + add;
             const float sl = lPl + ((lPh - sh) + add);
             split2(fmaxf(sh, kVoid), sl, Ks2, fs2);
-            ((int2*)(erow + 4))[k] = make_int2(emission_word(Kl, fl), emission_word(Ks2, fs2));
+            ((float2*)(erow + 4))[k] = make_float2(emission_linear(Kl, fl), emission_linear(Ks2, fs2));
         }
         __syncwarp();
         if (r + nstage < nrows) issue(r + nstage);
@@ -185,21 +187,23 @@ struct StarTrellisParams {
     int T, N, S;
     const int4* meta; const int* order; const int* tgt; int Sp;
     float* em; int E;          // emission rows in / occupancy rows out, in place (layout: star_em_floats)
-    float* tr; int SPX, JWp;   // stored row = [JWp slot bases][4*(L+1) Q11.20 ints: quads]
+    float* tr; int SPX, JWp;   // stored row = [JWp slot bases][4*(L+1) packed words: quads]
     float* loss; float* loss_ws;
     float pen2;                // star_penalty in log2 units
     int nstage, G, W;          // ring stages; frames per stage; compute warps per sweep direction
     int dir_bytes;
 };
 
-// Same CTA shape and ring protocol as ctc_trellis_kernel (one CTA per utterance, W compute warps +
-// one producer warp per sweep side, meet in the middle).  Both sides keep quad k in lane k%32 of slot
-// k/32 of warp k/(32 J); beta is not a mirror image of alpha here (labels have no self loop, stars have
-// a back edge), so it has its own update and its mailbox runs downwards.
-template <int J>
-__global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) {
+// Same CTA shape, ring protocol and number format as ctc_trellis_kernel (one CTA per utterance, W
+// compute warps + one producer warp per sweep side, meet in the middle, extended-range linear numbers).
+// Both sides keep quad k in lane k%32 of slot k/32 of warp k/(32 J); beta is not a mirror image of alpha
+// here (labels have no self loop, stars have a back edge), so it has its own update and its mailbox runs
+// downwards.  The star state's stored word is its PRE-emission sum: h_k = gamma(star k) / (P - p_y) is then
+// (my sum) x (other side's sum) x penalty / Z / 2^ct, without dividing by the star's emission.
+template <int J, int W>
+__global__ void __launch_bounds__(32 * (2 * W + 2)) star_trellis_kernel(StarTrellisParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int W = p.W, G = p.G, nstage = p.nstage;
+    const int G = p.G, nstage = p.nstage;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool producer = warp >= 2 * W;
     const int dir = producer ? warp - 2 * W : (warp >= W);
@@ -209,22 +213,28 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
     const int n = p.order[blockIdx.x];
     const int4 mt = p.meta[n];
     const int Tn = mt.x, L = mt.y;
-    if (mt.z || Tn == 0) {
+    // feasible iff there is a frame per label plus one between equal neighbours (labels have no self
+    // loop; every stored emission is a positive number) -- decided here as in ctc_trellis_kernel
+    if (mt.z || Tn == 0 || Tn < L + mt.w) {
         const float v = mt.z ? CUDART_NAN_F : CUDART_INF_F;
         if (threadIdx.x == 0) { p.loss[n] = v; p.loss_ws[n] = v; }
         return;
     }
     const int Q = L + 1, Ks = min(L + 1, p.S);
     const int E = p.E, SPX = p.SPX, JWp = p.JWp, OC = 4 + 2 * p.Sp;
-    const int SF_ = trellis_stage_floats(E, SPX, OC, G, W, 2);
-    const float Kp = round_int(p.pen2), fp = p.pen2 - Kp;
+    const int SF_ = trellis_stage_floats(E, SPX, OC, G, W, 64);
+    // star penalty 2^pen2 = pm * 2^pe, pm in [1, 2): the mantissa multiplies the star emission, the integer
+    // part goes straight into the exponent
+    const float pef = floorf(p.pen2);
+    const int pe = (int)pef;
+    const float pm = exp2f(p.pen2 - pef);
 
     unsigned char* db = smem_raw + (size_t)dir * p.dir_bytes;
     float* stages = (float*)db;
-    float4* mail = (float4*)(stages + nstage * SF_);              // [2][W]
-    double* redm = (double*)(mail + 2 * W);
-    float* reds = (float*)(redm + W);
-    uint64_t* full = (uint64_t*)(reds + 2 * W);
+    int4* mail = (int4*)(stages + nstage * SF_);                  // [2][W]
+    double* redd = (double*)(mail + 2 * W);                       // [W] Z partial sums
+    int* redi = (int*)(redd + W);                                 // [W] Z partial exponent maxima
+    uint64_t* full = (uint64_t*)(redi + 2 * W);
     if (producer && lane == 0)
         for (int s = 0; s < nstage; ++s) mbar_init(&full[s], 1);
     mbar_init_fence();
@@ -237,14 +247,17 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
     const int steps1 = dir ? Tn - tm : tm;
 
     if (producer) {
-        trellis_producer<2, false>(stages, SF_, full, nstage, G, W, E, SPX, OC, em_base, tr_base, occ_bytes,
-                            Tn, steps1, dir, lane);
+        trellis_producer<2, true>(stages, SF_, full, nstage, G, W, E, SPX, OC, em_base, tr_base, occ_bytes,
+                                  Tn, steps1, dir, lane);
         return;
     }
 
     const bool leader = (w == 0 && lane == 0);
-    const int nthr = 32 * W;
-    const int barid = 1 + dir;
+    constexpr int nthr = 32 * W;
+    auto side_barrier = [&]() {
+        if (dir) asm volatile("bar.sync 2, %0;" ::"n"(nthr) : "memory");
+        else asm volatile("bar.sync 1, %0;" ::"n"(nthr) : "memory");
+    };
     const int k0 = 32 * (w * J) + lane;           // my quad in slot 0
     // alpha: may label k be entered from label k-1?   beta: may label k be left for label k+1?
     unsigned allowed = 0, exclude = 0, hasq = 0, hasl = 0, hase = 0;   // exclude: star k excludes a class
@@ -270,187 +283,166 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
     // ... and none of them can still be on a complete path after this step (one quad per remaining frame)
     const int last = dir ? Tn - 32 * (w * J) + 1 : Tn - L + (32 * (w + 1) * J - 1) + 1;
 
-    SF b0[J], st[J], b1[J], lb[J];
-    float base[J];
+    // states of my quad in slot j, and the pre-emission sums they were made from
+    XF b0[J], st[J], b1[J], lb[J], s0[J], ss[J], s1[J], sl[J];
 #pragma unroll
-    for (int j = 0; j < J; ++j) { b0[j] = st[j] = b1[j] = lb[j] = sf_void(); base[j] = 0.0f; }
+    for (int j = 0; j < J; ++j)
+        b0[j] = st[j] = b1[j] = lb[j] = s0[j] = ss[j] = s1[j] = sl[j] = xf_make(1.0f, kVoidE);
 
-    float IZ = 0.0f, fZ = 0.0f, csum = 0.0f, ct = 0.0f, cin_h = kVoid;
+    float csum = 0.0f, rZ = 1.0f, rZp = 1.0f;
+    double logZ2 = 0.0;
+    int eZ = 0, cti = 0;
     bool feasible = true;
-    float Kb, fb, Kl[J], fl[J], Ks_[J], fs[J];   // blank / label / star emissions of my quad, split; the
-                                                  // star's include the penalty paid on entering it
-    int s = 0, g = 0, cnt = 0; uint32_t fpar = 0;
-    const float* stg = stages;
+    float psm[J];                 // star emission x penalty mantissa of the current frame
+    int s = 0; uint32_t fpar = 0;
 
-    auto fetch = [&](int i, int phase_end) {
-        if (g == 0) {
-            cnt = min(G, phase_end - i);
-            stg = stages + s * SF_;
-            mbar_wait(&full[s], fpar);
-        }
-        const int ridx = dir ? cnt - 1 - g : g;
-        const float* er = stg + ridx * E;
-        const int* ew = (const int*)er;
-        ct = er[0];
-        csum += ct;
-        emission_decode(ew[1], Kb, fb);
-        float Ka, fa;
-        emission_decode(ew[2], Ka, fa);
+    auto xf_norm = [](XF a) {
+        const int bits = __float_as_int(a.m);
+        return xf_make(__int_as_float((bits & 0x007fffff) | 0x3f800000), a.e + (bits >> 23) - 127);
+    };
+    // one step of the recursion on the emission row `er` (ha/star.py:123-145)
+    auto advance = [&](const float* er, int i, bool active) {
+        const float pb = er[1], pa = er[2];
+        cti = ((const int*)er)[3];
+        float pl[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int k = k0 + 32 * j;
-            const bool ve = (hase >> j) & 1u, vl = (hasl >> j) & 1u;
-            const int2 wv = ve ? ((const int2*)(ew + 4))[k] : make_int2(0, 0);
-            float K1, f1, K2, f2;
-            emission_decode(wv.x, K1, f1);
-            emission_decode(wv.y, K2, f2);
-            Kl[j] = vl ? K1 : kVoid;
-            fl[j] = vl ? f1 : 0.0f;
-            // the star of quad k: its own entry, or the all-star when k == L == S (ha/star.py:47)
-            const float ks = ve ? K2 : ((k == L) ? Ka : kVoid);
-            const float fs0 = ve ? f2 : ((k == L) ? fa : 0.0f);
-            Ks_[j] = fmaxf(ks + Kp, kVoid);
-            fs[j] = fs0 + fp;
+            // quads without an entry of their own (k == L == S: the all-star, ha/star.py:47; or no quad at
+            // all: a phantom of real magnitude) take the blank and the all-star emission
+            const float2 wv = ((hase >> j) & 1u) ? ((const float2*)(er + 4))[k] : make_float2(pb, pa);
+            pl[j] = wv.x;
+            psm[j] = wv.y * pm;
         }
-        return ridx;
-    };
-    auto advance = [&](int i) {
         if (dir == 0) {
-            if (i >= first && i <= last) {
-                // previous label, from the lane below (virtual state -1 holds 0.0 before the first frame)
-                float ch[J], cl[J];
+            if (active) {
+                // previous label, from the lane below (virtual state -1 holds probability 1 before the first frame)
+                float cm[J]; int ce[J];
                 {
-                    float rh[J], rl[J];
+                    float rm[J]; int re[J];
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
-                        rh[j] = __shfl_sync(0xffffffffu, lb[j].h, (lane + 31) & 31);
-                        rl[j] = __shfl_sync(0xffffffffu, lb[j].l, (lane + 31) & 31);
+                        rm[j] = __shfl_sync(0xffffffffu, lb[j].m, (lane + 31) & 31);
+                        re[j] = __shfl_sync(0xffffffffu, lb[j].e, (lane + 31) & 31);
                     }
-                    float4 in = make_float4((i == 0) ? 0.0f : kVoid, 0.0f, 0.0f, 0.0f);
+                    int4 in = make_int4(__float_as_int(1.0f), (i == 0) ? 0 : kVoidE, 0, 0);
                     if (w > 0) in = mail[((i - 1) & 1) * W + w - 1];
-                    cin_h = in.x;
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
-                        ch[j] = lane ? rh[j] : (j ? rh[j ? j - 1 : 0] : in.x);
-                        cl[j] = lane ? rl[j] : (j ? rl[j ? j - 1 : 0] : in.y);
+                        cm[j] = lane ? rm[j] : (j ? rm[j ? j - 1 : 0] : __int_as_float(in.x));
+                        ce[j] = lane ? re[j] : (j ? re[j ? j - 1 : 0] : in.y);
                     }
                 }
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    SF c; c.h = ch[j]; c.l = cl[j];
-                    const SF u = lae_sf(st[j], b1[j]);
-                    const SF v = lae_sf(u, b0[j]);
-                    const SF w0 = lae_sf(c, b0[j]);
-                    const SF vc = lae_sf(v, c);
-                    SF vl;
-                    vl.h = ((allowed >> j) & 1u) ? vc.h : v.h;
-                    vl.l = ((allowed >> j) & 1u) ? vc.l : v.l;
-                    b1[j] = add_norm(u, Kb, fb);
-                    st[j] = add_norm(v, Ks_[j], fs[j]);
-                    lb[j] = add_norm(vl, Kl[j], fl[j]);
-                    b0[j] = add_norm(w0, Kb, fb);
+                    const XF c = xf_make(cm[j], ce[j]);
+                    const XF u = xf_add(st[j], b1[j]);
+                    const XF v = xf_add(u, b0[j]);
+                    const XF w0 = xf_add(c, b0[j]);
+                    const XF vc = xf_add(v, c);
+                    const bool al = (allowed >> j) & 1u;
+                    const XF vl = xf_make(al ? vc.m : v.m, al ? vc.e : v.e);
+                    s0[j] = w0; ss[j] = v; s1[j] = u; sl[j] = vl;
+                    b1[j] = xf_mul_norm(u, pb);
+                    st[j] = xf_mul_norm(v, psm[j]); st[j].e += pe;
+                    lb[j] = xf_mul_norm(vl, pl[j]);
+                    b0[j] = xf_mul_norm(w0, pb);
                 }
             }
-            if (lane == 31 && w + 1 < W) mail[(i & 1) * W + w] = make_float4(lb[J - 1].h, lb[J - 1].l, 0.0f, 0.0f);
+            if (lane == 31 && w + 1 < W) mail[(i & 1) * W + w] = make_int4(__float_as_int(lb[J - 1].m), lb[J - 1].e, 0, 0);
         } else {
             if (i == 0) {
                 // beta at the last frame: the four final states (ha/star.py:156-163), emission included
-                SF z; z.h = 0.0f; z.l = 0.0f;
+                const XF one = xf_make(1.0f, 0);
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     const int k = k0 + 32 * j;
-                    if (k == L) { b0[j] = add_norm(z, Kb, fb); st[j] = add_norm(z, Ks_[j], fs[j]); b1[j] = b0[j]; }
-                    if (k == L - 1) lb[j] = add_norm(z, Kl[j], fl[j]);
+                    if (k == L) {
+                        s0[j] = ss[j] = s1[j] = one;
+                        b0[j] = xf_mul_norm(one, pb); b1[j] = b0[j];
+                        st[j] = xf_mul_norm(one, psm[j]); st[j].e += pe;
+                    }
+                    if (k == L - 1) { sl[j] = one; lb[j] = xf_mul_norm(one, pl[j]); }
                 }
-            } else if (i >= first && i <= last) {
+            } else if (active) {
                 // next quad's first blank and label, from the lane above (lane 31 takes lane 0 of the slot
                 // above, or the mailbox of the warp above)
-                float n0h[J], n0l[J], nlh[J], nll[J];
+                float n0m[J], nlm[J]; int n0e[J], nle[J];
                 {
-                    float r0h[J], r0l[J], rlh[J], rll[J];
+                    float r0m[J], rlm[J]; int r0e[J], rle[J];
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
-                        r0h[j] = __shfl_sync(0xffffffffu, b0[j].h, (lane + 1) & 31);
-                        r0l[j] = __shfl_sync(0xffffffffu, b0[j].l, (lane + 1) & 31);
-                        rlh[j] = __shfl_sync(0xffffffffu, lb[j].h, (lane + 1) & 31);
-                        rll[j] = __shfl_sync(0xffffffffu, lb[j].l, (lane + 1) & 31);
+                        r0m[j] = __shfl_sync(0xffffffffu, b0[j].m, (lane + 1) & 31);
+                        r0e[j] = __shfl_sync(0xffffffffu, b0[j].e, (lane + 1) & 31);
+                        rlm[j] = __shfl_sync(0xffffffffu, lb[j].m, (lane + 1) & 31);
+                        rle[j] = __shfl_sync(0xffffffffu, lb[j].e, (lane + 1) & 31);
                     }
-                    float4 in = make_float4(kVoid, 0.0f, kVoid, 0.0f);
+                    int4 in = make_int4(__float_as_int(1.0f), kVoidE, __float_as_int(1.0f), kVoidE);
                     if (w + 1 < W) in = mail[((i - 1) & 1) * W + w + 1];
-                    cin_h = fmaxf(in.x, in.z);
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
                         const bool edge = lane == 31;
                         const int jn = (j + 1 < J) ? j + 1 : j;
-                        n0h[j] = edge ? ((j + 1 < J) ? r0h[jn] : in.x) : r0h[j];
-                        n0l[j] = edge ? ((j + 1 < J) ? r0l[jn] : in.y) : r0l[j];
-                        nlh[j] = edge ? ((j + 1 < J) ? rlh[jn] : in.z) : rlh[j];
-                        nll[j] = edge ? ((j + 1 < J) ? rll[jn] : in.w) : rll[j];
+                        n0m[j] = edge ? ((j + 1 < J) ? r0m[jn] : __int_as_float(in.x)) : r0m[j];
+                        n0e[j] = edge ? ((j + 1 < J) ? r0e[jn] : in.y) : r0e[j];
+                        nlm[j] = edge ? ((j + 1 < J) ? rlm[jn] : __int_as_float(in.z)) : rlm[j];
+                        nle[j] = edge ? ((j + 1 < J) ? rle[jn] : in.w) : rle[j];
                     }
                 }
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    SF n0; n0.h = n0h[j]; n0.l = n0l[j];
-                    SF nl; nl.h = nlh[j]; nl.l = nll[j];
-                    const SF x = lae_sf(st[j], lb[j]);
-                    const SF z = lae_sf(b1[j], x);
-                    const SF w0 = lae_sf(b0[j], x);
-                    const SF nn = lae_sf(n0, nl);
-                    SF vl;
-                    vl.h = ((allowed >> j) & 1u) ? nn.h : n0.h;
-                    vl.l = ((allowed >> j) & 1u) ? nn.l : n0.l;
-                    b0[j] = add_norm(w0, Kb, fb);
-                    st[j] = add_norm(z, Ks_[j], fs[j]);
-                    b1[j] = add_norm(z, Kb, fb);
-                    lb[j] = add_norm(vl, Kl[j], fl[j]);
+                    const XF n0 = xf_make(n0m[j], n0e[j]), nl = xf_make(nlm[j], nle[j]);
+                    const XF x = xf_add(st[j], lb[j]);
+                    const XF z = xf_add(b1[j], x);
+                    const XF w0 = xf_add(b0[j], x);
+                    const XF nn = xf_add(n0, nl);
+                    const bool al = (allowed >> j) & 1u;
+                    const XF vl = xf_make(al ? nn.m : n0.m, al ? nn.e : n0.e);
+                    s0[j] = w0; ss[j] = z; s1[j] = z; sl[j] = vl;
+                    b0[j] = xf_mul_norm(w0, pb);
+                    st[j] = xf_mul_norm(z, psm[j]); st[j].e += pe;
+                    b1[j] = xf_mul_norm(z, pb);
+                    lb[j] = xf_mul_norm(vl, pl[j]);
                 }
             }
-            if (lane == 0 && w > 0) mail[(i & 1) * W + w] = make_float4(b0[0].h, b0[0].l, lb[0].h, lb[0].l);
+            if (lane == 0 && w > 0)
+                mail[(i & 1) * W + w] = make_int4(__float_as_int(b0[0].m), b0[0].e, __float_as_int(lb[0].m), lb[0].e);
         }
     };
-    auto step_end = [&]() {
-        named_bar_sync(barid, nthr);
-        if (++g == cnt) {
-            named_bar_arrive(kEmptyBarrier + 4 * dir + s, nthr + 32);
-            g = 0;
-            if (++s == nstage) { s = 0; fpar ^= 1u; }
-        }
-    };
-    auto smax = [&](int j) { return fmaxf(fmaxf(b0[j].h, st[j].h), fmaxf(b1[j].h, lb[j].h)); };
+    const int rsgn = dir ? -1 : 1;
 
     // ---------------------------------------------------------------------------- phase 1 ---
     {
         int4* prow = (int4*)(tr_base + (size_t)(dir ? Tn - 1 : 0) * SPX + JWp) + k0;
-        float* hrow = tr_base + (size_t)(dir ? Tn - 1 : 0) * SPX + w * J;
+        int* hrow = (int*)(tr_base + (size_t)(dir ? Tn - 1 : 0) * SPX) + w * J + lane;
         const long long rstep = dir ? -(long long)SPX : (long long)SPX;
-        for (int i = 0; i < steps1; ++i) {
-            fetch(i, steps1);
-            advance(i);
-            // Q11.20 storage is absolute in precision, so the per-slot base only has to stay within ~2000
-            // log2 units of the states that matter: reset to the slot maximum every 8th step; slots nobody
-            // has reached yet take the warp's maximum
-            if ((i & 7) == 0) {
-                float m[J], wm = kVoid;
+        const bool hstore = lane < J && 32 * (w * J + lane) < Q;
+        for (int i0 = 0; i0 < steps1; i0 += G) {
+            const int cnt = min(G, steps1 - i0);
+            const float* er = stages + s * SF_ + (dir ? cnt - 1 : 0) * E;
+            mbar_wait(&full[s], fpar);
+            for (int i = i0; i < i0 + cnt; ++i, er += rsgn * E) {
+                csum += er[0];
+                advance(er, i, i >= first && i <= last);
+                // stored relative to each slot's largest exponent of this very step; the star state's word is
+                // its (normalised) pre-emission sum
+                int bsel = 0;
 #pragma unroll
-                for (int j = 0; j < J; ++j) { m[j] = warp_max(smax(j)); wm = fmaxf(wm, m[j]); }
-                if (!(wm > kVoidTest)) wm = cin_h;          // nobody here yet: what the neighbouring warp sends
-                if (wm > kVoidTest) {
-#pragma unroll
-                    for (int j = 0; j < J; ++j) base[j] = (m[j] > kVoidTest) ? m[j] : wm;
+                for (int j = 0; j < J; ++j) {
+                    const XF sn = xf_norm(ss[j]);
+                    const int mx = __reduce_max_sync(0xffffffffu, max(max(b0[j].e, sn.e), max(b1[j].e, lb[j].e)));
+                    if ((hasq >> j) & 1u)
+                        prow[32 * j] = make_int4(xf_pack(b0[j].m, mx - b0[j].e), xf_pack(sn.m, mx - sn.e),
+                                                 xf_pack(b1[j].m, mx - b1[j].e), xf_pack(lb[j].m, mx - lb[j].e));
+                    bsel = (lane == j) ? mx : bsel;
                 }
+                if (hstore) *hrow = bsel;
+                prow = (int4*)((int*)prow + rstep);
+                hrow += rstep;
+                side_barrier();
             }
-            float bsel = base[0];
-#pragma unroll
-            for (int j = 1; j < J; ++j) bsel = (lane == j) ? base[j] : bsel;
-#pragma unroll
-            for (int j = 0; j < J; ++j)
-                if ((hasq >> j) & 1u)
-                    prow[32 * j] = make_int4(sf_to_fix(b0[j], base[j]), sf_to_fix(st[j], base[j]),
-                                             sf_to_fix(b1[j], base[j]), sf_to_fix(lb[j], base[j]));
-            if (lane < J && 32 * (w * J + lane) < Q) hrow[lane] = bsel;
-            prow = (int4*)((float*)prow + rstep);
-            hrow += rstep;
-            step_end();
+            named_bar_arrive(kEmptyBarrier + 4 * dir + s, nthr + 32);
+            if (++s == nstage) { s = 0; fpar ^= 1u; }
         }
     }
     __threadfence();
@@ -458,84 +450,97 @@ __global__ void __launch_bounds__(448) star_trellis_kernel(StarTrellisParams p) 
     cta_phase_barrier(kPhaseBarrier, (int)blockDim.x);
 
     // ---------------------------------------------------------------------------- phase 2 ---
-    for (int i = steps1; i < Tn; ++i) {
-        const int ridx = fetch(i, Tn);
-        advance(i);
-        const float* trow = stg + G * E + ridx * SPX;
-        const int4* orow = (const int4*)(trow + JWp) + k0;       // [32 j] = other side's copy of my quad
-        const float* obase = trow + w * J;                        // [j] = its slot base
-        // posterior exponent of a state = [h + other base + other integer part - K] + [l + other fraction - f] - log Z
-        auto expo = [&](int jj, float& xi0, float& xf0, float& xis, float& xfs, float& xi1, float& xf1,
-                        float& xil, float& xfl) {
-            const bool in = (hasq >> jj) & 1u;
-            const int4 o = in ? orow[32 * jj] : make_int4(kFixVoid, kFixVoid, kFixVoid, kFixVoid);
-            const float ob = in ? obase[jj] : 0.0f;
-            float h, l;
-            fix_to_parts(o.x, h, l); xi0 = ((b0[jj].h + ob) + h) - Kb;      xf0 = (b0[jj].l + l) - fb;
-            fix_to_parts(o.y, h, l); xis = ((st[jj].h + ob) + h) - Ks_[jj]; xfs = (st[jj].l + l) - fs[jj];
-            fix_to_parts(o.z, h, l); xi1 = ((b1[jj].h + ob) + h) - Kb;      xf1 = (b1[jj].l + l) - fb;
-            fix_to_parts(o.w, h, l); xil = ((lb[jj].h + ob) + h) - Kl[jj];  xfl = (lb[jj].l + l) - fl[jj];
-            if (!((hasl >> jj) & 1u)) xil = kVoid;
-        };
-        if (i == steps1) {
-            double mx = -1.0e300;
+    for (int i0 = steps1; i0 < Tn; i0 += G) {
+        const int cnt = min(G, Tn - i0);
+        const float* stg = stages + s * SF_;
+        const int r0 = dir ? cnt - 1 : 0;
+        const float* er = stg + r0 * E;
+        const int* trow = (const int*)(stg + G * E + r0 * SPX);
+        float* ob = (float*)stg + G * (E + SPX) + r0 * OC + 4;
+        float* ps = (float*)stg + G * (E + SPX) + G * OC + (r0 * W + w) * 64 + lane;
+        mbar_wait(&full[s], fpar);
+        for (int i = i0; i < i0 + cnt; ++i, er += rsgn * E, trow += rsgn * SPX, ob += rsgn * OC, ps += rsgn * (W * 64)) {
+            csum += er[0];
+            const bool active = i >= first && i <= last;
+            advance(er, i, active);
+            const bool live = active || (dir == 1 && i == 0);
+            const int4* orow = (const int4*)(trow + JWp) + k0;       // [32 j] = the other side's copy of my quad
+            const int* obase = trow + w * J;                         // [j] = its slot base
+            if (i == steps1) {
+                // Z = sum over my side's states at the meeting frame of (my pre-emission sum) x (the other
+                // side's value); the star states' stored words lack their emission, added here
+                XF z[4 * J];
+                int zm = 4 * kVoidE;
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                float a, b, c, d, e, f, gg, h;
-                expo(j, a, b, c, d, e, f, gg, h);
-                mx = fmax(mx, fmax(fmax((double)a + (double)b, (double)c + (double)d),
-                                   fmax((double)e + (double)f, (double)gg + (double)h)));
+                for (int j = 0; j < J; ++j) {
+                    const bool in = live && ((hasq >> j) & 1u);
+                    const int4 o = in ? orow[32 * j] : make_int4((int)kPackVoid, (int)kPackVoid, (int)kPackVoid, (int)kPackVoid);
+                    const int ob_ = in ? obase[j] : kVoidE;
+                    z[4 * j + 0] = xf_norm(xf_make(s0[j].m * xf_unpack_m(o.x), s0[j].e + ob_ - xf_unpack_below(o.x)));
+                    z[4 * j + 1] = xf_mul_norm(xf_make(ss[j].m * xf_unpack_m(o.y), ss[j].e + ob_ - xf_unpack_below(o.y) + pe), psm[j]);
+                    z[4 * j + 2] = xf_norm(xf_make(s1[j].m * xf_unpack_m(o.z), s1[j].e + ob_ - xf_unpack_below(o.z)));
+                    z[4 * j + 3] = xf_norm(xf_make(sl[j].m * xf_unpack_m(o.w), sl[j].e + ob_ - xf_unpack_below(o.w)));
+                    if (!(in && ((hasl >> j) & 1u))) z[4 * j + 3].e = 4 * kVoidE;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) zm = max(zm, z[4 * j + c].e);
+                }
+                zm = __reduce_max_sync(0xffffffffu, zm);
+                if (lane == 0) redi[w] = zm;
+                side_barrier();
+                for (int x = 0; x < W; ++x) zm = max(zm, redi[x]);
+                feasible = zm > kVoidETest;
+                double sm = 0.0;
+#pragma unroll
+                for (int c = 0; c < 4 * J; ++c)
+                    sm += (double)(z[c].m * __int_as_float((max(z[c].e - zm, -127) + 127) << 23));
+#pragma unroll
+                for (int o = 16; o; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                if (lane == 0) redd[w] = sm;
+                side_barrier();
+                sm = 0.0;
+                for (int x = 0; x < W; ++x) sm += redd[x];
+                const int ex = feasible ? ilogb(sm) : 0;
+                rZ = feasible ? (float)(1.0 / scalbn(sm, -ex)) : 1.0f;
+                rZp = rZ * pm;
+                eZ = feasible ? zm + ex : (1 << 29);
+                logZ2 = feasible ? (double)zm + log2(sm) : 0.0;
             }
-            mx = warp_max_d(mx);
-            if (lane == 0) redm[w] = mx;
-            named_bar_sync(barid, nthr);
-            for (int x = 0; x < W; ++x) mx = fmax(mx, redm[x]);
-            feasible = mx > (double)kVoidTest;
-            float sm = 0.0f;
+            float bsum = 0.0f, gsum = 0.0f;
+            if (live) {
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                float a, b, c, d, e, f, gg, h;
-                expo(j, a, b, c, d, e, f, gg, h);
-                sm += ex2f((float)((double)a + (double)b - mx)) + ex2f((float)((double)c + (double)d - mx)) +
-                      ex2f((float)((double)e + (double)f - mx)) + ex2f((float)((double)gg + (double)h - mx));
+                for (int j = 0; j < J; ++j) {
+                    const int k = k0 + 32 * j;
+                    const bool in = (hasq >> j) & 1u;
+                    const int4 o = in ? orow[32 * j] : make_int4((int)kPackVoid, (int)kPackVoid, (int)kPackVoid, (int)kPackVoid);
+                    const int xb = (in ? obase[j] : kVoidE) - eZ;
+                    const float g0 = xf_scale(s0[j].m * xf_unpack_m(o.x) * rZ, max(s0[j].e + xb - xf_unpack_below(o.x), -126));
+                    const float g1 = xf_scale(s1[j].m * xf_unpack_m(o.z) * rZ, max(s1[j].e + xb - xf_unpack_below(o.z), -126));
+                    float gl = xf_scale(sl[j].m * xf_unpack_m(o.w) * rZ, max(sl[j].e + xb - xf_unpack_below(o.w), -126));
+                    // h = gamma(star) / (P - p_y): both sides' pre-emission sums, the penalty, and the row shift
+                    // taken back out (the shift cancels in gamma, not in P - p_y)
+                    const float h = xf_scale(ss[j].m * xf_unpack_m(o.y) * rZp,
+                                             max(ss[j].e + xb - xf_unpack_below(o.y) + (pe - cti), -126));
+                    if (!((hasl >> j) & 1u)) gl = 0.0f;
+                    bsum += g0 + g1;
+                    gsum += h;
+                    if (k < Ks) ((float2*)ob)[k] = make_float2(gl, ((exclude >> j) & 1u) ? h : 0.0f);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int k = k0 + 32 * j;
+                    if (k < Ks) ((float2*)ob)[k] = make_float2(0.0f, 0.0f);
+                }
             }
-            sm = warp_sum(sm);
-            if (lane == 0) reds[w] = sm;
-            named_bar_sync(barid, nthr);
-            sm = 0.0f;
-            for (int x = 0; x < W; ++x) sm += reds[x];
-            const double logZ2 = mx + (double)log2f(sm);
-            const double fl2 = floor(logZ2);
-            IZ = feasible ? (float)fl2 : 0.0f;
-            fZ = feasible ? (float)(logZ2 - fl2) : 0.0f;
+            ps[0] = bsum; ps[32] = gsum;     // per-lane partial sums; the producer warp reduces them into floats [1], [2]
+            if (i == i0 + cnt - 1) fence_async_smem();
+            side_barrier();
         }
-        float* ob = (float*)stg + G * (E + SPX) + ridx * OC;
-        float* ps = (float*)stg + G * (E + SPX) + G * OC;
-        float bsum = 0.0f, gsum = 0.0f;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const int k = k0 + 32 * j;
-            float xi0, xf0, xis, xfs, xi1, xf1, xil, xfl;
-            expo(j, xi0, xf0, xis, xfs, xi1, xf1, xil, xfl);
-            const float g0 = feasible ? ex2f((xi0 - IZ) + (xf0 - fZ)) : 0.0f;
-            const float g1 = feasible ? ex2f((xi1 - IZ) + (xf1 - fZ)) : 0.0f;
-            const float gl = feasible ? ex2f((xil - IZ) + (xfl - fZ)) : 0.0f;
-            // h = gamma(star) / (P - p_y) = 2^(log2 gamma - es), es = the star's TRUE emission: without the
-            // penalty and with the row shift added back (the shift cancels in gamma, not in P - p_y)
-            const float h = (feasible && ((hasq >> j) & 1u))
-                                ? ex2f(((xis - IZ) - ((Ks_[j] - Kp) + ct)) + ((xfs - fZ) - (fs[j] - fp))) : 0.0f;
-            bsum += g0 + g1;
-            gsum += h;
-            if (k < Ks) ((float2*)(ob + 4))[k] = make_float2(gl, ((exclude >> j) & 1u) ? h : 0.0f);
-        }
-        bsum = warp_sum(bsum);
-        gsum = warp_sum(gsum);
-        if (lane == 0) { ps[(ridx * W + w) * 2] = bsum; ps[(ridx * W + w) * 2 + 1] = gsum; }
-        if (g == cnt - 1) fence_async_smem();
-        step_end();
+        named_bar_arrive(kEmptyBarrier + 4 * dir + s, nthr + 32);
+        if (++s == nstage) { s = 0; fpar ^= 1u; }
     }
     if (dir == 0 && leader) {
-        const float v = feasible ? (float)(-((double)IZ + (double)fZ + (double)csum) * kLn2) : CUDART_INF_F;
+        const float v = feasible ? (float)(-(logZ2 + (double)csum) * kLn2) : CUDART_INF_F;
         p.loss[n] = v; p.loss_ws[n] = v;
     }
 }
