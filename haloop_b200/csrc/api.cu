@@ -381,7 +381,7 @@ int ha_rnnt_fwd(const float* joint, int N, int T, int U1, int V,
     RnntRowsParams rp{};
     rp.x = joint; rp.N = N; rp.T = T; rp.U1 = U1; rp.V = V;
     rp.meta = pp.meta; rp.tgt = pp.tgt; rp.Up = w.Up;
-    rp.lse2 = (float*)(base + w.lse2); rp.bl = (float*)(base + w.bl); rp.lb = (float*)(base + w.lb); rp.D = w.D;
+    rp.lse2 = (float*)(base + w.lse2); rp.bl = (float2*)(base + w.bl); rp.lb = (float2*)(base + w.lb); rp.D = w.D;
     rp.from_logits = from_logits;
     const bool vec = (V % 4 == 0) && aligned16(joint);
     rp.use_bulk = vec ? 1 : 0;
@@ -406,7 +406,11 @@ int ha_rnnt_fwd(const float* joint, int N, int T, int U1, int V,
     lp.N = N; lp.T = T; lp.U1 = U1; lp.D = w.D; lp.meta = pp.meta;
     lp.bl = rp.bl; lp.lb = rp.lb; lp.alpha = (double*)(base + w.alpha); lp.beta = (double*)(base + w.beta); lp.occ = (float2*)(base + w.occ);
     lp.loss = loss; lp.loss_ws = (float*)(base + w.loss);
-    rnnt_lattice_kernel<<<N, round_up(U1, 32) * (round_up(U1, 32) <= 512 ? 2 : 1), 0, st>>>(lp);
+    {
+        const int half = round_up(U1, 32), nthreads = half * (half <= 512 ? 2 : 1);
+        if (nthreads <= 256) rnnt_lattice_kernel<256><<<N, nthreads, 0, st>>>(lp);
+        else rnnt_lattice_kernel<1024><<<N, nthreads, 0, st>>>(lp);
+    }
     return check_launch("rnnt_lattice_kernel");
 }
 

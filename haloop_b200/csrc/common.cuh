@@ -159,6 +159,18 @@ __device__ __forceinline__ XF xf_mul_norm(XF s, float p) {
     const int rb = __float_as_int(s.m * p);
     return xf_make(__int_as_float((rb & 0x007fffff) | 0x3f800000), s.e + (rb >> 23) - 127);
 }
+// 2^f for |f| <= 0.5: degree-7 polynomial on the FP32 pipe, relative error ~1e-7
+__device__ __forceinline__ float exp2_poly(float f) {
+    float r = 1.5252733804059841e-05f;
+    r = fmaf(r, f, 1.5403530393381608e-04f);
+    r = fmaf(r, f, 1.3333558146428443e-03f);
+    r = fmaf(r, f, 9.618129107628477e-03f);
+    r = fmaf(r, f, 5.550410866482158e-02f);
+    r = fmaf(r, f, 2.402265069591007e-01f);
+    r = fmaf(r, f, 6.931471805599453e-01f);
+    return fmaf(r, f, 1.0f);
+}
+
 // stored trellis word: [12 bits: exponent distance below the slot base, saturating][20 mantissa bits]
 constexpr unsigned kPackVoid = 0xfff00000u;
 __device__ __forceinline__ int xf_pack(float m, int below) {     // m in [1,2), below >= 0

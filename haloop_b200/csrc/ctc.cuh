@@ -30,19 +30,11 @@ struct CtcWs {                 // workspace layout (byte offsets), filled by ctc
 // the linear domain on extended-range numbers (common.cuh, XF).  The occupancy row written in place:
 // [1] blank occupancy, [4+k] label occupancy.
 __host__ __device__ inline int ctc_em_floats(int Sp) { return 4 + Sp; }
-// 2^(K + f) for an integer-valued K in [-127, 1] and |f| <= 0.5: degree-7 polynomial (relative error
-// ~1e-7, no MUFU), exponent added into the bit pattern
+// 2^(K + f) for an integer-valued K in [-127, 1] and |f| <= 0.5 (exp2_poly: relative error ~1e-7, no
+// MUFU), exponent added into the bit pattern
 __device__ __forceinline__ float emission_linear(float K, float f) {
-    float r = 1.5252733804059841e-05f;
-    r = fmaf(r, f, 1.5403530393381608e-04f);
-    r = fmaf(r, f, 1.3333558146428443e-03f);
-    r = fmaf(r, f, 9.618129107628477e-03f);
-    r = fmaf(r, f, 5.550410866482158e-02f);
-    r = fmaf(r, f, 2.402265069591007e-01f);
-    r = fmaf(r, f, 6.931471805599453e-01f);
-    r = fmaf(r, f, 1.0f);
     const int k = __float2int_rn(K);
-    return (k < -125) ? 1.1754943508222875e-38f : xf_scale(r, k);
+    return (k < -125) ? 1.1754943508222875e-38f : xf_scale(exp2_poly(f), k);
 }
 // star-CTC emission words (star.cuh): Q8.24 fixed-point value of log2 p - ct
 __device__ __forceinline__ int emission_word(float K, float f) {

@@ -5,10 +5,10 @@
 //   rnnt_prep_kernel     lengths/targets -> int32 metadata
 //   rnnt_rows_kernel     one warp per lattice node (n,t,u): row log-sum-exp + the blank and label
 //                        log-probs, written in a diagonal-major ("skewed") layout
-//   rnnt_lattice_kernel  one CTA per utterance, one thread per u: alpha swept along anti-diagonals,
-//                        then beta swept back with the arc occupancies produced on the fly; float64
-//                        accumulators with fp32 MUFU for the log1p(exp) correction (the lattice is
-//                        ~V times smaller than the joint, so this costs nothing)
+//   rnnt_lattice_kernel  one CTA per utterance, one thread per u: alpha and beta swept along the
+//                        anti-diagonals concurrently (two halves of the CTA) in the linear domain on
+//                        extended-range numbers (fp32 mantissa + int32 exponent), then one parallel
+//                        arc-occupancy pass
 //   rnnt_grad_kernel     one warp per node: softmax * occ_node - occ_blank - occ_label, in place in
 //                        shared memory between a bulk load and a bulk store
 //   rnnt_zero_kernel     zero gradient rows of padded nodes (t >= T_n or u > U_n)
@@ -32,8 +32,8 @@ __host__ inline RnntWs rnnt_ws_layout(int N, int T, int U1) {
     w.tgt = take(sizeof(int) * (size_t)N * w.Up);
     w.loss = take(sizeof(float) * (size_t)N);
     w.lse2 = take(sizeof(float) * (size_t)N * T * U1);          // row-major (t,u)
-    w.bl = take(sizeof(float) * (size_t)N * w.D * U1);          // skewed (t+u, u)
-    w.lb = take(sizeof(float) * (size_t)N * w.D * U1);
+    w.bl = take(sizeof(float2) * (size_t)N * w.D * U1);         // skewed (t+u, u); probability = x * 2^(int)y
+    w.lb = take(sizeof(float2) * (size_t)N * w.D * U1);
     w.alpha = take(sizeof(double) * (size_t)N * w.D * U1);
     w.beta = take(sizeof(double) * (size_t)N * w.D * U1);
     w.occ = take(sizeof(float2) * (size_t)N * w.D * U1);        // (occ_blank, occ_label), skewed
@@ -70,9 +70,16 @@ struct RnntRowsParams {
     const float* x;            // (N,T,U1,V) contiguous
     int N, T, U1, V;
     const int4* meta; const int* tgt; int Up;
-    float* lse2; float* bl; float* lb; int D;
+    float* lse2; float2* bl; float2* lb; int D;
     int from_logits, use_bulk, rows_per_warp, nstage, nwarps;
 };
+
+// 2^x for an fp32 log2-probability x = pm * 2^K, pm in [0.707, 1.415], as (pm, bits of K)
+__device__ __forceinline__ float2 log2_to_parts(float x) {
+    const bool tiny = !(x > -1.0e6f);
+    const float k = rintf(tiny ? 0.0f : x);
+    return make_float2(tiny ? 1.0f : exp2_poly(x - k), __int_as_float(tiny ? -(1 << 24) : (int)k));
+}
 
 __host__ __device__ inline size_t rnnt_rows_smem_bytes(int V, int nstage, int nwarps) {
     return round_up_sz((size_t)nwarps * nstage * 8, 128) + (size_t)nwarps * nstage * V * 4;
@@ -154,11 +161,11 @@ __global__ void __launch_bounds__(256) rnnt_rows_kernel(RnntRowsParams p) {
             s = warp_sum(s);
             l2 = m2 + log2f(s);
         }
-        if (lane == 0) {
+        if (lane < 2) {     // lane 0: blank, lane 1: label
             const size_t sk = ((size_t)n * p.D + (t + u)) * p.U1 + u;
-            p.lse2[((size_t)n * p.T + t) * p.U1 + u] = l2;
-            p.bl[sk] = fmaf(row[0], kLog2e, -l2);
-            p.lb[sk] = (u < W - 1) ? fmaf(row[y[u]], kLog2e, -l2) : kVoid;
+            if (lane == 0) p.lse2[((size_t)n * p.T + t) * p.U1 + u] = l2;
+            const float v = lane ? ((u < W - 1) ? fmaf(row[y[u < W - 1 ? u : 0]], kLog2e, -l2) : kVoid) : fmaf(row[0], kLog2e, -l2);
+            (lane ? p.lb : p.bl)[sk] = log2_to_parts(v);
         }
         __syncwarp();
         if (r + nstage < nrows) issue(r + nstage);
@@ -169,28 +176,37 @@ __global__ void __launch_bounds__(256) rnnt_rows_kernel(RnntRowsParams p) {
 struct RnntLatticeParams {
     int N, T, U1, D;
     const int4* meta;
-    const float* bl; const float* lb;
+    const float2* bl; const float2* lb;
     double* alpha; double* beta; float2* occ;
     float* loss; float* loss_ws;
 };
 
-// log2(2^a + 2^b) with float64 accumulators; only the [0,1] correction term is fp32
-__device__ __forceinline__ double lae2_d(double a, double b) {
-    const double m = fmax(a, b);
-    const float d = (float)(fmin(a, b) - m);
-    return m + (double)lg2f(1.0f + ex2f(d));
-}
+// Lattice values are extended-range linear numbers (common.cuh, XF: fp32 mantissa in [1, 2) + int32
+// exponent).  alpha/beta are sums of products of probabilities, so the recursion is one aligned FADD and
+// one FMUL per arc (no log-add-exp); every rounding is 6e-8 relative whatever the magnitude.
 
-constexpr double kVoidD = -1.0e30;
+__device__ __forceinline__ XF xf_mul_parts(XF a, float2 p) {       // p = (mantissa, exponent bits), rnnt_rows_kernel
+    XF r = xf_mul_norm(a, p.x);
+    r.e += __float_as_int(p.y);
+    return r;
+}
+__device__ __forceinline__ XF xf_normalise(XF a) {
+    const int bits = __float_as_int(a.m);
+    return xf_make(__int_as_float((bits & 0x007fffff) | 0x3f800000), a.e + (bits >> 23) - 127);
+}
 
 // grid N, block sides * round_up(U1, 32).  Thread u of a side owns column u; on anti-diagonal d it is
 // at t = d - u.  With sides == 2 the alpha sweep (threads [0, half)) and the beta sweep (threads
 // [half, 2 half)) run concurrently, each behind its own named barrier; with sides == 1 (U+1 > 512)
 // the same threads run them one after the other.  Arc occupancies are then one parallel pass.
-//   alpha[t,u] = (alpha[t-1,u] + blank[t-1,u]) (+) (alpha[t,u-1] + label[t,u-1])   ha/transducer.py:197-202
-__global__ void __launch_bounds__(1024) rnnt_lattice_kernel(RnntLatticeParams p) {
-    __shared__ double s_edge[2][2][32];     // [side][diagonal parity][warp]
-    __shared__ double s_logz;
+//   alpha[t,u] = alpha[t-1,u] blank[t-1,u] + alpha[t,u-1] label[t,u-1]        ha/transducer.py:197-202
+// Each thread forms the two outgoing arc products of its node right away (the one along u travels to
+// lane u+1 by shuffle), and reads and decodes its node's emissions kPre diagonals ahead.
+constexpr int kPre = 8;
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) rnnt_lattice_kernel(RnntLatticeParams p) {
+    __shared__ int2 s_edge[2][2][32];       // [side][diagonal parity][warp]
+    __shared__ int2 s_z;
     const int n = blockIdx.x;
     const int U1 = p.U1;
     const int half = round_up(U1, 32);
@@ -200,91 +216,159 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(RnntLatticeParams p)
     const int4 mt = p.meta[n];
     const int Tn = mt.x, Un = mt.y;
     if (mt.z) { if (threadIdx.x == 0) { p.loss[n] = CUDART_NAN_F; p.loss_ws[n] = CUDART_NAN_F; } return; }
-    const float* bl = p.bl + (size_t)n * p.D * U1;
-    const float* lb = p.lb + (size_t)n * p.D * U1;
-    double* al = p.alpha + (size_t)n * p.D * U1;
-    double* be = p.beta + (size_t)n * p.D * U1;
-    float2* occ = p.occ + (size_t)n * p.D * U1;
+    const float2* __restrict__ bl = p.bl + (size_t)n * p.D * U1;
+    const float2* __restrict__ lb = p.lb + (size_t)n * p.D * U1;
+    int2* __restrict__ al = (int2*)(p.alpha + (size_t)n * p.D * U1);
+    int2* __restrict__ be = (int2*)(p.beta + (size_t)n * p.D * U1);
+    float2* __restrict__ occ = p.occ + (size_t)n * p.D * U1;
     const int nd = Tn + Un;                 // diagonals 0 .. nd-1
     const bool col = u <= Un;
+    const XF vd = xf_make(1.0f, kVoidE);
+    const int2 vd2 = make_int2(__float_as_int(1.0f), kVoidE);
+    const float2 one2 = make_float2(1.0f, 0.0f);
+    auto pack = [](XF a) { return make_int2(__float_as_int(a.m), a.e); };
+    // Both sweeps run whole blocks of kPre diagonals: the steps past the last diagonal are no-ops (no node
+    // is valid there), which keeps the per-step code free of bounds branches.
 
     if (side == 0) {
-        // ---- alpha, forward over diagonals; emissions of the next diagonal are fetched a step ahead
-        double a = kVoidD;                  // alpha of my node on the previous diagonal
-        float nbl = 0.0f, nlb = 0.0f;       // blank[t-1,u], label[t,u-1] for the coming diagonal
-        for (int d = 0; d < nd; ++d) {
-            const int t = d - u;
-            const float cbl = nbl, clb = nlb;
-            if (d + 1 < nd && col) {
-                nbl = bl[(size_t)d * U1 + u];
-                nlb = (u >= 1) ? lb[(size_t)d * U1 + u - 1] : 0.0f;
-            }
-            double left = __shfl_up_sync(0xffffffffu, a, 1);       // alpha[t, u-1]
-            if (lane == 0) left = (warp > 0) ? s_edge[0][(d + 1) & 1][warp - 1] : kVoidD;
-            double cur = kVoidD;
-            if (col && t >= 0 && t < Tn) {
-                if (d == 0) cur = 0.0;      // alpha[0,0]
-                else {
-                    const double up = (t >= 1) ? a + (double)cbl : kVoidD;
-                    const double lf = (u >= 1) ? left + (double)clb : kVoidD;
-                    cur = lae2_d(lf, up);
-                }
-                al[(size_t)d * U1 + u] = cur;
-            }
-            a = cur;
-            if (lane == 31) s_edge[0][d & 1][warp] = a;
-            named_bar_sync(1, half);
+        // ---- alpha, forward over diagonals
+        XF ob = vd, ol = vd;                // my previous node times its blank / label emission
+        float2 fb[kPre], fl[kPre];          // emissions of my node on diagonals d .. d+kPre-1
+        const float2* pb = bl + u;          // -> diagonal d + kPre
+        const float2* pl = lb + u;
+        int2* pa = al + u;                  // -> diagonal d
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const bool in = col && k < nd;
+            fb[k] = in ? pb[0] : one2;
+            fl[k] = in ? pl[0] : one2;
+            pb += U1; pl += U1;
         }
-        // log Z = alpha[T-1,U] + blank[T-1,U]                                  ha/transducer.py:204-205
-        if (u == Un) s_logz = a + (double)bl[(size_t)(nd - 1) * U1 + Un];
+        const int2* ein = &s_edge[0][0][warp > 0 ? warp - 1 : 0];
+        int2* eout = &s_edge[0][0][warp];
+        for (int d0 = 0; d0 < nd; d0 += kPre) {
+#pragma unroll
+            for (int k = 0; k < kPre; ++k) {
+                const int d = d0 + k;
+                const float2 cb = fb[k], cl = fl[k];
+                {
+                    const bool in = col && d + kPre < nd;
+                    fb[k] = in ? pb[0] : one2;
+                    fl[k] = in ? pl[0] : one2;
+                    pb += U1; pl += U1;
+                }
+                float xm = __shfl_up_sync(0xffffffffu, ol.m, 1);           // alpha[t, u-1] label[t, u-1]
+                int xe = __shfl_up_sync(0xffffffffu, ol.e, 1);
+                {
+                    const int2 in = ein[((d + 1) & 1) * 32];
+                    if (lane == 0) { xm = (warp > 0) ? __int_as_float(in.x) : 1.0f; xe = (warp > 0) ? in.y : kVoidE; }
+                }
+                const bool valid = col && (unsigned)(d - u) < (unsigned)Tn;
+                XF cur = (d == 0) ? xf_make(1.0f, 0) : xf_normalise(xf_add(ob, xf_make(xm, xe)));   // alpha[0,0] = 1
+                if (valid) *pa = pack(cur);
+                pa += U1;
+                ob = valid ? xf_mul_parts(cur, cb) : vd;
+                ol = (valid && u < Un) ? xf_mul_parts(cur, cl) : vd;
+                if (lane == 31) eout[(d & 1) * 32] = pack(ol);
+                // Z = alpha[T-1,U] blank[T-1,U]                                  ha/transducer.py:204-205
+                if (d == nd - 1 && u == Un) s_z = pack(ob);
+                named_bar_sync(1, half);
+            }
+        }
     }
     if (side == sides - 1) {
         // ---- beta, backward over diagonals
-        double b = kVoidD;                  // beta[t+1,u]: my node on the next diagonal
-        float nbl = 0.0f, nlb = 0.0f;
-        if (col && nd >= 1) { nbl = bl[(size_t)(nd - 1) * U1 + u]; nlb = lb[(size_t)(nd - 1) * U1 + u]; }
-        for (int d = nd - 1; d >= 0; --d) {
-            const int t = d - u;
-            const float cbl = nbl, clb = nlb;
-            if (d >= 1 && col) { nbl = bl[(size_t)(d - 1) * U1 + u]; nlb = lb[(size_t)(d - 1) * U1 + u]; }
-            double right = __shfl_down_sync(0xffffffffu, b, 1);    // beta[t, u+1]
-            if (lane == 31) right = (warp + 1 < nwarp) ? s_edge[1][(d + 1) & 1][warp + 1] : kVoidD;
-            double cur = kVoidD;
-            if (col && t >= 0 && t < Tn) {
-                double tb, tl;
-                if (t == Tn - 1) tb = (u == Un) ? (double)cbl : kVoidD;   // only the terminal blank leaves the last frame
-                else tb = b + (double)cbl;
-                tl = (u < Un) ? right + (double)clb : kVoidD;
-                cur = lae2_d(tb, tl);
-                be[(size_t)d * U1 + u] = cur;
+        XF b = vd;                          // beta[t+1,u]: my node on the next diagonal
+        float2 fb[kPre], fl[kPre];
+        const float2* pb = bl + (size_t)(nd - 1) * U1 + u;     // -> diagonal d - kPre
+        const float2* pl = lb + (size_t)(nd - 1) * U1 + u;
+        int2* pe = be + (size_t)(nd - 1) * U1 + u;             // -> diagonal d
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const bool in = col && nd - 1 - k >= 0;
+            fb[k] = in ? pb[0] : one2;
+            fl[k] = in ? pl[0] : one2;
+            pb -= U1; pl -= U1;
+        }
+        const int2* ein = &s_edge[1][0][warp + 1 < nwarp ? warp + 1 : warp];
+        int2* eout = &s_edge[1][0][warp];
+        for (int d0 = nd - 1; d0 >= 0; d0 -= kPre) {
+#pragma unroll
+            for (int k = 0; k < kPre; ++k) {
+                const int d = d0 - k;
+                const int t = d - u;
+                const float2 cb = fb[k], cl = fl[k];
+                {
+                    const bool in = col && d - kPre >= 0;
+                    fb[k] = in ? pb[0] : one2;
+                    fl[k] = in ? pl[0] : one2;
+                    pb -= U1; pl -= U1;
+                }
+                float xm = __shfl_down_sync(0xffffffffu, b.m, 1);          // beta[t, u+1]
+                int xe = __shfl_down_sync(0xffffffffu, b.e, 1);
+                {
+                    const int2 in = ein[((d + 1) & 1) * 32];
+                    if (lane == 31) { xm = (warp + 1 < nwarp) ? __int_as_float(in.x) : 1.0f; xe = (warp + 1 < nwarp) ? in.y : kVoidE; }
+                }
+                const bool valid = col && (unsigned)t < (unsigned)Tn;
+                // only the terminal blank leaves the last frame
+                const bool lastf = t == Tn - 1;
+                const XF bsrc = lastf ? xf_make(1.0f, (u == Un) ? 0 : kVoidE) : b;
+                const XF tb = xf_mul_parts(bsrc, cb);
+                const XF tl = xf_mul_parts(xf_make(xm, (u < Un) ? xe : kVoidE), cl);
+                const XF sum = xf_normalise(xf_add(tb, tl));
+                const XF cur = valid ? sum : vd;
+                if (valid) *pe = pack(cur);
+                pe -= U1;
+                b = cur;
+                if (lane == 0) eout[(d & 1) * 32] = pack(b);
+                named_bar_sync(2, half);
             }
-            b = cur;
-            if (lane == 0) s_edge[1][d & 1][warp] = b;
-            named_bar_sync(2, half);
         }
     }
     __syncthreads();
-    const double logz = s_logz;
-    const bool feasible = logz > -1.0e29;
+    const float zm = __int_as_float(s_z.x);
+    const int ze = s_z.y;
+    const bool feasible = ze > kVoidETest;
     if (threadIdx.x == 0) {
-        const float v = feasible ? (float)(-logz * kLn2) : CUDART_INF_F;
+        const float v = feasible ? (float)(-((double)ze + log2((double)zm)) * kLn2) : CUDART_INF_F;
         p.loss[n] = v; p.loss_ws[n] = v;
     }
-    // ---- arc occupancies: occ_blank = alpha + blank + beta[t+1,u] - logZ, occ_label = alpha + label + beta[t,u+1] - logZ
-    for (int k = threadIdx.x; k < nd * U1; k += blockDim.x) {
-        const int d = k / U1, uu = k - d * U1, t = d - uu;
-        if (uu > Un || t < 0 || t >= Tn) continue;
-        float2 o = make_float2(0.0f, 0.0f);
-        if (feasible) {
-            const double base = al[k] - logz;
-            double tb, tl;
-            if (t == Tn - 1) tb = (uu == Un) ? (double)bl[k] : kVoidD;
-            else tb = be[(size_t)(d + 1) * U1 + uu] + (double)bl[k];
-            tl = (uu < Un) ? be[(size_t)(d + 1) * U1 + uu + 1] + (double)lb[k] : kVoidD;
-            o.x = ex2f((float)fmax(base + tb, -200.0));
-            o.y = ex2f((float)fmax(base + tl, -200.0));
+    // ---- arc occupancies: occ_blank = alpha blank beta[t+1,u] / Z, occ_label = alpha label beta[t,u+1] / Z
+    const float rz = 1.0f / zm;
+    auto arc = [&](int2 a, int2 b2, float2 x) {
+        const float m = __int_as_float(a.x) * __int_as_float(b2.x) * x.x * rz;         // < 6
+        const int ex = min(max(a.y + b2.y + __float_as_int(x.y) - ze, -127), 2);
+        return m * __int_as_float((ex + 127) << 23);
+    };
+    // four nodes per thread and pass: all loads first, so that their latencies overlap
+    const int total = nd * U1;
+    for (int k0 = threadIdx.x; k0 < total; k0 += 4 * blockDim.x) {
+        int2 a[4], b0[4], b1[4]; float2 xb[4], xl[4]; int flag[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + q * blockDim.x;
+            const int d = k / U1, uu = k - d * U1, t = d - uu;
+            const bool in = k < total && uu <= Un && t >= 0 && t < Tn;
+            const bool hb = in && t < Tn - 1, hl = in && uu < Un;
+            flag[q] = (in ? 1 : 0) | (hb ? 2 : 0) | (hl ? 4 : 0) | ((in && t == Tn - 1 && uu == Un) ? 8 : 0);
+            const int2 one = make_int2(__float_as_int(1.0f), 0);
+            a[q] = in ? al[k] : one;
+            xb[q] = in ? bl[k] : make_float2(1.0f, 0.0f);
+            xl[q] = hl ? lb[k] : make_float2(1.0f, 0.0f);
+            b0[q] = hb ? be[(size_t)(d + 1) * U1 + uu] : one;
+            b1[q] = hl ? be[(size_t)(d + 1) * U1 + uu + 1] : one;
         }
-        occ[k] = o;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (!(flag[q] & 1)) continue;
+            float2 o = make_float2(0.0f, 0.0f);
+            if (feasible) {
+                if (flag[q] & (2 | 8)) o.x = arc(a[q], b0[q], xb[q]);     // terminal blank: b0 = 1
+                if (flag[q] & 4) o.y = arc(a[q], b1[q], xl[q]);
+            }
+            occ[k0 + q * blockDim.x] = o;
+        }
     }
 }
 
