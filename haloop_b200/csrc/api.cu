@@ -144,7 +144,7 @@ int ha_ctc_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
     pp.T = T; pp.N = N; pp.V = V; pp.S = S; pp.Sp = w.Sp;
     pp.meta = (int4*)(base + w.meta); pp.order = (int*)(base + w.order);
     pp.tgt = (int*)(base + w.tgt); pp.dupnext = (int*)(base + w.dupnext); pp.star = 0;
-    ctc_prep_kernel<<<N, 128, (size_t)(S > 0 ? S : 1) * 4, st>>>(pp);
+    ctc_prep_kernel<<<N, 256, (size_t)round_up(S > 0 ? S : 1, 4) * 4, st>>>(pp);
     if ((rc = check_launch("ctc_prep_kernel"))) return rc;
 
     RowsParams rp{};
@@ -280,7 +280,7 @@ int ha_star_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
     pp.T = T; pp.N = N; pp.V = V; pp.S = S; pp.Sp = w.Sp;
     pp.meta = (int4*)(base + w.meta); pp.order = (int*)(base + w.order);
     pp.tgt = (int*)(base + w.tgt); pp.dupnext = (int*)(base + w.dupnext); pp.star = 1;
-    ctc_prep_kernel<<<N, 128, (size_t)(S > 0 ? S : 1) * 4, st>>>(pp);
+    ctc_prep_kernel<<<N, 256, (size_t)round_up(S > 0 ? S : 1, 4) * 4, st>>>(pp);
     if ((rc = check_launch("ctc_prep_kernel"))) return rc;
 
     StarRowsParams rp{};
@@ -492,7 +492,7 @@ int ha_ctc_viterbi(const float* lp, int64_t sx_t, int64_t sx_n, int T, int N, in
     pp.T = T; pp.N = N; pp.V = V; pp.S = S; pp.Sp = w.Sp;
     pp.meta = (int4*)(base + w.meta); pp.order = (int*)(base + w.order);
     pp.tgt = (int*)(base + w.tgt); pp.dupnext = (int*)(base + w.dupnext); pp.star = 0;
-    ctc_prep_kernel<<<N, 128, (size_t)(S > 0 ? S : 1) * 4, st>>>(pp);
+    ctc_prep_kernel<<<N, 256, (size_t)round_up(S > 0 ? S : 1, 4) * 4, st>>>(pp);
     if ((rc = check_launch("ctc_prep_kernel"))) return rc;
     ViterbiParams vp{};
     vp.lp = lp; vp.sx_t = sx_t; vp.sx_n = sx_n; vp.T = T; vp.N = N; vp.V = V; vp.S_ = w.S_;

@@ -75,9 +75,9 @@ struct PrepParams {
     int star;   // duplicate chains also cover position L_n (< S): star-CTC's last star reads targets[n, L_n]
 };
 
-// grid N, block 128.  meta[n] = {T_n, L_n, invalid, number of adjacent equal labels}.
-__global__ void __launch_bounds__(128) ctc_prep_kernel(PrepParams p) {
-    extern __shared__ int s_y[];
+// grid N, block 256.  meta[n] = {T_n, L_n, invalid, number of adjacent equal labels}.
+__global__ void __launch_bounds__(256) ctc_prep_kernel(PrepParams p) {
+    extern __shared__ __align__(16) int s_y[];
     __shared__ int s_bad, s_rank, s_rep;
     const int n = blockIdx.x;
     long long Tn = load_idx(p.in_len, n, p.len64), Ln = load_idx(p.tgt_len, n, p.len64);
@@ -91,15 +91,33 @@ __global__ void __launch_bounds__(128) ctc_prep_kernel(PrepParams p) {
         s_y[k] = (int)y;
     }
     __syncthreads();
+    // duplicate-label chains: for position k the next position holding the same label, and whether an
+    // earlier one does.  One branch-free scan of all positions per k (vector loads, no dependent exits):
+    // L^2 / 4 shared-memory loads per utterance, issue-bound instead of latency-bound.
+    const int Lc = p.star ? min(L + 1, p.S) : L;
+    const int Lc4 = (Lc + 3) & ~3;
+    for (int k = p.S + threadIdx.x; k < p.Sp; k += blockDim.x) s_y[k] = -1;   // s_y has Sp = round_up(S, 4) entries
+    __syncthreads();
     for (int k = threadIdx.x; k < p.S; k += blockDim.x) {
-        int y = s_y[k], nxt = -1, notfirst = 0;
-        const int Lc = p.star ? min(L + 1, p.S) : L;
+        const int y = s_y[k];
+        int nxt = 0x7fffffff, notfirst = 0;
         if (k < Lc) {
-            for (int j = k + 1; j < Lc; ++j) if (s_y[j] == y) { nxt = j; break; }
-            for (int j = 0; j < k; ++j) if (s_y[j] == y) { notfirst = 1; break; }
+            const int4* y4 = (const int4*)s_y;
+#pragma unroll 4
+            for (int j4 = 0; j4 < (Lc4 >> 2); ++j4) {
+                const int4 v = y4[j4];
+                const int j = 4 * j4;
+                const int m0 = (v.x == y) & (j < Lc), m1 = (v.y == y) & (j + 1 < Lc);
+                const int m2 = (v.z == y) & (j + 2 < Lc), m3 = (v.w == y) & (j + 3 < Lc);
+                notfirst |= (m0 & (j < k)) | (m1 & (j + 1 < k)) | (m2 & (j + 2 < k)) | (m3 & (j + 3 < k));
+                nxt = min(nxt, (m0 && j > k) ? j : 0x7fffffff);
+                nxt = min(nxt, (m1 && j + 1 > k) ? j + 1 : 0x7fffffff);
+                nxt = min(nxt, (m2 && j + 2 > k) ? j + 2 : 0x7fffffff);
+                nxt = min(nxt, (m3 && j + 3 > k) ? j + 3 : 0x7fffffff);
+            }
         }
         p.tgt[(size_t)n * p.Sp + k] = y | (notfirst ? kNotFirst : 0);
-        p.dupnext[(size_t)n * p.Sp + k] = nxt;
+        p.dupnext[(size_t)n * p.Sp + k] = (nxt == 0x7fffffff) ? -1 : nxt;
         if (k >= 1 && k < L && s_y[k - 1] == y) atomicAdd(&s_rep, 1);
     }
     __syncthreads();

@@ -151,31 +151,24 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
             K = Kt - ct;
             f = (s1 - Kt) + (err + vl);
         };
+        float Ka, fa;
+        split2(fmaxf(lPh, kVoid), lPl, Ka, fa);
+        const float Plin = emission_linear(Ka, fa);              // all-star: P_t
         if (lane == 0) {
             p.lse2[(size_t)n * p.T + t] = l2;
-            float Kb, fb, Ka, fa;
+            float Kb, fb;
             emission_split(row[0], l2, ct, Kb, fb);
-            split2(fmaxf(lPh, kVoid), lPl, Ka, fa);
-            *(float4*)erow = make_float4(ct, emission_linear(Kb, fb), emission_linear(Ka, fa),
-                                         __int_as_float(__float2int_rn(ct)));
+            *(float4*)erow = make_float4(ct, emission_linear(Kb, fb), Plin, __int_as_float(__float2int_rn(ct)));
         }
         for (int k = lane; k < Ks; k += 32) {
             const int y = s_tgt[k];
-            float Kl, fl, Ks2, fs2;
+            float Kl, fl;
             emission_split(row[y], l2, ct, Kl, fl);
-            float add = 0.0f;
-            if (y != 0) {
-                // logsubexp (ha/star.py:4-5): log2 P + log2(1 - 2^(lab - log2 P)), via expm1 so that a
-                // label holding almost all of P does not cancel
-                const float d = fminf(fmaf(row[y], kLog2e, -lPh), 0.0f);   // lab - log2 P (l2 cancels)
-                add = fmaxf(log2f(-expm1f(d * (float)kLn2)), kVoid);
-            }
-            // star emission = log2 P + add: fold `add` into the low word (|add| is small unless the label
-            // holds nearly all of P, where its own relative error dominates anyway)
-            const float sh = lPh + add;
-            const float sl = lPl + ((lPh - sh) + add);
-            split2(fmaxf(sh, kVoid), sl, Ks2, fs2);
-            ((float2*)(erow + 4))[k] = make_float2(emission_linear(Kl, fl), emission_linear(Ks2, fs2));
+            const float pl = emission_linear(Kl, fl);
+            // star emission P_t - p_y (ha/star.py:4-5 logsubexp), subtracted in the linear domain: both terms are
+            // good to ~1e-7 relative, which is all fp32 knows about P_t anyway; never below the smallest normal
+            const float ps = (y != 0) ? fmaxf(Plin - pl, 1.1754943508222875e-38f) : Plin;
+            ((float2*)(erow + 4))[k] = make_float2(pl, ps);
         }
         __syncwarp();
         if (r + nstage < nrows) issue(r + nstage);
