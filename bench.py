@@ -204,21 +204,152 @@ def cpu_reference_run(kind, B, T, V, U, seconds_target, threads):
     return b * T / t, f"B_cpu={b} of B={B}, same T={T} V={V} U={U}, float64, loss+grad", b, t
 
 
+def run_sweep(args, rank, world, local_rank):
+    """BASELINE.json configs[4] / SURVEY 8(d) C5: a pool of variable-length utterances, sorted by length, cut
+    into buckets by padded byte cost (the DurationBatchSampler rule, ha/sampler.py:13-29), dealt to the ranks
+    greedily by cost; a step is one pass over the pool (loss + gradient of every bucket) and one all-reduce of
+    [sum loss, count].  Strong scaling: the pool is fixed as the number of GPUs grows."""
+    import random
+    import torch
+    import torch.distributed as dist
+    from haloop_b200 import ops, sharding
+    kind = "rnnt" if args.workload == "sweep_rnnt" else "ctc"
+    V = 1024
+    rnd = random.Random(0)
+    if kind == "ctc":
+        n_pool = 4096
+        tl_ = [10 * rnd.randint(20, 150) for _ in range(n_pool)]
+        ul_ = [max(1, min((t - 1) // 2, round(t / 5 * rnd.uniform(0.6, 1.0)))) for t in tl_]
+        budget = 393_216_000                         # a quarter of BASELINE config 2's padded logits: 38 buckets
+    else:
+        n_pool = 256                                 # 4096 RNN-T joints (~300 GB) do not fit one GPU: 256 do
+        tl_ = [rnd.randint(100, 500) for _ in range(n_pool)]
+        ul_ = [rnd.randint(20, 100) for _ in range(n_pool)]
+        budget = 1_654_784_000                       # a quarter of BASELINE config 4's padded joint: 20 buckets
+    buckets = sharding.bucket_by_length(tl_, ul_, V, budget, kind)
+    mine = sharding.deal_buckets(buckets, world)[rank]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    data = []
+    for bi in mine:
+        b = buckets[bi]
+        Bk = len(b.indices)
+        shape = (Bk, b.t_max, V) if kind == "ctc" else (Bk, b.t_max, b.u_max + 1, V)
+        x = torch.randn(shape, device=dev, generator=g)
+        il = torch.tensor([tl_[i] for i in b.indices], device=dev)
+        tl = torch.tensor([ul_[i] for i in b.indices], device=dev)
+        tg = torch.randint(1, V, (Bk, b.u_max), device=dev, generator=g)
+        tg = tg * (torch.arange(b.u_max, device=dev)[None, :] < tl[:, None])       # 0-padded (ha/loop.py:40)
+        data.append((x, tg, il, tl, torch.ones(Bk, device=dev)))
+    red = torch.zeros(2, device=dev, dtype=torch.float64)
+
+    # buckets alternate over two streams: a short bucket's trellis kernel (one CTA per utterance) does not fill
+    # the GPU on its own, the next bucket's streaming kernels run beside it
+    main_stream = torch.cuda.current_stream()
+    side = [torch.cuda.Stream(), torch.cuda.Stream()]
+    partial = [torch.zeros(2, device=dev, dtype=torch.float64) for _ in side]
+
+    def step():
+        for k, st in enumerate(side):
+            st.wait_stream(main_stream)
+            with torch.cuda.stream(st):
+                partial[k].zero_()
+        for j, (x, tg, il, tl, go) in enumerate(data):
+            with torch.cuda.stream(side[j & 1]):
+                if kind == "ctc":
+                    xv = x.permute(1, 0, 2)
+                    loss, ws = ops.ctc_fwd(xv, tg, il, tl, True)
+                    ops.ctc_bwd(xv, ws, go, tg.shape[1], True)
+                else:
+                    loss, ws = ops.rnnt_fwd(x, tg, il, tl, True)
+                    ops.rnnt_bwd(x, ws, go, True)
+                partial[j & 1][0] += loss.sum(); partial[j & 1][1] += loss.numel()
+        for st in side:
+            main_stream.wait_stream(st)
+        red.copy_(partial[0] + partial[1])
+        if world > 1:
+            dist.all_reduce(red)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t) / steps
+    if rank == 0:
+        frames = sum(tl_)
+        if kind == "ctc":
+            ab = 8 * V * frames
+            padded = sum(len(b.indices) * b.t_max for b in buckets)
+        else:
+            ab = 8 * V * sum(t * (u + 1) for t, u in zip(tl_, ul_))
+            padded = sum(len(b.indices) * b.t_max * (b.u_max + 1) for b in buckets)
+        peak, peak_src = measured_peak()
+        gbs = ab / (ms_step * 1e-3) / 1e9
+        loads = [sum(buckets[k].cost for k in o) for o in sharding.deal_buckets(buckets, world)]
+        print(json.dumps({
+            "metric": "utterance-frames/sec (loss + logit gradient)", "value": frames / (ms_step * 1e-3),
+            "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {kind} pool of {n_pool} variable-length utterances, V={V}, "
+                                   f"{len(buckets)} length buckets of <= {budget / 1e9:.2f} GB padded logits, dealt to "
+                                   f"{world} rank(s) by cost; one pass over the pool per step",
+                       "frames": frames, "buckets": len(buckets),
+                       "padding_overhead": padded / (frames if kind == "ctc" else sum(t * (u + 1) for t, u in zip(tl_, ul_))),
+                       "rank_load_imbalance": max(loads) / (sum(loads) / len(loads)),
+                       "l2": "every bucket's logits are larger than L2"},
+            "mean_loss": float(red[0] / red[1]),
+            "gpu_launches": (4 if kind == "ctc" else 5) * len(mine) * steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "scope": "whole step (all buckets of rank 0's share), algorithmic bytes of the "
+                                                  "TRUE lengths", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                         "frac": gbs / peak / world, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": ab},
+            "e2e": None, "cpu_baseline": None,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="ctc", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="ctc", choices=sorted(WORKLOADS) + ["sweep_ctc", "sweep_rnnt"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-library-baseline", action="store_true",
+                    help="skip timing F.ctc_loss / torchaudio.rnnt_loss on the same GPU (SURVEY 8d)")
     args = ap.parse_args()
-    kind, B, T, V, U = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload.startswith("sweep"):
+        return run_sweep(args, rank, world, local_rank)
+    kind, B, T, V, U = WORKLOADS[args.workload]
     metric = "utterance-frames/sec (loss + logit gradient)"
     config = {"workload": f"{args.workload}: {kind} B={B}/GPU T={T} V={V} U={U} fp32, full lengths, from logits",
               "batch_per_gpu": B, "T": T, "V": V, "U": U, "sharding": f"batch x{max(world, args.gpus)} (utterances independent)",
@@ -435,6 +566,41 @@ def main():
     }
     if e2e:
         out["e2e"] = e2e
+    if not args.no_library_baseline and world == 1 and kind in ("ctc", "rnnt"):
+        # the strongest same-box library baselines: log_softmax + F.ctc_loss (reduction='sum') and
+        # torchaudio's fused rnnt_loss on the same inputs, forward + backward, CUDA events
+        try:
+            x, tg, il, tl = sets[0]
+            xl = x.detach().clone().requires_grad_(True)
+            if kind == "ctc":
+                def lib():
+                    lp = torch.nn.functional.log_softmax(view(xl), dim=-1)
+                    return torch.nn.functional.ctc_loss(lp, tg, il, tl, blank=0, reduction="sum", zero_infinity=False)
+                name = "torch.nn.functional.log_softmax + ctc_loss"
+            else:
+                from torchaudio.functional import rnnt_loss
+                tg32, il32, tl32 = tg.int(), il.int(), tl.int()
+                def lib():
+                    return rnnt_loss(xl, tg32, il32, tl32, blank=0, reduction="sum", fused_log_softmax=True)
+                name = "torchaudio.functional.rnnt_loss"
+            for _ in range(2):
+                xl.grad = None
+                lib().backward()
+            torch.cuda.synchronize()
+            n_lib = 5
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n_lib):
+                xl.grad = None
+                lib().backward()
+            b_.record()
+            torch.cuda.synchronize()
+            lib_ms = a.elapsed_time(b_) / n_lib
+            out["library_baseline"] = {"name": name, "value": B * T / (lib_ms * 1e-3), "unit": "frames/s",
+                                       "ms_per_step": lib_ms, "torch": torch.__version__}
+            del xl
+        except Exception as e:                      # library not importable / out of memory: report, do not fail
+            out["library_baseline"] = {"unavailable": repr(e)[:200]}
     if not args.no_cpu_baseline and world == 1:
         fps, sample, b, tcpu = cpu_reference_run(kind, B, T, V, U, args.cpu_seconds, threads)
         out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",

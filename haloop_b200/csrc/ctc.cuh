@@ -33,7 +33,7 @@ __host__ __device__ inline int ctc_em_floats(int Sp) { return 4 + Sp; }
 // 2^(K + f) for an integer-valued K in [-127, 1] and |f| <= 0.5 (exp2_poly: relative error ~1e-7, no
 // MUFU), exponent added into the bit pattern
 __device__ __forceinline__ float emission_linear(float K, float f) {
-    const int k = __float2int_rn(K);
+    const int k = __float_as_int(K + kMagic) - 0x4B400000;          // K is integer valued: exact, no F2I
     return (k < -125) ? 1.1754943508222875e-38f : xf_scale(exp2_poly(f), k);
 }
 // star-CTC emission words (star.cuh): Q8.24 fixed-point value of log2 p - ct
@@ -205,31 +205,56 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_rows_kernel(RowsParams 
         const int t = t0 + warp + kRowWarps * r;
         float l2 = 0.0f;                       // log2-sum-exp2 of the row; 0 when x already holds log-probs
         float mx = -CUDART_INF_F;
-        if (VEC4) {
+        if (VEC4 && V <= 1024) {
+            // the whole row in registers (<= 8 float4 per lane): one shared-memory pass for max and sum
             const float4* r4 = (const float4*)row;
-            for (int c = lane; c < (V >> 2); c += 32) {
-                float4 v = r4[c];
-                mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+            const int V4 = V >> 2;
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = lane + 32 * i;
+                v[i] = (c < V4) ? r4[c] : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+            mx = warp_max(mx);
+            if (p.from_logits) {
+                const float m2 = mx * kLog2e;
+                float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    s0 += ex2f(fmaf(v[i].x, kLog2e, -m2)) + ex2f(fmaf(v[i].y, kLog2e, -m2));
+                    s1 += ex2f(fmaf(v[i].z, kLog2e, -m2)) + ex2f(fmaf(v[i].w, kLog2e, -m2));
+                }
+                l2 = m2 + log2f(warp_sum(s0 + s1));
             }
         } else {
-            for (int c = lane; c < V; c += 32) mx = fmaxf(mx, row[c]);
-        }
-        mx = warp_max(mx);
-        if (p.from_logits) {
-            const float m2 = mx * kLog2e;
-            float s = 0.0f;
             if (VEC4) {
                 const float4* r4 = (const float4*)row;
                 for (int c = lane; c < (V >> 2); c += 32) {
                     float4 v = r4[c];
-                    s += ex2f(fmaf(v.x, kLog2e, -m2)) + ex2f(fmaf(v.y, kLog2e, -m2)) +
-                         ex2f(fmaf(v.z, kLog2e, -m2)) + ex2f(fmaf(v.w, kLog2e, -m2));
+                    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
                 }
             } else {
-                for (int c = lane; c < V; c += 32) s += ex2f(fmaf(row[c], kLog2e, -m2));
+                for (int c = lane; c < V; c += 32) mx = fmaxf(mx, row[c]);
             }
-            s = warp_sum(s);
-            l2 = m2 + log2f(s);
+            mx = warp_max(mx);
+            if (p.from_logits) {
+                const float m2 = mx * kLog2e;
+                float s = 0.0f;
+                if (VEC4) {
+                    const float4* r4 = (const float4*)row;
+                    for (int c = lane; c < (V >> 2); c += 32) {
+                        float4 v = r4[c];
+                        s += ex2f(fmaf(v.x, kLog2e, -m2)) + ex2f(fmaf(v.y, kLog2e, -m2)) +
+                             ex2f(fmaf(v.z, kLog2e, -m2)) + ex2f(fmaf(v.w, kLog2e, -m2));
+                    }
+                } else {
+                    for (int c = lane; c < V; c += 32) s += ex2f(fmaf(row[c], kLog2e, -m2));
+                }
+                s = warp_sum(s);
+                l2 = m2 + log2f(s);
+            }
         }
         // Emissions are stored relative to an integer per-row shift c_t = rint(log2 p of the row's likeliest
         // class), so every stored probability is <= 2^0.5 and anything within 2^-126 of the row maximum is a

@@ -212,6 +212,61 @@ def test_rnnt_vs_oracle(hb, oracle, cfg):
     assert err < GRAD_ATOL, f"{err:.3e}"
 
 
+@pytest.mark.parametrize("S", [1, 2, 33, 64, 65, 129, 200, 333, 420, 520, 650, 800, 1000])
+def test_ctc_target_length_sweep(hb, oracle, S):
+    """every (slots per warp, warps per side) instantiation of the trellis kernel the launcher can pick"""
+    T = S + S // 3 + 24
+    x, tg, il, tl = _rand_ctc(900 + S, T, 2, 16, S)
+    tl[0] = S; il[0] = T
+    ol, og = oracle.ctc(x.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    xd = x.to(dev()).requires_grad_(True)
+    loss = hb.ctc_forward_score3(xd, tg.to(dev()), il.to(dev()), tl.to(dev()), from_logits=True)
+    loss.sum().backward()
+    lo = loss.detach().double().cpu().numpy()
+    fin = np.isfinite(ol)
+    assert (np.isinf(lo) == np.isinf(ol)).all()
+    np.testing.assert_allclose(lo[fin], ol[fin], rtol=LOSS_RTOL)
+    err = np.abs(xd.grad.double().cpu().numpy() - og).max()
+    assert err < GRAD_ATOL, f"{err:.3e}"
+
+
+@pytest.mark.parametrize("S", [1, 33, 65, 100, 129, 260, 400, 511])
+def test_star_target_length_sweep(hb, oracle, S):
+    T = S + S // 3 + 24
+    x, tg, il, tl = _rand_ctc(950 + S, T, 2, 16, S)
+    tl[0] = S; il[0] = T
+    for n in range(tg.shape[0]):
+        tg[n, tl[n]:] = 0
+    ol, og = oracle.star(x.numpy(), tg.numpy(), il.numpy(), tl.numpy(), star_penalty=-1.25)
+    xd = x.to(dev()).requires_grad_(True)
+    loss = hb.star_ctc_forward_score(xd, tg.to(dev()), il.to(dev()), tl.to(dev()), star_penalty=-1.25,
+                                     from_logits=True)
+    loss.sum().backward()
+    lo = loss.detach().double().cpu().numpy()
+    fin = np.isfinite(ol)
+    assert (np.isinf(lo) == np.isinf(ol)).all()
+    np.testing.assert_allclose(lo[fin], ol[fin], rtol=LOSS_RTOL)
+    err = np.abs(xd.grad.double().cpu().numpy() - og).max()
+    assert err < GRAD_ATOL, f"{err:.3e}"
+
+
+@pytest.mark.parametrize("cfg", [dict(N=2, T=30, U=200, V=8), dict(N=2, T=6, U=520, V=4)])
+def test_rnnt_wide_lattice(hb, oracle, cfg):
+    """U+1 > 128 (the 1024-thread lattice instantiation) and U+1 > 512 (alpha and beta share the threads)"""
+    N, T, U, V = cfg["N"], cfg["T"], cfg["U"], cfg["V"]
+    g = torch.Generator().manual_seed(400 + U)
+    x = torch.randn(N, T, U + 1, V, generator=g)
+    tg = torch.randint(0, V, (N, U), generator=g)
+    il = torch.tensor([T, max(1, T - 2)]); tl = torch.tensor([U, U - 7])
+    ol, og = oracle.rnnt(x.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    xd = x.to(dev()).requires_grad_(True)
+    loss = hb.transducer_forward_score(xd, tg.to(dev()), il.to(dev()), tl.to(dev()), from_logits=True)
+    loss.sum().backward()
+    np.testing.assert_allclose(loss.detach().double().cpu().numpy(), ol, rtol=LOSS_RTOL)
+    err = np.abs(xd.grad.double().cpu().numpy() - og).max()
+    assert err < GRAD_ATOL, f"{err:.3e}"
+
+
 def test_permuted_view_and_strided_grad(hb, oracle):
     """ha/recognizer.py:70: the loss sees logits.permute(1,0,2) of an (N,T,C) buffer; no copy is made
     and the gradient comes back with the same strides."""
