@@ -27,11 +27,16 @@ WORKLOADS = {
     "star": ("star", 128, 1000, 512, 200),
     "rnnt": ("rnnt", 32, 500, 1024, 100),
     "ctc_c1": ("ctc", 8, 200, 256, 50),
+    # the same RNN-T batch given as its two factors f (N,T,V), g (N,U+1,V) instead of the
+    # 6.6 GB joint f[:, :, None, :] + g[:, None, :, :] (ha/recognizer.py:114)
+    "rnnt_fg": ("rnnt_fg", 32, 500, 1024, 100),
 }
 
 
 def alg_bytes(kind, B, T, V, U):
     """read the logits once + write the logit gradient once, fp32."""
+    if kind == "rnnt_fg":
+        return 8 * V * B * (T + U + 1)          # read f and g once, write their gradients once
     return 8 * V * B * T * ((U + 1) if kind == "rnnt" else 1)
 
 
@@ -159,6 +164,15 @@ def make_inputs(kind, B, T, V, U, seed, device=None, pin=False):
     """Synthetic batch, SURVEY.md §8(d): randn logits, labels in 1..V-1, full lengths."""
     import torch
     g = torch.Generator().manual_seed(seed)
+    if kind == "rnnt_fg":
+        f = torch.randn(B, T, V, generator=g); gg = torch.randn(B, U + 1, V, generator=g)
+        if pin:
+            f, gg = f.pin_memory(), gg.pin_memory()
+        tg = torch.randint(1, V, (B, U), generator=g)
+        il = torch.full((B,), T, dtype=torch.int64); tl = torch.full((B,), U, dtype=torch.int64)
+        if device is not None:
+            f, gg, tg, il, tl = (t.to(device) for t in (f, gg, tg, il, tl))
+        return (f, gg), tg, il, tl
     shape = (B, T, V) if kind != "rnnt" else (B, T, U + 1, V)
     x = torch.empty(shape, dtype=torch.float32, pin_memory=pin)
     # filled in chunks: one 6.6 GB randn call is slow and doubles peak host memory
@@ -190,9 +204,14 @@ def cpu_reference_run(kind, B, T, V, U, seconds_target, threads):
     rng = np.random.default_rng(0)
 
     def run(b):
+        tg = rng.integers(1, V, (b, U)); il = np.full(b, T); tl = np.full(b, U)
+        if kind == "rnnt_fg":
+            f = rng.standard_normal((b, T, V), dtype=np.float32); g = rng.standard_normal((b, U + 1, V), dtype=np.float32)
+            t0 = time.perf_counter()
+            oracle.rnnt_fg(f, g, tg, il, tl)        # builds the float64 joint, as the reference call site does
+            return time.perf_counter() - t0
         shape = (T, b, V) if kind != "rnnt" else (b, T, U + 1, V)
         x = rng.standard_normal(shape, dtype=np.float32).astype(np.float64)
-        tg = rng.integers(1, V, (b, U)); il = np.full(b, T); tl = np.full(b, U)
         t0 = time.perf_counter()
         if kind == "ctc":
             oracle.ctc(x, tg, il, tl)
@@ -203,11 +222,11 @@ def cpu_reference_run(kind, B, T, V, U, seconds_target, threads):
         return time.perf_counter() - t0
 
     b0 = max(1, min(B, threads))
-    if kind == "rnnt":
+    if kind in ("rnnt", "rnnt_fg"):
         b0 = max(1, min(B, threads // 2, 4))
     t_probe = run(b0)
     b = int(max(b0, min(B, b0 * seconds_target / max(t_probe, 1e-3))))
-    if kind == "rnnt":
+    if kind in ("rnnt", "rnnt_fg"):
         b = min(b, 8)            # 0.8 GB of float64 joint per utterance
     b = max(b0, (b // b0) * b0)
     t = run(b) if b != b0 else t_probe
@@ -416,7 +435,7 @@ def main():
 
     def view(x):
         # the reference's call site hands the loss logits.permute(1,0,2) of an (N,T,C) buffer
-        return x.permute(1, 0, 2) if kind != "rnnt" else x
+        return x.permute(1, 0, 2) if kind in ("ctc", "star") else x
 
     fwd_ev, bwd_ev = [], []
 
@@ -430,6 +449,8 @@ def main():
             loss, ws = ops.ctc_fwd(xv, tg, il, tl, True)
         elif kind == "star":
             loss, ws = ops.star_fwd(xv, tg, il, tl, -0.5, True)
+        elif kind == "rnnt_fg":
+            loss, ws = ops.rnnt_fg_fwd(xv[0], xv[1], tg, il, tl)
         else:
             loss, ws = ops.rnnt_fwd(xv, tg, il, tl, True)
         if timed:
@@ -438,6 +459,8 @@ def main():
             gx = ops.ctc_bwd(xv, ws, gout, U, True)
         elif kind == "star":
             gx = ops.star_bwd(xv, ws, gout, U, True)
+        elif kind == "rnnt_fg":
+            gx = ops.rnnt_fg_bwd(xv[0], xv[1], ws, gout)
         else:
             gx = ops.rnnt_bwd(xv, ws, gout, True)
         if timed:
@@ -492,7 +515,8 @@ def main():
         hx, htg, hil, htl = make_inputs(kind, B, T, V, U, seed=77 + rank, pin=True)
         htg, hil, htl = htg.pin_memory(), hil.pin_memory(), htl.pin_memory()
         hloss = torch.empty(B, dtype=torch.float32).pin_memory()
-        dbuf = [torch.empty_like(sets[0][0]) for _ in range(2)]
+        fg = kind == "rnnt_fg"
+        dbuf = [tuple(torch.empty_like(t) for t in sets[0][0]) if fg else torch.empty_like(sets[0][0]) for _ in range(2)]
         dtg = [torch.empty_like(sets[0][1]) for _ in range(2)]
         dil = [torch.empty_like(sets[0][2]) for _ in range(2)]
         dtl = [torch.empty_like(sets[0][3]) for _ in range(2)]
@@ -505,14 +529,20 @@ def main():
             s = k & 1
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[s])
-                dbuf[s].copy_(hx, non_blocking=True); dtg[s].copy_(htg, non_blocking=True)
+                if fg:
+                    dbuf[s][0].copy_(hx[0], non_blocking=True); dbuf[s][1].copy_(hx[1], non_blocking=True)
+                else:
+                    dbuf[s].copy_(hx, non_blocking=True)
+                dtg[s].copy_(htg, non_blocking=True)
                 dil[s].copy_(hil, non_blocking=True); dtl[s].copy_(htl, non_blocking=True)
                 ready[s].record(copy_stream)
 
         def compute(s):
             main_stream.wait_event(ready[s])
-            xd = view(dbuf[s]).requires_grad_(True)
-            if kind == "ctc":
+            xd = tuple(t.requires_grad_(True) for t in dbuf[s]) if fg else view(dbuf[s]).requires_grad_(True)
+            if fg:
+                loss = hb.transducer_forward_score_fg(xd[0], xd[1], dtg[s], dil[s], dtl[s])
+            elif kind == "ctc":
                 loss = hb.ctc_forward_score3(xd, dtg[s], dil[s], dtl[s], from_logits=True)
             elif kind == "star":
                 loss = hb.star_ctc_forward_score(xd, dtg[s], dil[s], dtl[s], star_penalty=-0.5, from_logits=True)
@@ -521,7 +551,8 @@ def main():
             loss.sum().backward()
             hloss.copy_(loss.detach(), non_blocking=True)
             freed[s].record(main_stream)
-            dbuf[s].requires_grad_(False)
+            for t in (dbuf[s] if fg else (dbuf[s],)):
+                t.requires_grad_(False); t.grad = None
 
         for s in range(2):
             freed[s].record(main_stream)
@@ -542,7 +573,7 @@ def main():
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e_ms = float(t2) / n_e2e
-        h2d = hx.numel() * 4 + htg.numel() * 8 + 16 * B
+        h2d = sum(t.numel() for t in (hx if fg else (hx,))) * 4 + htg.numel() * 8 + 16 * B
         e2e = {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4 * B, "ms_per_step": e2e_ms, "steps": n_e2e,
                "note": "pinned host logits -> device every step (double-buffered on a copy stream), loss read back"}
@@ -554,10 +585,13 @@ def main():
 
     peak, peak_src = measured_peak()
     ab = alg_bytes(kind, B, T, V, U)
-    mid = "lattice" if kind == "rnnt" else "trellis"
+    mid = "lattice" if kind.startswith("rnnt") else "trellis"
     names = [f"{kind}_rows_kernel", f"{kind}_{mid}_kernel", f"{kind}_grad_kernel"]
+    if kind == "rnnt_fg":
+        names = ["rnnt_fg_stats_kernel + rnnt_fg_gemm_kernel<E>", "rnnt_lattice_kernel",
+                 "rnnt_fg_gemm_kernel<DF> + rnnt_fg_gemm_kernel<DG> + rnnt_fg_fix_kernel"]
     tr = [ncu_traffic(k) if args.workload in ("ctc", "star", "rnnt") else None for k in names]
-    launches_per_step = {"ctc": 4, "star": 4, "rnnt": 5}[kind]
+    launches_per_step = {"ctc": 4, "star": 4, "rnnt": 5, "rnnt_fg": 8}[kind]
     step_gbs = ab / (ms_step * 1e-3) / 1e9
     grad_gbs = ab / (bwd_ms * 1e-3) / 1e9
     out = {
@@ -586,8 +620,45 @@ def main():
             },
         },
     }
+    if kind == "rnnt_fg":
+        # not an HBM-bound path any more: three fp32 GEMMs (6 N T (U+1) V flop) around the latency-bound lattice
+        flops = 6.0 * B * T * (U + 1) * V
+        out["roofline"]["note"] = ("joint-free RNN-T moves 8 V (T+U+1) bytes per utterance instead of 8 V T (U+1): the "
+                                   "step is bound by its fp32 SIMT GEMMs and the lattice sweep, not by HBM")
+        out["roofline"]["kernels"] = {"fp32 GEMMs (E = F G^T, W G, W^T F)": {
+            "flop_per_step": flops, "achieved_tflops_over_whole_step": flops / (ms_step * 1e-3) / 1e12,
+            "peak_tflops_fp32_simt_nominal": 148 * 128 * 2 * 1.965e9 / 1e12}}
+        out["joint_path_equivalent"] = {"note": "the same batch through the materialised joint is --workload rnnt",
+                                        "joint_bytes": 4 * B * T * (U + 1) * V}
     if e2e:
         out["e2e"] = e2e
+    if not args.no_library_baseline and world == 1 and kind == "rnnt_fg":
+        try:
+            from torchaudio.functional import rnnt_loss
+            (f0, g0), tg, il, tl = sets[0]
+            fl = f0.detach().clone().requires_grad_(True); gl = g0.detach().clone().requires_grad_(True)
+            tg32, il32, tl32 = tg.int(), il.int(), tl.int()
+
+            def lib():       # the reference call site: broadcast joint (ha/recognizer.py:114) + rnnt_loss (:121-126)
+                return rnnt_loss(fl[:, :, None, :] + gl[:, None, :, :], tg32, il32, tl32, blank=0, reduction="sum",
+                                 fused_log_softmax=True)
+            for _ in range(2):
+                fl.grad = None; gl.grad = None
+                lib().backward()
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                fl.grad = None; gl.grad = None
+                lib().backward()
+            b_.record()
+            torch.cuda.synchronize()
+            lib_ms = a.elapsed_time(b_) / 3
+            out["library_baseline"] = {"name": "f[:, :, None, :] + g[:, None, :, :] -> torchaudio.functional.rnnt_loss",
+                                       "value": B * T / (lib_ms * 1e-3), "unit": "frames/s", "ms_per_step": lib_ms,
+                                       "torch": torch.__version__}
+        except Exception as e:
+            out["library_baseline"] = {"unavailable": repr(e)[:200]}
     if not args.no_library_baseline and world == 1 and kind in ("ctc", "rnnt"):
         # the strongest same-box library baselines: log_softmax + F.ctc_loss (reduction='sum') and
         # torchaudio's fused rnnt_loss on the same inputs, forward + backward, CUDA events

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "ctc.cuh"
 #include "rnnt.cuh"
+#include "rnnt_fg.cuh"
 #include "star.cuh"
 
 using namespace hab;
@@ -450,6 +451,89 @@ int ha_rnnt_bwd(const float* joint, int N, int T, int U1, int V,
         rnnt_grad_kernel<false><<<grid, block, rc_.smem, st>>>(gp);
     }
     return check_launch("rnnt_grad_kernel");
+}
+
+// ------------------------------------------------------------- joint-free (factored) RNN-T ---
+size_t ha_rnnt_fg_workspace_bytes(int N, int T, int U1, int V) {
+    (void)V;
+    if (T <= 0 || N <= 0 || U1 <= 0) return 0;
+    return rnnt_fg_ws_layout(N, T, U1).total;
+}
+
+static RnntFgParams rnnt_fg_params(const float* f, const float* g, int N, int T, int U1, int V,
+                                   const RnntFgWs& w, unsigned char* base) {
+    RnntFgParams p{};
+    p.f = f; p.g = g; p.N = N; p.T = T; p.U1 = U1; p.V = V; p.Up = w.Up; p.D = w.D;
+    p.meta = (const int4*)(base + w.meta); p.tgt = (int*)(base + w.tgt); p.nxt = (int*)(base + w.nxt);
+    p.mf = (float*)(base + w.mf); p.mg = (float*)(base + w.mg);
+    p.lf0 = (float*)(base + w.lf0); p.lg0 = (float*)(base + w.lg0); p.lgy = (float*)(base + w.lgy);
+    p.E = (float*)(base + w.E);
+    p.bl = (float2*)(base + w.bl); p.lb = (float2*)(base + w.lb); p.occ = (const float2*)(base + w.occ);
+    p.loss = (const float*)(base + w.loss);
+    return p;
+}
+
+int ha_rnnt_fg_fwd(const float* f, const float* g, int N, int T, int U1, int V,
+                   const void* targets, int64_t tgt_stride, int targets_i64,
+                   const void* in_len, const void* tgt_len, int lengths_i64,
+                   float* loss, void* ws, size_t ws_bytes, void* stream) {
+    if (U1 <= 0) return fail(HA_ERR_INVALID_ARGUMENT, "U1 must be >= 1");
+    const RnntFgWs w = rnnt_fg_ws_layout(N, T, U1);
+    int rc = common_checks(f, T, N, V, U1 - 1, ws, ws_bytes, w.total);
+    if (rc) return rc;
+    if (!g || !in_len || !tgt_len || !loss || (U1 > 1 && !targets)) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+    if (U1 > 1024) return fail(HA_ERR_UNSUPPORTED_SHAPE, "U+1 > 1024 is not supported");
+    if ((long long)(T + U1) * U1 >= (1ll << 31)) return fail(HA_ERR_UNSUPPORTED_SHAPE, "T*(U+1) too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* base = (unsigned char*)ws;
+
+    RnntPrepParams pp{};
+    pp.targets = targets; pp.tgt_stride = tgt_stride; pp.tgt64 = targets_i64;
+    pp.in_len = in_len; pp.tgt_len = tgt_len; pp.len64 = lengths_i64;
+    pp.N = N; pp.T = T; pp.U = U1 - 1; pp.V = V; pp.Up = w.Up;
+    pp.meta = (int4*)(base + w.meta); pp.tgt = (int*)(base + w.tgt);
+    rnnt_prep_kernel<<<N, 128, 0, st>>>(pp);
+    if ((rc = check_launch("rnnt_prep_kernel"))) return rc;
+
+    RnntFgParams p = rnnt_fg_params(f, g, N, T, U1, V, w, base);
+    rnnt_fg_chain_kernel<<<N, 128, (size_t)w.Up * 4, st>>>(p);
+    if ((rc = check_launch("rnnt_fg_chain_kernel"))) return rc;
+    rnnt_fg_stats_kernel<<<dim3((T + U1 + 7) / 8, N), 256, 0, st>>>(p);
+    if ((rc = check_launch("rnnt_fg_stats_kernel"))) return rc;
+    rnnt_fg_gemm_kernel<kE><<<dim3((T + kGM - 1) / kGM, (U1 + kGN - 1) / kGN, N), 256, 0, st>>>(p);
+    if ((rc = check_launch("rnnt_fg_gemm_kernel<E>"))) return rc;
+
+    RnntLatticeParams lp{};
+    lp.N = N; lp.T = T; lp.U1 = U1; lp.D = w.D; lp.meta = p.meta;
+    lp.bl = p.bl; lp.lb = p.lb; lp.alpha = (double*)(base + w.alpha); lp.beta = (double*)(base + w.beta);
+    lp.occ = (float2*)(base + w.occ);
+    lp.loss = loss; lp.loss_ws = (float*)(base + w.loss);
+    {
+        const int half = round_up(U1, 32), nthreads = half * (half <= 512 ? 2 : 1);
+        if (nthreads <= 256) rnnt_lattice_kernel<256><<<N, nthreads, 0, st>>>(lp);
+        else rnnt_lattice_kernel<1024><<<N, nthreads, 0, st>>>(lp);
+    }
+    return check_launch("rnnt_lattice_kernel");
+}
+
+int ha_rnnt_fg_bwd(const float* f, const float* g, int N, int T, int U1, int V,
+                   const float* grad_loss, float* gf, float* gg,
+                   void* ws, size_t ws_bytes, void* stream) {
+    if (U1 <= 0) return fail(HA_ERR_INVALID_ARGUMENT, "U1 must be >= 1");
+    const RnntFgWs w = rnnt_fg_ws_layout(N, T, U1);
+    int rc = common_checks(f, T, N, V, U1 - 1, ws, ws_bytes, w.total);
+    if (rc) return rc;
+    if (!g || !grad_loss || !gf || !gg) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* base = (unsigned char*)ws;
+    RnntFgParams p = rnnt_fg_params(f, g, N, T, U1, V, w, base);
+    p.gf = gf; p.gg = gg; p.gout = grad_loss;
+    rnnt_fg_gemm_kernel<kDF><<<dim3((T + kGM - 1) / kGM, (V + kGN - 1) / kGN, N), 256, 0, st>>>(p);
+    if ((rc = check_launch("rnnt_fg_gemm_kernel<DF>"))) return rc;
+    rnnt_fg_gemm_kernel<kDG><<<dim3((U1 + kGM - 1) / kGM, (V + kGN - 1) / kGN, N), 256, 0, st>>>(p);
+    if ((rc = check_launch("rnnt_fg_gemm_kernel<DG>"))) return rc;
+    rnnt_fg_fix_kernel<<<dim3((T + U1 + 7) / 8, N), 256, 0, st>>>(p);
+    return check_launch("rnnt_fg_fix_kernel");
 }
 
 // ------------------------------------------------------------------------------- alignment ---

@@ -270,6 +270,79 @@ def _rnnt_backward(ctx, grad_loss, _grad_ws):
 rnnt_fwd.register_autograd(_rnnt_backward, setup_context=_rnnt_setup)
 
 
+# --------------------------------------------------------------------------- joint-free RNN-T
+@torch.library.custom_op("ha_b200::rnnt_fg_fwd", mutates_args=())
+def rnnt_fg_fwd(f: torch.Tensor, g: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor,
+                tgt_len: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    _check_cuda_f32(f, "f")
+    _check_cuda_f32(g, "g")
+    f = f.contiguous(); g = g.contiguous()
+    if f.dim() != 3 or g.dim() != 3 or f.shape[0] != g.shape[0] or f.shape[2] != g.shape[2]:
+        raise ValueError("expected f (N,T,V) and g (N,U+1,V)")
+    N, T, V = f.shape
+    U1 = g.shape[1]
+    tg, tg64 = _idx(targets, f.device, "targets")
+    il, il64 = _idx(in_len, f.device, "joint_lengths")
+    tl, tl64 = _idx(tgt_len, f.device, "target_lengths")
+    if il64 != tl64:
+        il, tl, il64 = il.to(torch.int64), tl.to(torch.int64), 1
+    if tg.dim() != 2 or tg.shape != (N, U1 - 1) or il.shape != (N,) or tl.shape != (N,):
+        raise ValueError("expected f (N,T,V), g (N,U+1,V), targets (N,U), joint_lengths (N,), target_lengths (N,)")
+    L = _lib.lib()
+    nbytes = L.ha_rnnt_fg_workspace_bytes(N, T, U1, V)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=f.device)
+    loss = torch.empty(N, dtype=_F32, device=f.device)
+    with torch.cuda.device(f.device):
+        rc = L.ha_rnnt_fg_fwd(f.data_ptr(), g.data_ptr(), N, T, U1, V,
+                              tg.data_ptr() if U1 > 1 else None, tg.stride(0) if U1 > 1 else 0, tg64,
+                              il.data_ptr(), tl.data_ptr(), il64,
+                              loss.data_ptr(), ws.data_ptr(), nbytes, _stream(f))
+    _lib.check(rc, "ha_rnnt_fg_fwd")
+    return loss, ws
+
+
+@rnnt_fg_fwd.register_fake
+def _(f, g, targets, in_len, tgt_len):
+    return f.new_empty(f.shape[0]), f.new_empty(1, dtype=torch.uint8)
+
+
+@torch.library.custom_op("ha_b200::rnnt_fg_bwd", mutates_args=())
+def rnnt_fg_bwd(f: torch.Tensor, g: torch.Tensor, ws: torch.Tensor,
+                grad_loss: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    f = f.contiguous(); g = g.contiguous()
+    N, T, V = f.shape
+    U1 = g.shape[1]
+    gf = torch.empty_like(f, memory_format=torch.contiguous_format)
+    gg = torch.empty_like(g, memory_format=torch.contiguous_format)
+    go = grad_loss.to(_F32).contiguous()
+    L = _lib.lib()
+    with torch.cuda.device(f.device):
+        rc = L.ha_rnnt_fg_bwd(f.data_ptr(), g.data_ptr(), N, T, U1, V, go.data_ptr(), gf.data_ptr(), gg.data_ptr(),
+                              ws.data_ptr(), ws.numel(), _stream(f))
+    _lib.check(rc, "ha_rnnt_fg_bwd")
+    return gf, gg
+
+
+@rnnt_fg_bwd.register_fake
+def _(f, g, ws, grad_loss):
+    return torch.empty_like(f), torch.empty_like(g)
+
+
+def _rnnt_fg_setup(ctx, inputs, output):
+    f, g, _, _, _ = inputs
+    _, ws = output
+    ctx.save_for_backward(f, g, ws)
+
+
+def _rnnt_fg_backward(ctx, grad_loss, _grad_ws):
+    f, g, ws = ctx.saved_tensors
+    gf, gg = rnnt_fg_bwd(f, g, ws, grad_loss)
+    return gf, gg, None, None, None
+
+
+rnnt_fg_fwd.register_autograd(_rnnt_fg_backward, setup_context=_rnnt_fg_setup)
+
+
 # ------------------------------------------------------------------------------------- alignment
 def greedy_decode(x, in_len=None):
     """x (N,T,V) -> alignment (N,T) i64, score (N,T) f32, hyp (N,T) i64 padded with -1, hyp_len (N,)."""

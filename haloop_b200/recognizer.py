@@ -11,7 +11,7 @@ import torch
 
 from .ctc import ctc_forward_score3, ctc_reduce_mean
 from .star import star_ctc_forward_score
-from .transducer import transducer_forward_score, rnnt_loss
+from .transducer import transducer_forward_score, transducer_forward_score_fg, rnnt_loss
 
 
 def temporal_classifier_forward(self, features, targets, input_lengths=None, target_lengths=None,
@@ -37,17 +37,17 @@ def temporal_classifier_forward(self, features, targets, input_lengths=None, tar
 
 def transducer_forward(self, features, targets, input_lengths=None, target_lengths=None,
                        star_penalty=None, measure_entropy=False, drop_labels=False):
-    """Transducer.forward (ha/recognizer.py:95-127) with rnnt_loss replaced by the fused lattice loss."""
+    """Transducer.forward (ha/recognizer.py:95-127) with the broadcast joint (:114) and rnnt_loss (:121-126)
+    replaced by the joint-free lattice loss: the (N,T,U+1,C) tensor is never built."""
     N = features.shape[0]
     hidden = self.lm.init_hidden(N)
     lm_targets = torch.cat([targets.new_zeros((N, 1)), targets], dim=1)
     lm_outputs, _ = self.lm.forward_batch_first(lm_targets, hidden)
     features = self.classifier(self.dropout(features))
     with torch.autocast(device_type="cuda", enabled=False):
-        joint = features.float()[:, :, None, :] + lm_outputs.float()[:, None, :, :]
-        loss = rnnt_loss(joint, targets, input_lengths, target_lengths, blank=0, reduction="mean",
-                         fused_log_softmax=True)
-    return loss, {}
+        losses = transducer_forward_score_fg(features.float(), lm_outputs.float(), targets,
+                                             input_lengths, target_lengths)
+    return losses.mean(), {}          # torchaudio's reduction='mean' is a plain batch mean
 
 
 def patch_haloop(recognizer_module=None, patch_forward=True):

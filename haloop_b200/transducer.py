@@ -1,6 +1,7 @@
 """Drop-in for ha/transducer.py: RNN-T lattice loss.
 
     transducer_forward_score(joint, targets, joint_lengths, target_lengths) -> (N,)   ha/transducer.py:175-205
+    transducer_forward_score_fg(f, g, targets, joint_lengths, target_lengths) -> (N,)  joint-free variant
 """
 from . import ops
 
@@ -14,6 +15,19 @@ def transducer_forward_score(joint, targets, joint_lengths, target_lengths, from
     power-of-two restriction on T (ha/transducer.py:194-195) and no -10000 scan seed (ha/scan.py:116).
     """
     loss, _ = ops.rnnt_fwd(joint, targets, joint_lengths, target_lengths, bool(from_logits))
+    return loss
+
+
+def transducer_forward_score_fg(f, g, targets, joint_lengths, target_lengths):
+    """RNN-T negative log-likelihood per utterance of the additive joint the reference builds at
+    ha/recognizer.py:114, `joint = f[:, :, None, :] + g[:, None, :, :]`, WITHOUT building it.
+
+    f (N,T,K) = classifier(features), g (N,U+1,K) = lm outputs: raw float32 CUDA logits (the log-softmax over
+    K is fused).  Equals transducer_forward_score(joint.log_softmax(-1), ...) and back-propagates
+    d loss/d f = (d loss/d joint).sum(2), d loss/d g = (d loss/d joint).sum(1); the (N,T,U+1,K) tensor and
+    its gradient (6.6 GB each at BASELINE config 4) never exist.
+    """
+    loss, _ = ops.rnnt_fg_fwd(f, g, targets, joint_lengths, target_lengths)
     return loss
 
 

@@ -77,6 +77,20 @@ int ha_rnnt_bwd(const float* joint, int N, int T, int U1, int V,
                 const float* grad_loss, int from_logits, float* gjoint,
                 void* ws, size_t ws_bytes, void* stream);
 
+/* ---- joint-free RNN-T: the reference's joint is a broadcast sum, ha/recognizer.py:104-114 ------
+ * joint[n,t,u,:] = f[n,t,:] + g[n,u,:] with f = classifier(features) (N,T,V) and g = lm outputs
+ * (N,U+1,V), both contiguous raw logits (the log-softmax over the joint is fused).  Same loss as
+ * ha_rnnt_fwd on the materialised joint, and the gradients w.r.t. f and g (the reductions of the joint
+ * gradient over u and over t), without ever forming the (N,T,U+1,V) tensor or its gradient. */
+size_t ha_rnnt_fg_workspace_bytes(int N, int T, int U1, int V);
+int ha_rnnt_fg_fwd(const float* f, const float* g, int N, int T, int U1, int V,
+                   const void* targets, int64_t tgt_stride, int targets_i64,
+                   const void* in_len, const void* tgt_len, int lengths_i64,
+                   float* loss, void* ws, size_t ws_bytes, void* stream);
+int ha_rnnt_fg_bwd(const float* f, const float* g, int N, int T, int U1, int V,
+                   const float* grad_loss, float* gf, float* gg,
+                   void* ws, size_t ws_bytes, void* stream);
+
 /* ---- greedy alignment: ha/recognizer.py:48-59 TemporalClassifier.decode -------------------- */
 /* x (N,T,V) through (sx_n, sx_t, 1).  alignment (N,T) int64 = per-frame argmax (first index wins,
  * as torch.max), score (N,T) = the max, hyp (N,T) int64 = collapsed repeats with blanks dropped,

@@ -148,6 +148,32 @@ def kat_appendix_d():
     print("kat_appendix_d ok")
 
 
+def rnnt_fg_case(name, N, T, U, V, seed, var=False, zero_targets=False):
+    """The reference's own additive joint (ha/recognizer.py:114) differentiated w.r.t. its two factors."""
+    assert 2 ** round(np.log2(T)) >= T, "reference scan width bug (SURVEY finding 4)"
+    g_ = torch.Generator().manual_seed(seed)
+    f32 = torch.randn(N, T, V, generator=g_, dtype=torch.float32)
+    g32 = torch.randn(N, U + 1, V, generator=g_, dtype=torch.float32)
+    tg = torch.randint(0 if zero_targets else 1, V, (N, U), generator=g_)
+    il = var_lengths(g_, T, N) if var else torch.full((N,), T)
+    tl = var_lengths(g_, U, N) if var else torch.full((N,), U)
+    f = f32.double().requires_grad_(True); g = g32.double().requires_grad_(True)
+    joint = f[:, :, None, :] + g[:, None, :, :]
+    losses = transducer_forward_score(joint.log_softmax(-1), tg, il, tl)
+    losses.sum().backward()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kind="rnnt_fg", seed=seed, f=f32.numpy(), g=g32.numpy(),
+                        targets=tg.numpy(), in_len=il.numpy(), tgt_len=tl.numpy(), loss=losses.detach().numpy(),
+                        grad_f=f.grad.numpy(), grad_g=g.grad.numpy())
+    print(f"{name}: loss[0]={float(losses[0]):.8f}")
+
+
+def main_fg():
+    os.makedirs(OUT, exist_ok=True)
+    rnnt_fg_case("rnntfg_small_var", 5, 16, 6, 10, seed=51, var=True)
+    rnnt_fg_case("rnntfg_zero_labels", 4, 8, 5, 6, seed=52, var=True, zero_targets=True)
+    rnnt_fg_case("rnntfg_medium", 3, 64, 20, 40, seed=53, var=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -177,4 +203,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "fg":
+        main_fg()             # only the joint-free RNN-T cases (added after the first set was committed)
+    else:
+        main()
+        main_fg()

@@ -108,6 +108,16 @@ def rnnt(joint, targets, in_len, tgt_len, from_logits=True, grad_out=None, want_
     return loss, grad
 
 
+def rnnt_fg(f, g, targets, in_len, tgt_len, grad_out=None):
+    """Joint-free RNN-T: f (N,T,V), g (N,U+1,V) raw logits -> (loss (N,), grad_f, grad_g).  The joint of
+    ha/recognizer.py:114, joint = f[:, :, None, :] + g[:, None, :, :], is built here in float64 and handed to
+    rnnt(); the gradients are its reductions over u and over t."""
+    f = _f64(f); g = _f64(g)
+    joint = np.ascontiguousarray(f[:, :, None, :] + g[:, None, :, :])
+    loss, gj = rnnt(joint, targets, in_len, tgt_len, from_logits=True, grad_out=grad_out)
+    return loss, gj.sum(axis=2), gj.sum(axis=1)
+
+
 def greedy(x, in_len=None):
     """x (N,T,V) -> alignment (N,T) i64, score (N,T) f64, hyp (N,T) i64 (-1 padded), hyp_len (N,).
     ha/recognizer.py:48-59 (in_len=None reproduces the reference, which ignores lengths)."""

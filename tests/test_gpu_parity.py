@@ -267,6 +267,65 @@ def test_rnnt_wide_lattice(hb, oracle, cfg):
     assert err < GRAD_ATOL, f"{err:.3e}"
 
 
+@pytest.mark.parametrize("name", _cases("rnntfg"))
+def test_rnnt_joint_free_golden(hb, name):
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    f = torch.from_numpy(d["f"]).to(dev()).requires_grad_(True)
+    g = torch.from_numpy(d["g"]).to(dev()).requires_grad_(True)
+    tg, il, tl = (torch.from_numpy(d[k]).to(dev()) for k in ("targets", "in_len", "tgt_len"))
+    loss = hb.transducer_forward_score_fg(f, g, tg, il, tl)
+    loss.sum().backward()
+    np.testing.assert_allclose(loss.detach().double().cpu().numpy(), d["loss"], rtol=LOSS_RTOL)
+    assert np.abs(f.grad.double().cpu().numpy() - d["grad_f"]).max() < GRAD_ATOL
+    assert np.abs(g.grad.double().cpu().numpy() - d["grad_g"]).max() < GRAD_ATOL
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(N=3, T=50, U=20, V=64),
+    dict(N=2, T=130, U=70, V=33),                  # several tiles in every GEMM, V % 4 != 0
+    dict(N=4, T=61, U=9, V=200, zero=True),        # label 0 in the targets
+    dict(N=2, T=200, U=100, V=96, scale=3.0),      # the C4 lattice width, peaky
+])
+def test_rnnt_joint_free_vs_oracle(hb, oracle, cfg):
+    N, T, U, V = cfg["N"], cfg["T"], cfg["U"], cfg["V"]
+    gen = torch.Generator().manual_seed(500 + T)
+    f = torch.randn(N, T, V, generator=gen) * cfg.get("scale", 1.0)
+    g = torch.randn(N, U + 1, V, generator=gen) * cfg.get("scale", 1.0)
+    tg = torch.randint(0 if cfg.get("zero") else 1, V, (N, U), generator=gen)
+    il = torch.randint(T // 2, T + 1, (N,), generator=gen); il[0] = T
+    tl = torch.randint(U // 2, U + 1, (N,), generator=gen); tl[0] = U
+    go = torch.linspace(0.5, 2.0, N)
+    ol, ogf, ogg = oracle.rnnt_fg(f.numpy(), g.numpy(), tg.numpy(), il.numpy(), tl.numpy(), grad_out=go.numpy())
+    fd = f.to(dev()).requires_grad_(True); gd = g.to(dev()).requires_grad_(True)
+    loss = hb.transducer_forward_score_fg(fd, gd, tg.to(dev()), il.to(dev()), tl.to(dev()))
+    (loss * go.to(dev())).sum().backward()
+    np.testing.assert_allclose(loss.detach().double().cpu().numpy(), ol, rtol=LOSS_RTOL)
+    # a gradient w.r.t. f sums U+1 joint gradients and one w.r.t. g sums T of them (the blank column reaches
+    # magnitudes of ~T/2, where an fp32 ulp is already 4e-6): 1e-5 absolute plus 2e-6 relative
+    for got, ref in ((fd.grad, ogf), (gd.grad, ogg)):
+        err = np.abs(got.double().cpu().numpy() - ref)
+        assert (err <= GRAD_ATOL + 2e-6 * np.abs(ref)).all(), f"{err.max():.3e}"
+
+
+def test_rnnt_joint_free_equals_joint_path(hb):
+    """same loss and (reduced) gradients as the materialised-joint op on the same GPU"""
+    gen = torch.Generator().manual_seed(77)
+    N, T, U, V = 3, 40, 12, 48
+    f = torch.randn(N, T, V, generator=gen).to(dev()).requires_grad_(True)
+    g = torch.randn(N, U + 1, V, generator=gen).to(dev()).requires_grad_(True)
+    tg = torch.randint(1, V, (N, U), generator=gen).to(dev())
+    il = torch.tensor([T, T - 3, T // 2]).to(dev()); tl = torch.tensor([U, U - 1, U // 2]).to(dev())
+    l1 = hb.transducer_forward_score_fg(f, g, tg, il, tl)
+    l1.sum().backward()
+    gf1, gg1 = f.grad.clone(), g.grad.clone()
+    f.grad = None; g.grad = None
+    joint = f[:, :, None, :] + g[:, None, :, :]
+    l2 = hb.transducer_forward_score(joint, tg, il, tl, from_logits=True)
+    l2.sum().backward()
+    torch.testing.assert_close(l1, l2, rtol=1e-5, atol=1e-4)
+    assert (gf1 - f.grad).abs().max() < GRAD_ATOL and (gg1 - g.grad).abs().max() < GRAD_ATOL
+
+
 def test_permuted_view_and_strided_grad(hb, oracle):
     """ha/recognizer.py:70: the loss sees logits.permute(1,0,2) of an (N,T,C) buffer; no copy is made
     and the gradient comes back with the same strides."""

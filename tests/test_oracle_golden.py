@@ -104,6 +104,16 @@ def test_rnnt_golden(oracle, name):
     _check(d, loss, grad, lambda: oracle.rnnt(lp, *args, from_logits=False)[1], 0)
 
 
+@pytest.mark.parametrize("name", _cases("rnntfg"))
+def test_rnnt_joint_free_golden(oracle, name):
+    """the reference's additive joint (ha/recognizer.py:114) differentiated w.r.t. its factors f and g"""
+    d = np.load(golden_path(name))
+    loss, gf, gg = oracle.rnnt_fg(d["f"], d["g"], d["targets"], d["in_len"], d["tgt_len"])
+    np.testing.assert_allclose(loss, d["loss"], rtol=1e-11)
+    assert np.abs(gf - d["grad_f"]).max() < 1e-10
+    assert np.abs(gg - d["grad_g"]).max() < 1e-10
+
+
 def test_ctc_matches_torch_ctc_loss(oracle):
     """ha/ctc.py:205-238 prints agreement with F.ctc_loss; fp64 agreement is exact."""
     import torch
