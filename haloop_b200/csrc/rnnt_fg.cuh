@@ -125,8 +125,8 @@ constexpr int kGM = 64, kGN = 64, kGK = 16;
 
 template <int MODE>
 __global__ void __launch_bounds__(256) rnnt_fg_gemm_kernel(RnntFgParams p) {
-    __shared__ float As[kGK][kGM + 4];
-    __shared__ float Bs[kGK][kGN + 4];
+    __shared__ float As[2][kGK][kGM + 4];
+    __shared__ float Bs[2][kGK][kGN + 4];
     const int n = blockIdx.z;
     const int4 mt = p.meta[n];
     const float lossn = (MODE == kE) ? 0.0f : p.loss[n];
@@ -134,12 +134,12 @@ __global__ void __launch_bounds__(256) rnnt_fg_gemm_kernel(RnntFgParams p) {
     const int T = p.T, U1 = p.U1, V = p.V;
     const int M = (MODE == kDG) ? U1 : T;
     const int m0 = blockIdx.x * kGM, n0 = blockIdx.y * kGN;
-    const float* f = p.f + (size_t)n * T * V;
-    const float* g = p.g + (size_t)n * U1 * V;
-    const float* mf = p.mf + (size_t)n * T;
-    const float* mg = p.mg + (size_t)n * U1;
-    const float* Em = p.E + (size_t)n * T * U1;
-    const float2* occ = p.occ + (size_t)n * p.D * U1;
+    const float* __restrict__ f = p.f + (size_t)n * T * V;
+    const float* __restrict__ g = p.g + (size_t)n * U1 * V;
+    const float* __restrict__ mf = p.mf + (size_t)n * T;
+    const float* __restrict__ mg = p.mg + (size_t)n * U1;
+    const float* __restrict__ Em = p.E + (size_t)n * T * U1;
+    const float2* __restrict__ occ = p.occ + (size_t)n * p.D * U1;
     const int tid = threadIdx.x;
     // valid extents of the operands (everything outside contributes 0)
     const int Mv = (MODE == kDG) ? Un + 1 : Tn;              // rows of C that matter
@@ -148,10 +148,56 @@ __global__ void __launch_bounds__(256) rnnt_fg_gemm_kernel(RnntFgParams p) {
 
     auto Fx = [&](int t, int c) { return ex2f(fmaf(f[(size_t)t * V + c], kLog2e, -mf[t])); };
     auto Gx = [&](int u, int c) { return ex2f(fmaf(g[(size_t)u * V + c], kLog2e, -mg[u])); };
-    auto Wx = [&](int t, int u) {                            // node occupancy / E
-        const float2 o = occ[(size_t)(t + u) * U1 + u];
-        const float e = Em[(size_t)t * U1 + u];
-        return (e > 0.0f) ? (o.x + o.y) / e : 0.0f;
+
+    // Operand elements are fetched RAW into registers one k-chunk ahead (the loads are in flight while the
+    // current chunk is multiplied), then converted -- exp2 of the shifted logit, or node occupancy / E --
+    // as they are committed to the other shared-memory buffer.  An element outside the valid extent is
+    // fetched as (-inf, 0) / (0, 1), which converts to exactly 0.
+    float ax[4], ay[4], bx[4], by[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + 256 * i;
+            if (MODE == kE) {            // A(m=t, k=c): c contiguous;  B(k=c, n=u): c contiguous
+                const int kk = e & 15, mm = e >> 4;
+                const int t = m0 + mm, c = k0 + kk, u = n0 + mm;
+                const bool va = t < Tn && c < V, vb = u <= Un && c < V;
+                ax[i] = va ? f[(size_t)t * V + c] : -CUDART_INF_F; ay[i] = va ? mf[t] : 0.0f;
+                bx[i] = vb ? g[(size_t)u * V + c] : -CUDART_INF_F; by[i] = vb ? mg[u] : 0.0f;
+            } else if (MODE == kDF) {    // A(m=t, k=u): u contiguous;  B(k=u, n=c): c contiguous
+                const int kk = e & 15, mm = e >> 4;
+                const int t = m0 + mm, u = k0 + kk;
+                const bool va = t < Tn && u <= Un;
+                const float2 o = va ? occ[(size_t)(t + u) * U1 + u] : make_float2(0.0f, 0.0f);
+                ax[i] = o.x + o.y; ay[i] = va ? Em[(size_t)t * U1 + u] : 1.0f;
+                const int nn = e & 63, k2 = e >> 6;
+                const int u2 = k0 + k2, c = n0 + nn;
+                const bool vb = u2 <= Un && c < V;
+                bx[i] = vb ? g[(size_t)u2 * V + c] : -CUDART_INF_F; by[i] = vb ? mg[u2] : 0.0f;
+            } else {                     // A(m=u, k=t): u contiguous;  B(k=t, n=c): c contiguous
+                const int mm = e & 63, kk = e >> 6;
+                const int u = m0 + mm, t = k0 + kk, c = n0 + mm;
+                const bool va = t < Tn && u <= Un, vb = t < Tn && c < V;
+                const float2 o = va ? occ[(size_t)(t + u) * U1 + u] : make_float2(0.0f, 0.0f);
+                ax[i] = o.x + o.y; ay[i] = va ? Em[(size_t)t * U1 + u] : 1.0f;
+                bx[i] = vb ? f[(size_t)t * V + c] : -CUDART_INF_F; by[i] = vb ? mf[t] : 0.0f;
+            }
+        }
+    };
+    auto commit = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + 256 * i;
+            const float av = (MODE == kE) ? ex2f(fmaf(ax[i], kLog2e, -ay[i])) : ((ay[i] > 0.0f) ? ax[i] / ay[i] : 0.0f);
+            const float bv = ex2f(fmaf(bx[i], kLog2e, -by[i]));
+            if (MODE == kE) {
+                As[buf][e & 15][e >> 4] = av; Bs[buf][e & 15][e >> 4] = bv;
+            } else if (MODE == kDF) {
+                As[buf][e & 15][e >> 4] = av; Bs[buf][e >> 6][e & 63] = bv;
+            } else {
+                As[buf][e >> 6][e & 63] = av; Bs[buf][e >> 6][e & 63] = bv;
+            }
+        }
     };
     float acc[4][4];
 #pragma unroll
@@ -160,33 +206,12 @@ __global__ void __launch_bounds__(256) rnnt_fg_gemm_kernel(RnntFgParams p) {
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
     const int tm = (tid >> 4) * 4, tn = (tid & 15) * 4;      // my 4 x 4 outputs inside the tile
 
+    int buf = 0;
+    if (Kv > 0) { fetch(0); commit(0); }
+    __syncthreads();
     for (int k0 = 0; k0 < Kv; k0 += kGK) {
-        // stage A (kGM x kGK) and B (kGK x kGN): 4 elements each per thread, the fast index of the load
-        // follows the operand's contiguous axis
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int e = tid + 256 * i;
-            if (MODE == kE) {            // A(m=t, k=c): c contiguous;  B(k=c, n=u): c contiguous
-                const int kk = e & 15, mm = e >> 4;
-                const int t = m0 + mm, c = k0 + kk, u = n0 + mm;
-                As[kk][mm] = (t < Tn && c < V) ? Fx(t, c) : 0.0f;
-                Bs[kk][mm] = (u <= Un && c < V) ? Gx(u, c) : 0.0f;
-            } else if (MODE == kDF) {    // A(m=t, k=u): u contiguous;  B(k=u, n=c): c contiguous
-                const int kk = e & 15, mm = e >> 4;
-                const int t = m0 + mm, u = k0 + kk;
-                As[kk][mm] = (t < Tn && u <= Un) ? Wx(t, u) : 0.0f;
-                const int nn = e & 63, k2 = e >> 6;
-                const int u2 = k0 + k2, c = n0 + nn;
-                Bs[k2][nn] = (u2 <= Un && c < V) ? Gx(u2, c) : 0.0f;
-            } else {                     // A(m=u, k=t): u contiguous;  B(k=t, n=c): c contiguous
-                const int mm = e & 63, kk = e >> 6;
-                const int u = m0 + mm, t = k0 + kk;
-                As[kk][mm] = (t < Tn && u <= Un) ? Wx(t, u) : 0.0f;
-                const int c = n0 + mm;
-                Bs[kk][mm] = (t < Tn && c < V) ? Fx(t, c) : 0.0f;
-            }
-        }
-        __syncthreads();
+        const bool more = k0 + kGK < Kv;
+        if (more) fetch(k0 + kGK);
         // two-level accumulation: the 16 products of a chunk are summed on their own and added to the running
         // total once, so the total is rounded K/16 times instead of K times (the blank column of gg is a
         // difference of two sums over T frames)
@@ -197,8 +222,8 @@ __global__ void __launch_bounds__(256) rnnt_fg_gemm_kernel(RnntFgParams p) {
             for (int j = 0; j < 4; ++j) part[i][j] = 0.0f;
 #pragma unroll
         for (int kk = 0; kk < kGK; ++kk) {
-            const float4 a = *(const float4*)&As[kk][tm];
-            const float4 b = *(const float4*)&Bs[kk][tn];
+            const float4 a = *(const float4*)&As[buf][kk][tm];
+            const float4 b = *(const float4*)&Bs[buf][kk][tn];
             const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -209,7 +234,9 @@ __global__ void __launch_bounds__(256) rnnt_fg_gemm_kernel(RnntFgParams p) {
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
+        if (more) commit(buf ^ 1);
         __syncthreads();
+        buf ^= 1;
     }
 
     if (MODE == kE) {
