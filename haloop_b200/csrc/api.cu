@@ -175,7 +175,6 @@ int ha_ctc_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
     tp.T = T; tp.N = N; tp.meta = pp.meta; tp.order = pp.order; tp.tgt = pp.tgt; tp.Sp = w.Sp;
     tp.em = rp.em; tp.E = w.E; tp.tr = (float*)(base + w.tr); tp.SPX = w.SPX; tp.JWp = w.JWp;
     tp.loss = loss; tp.loss_ws = (float*)(base + w.loss);
-    tp.probe = (long long*)base;   // first 256 workspace bytes are reserved (HAB_PROBE builds)
     if ((rc = ctc_trellis_launch(tp, (S + 1 + 31) / 32, N, st))) return rc;
 
     return HA_OK;

@@ -1,7 +1,7 @@
 // common.cuh — sm_100a device helpers shared by the CTC / star-CTC / RNN-T kernels.
 //
-// Everything in the log semiring is kept in LOG2 units (values are log2-probabilities):
-// ex2.approx / lg2.approx are single MUFU ops, so logaddexp costs 2 MUFU + 4 FP32 ops.
+// Log-domain quantities (row log-sum-exps, emission exponents) are kept in LOG2 units; the recursions
+// themselves run in the linear domain on extended-range numbers (XF below).
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -31,27 +31,12 @@ __device__ __forceinline__ float lg2f(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// log2(2^a + 2^b); void-safe because kVoid is finite
-__device__ __forceinline__ float lae2(float a, float b) {
-    float m = fmaxf(a, b);
-    float d = fminf(a, b) - m;
-    return m + lg2f(1.0f + ex2f(d));
-}
-
-// ---- split log-domain numbers -------------------------------------------------------------------
-// A trellis value is kept as h + l with h an integer-valued float and |l| <~ 1, so every rounding
-// happens at magnitude ~1 (6e-8) however large the log-probability itself is: fp32 alpha/beta then
-// carry ~1e-7 of error instead of ulp(T * log V) (SURVEY.md finding 3).  All on the FP32 pipe.
-struct SF { float h, l; };
-constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: (x + kMagic) - kMagic == rint(x) for |x| < 2^22
+constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: (x + kMagic) - kMagic == rint(x) for |x| < 2^22 (F2I-free)
 __device__ __forceinline__ float round_int(float x) { return __fsub_rn(__fadd_rn(x, kMagic), kMagic); }
-// integer -> float: I2FP.F32.S32 is a fast ALU-class instruction on sm_100 (F2I is not: float -> int goes
-// through the magic constant instead)
-__device__ __forceinline__ float small_int_to_float(int k) { return (float)k; }
 // ---- emissions in float-float arithmetic ----------------------------------------------------------
-// e = x * log2(e) - l2 - ct for an fp32 logit x, split into an integer part K (clamped to int8 range)
-// and a fraction f with |error| ~1e-8: two-product and two-sum error-free transformations on the FP32
-// pipe (float64 conversions run at 1/16 rate and made the row kernels compute bound).
+// e = x * log2(e) - l2 - ct for an fp32 logit x, split into an integer part K (clamped at -127) and a
+// fraction f with |error| ~1e-8: two-product and two-sum error-free transformations on the FP32 pipe
+// (float64 conversions run at 1/16 rate and made the row kernels compute bound).
 constexpr float kLog2eHi = 1.4426950216293335f;             // fl(log2 e)
 constexpr float kLog2eLo = 1.9259629911266175e-8f;          // log2 e - fl(log2 e)
 __device__ __forceinline__ void emission_split(float x, float l2, float ct, float& K, float& f) {
@@ -65,78 +50,11 @@ __device__ __forceinline__ void emission_split(float x, float l2, float ct, floa
     f = (s - Kt) + (err + pl);
 }
 
-// ---- packed FP32x2 arithmetic (sm_100: FADD2 / FFMA2 issue two fp32 operations per instruction) -------
-// The trellis kernels are bound by instruction issue and half of their instructions are fp32 adds, so
-// per-slot quantities are kept as float2 over pairs of slots and added two at a time.
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-    unsigned long long ra, rb, rc;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
-    float2 c;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(rc));
-    return c;
-}
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
-    unsigned long long ra, rb, rc;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
-    float2 c;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(rc));
-    return c;
-}
-// J per-slot floats stored as float2 over slot pairs; [j] with a compile-time j resolves to one register
-template <int J>
-struct SlotVec {
-    float2 v[(J + 1) / 2];
-    __device__ __forceinline__ float& operator[](int j) { return (j & 1) ? v[j >> 1].y : v[j >> 1].x; }
-    __device__ __forceinline__ float operator[](int j) const { return (j & 1) ? v[j >> 1].y : v[j >> 1].x; }
-};
-
-// ---- stored trellis values: Q11.20 fixed point relative to a per-slot integer base -----------------
-// A split number (h, l) is stored as round((h - base + l) * 2^20) in one int32: absolute precision
-// 5e-7 at any distance up to 2047 log2 units below the base (the state that matters for a posterior
-// can sit hundreds of units below its slot's maximum when posteriors are peaky); void -> INT_MIN.
-constexpr int kFixVoid = (int)0x80000000;
-__device__ __forceinline__ int sf_to_fix(SF a, float base) {
-    const float d = a.h - base;                                   // integer valued
-    const int id = __float_as_int(fmaxf(d, -2047.0f) + kMagic) - 0x4B400000;
-    const int il = __float_as_int(fmaf(a.l, 1048576.0f, kMagic)) - 0x4B400000;
-    return (d < kVoidTest) ? kFixVoid : id * 1048576 + il;
-}
-// fixed -> (integer part, fraction in [0,1)) as floats; void -> (kVoid, 0)
-__device__ __forceinline__ void fix_to_parts(int v, float& hi, float& lo) {
-    const int ih = v >> 20;
-    const int il = v - (ih << 20);
-    hi = (v == kFixVoid) ? kVoid : small_int_to_float(ih);
-    lo = small_int_to_float(il) * (1.0f / 1048576.0f);
-}
-__device__ __forceinline__ SF sf_void() { SF r; r.h = kVoid; r.l = 0.0f; return r; }
-// log2(2^a + 2^b); the result's l is in [-0.5, 1.5] (not renormalised)
-__device__ __forceinline__ SF lae_sf(SF a, SF b) {
-    const float d = (a.h - b.h) + (a.l - b.l);
-    const bool p = d > 0.0f;
-    SF r;
-    r.h = p ? a.h : b.h;
-    r.l = (p ? a.l : b.l) + lg2f(1.0f + ex2f(-fabsf(d)));
-    return r;
-}
-// a + (K + f) with K integer-valued, renormalised so that |l| <= 0.5; void stays void
-__device__ __forceinline__ SF add_norm(SF a, float K, float f) {
-    const float l = a.l + f;
-    const float r = round_int(l);
-    SF o;
-    o.h = fmaxf((a.h + K) + r, kVoid);
-    o.l = l - r;
-    return o;
-}
-
 // ---- extended-range linear numbers ----------------------------------------------------------------
 // value = m * 2^e with m an fp32 in [1, 2) (or a small multiple of it between a sum and the next
 // normalisation) and e an int32.  The CTC trellis runs in this representation: the sum-product
 // recursion costs integer exponent alignment + one FADD + one FMUL per transition instead of a
-// log-add-exp (2 MUFU + ~15 FP32 on split numbers), keeps 24 significant bits whatever the magnitude, and
+// log-add-exp (2 MUFU + ~15 FP32 on the split log-domain numbers this replaced), keeps 24 significant bits whatever the magnitude, and
 // has no range limit (the exponent is a full int).  "void" (probability 0) is m = 1, e = kVoidE: it
 // aligns to +0 against anything real, and adding voids keeps the exponent far below kVoidETest.
 struct XF { float m; int e; };
@@ -191,12 +109,6 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ double warp_max_d(double v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
 // ---- mbarrier + bulk async copy (TMA engine; SASS: UBLKCP / SYNCS) ---------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

@@ -12,9 +12,9 @@
 //                       (cp.async.bulk) ring; posterior occupancies overwrite the emission buffer
 //   ctc_grad_kernel     one warp per row: softmax - occupancy, times grad_out, written once
 //
-// All log-domain values are log2.  alpha/beta are split numbers (integer part + fraction, common.cuh)
-// and gathered emissions are stored as int8 integer part + fp32 fraction, so every fp32 rounding in the
-// recursions happens at magnitude ~1 whatever T and log V are (SURVEY.md finding 3).
+// alpha/beta are extended-range linear numbers (fp32 mantissa + int32 exponent, common.cuh XF) and the
+// gathered emissions are linear fp32 probabilities relative to a per-row integer shift, so every fp32
+// rounding in the recursions is 6e-8 relative whatever T and log V are (SURVEY.md finding 3).
 #pragma once
 #include "common.cuh"
 
@@ -22,7 +22,7 @@ namespace hab {
 
 struct CtcWs {                 // workspace layout (byte offsets), filled by ctc_ws_layout()
     size_t meta, order, tgt, dupnext, loss, lse2, em, tr, total;
-    int Sp, E, JWp, SPX;       // E: floats per emission row (header + fractions + packed int8 parts)
+    int Sp, E, JWp, SPX;       // E: floats per emission row (4 header floats + one per label)
 };
 
 // CTC emission row (floats): [0] ct (integer row shift)  [1] blank  [4+k] label k, where an emission is
@@ -36,16 +36,6 @@ __device__ __forceinline__ float emission_linear(float K, float f) {
     const int k = __float_as_int(K + kMagic) - 0x4B400000;          // K is integer valued: exact, no F2I
     return (k < -125) ? 1.1754943508222875e-38f : xf_scale(exp2_poly(f), k);
 }
-// star-CTC emission words (star.cuh): Q8.24 fixed-point value of log2 p - ct
-__device__ __forceinline__ int emission_word(float K, float f) {
-    const int fi = __float2int_rn(fmaxf(f, -0.5f) * 16777216.0f);
-    return (int)(((unsigned)__float2int_rn(K) << 24) + (unsigned)fi);
-}
-__device__ __forceinline__ void emission_decode(int v, float& K, float& f) {
-    K = (float)(v >> 24);
-    f = (float)(v & 0xffffff) * (1.0f / 16777216.0f);
-}
-
 __host__ inline CtcWs ctc_ws_layout(int T, int N, int S) {
     CtcWs w;
     w.Sp = round_up(S > 0 ? S : 1, 4);
@@ -288,7 +278,6 @@ struct TrellisParams {
     float* loss; float* loss_ws;
     int nstage, G, W;          // ring stages; frames per stage; compute warps per sweep direction
     int dir_bytes;             // shared memory per direction
-    long long* probe;          // HAB_PROBE builds only
 };
 
 constexpr int kMaxG = 4;
@@ -310,7 +299,6 @@ __host__ __device__ inline int trellis_dir_bytes(int E, int SPX, int OC, int nst
     return round_up(nstage * trellis_stage_floats(E, SPX, OC, G, W, NP) * 4 + 2 * W * 16 + W * 16 + 2 * nstage * 8, 128);
 }
 
-constexpr float kRebase = 24.0f;   // (star-CTC) a slot is re-based when its states drift this far from the base
 
 // The producer warp of one sweep side (shared by the CTC and star-CTC trellis kernels): lane 0 issues
 // every bulk copy.  Group k (counted over both phases) lives in stage k % nstage and holds up to G
