@@ -160,14 +160,18 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_rows_kernel(StarRowsPa
             emission_split(row[0], l2, ct, Kb, fb);
             *(float4*)erow = make_float4(ct, emission_linear(Kb, fb), Plin, __int_as_float(__float2int_rn(ct)));
         }
+        // star emission P_t - p_y (ha/star.py:4-5 logsubexp) in the linear domain: (s - e_y) * (P_t / s) with e_y the
+        // very term class y contributed to the sum s, so the difference is the sum over the other classes up to
+        // the rounding of s (6e-8 s) -- subtracting an independently rounded p_y would leave 2^-22 p_y behind,
+        // which matters when one label holds nearly all of P_t.  Never below the smallest normal.
+        const float pscale = (s > 0.0f) ? Plin / s : 0.0f;
         for (int k = lane; k < Ks; k += 32) {
             const int y = s_tgt[k];
             float Kl, fl;
             emission_split(row[y], l2, ct, Kl, fl);
             const float pl = emission_linear(Kl, fl);
-            // star emission P_t - p_y (ha/star.py:4-5 logsubexp), subtracted in the linear domain: both terms are
-            // good to ~1e-7 relative, which is all fp32 knows about P_t anyway; never below the smallest normal
-            const float ps = (y != 0) ? fmaxf(Plin - pl, 1.1754943508222875e-38f) : Plin;
+            const float ey = ex2f(fmaf(row[y], kLog2e, -m2));
+            const float ps = (y != 0) ? fmaxf((s - ey) * pscale, 1.1754943508222875e-38f) : Plin;
             ((float2*)(erow + 4))[k] = make_float2(pl, ps);
         }
         __syncwarp();

@@ -421,3 +421,76 @@ def test_viterbi_bit_exact(hb, oracle):
     o_ali, o_sc = oracle.ctc_viterbi(lp.numpy(), tg.numpy(), il.numpy(), tl.numpy())
     assert np.array_equal(ali.cpu().numpy(), o_ali)
     assert np.array_equal(sc.cpu().numpy().view(np.int32), o_sc.view(np.int32)), "scores must match bit for bit"
+
+
+# ------------------------------------------------------------------------------------ fuzz ---
+def _fuzz_shapes(seed, n):
+    import random
+    r = random.Random(seed)
+    out = []
+    for _ in range(n):
+        S = r.choice([0, 1, 2, 3, 7, 31, 32, 33, 40, 63, 64, 65, 90])
+        T = max(1, S + r.choice([-2, 0, 1, 2, 5, 17, 40]))
+        out.append(dict(T=T, N=r.choice([1, 2, 3, 5]), V=r.choice([2, 3, 5, 8, 17, 32, 100]), S=S,
+                        scale=r.choice([0.3, 1.0, 1.0, 3.0, 6.0]), seed=r.randrange(1 << 30)))
+    return out
+
+
+@pytest.mark.parametrize("cfg", _fuzz_shapes(1, 40), ids=lambda c: f"T{c['T']}N{c['N']}V{c['V']}S{c['S']}x{c['scale']}")
+def test_ctc_star_fuzz(hb, oracle, cfg):
+    """random small shapes around the slot / warp boundaries, random lengths (0 .. S, 1 .. T), labels with
+    repeats, mixed feasible and infeasible utterances, several logit scales"""
+    g = torch.Generator().manual_seed(cfg["seed"])
+    T, N, V, S = cfg["T"], cfg["N"], cfg["V"], cfg["S"]
+    x = torch.randn(T, N, V, generator=g) * cfg["scale"]
+    tg = torch.randint(1, V, (N, max(S, 1)), generator=g)[:, :S] if S else torch.zeros(N, 0, dtype=torch.long)
+    il = torch.randint(1, T + 1, (N,), generator=g); il[0] = T
+    tl = torch.randint(0, S + 1, (N,), generator=g); tl[0] = S
+    args = (tg.numpy(), il.numpy(), tl.numpy())
+    for kind in ("ctc", "star"):
+        if kind == "star" and (V < 2 or S > 511):
+            continue
+        tgz = tg.clone()
+        for n in range(N):
+            tgz[n, tl[n]:] = 0
+        a = (tgz.numpy(),) + args[1:]
+        ol, og = (oracle.ctc(x.numpy(), *a) if kind == "ctc" else oracle.star(x.numpy(), *a, star_penalty=-0.7))
+        xd = x.to(dev()).requires_grad_(True)
+        targs = (tgz.to(dev()), il.to(dev()), tl.to(dev()))
+        loss = (hb.ctc_forward_score3(xd, *targs, from_logits=True) if kind == "ctc"
+                else hb.star_ctc_forward_score(xd, *targs, star_penalty=-0.7, from_logits=True))
+        fin = np.isfinite(ol)
+        (loss[torch.from_numpy(fin).to(dev())]).sum().backward() if fin.any() else None
+        lo = loss.detach().double().cpu().numpy()
+        assert (np.isinf(lo) == np.isinf(ol)).all(), (kind, lo, ol)
+        np.testing.assert_allclose(lo[fin], ol[fin], rtol=LOSS_RTOL, atol=1e-5, err_msg=kind)
+        if fin.any():
+            ogm = og.copy(); ogm[:, ~fin] = 0
+            err = np.abs(xd.grad.double().cpu().numpy() - ogm).max()
+            assert err < GRAD_ATOL, f"{kind} {err:.3e}"
+
+
+@pytest.mark.parametrize("cfg", _fuzz_shapes(2, 24), ids=lambda c: f"T{c['T']}N{c['N']}V{c['V']}U{c['S']}x{c['scale']}")
+def test_rnnt_fuzz(hb, oracle, cfg):
+    g = torch.Generator().manual_seed(cfg["seed"])
+    N, V, U = cfg["N"], cfg["V"], min(cfg["S"], 40)
+    T = max(1, min(cfg["T"], 40))
+    f = torch.randn(N, T, V, generator=g) * cfg["scale"]
+    gg = torch.randn(N, U + 1, V, generator=g) * cfg["scale"]
+    tg = torch.randint(0, V, (N, max(U, 1)), generator=g)[:, :U] if U else torch.zeros(N, 0, dtype=torch.long)
+    il = torch.randint(1, T + 1, (N,), generator=g); il[0] = T
+    tl = torch.randint(0, U + 1, (N,), generator=g); tl[0] = U
+    joint = (f[:, :, None, :] + gg[:, None, :, :]).contiguous()
+    ol, og = oracle.rnnt(joint.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    jd = joint.to(dev()).requires_grad_(True)
+    loss = hb.transducer_forward_score(jd, tg.to(dev()), il.to(dev()), tl.to(dev()), from_logits=True)
+    loss.sum().backward()
+    np.testing.assert_allclose(loss.detach().double().cpu().numpy(), ol, rtol=LOSS_RTOL, atol=1e-5)
+    assert np.abs(jd.grad.double().cpu().numpy() - og).max() < GRAD_ATOL
+    fd = f.to(dev()).requires_grad_(True); gd = gg.to(dev()).requires_grad_(True)
+    l2 = hb.transducer_forward_score_fg(fd, gd, tg.to(dev()), il.to(dev()), tl.to(dev()))
+    l2.sum().backward()
+    np.testing.assert_allclose(l2.detach().double().cpu().numpy(), ol, rtol=LOSS_RTOL, atol=1e-5)
+    for got, ref in ((fd.grad, og.sum(2)), (gd.grad, og.sum(1))):
+        err = np.abs(got.double().cpu().numpy() - ref)
+        assert (err <= GRAD_ATOL + 2e-6 * np.abs(ref)).all(), f"{err.max():.3e}"
