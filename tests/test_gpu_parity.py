@@ -494,3 +494,35 @@ def test_rnnt_fuzz(hb, oracle, cfg):
     for got, ref in ((fd.grad, og.sum(2)), (gd.grad, og.sum(1))):
         err = np.abs(got.double().cpu().numpy() - ref)
         assert (err <= GRAD_ATOL + 2e-6 * np.abs(ref)).all(), f"{err.max():.3e}"
+
+
+def test_cuda_graph_capture_and_replay(hb):
+    """the ops never synchronise or allocate outside torch: a loss+gradient step can be captured once and
+    replayed on new inputs written into the captured buffers (launch-bound small batches, BASELINE config 1)"""
+    g = torch.Generator().manual_seed(9)
+    T, N, V, S = 200, 8, 256, 50
+    xs = [torch.randn(T, N, V, generator=g).to(dev()) for _ in range(3)]
+    tg = torch.randint(1, V, (N, S), generator=g).to(dev())
+    il = torch.full((N,), T).to(dev()); tl = torch.full((N,), S).to(dev())
+    go = torch.ones(N, device=dev())
+    from haloop_b200 import ops
+    eager = []
+    for x in xs:
+        loss, ws = ops.ctc_fwd(x, tg, il, tl, True)
+        eager.append((loss.clone(), ops.ctc_bwd(x, ws, go, S, True).clone()))
+    xbuf = xs[0].clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                       # warm-up on the capture stream
+        loss, ws = ops.ctc_fwd(xbuf, tg, il, tl, True)
+        ops.ctc_bwd(xbuf, ws, go, S, True)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        gl, gws = ops.ctc_fwd(xbuf, tg, il, tl, True)
+        gg = ops.ctc_bwd(xbuf, gws, go, S, True)
+    for x, (el, eg) in zip(xs, eager):
+        xbuf.copy_(x)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(gl, el) and torch.equal(gg, eg)      # deterministic kernels: bit-identical
