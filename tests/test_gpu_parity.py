@@ -526,3 +526,80 @@ def test_cuda_graph_capture_and_replay(hb):
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(gl, el) and torch.equal(gg, eg)      # deterministic kernels: bit-identical
+
+
+# ------------------------------------------------------------- BASELINE sizes: properties ---
+def _full_size_checks(kind, loss_fn, x, grad, oracle_fn, sub, row_axis_sum):
+    # (1) shift invariance of a softmax-fed loss: every gradient row sums to zero
+    rs = grad.sum(-1).abs().max().item()
+    assert rs < 2e-5, f"{kind}: gradient rows sum to {rs:.2e}"
+    # (2) a few utterances of the full batch against the float64 oracle
+    for n, (ol, og) in sub.items():
+        l = float(loss_fn[n])
+        assert abs(l / ol - 1) < LOSS_RTOL, (kind, n, l, ol)
+        err = np.abs(row_axis_sum(grad, n).double().cpu().numpy() - og).max()
+        assert err < GRAD_ATOL, f"{kind} utterance {n}: {err:.3e}"
+
+
+def test_full_size_ctc_c2(hb, oracle):
+    """BASELINE config 2 (B=256, T=1500, V=1024, U=300): row sums, determinism, linearity in grad_output,
+    and three utterances of the batch against the oracle"""
+    g = torch.Generator(device=dev()).manual_seed(2)
+    B, T, V, U = 256, 1500, 1024, 300
+    x = torch.randn(B, T, V, device=dev(), generator=g).permute(1, 0, 2)
+    tg = torch.randint(1, V, (B, U), device=dev(), generator=g)
+    il = torch.randint(T // 2, T + 1, (B,), device=dev(), generator=g); il[0] = T
+    tl = torch.randint(U // 2, U + 1, (B,), device=dev(), generator=g); tl[0] = U
+    from haloop_b200 import ops
+    loss, ws = ops.ctc_fwd(x, tg, il, tl, True)
+    g1 = ops.ctc_bwd(x, ws, torch.ones(B, device=dev()), U, True)
+    g2 = ops.ctc_bwd(x, ws, torch.full((B,), 2.0, device=dev()), U, True)
+    assert torch.equal(g2, 2 * g1), "gradient is linear in grad_output (exactly, for a power of two)"
+    loss_b, ws_b = ops.ctc_fwd(x, tg, il, tl, True)
+    assert torch.equal(loss, loss_b) and torch.equal(ops.ctc_bwd(x, ws_b, torch.ones(B, device=dev()), U, True), g1), \
+        "bit-identical when repeated"
+    sub = {}
+    for n in (0, 17, 255):
+        ol, og = oracle.ctc(x[:, n:n + 1].cpu().numpy(), tg[n:n + 1].cpu().numpy(), il[n:n + 1].cpu().numpy(),
+                            tl[n:n + 1].cpu().numpy())
+        sub[n] = (float(ol[0]), og[:, 0])
+    _full_size_checks("ctc", loss, x, g1, None, sub, lambda gr, n: gr[:, n])
+    assert not g1[int(il[17]):, 17].any(), "frames past the utterance's length carry no gradient"
+
+
+def test_full_size_star_c3(hb, oracle):
+    g = torch.Generator(device=dev()).manual_seed(3)
+    B, T, V, U = 128, 1000, 512, 200
+    x = torch.randn(B, T, V, device=dev(), generator=g).permute(1, 0, 2)
+    tg = torch.randint(1, V, (B, U), device=dev(), generator=g)
+    il = torch.randint(T // 2, T + 1, (B,), device=dev(), generator=g); il[0] = T
+    tl = torch.randint(U // 2, U + 1, (B,), device=dev(), generator=g); tl[0] = U
+    tg = tg * (torch.arange(U, device=dev())[None, :] < tl[:, None])
+    from haloop_b200 import ops
+    loss, ws = ops.star_fwd(x, tg, il, tl, -0.5, True)
+    g1 = ops.star_bwd(x, ws, torch.ones(B, device=dev()), U, True)
+    sub = {}
+    for n in (0, 77):
+        ol, og = oracle.star(x[:, n:n + 1].cpu().numpy(), tg[n:n + 1].cpu().numpy(), il[n:n + 1].cpu().numpy(),
+                             tl[n:n + 1].cpu().numpy(), star_penalty=-0.5)
+        sub[n] = (float(ol[0]), og[:, 0])
+    _full_size_checks("star", loss, x, g1, None, sub, lambda gr, n: gr[:, n])
+
+
+def test_full_size_rnnt_c4(hb, oracle):
+    g = torch.Generator(device=dev()).manual_seed(4)
+    B, T, U, V = 32, 500, 100, 1024
+    x = torch.randn(B, T, U + 1, V, device=dev(), generator=g)
+    tg = torch.randint(1, V, (B, U), device=dev(), generator=g)
+    il = torch.randint(T // 2, T + 1, (B,), device=dev(), generator=g); il[0] = T
+    tl = torch.randint(U // 2, U + 1, (B,), device=dev(), generator=g); tl[0] = U
+    from haloop_b200 import ops
+    loss, ws = ops.rnnt_fwd(x, tg, il, tl, True)
+    g1 = ops.rnnt_bwd(x, ws, torch.ones(B, device=dev()), True)
+    sub = {}
+    for n in (0, 13):
+        ol, og = oracle.rnnt(x[n:n + 1].cpu().numpy(), tg[n:n + 1].cpu().numpy(), il[n:n + 1].cpu().numpy(),
+                             tl[n:n + 1].cpu().numpy())
+        sub[n] = (float(ol[0]), og[0])
+    _full_size_checks("rnnt", loss, x, g1, None, sub, lambda gr, n: gr[n])
+    assert not g1[13, int(il[13]):].any() and not g1[13, :, int(tl[13]) + 1:].any(), "padded nodes carry no gradient"
