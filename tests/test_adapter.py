@@ -77,8 +77,12 @@ def test_patched_forwards_match_the_live_call_sites():
     torchaudio = pytest.importorskip("torchaudio")
     import torch.nn.functional as F
     dev = torch.device("cuda")
+    torch.manual_seed(1234)                    # module parameters come from the global generator
     m = _stub_module()
     saved = hb.patch_haloop(m)
+
+    def close(a, b):                           # the library side of the comparison is plain fp32
+        return (a - b).abs().max() <= 1e-4 + 1e-3 * b.abs().max()
     try:
         g = torch.Generator().manual_seed(3)
         N, T, D, V, U = 4, 30, 12, 9, 6
@@ -94,7 +98,7 @@ def test_patched_forwards_match_the_live_call_sites():
         ref = F.ctc_loss(lp.double(), tg, il, tl)               # reduction='mean': / target_lengths, batch mean
         ref.backward()
         assert abs(float(loss) / float(ref) - 1) < 1e-4
-        assert (got - tc.classifier.weight.grad).abs().max() < 1e-4
+        assert close(got, tc.classifier.weight.grad)
 
         tr = m.Transducer(D, V).to(dev)
         loss, _ = tr(feats, tg, il, tl)
@@ -107,6 +111,6 @@ def test_patched_forwards_match_the_live_call_sites():
         ref.backward()
         assert abs(float(loss) / float(ref) - 1) < 1e-4
         for a, p in zip(got, tr.parameters()):
-            assert (a - p.grad).abs().max() < 1e-4
+            assert close(a, p.grad)
     finally:
         adapter.unpatch_haloop(saved)
