@@ -603,3 +603,46 @@ def test_full_size_rnnt_c4(hb, oracle):
         sub[n] = (float(ol[0]), og[0])
     _full_size_checks("rnnt", loss, x, g1, None, sub, lambda gr, n: gr[n])
     assert not g1[13, int(il[13]):].any() and not g1[13, :, int(tl[13]) + 1:].any(), "padded nodes carry no gradient"
+
+
+# -------------------------------------------------------------------------------- limits ---
+@pytest.mark.parametrize("cfg", [
+    dict(T=3, N=65535, V=8, S=1),            # the largest batch one launch takes
+    dict(T=6, N=2, V=27000, S=3),            # a vocabulary whose rows barely fit two shared-memory stages
+    dict(T=30000, N=1, V=16, S=40),          # a very long utterance
+    dict(T=1400, N=1, V=12, S=1023),         # the longest target
+])
+def test_ctc_limits(hb, oracle, cfg):
+    x, tg, il, tl = _rand_ctc(600 + cfg["S"], cfg["T"], cfg["N"], cfg["V"], cfg["S"])
+    ol, og = oracle.ctc(x.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    xd = x.to(dev()).requires_grad_(True)
+    loss = hb.ctc_forward_score3(xd, tg.to(dev()), il.to(dev()), tl.to(dev()), from_logits=True)
+    fin = np.isfinite(ol)
+    loss[torch.from_numpy(fin).to(dev())].sum().backward()
+    lo = loss.detach().double().cpu().numpy()
+    assert (np.isinf(lo) == np.isinf(ol)).all()
+    np.testing.assert_allclose(lo[fin], ol[fin], rtol=LOSS_RTOL)
+    og[:, ~fin] = 0
+    assert np.abs(xd.grad.double().cpu().numpy() - og).max() < GRAD_ATOL
+
+
+def test_rnnt_limits_and_errors(hb, oracle):
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(1, 3, 1024, 4, generator=g)                   # U+1 = 1024: the widest lattice
+    tg = torch.randint(0, 4, (1, 1023), generator=g)
+    il = torch.tensor([3]); tl = torch.tensor([1023])
+    ol, og = oracle.rnnt(x.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    xd = x.to(dev()).requires_grad_(True)
+    loss = hb.transducer_forward_score(xd, tg.to(dev()), il.to(dev()), tl.to(dev()), from_logits=True)
+    loss.sum().backward()
+    np.testing.assert_allclose(loss.detach().double().cpu().numpy(), ol, rtol=LOSS_RTOL)
+    assert np.abs(xd.grad.double().cpu().numpy() - og).max() < GRAD_ATOL
+    with pytest.raises(Exception):                                # unsupported shapes fail loudly, never silently
+        hb.transducer_forward_score(torch.zeros(1, 2, 1026, 4, device=dev()), torch.zeros(1, 1025, dtype=torch.long),
+                                    torch.tensor([2]), torch.tensor([1025]), from_logits=True)
+    with pytest.raises(Exception):
+        hb.ctc_forward_score3(torch.zeros(2, 70000, 4, device=dev()), torch.zeros(70000, 1, dtype=torch.long),
+                              torch.full((70000,), 2), torch.ones(70000, dtype=torch.long), from_logits=True)
+    with pytest.raises(Exception):
+        hb.ctc_forward_score3(torch.zeros(1500, 2, 8, device=dev()), torch.ones(2, 1024, dtype=torch.long),
+                              torch.full((2,), 1500), torch.full((2,), 1024), from_logits=True)
