@@ -124,7 +124,7 @@ enum { kE = 0, kDF = 1, kDG = 2 };
 constexpr int kGM = 64, kGN = 64, kGK = 16;
 
 template <int MODE>
-__global__ void __launch_bounds__(256) rnnt_fg_gemm_kernel(RnntFgParams p) {
+__global__ void __launch_bounds__(256, 3) rnnt_fg_gemm_kernel(RnntFgParams p) {
     __shared__ float As[2][kGK][kGM + 4];
     __shared__ float Bs[2][kGK][kGN + 4];
     const int n = blockIdx.z;

@@ -92,7 +92,8 @@ def ctc_fwd(x: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, tgt_le
 @ctc_fwd.register_fake
 def _(x, targets, in_len, tgt_len, from_logits):
     T, N, V = x.shape
-    return x.new_empty(N), x.new_empty(1, dtype=torch.uint8)
+    nbytes = _lib.lib().ha_ctc_workspace_bytes(int(T), int(N), int(V), int(targets.shape[1]))   # host-only query
+    return x.new_empty(N), x.new_empty(nbytes, dtype=torch.uint8)
 
 
 @torch.library.custom_op("ha_b200::ctc_bwd", mutates_args=())
@@ -163,7 +164,8 @@ def star_fwd(x: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, tgt_l
 @star_fwd.register_fake
 def _(x, targets, in_len, tgt_len, star_penalty, from_logits):
     T, N, V = x.shape
-    return x.new_empty(N), x.new_empty(1, dtype=torch.uint8)
+    nbytes = _lib.lib().ha_star_workspace_bytes(int(T), int(N), int(V), int(targets.shape[1]))
+    return x.new_empty(N), x.new_empty(nbytes, dtype=torch.uint8)
 
 
 @torch.library.custom_op("ha_b200::star_bwd", mutates_args=())
@@ -232,7 +234,9 @@ def rnnt_fwd(joint: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, t
 
 @rnnt_fwd.register_fake
 def _(joint, targets, in_len, tgt_len, from_logits):
-    return joint.new_empty(joint.shape[0]), joint.new_empty(1, dtype=torch.uint8)
+    N, T, U1, V = joint.shape
+    nbytes = _lib.lib().ha_rnnt_workspace_bytes(int(N), int(T), int(U1), int(V))
+    return joint.new_empty(N), joint.new_empty(nbytes, dtype=torch.uint8)
 
 
 @torch.library.custom_op("ha_b200::rnnt_bwd", mutates_args=())
@@ -303,7 +307,9 @@ def rnnt_fg_fwd(f: torch.Tensor, g: torch.Tensor, targets: torch.Tensor, in_len:
 
 @rnnt_fg_fwd.register_fake
 def _(f, g, targets, in_len, tgt_len):
-    return f.new_empty(f.shape[0]), f.new_empty(1, dtype=torch.uint8)
+    N, T, V = f.shape
+    nbytes = _lib.lib().ha_rnnt_fg_workspace_bytes(int(N), int(T), int(g.shape[1]), int(V))
+    return f.new_empty(N), f.new_empty(nbytes, dtype=torch.uint8)
 
 
 @torch.library.custom_op("ha_b200::rnnt_fg_bwd", mutates_args=())

@@ -646,3 +646,40 @@ def test_rnnt_limits_and_errors(hb, oracle):
     with pytest.raises(Exception):
         hb.ctc_forward_score3(torch.zeros(1500, 2, 8, device=dev()), torch.ones(2, 1024, dtype=torch.long),
                               torch.full((2,), 1500), torch.full((2,), 1024), from_logits=True)
+
+
+def test_custom_op_registration(hb):
+    """torch.library.opcheck: schema (no hidden mutation/aliasing), fake-tensor kernels (so torch.compile traces
+    through, ha/init.py:267) and autograd registration of the four forward ops"""
+    from haloop_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(12, 3, 10, generator=g).to(dev()).requires_grad_(True)
+    tg = torch.randint(1, 10, (3, 4), generator=g).to(dev())
+    il = torch.tensor([12, 10, 9]).to(dev()); tl = torch.tensor([4, 3, 2]).to(dev())
+    utils = ("test_schema", "test_faketensor", "test_autograd_registration")
+    torch.library.opcheck(ops.ctc_fwd, (x, tg, il, tl, True), test_utils=utils)
+    torch.library.opcheck(ops.star_fwd, (x, tg, il, tl, -0.5, True), test_utils=utils)
+    j = torch.randn(3, 6, 5, 10, generator=g).to(dev()).requires_grad_(True)
+    torch.library.opcheck(ops.rnnt_fwd, (j, tg, torch.tensor([6, 5, 4]).to(dev()), tl, True), test_utils=utils)
+    f = torch.randn(3, 6, 10, generator=g).to(dev()).requires_grad_(True)
+    gg = torch.randn(3, 5, 10, generator=g).to(dev()).requires_grad_(True)
+    torch.library.opcheck(ops.rnnt_fg_fwd, (f, gg, tg, torch.tensor([6, 5, 4]).to(dev()), tl), test_utils=utils)
+
+
+def test_torch_compile_traces_through(hb):
+    """--compile (ha/init.py:267): the custom ops carry fake kernels and an autograd formula, so a compiled
+    training step runs them without graph breaks (aot_eager: traced forward and backward, no codegen)"""
+    g = torch.Generator().manual_seed(2)
+    tg = torch.randint(1, 10, (3, 4), generator=g).to(dev())
+    il = torch.tensor([12, 10, 9]).to(dev()); tl = torch.tensor([4, 3, 2]).to(dev())
+
+    def step(x):
+        return hb.ctc_reduce_mean(hb.ctc_forward_score3(x * 1.5, tg, il, tl, from_logits=True), tl)
+
+    x1 = torch.randn(12, 3, 10, generator=g).to(dev()).requires_grad_(True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    step(x1).backward()
+    compiled = torch.compile(step, backend="aot_eager", fullgraph=True)
+    l2 = compiled(x2)
+    l2.backward()
+    assert torch.equal(step(x1.detach()), l2.detach()) and torch.equal(x1.grad, x2.grad)
