@@ -28,7 +28,7 @@ struct CtcWs {                 // workspace layout (byte offsets), filled by ctc
 // CTC emission row (floats): [0] ct (integer row shift)  [1] blank  [4+k] label k, where an emission is
 // the probability 2^(log2 p - ct) as a plain fp32 (<= 2^0.5, clamped below at 2^-126): the trellis runs in
 // the linear domain on extended-range numbers (common.cuh, XF).  The occupancy row written in place:
-// [1] blank occupancy, [4+k] label occupancy.
+// [1] sum of the label occupancies (the blank's is one minus it), [4+k] label occupancy.
 __host__ __device__ inline int ctc_em_floats(int Sp) { return 4 + Sp; }
 // 2^(K + f) for an integer-valued K in [-127, 1] and |f| <= 0.5 (exp2_poly: relative error ~1e-7, no
 // MUFU), exponent added into the bit pattern
@@ -666,16 +666,16 @@ __global__ void __launch_bounds__(32 * (2 * W + 2)) ctc_trellis_kernel(TrellisPa
                 eZ = feasible ? pm + ex : (1 << 29);          // infeasible: every occupancy underflows to ~0
                 logZ2 = feasible ? (double)pm + log2(sm) : 0.0;
             }
+            // Only the label states' occupancies are formed: the occupancies of a frame sum to one, so the gradient
+            // kernel takes the blank column as 1 - (sum of the label occupancies), which this row carries in [1].
             float bsum = 0.0f;
             if (active) {
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    float g0, g1; int x0, x1;
-                    prod(trow, j, g0, x0, g1, x1);
-                    g0 = xf_scale(g0 * rZ, max(x0 - eZ, -126));
-                    g1 = xf_scale(g1 * rZ, max(x1 - eZ, -126));
-                    bsum += ((hasp >> j) & 1u) ? g0 : 0.0f;
-                    if ((hasl >> j) & 1u) ob[pstep * j] = g1;
+                    const int o1 = trow[ooff - 64 * j - 1], b1 = trow[B1 - j];
+                    float g1 = sv[j] * xf_unpack_m(o1);
+                    g1 = xf_scale(g1 * rZ, max(ev[j] + b1 - xf_unpack_below(o1) - eZ, -126));
+                    if ((hasl >> j) & 1u) { ob[pstep * j] = g1; bsum += g1; }
                 }
             } else {
                 // none of my states is on any complete path at this frame: their posteriors are exactly zero
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(32 * (2 * W + 2)) ctc_trellis_kernel(TrellisPa
                 for (int j = 0; j < J; ++j)
                     if ((hasl >> j) & 1u) ob[pstep * j] = 0.0f;
             }
-            *ps = bsum;         // per-lane blank occupancy; the producer warp sums the 32 W of a row into float [1]
+            *ps = bsum;         // per-lane label occupancy; the producer warp sums the 32 W of a row into float [1]
             if (i == i0 + cnt - 1) fence_async_smem();   // this group's occupancy writes -> the producer's bulk stores
             side_barrier();
         }
@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) ctc_grad_kernel(GradParams 
             }
         }
         __syncwarp();
-        if (lane == 0) row[0] -= g * occ[1];
+        if (lane == 0) row[0] -= g * (1.0f - occ[1]);      // occ[1] = sum of the label occupancies of the frame
         float* dstg = gb + (long long)t * p.sg_t;
         if (p.use_bulk) {
             fence_async_smem();
