@@ -21,7 +21,7 @@ struct StarWs {
 
 // emission row (floats): [0] ct (integer row shift)  [1] blank  [2] all-star P  [3] ct as an int
 // [4+2k] label y_k  [5+2k] star "anything but y_k", each the probability 2^(log2 p - ct) as a plain fp32
-// (emission_linear, ctc.cuh).  The occupancy row written in place (floats): [1] blank occupancy
+// (emission_linear, ctc.cuh).  The occupancy row written in place (floats): [1] label + star occupancy (blanks: 1 - it)
 // [2] G = sum_k h_k  [4+2k] label occupancy  [5+2k] h_k (0 if y_k == 0), h_k = gamma(star k) / (P - p_{y_k}).
 __host__ __device__ inline int star_em_floats(int Sp) { return 4 + 2 * Sp; }
 
@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(32 * (2 * W + 2)) star_trellis_kernel(StarTrel
     const float pef = floorf(p.pen2);
     const int pe = (int)pef;
     const float pm = exp2f(p.pen2 - pef);
+    const float rpm = 1.0f / pm;
 
     unsigned char* db = smem_raw + (size_t)dir * p.dir_bytes;
     float* stages = (float*)db;
@@ -510,15 +511,18 @@ __global__ void __launch_bounds__(32 * (2 * W + 2)) star_trellis_kernel(StarTrel
                     const bool in = (hasq >> j) & 1u;
                     const int4 o = in ? orow[32 * j] : make_int4((int)kPackVoid, (int)kPackVoid, (int)kPackVoid, (int)kPackVoid);
                     const int xb = (in ? obase[j] : kVoidE) - eZ;
-                    const float g0 = xf_scale(s0[j].m * xf_unpack_m(o.x) * rZ, max(s0[j].e + xb - xf_unpack_below(o.x), -126));
-                    const float g1 = xf_scale(s1[j].m * xf_unpack_m(o.z) * rZ, max(s1[j].e + xb - xf_unpack_below(o.z), -126));
                     float gl = xf_scale(sl[j].m * xf_unpack_m(o.w) * rZ, max(sl[j].e + xb - xf_unpack_below(o.w), -126));
                     // h = gamma(star) / (P - p_y): both sides' pre-emission sums, the penalty, and the row shift
                     // taken back out (the shift cancels in gamma, not in P - p_y)
-                    const float h = xf_scale(ss[j].m * xf_unpack_m(o.y) * rZp,
-                                             max(ss[j].e + xb - xf_unpack_below(o.y) + (pe - cti), -126));
+                    const float hm = ss[j].m * xf_unpack_m(o.y) * rZp;
+                    const int hx = ss[j].e + xb - xf_unpack_below(o.y) + pe;
+                    const float h = xf_scale(hm, max(hx - cti, -126));
+                    // gamma(star) itself = the same product times the star's (shifted) emission.  The two blank
+                    // states' occupancies are not formed: a frame's occupancies sum to one, so the gradient
+                    // kernel takes the blank column as 1 - (labels + stars), which this row carries in [1].
+                    const float gs = hm * ((psm[j] * rpm) * __int_as_float((min(max(hx, -127), 127) + 127) << 23));
                     if (!((hasl >> j) & 1u)) gl = 0.0f;
-                    bsum += g0 + g1;
+                    bsum += in ? gl + gs : 0.0f;
                     gsum += h;
                     if (k < Ks) ((float2*)ob)[k] = make_float2(gl, ((exclude >> j) & 1u) ? h : 0.0f);
                 }
@@ -628,7 +632,7 @@ __global__ void __launch_bounds__(kMaxRowWarps * 32) star_grad_kernel(StarGradPa
         float* occ = row + V;
         const int t = t0 + warp + nw * r;
         const float l2 = p.lse2[(size_t)n * p.T + t];
-        const float occ_blank = occ[1], G = occ[2];
+        const float occ_blank = 1.0f - occ[1], G = occ[2];      // occ[1] = sum of the label and star occupancies
         const float p0 = ex2f(fmaf(row[0], kLog2e, -l2));
         // per-class corrections, computed from the untouched logits by the first position of each
         // label chain and parked in that position's occupancy slot
