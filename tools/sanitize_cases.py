@@ -16,6 +16,12 @@ for (N, T, U, V) in [(2, 17, 6, 16), (2, 12, 40, 37)]:
     tg = torch.randint(1, V, (N, U), generator=g).to(dev)
     il = torch.tensor([T, T - 3]).to(dev); tl = torch.tensor([U, U // 2]).to(dev)
     hb.transducer_forward_score(j, tg, il, tl, from_logits=True).sum().backward()
+    f = torch.randn(N, T + 60, V, generator=g).to(dev).requires_grad_(True)          # several GEMM tiles
+    gg = torch.randn(N, U + 1, V, generator=g).to(dev).requires_grad_(True)
+    hb.transducer_forward_score_fg(f, gg, tg, torch.tensor([T + 60, T]).to(dev), tl).sum().backward()
+j = torch.randn(1, 4, 200, 8, generator=g).to(dev).requires_grad_(True)                # the 1024-thread lattice
+hb.transducer_forward_score(j, torch.randint(0, 8, (1, 199), generator=g).to(dev), torch.tensor([4]).to(dev),
+                            torch.tensor([199]).to(dev), from_logits=True).sum().backward()
 lp = torch.randn(3, 50, 20, generator=g).log_softmax(-1).to(dev)
 hb.greedy_decode(lp, torch.tensor([50, 40, 3]).to(dev))
 hb.ctc_viterbi_align(lp.permute(1, 0, 2), torch.randint(1, 20, (3, 8), generator=g).to(dev), torch.tensor([50, 40, 30]).to(dev), torch.tensor([8, 5, 2]).to(dev))
