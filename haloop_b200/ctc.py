@@ -5,7 +5,7 @@
 """
 import torch
 
-from . import ops
+from . import functional, ops
 
 
 def ctc_forward_score3(emissions, targets, emission_lengths, target_lengths, from_logits=False):
@@ -18,6 +18,8 @@ def ctc_forward_score3(emissions, targets, emission_lengths, target_lengths, fro
     the log-softmax and returns (softmax - occupancy) * grad: one read and one write of (T,N,C).
     Infeasible alignments give +inf and a zero gradient (the reference gives ~3.4e38).
     """
+    if functional.transforms_active():          # torch.func.grad / vmap: see functional.py
+        return functional.ctc(emissions, targets, emission_lengths, target_lengths, from_logits)
     loss, _ = ops.ctc_fwd(emissions, targets, emission_lengths, target_lengths, bool(from_logits))
     return loss
 

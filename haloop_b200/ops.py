@@ -205,6 +205,48 @@ def _star_backward(ctx, grad_loss, _grad_ws):
 star_fwd.register_autograd(_star_backward, setup_context=_star_setup)
 
 
+# ------------------------------------------------------------------------------------------ vmap
+# Utterances are independent, so the batching rule of every op is "fold the vmapped dimension into the
+# utterance dimension and run once" (the reference has to drop its CTC term under torch.func.vmap for lack
+# of a rule, ha/grad_norm.py:14-16).  The workspace of the merged call is returned unbatched: the matching
+# backward op is vmapped the same way and finds the merged layout.
+def _fold(t, d, B, at):
+    """Move vmap dim `d` of `t` (or broadcast if None) next to dim `at` and merge the two."""
+    if t is None:
+        return None
+    if d is None:
+        t = t.unsqueeze(at).expand(*t.shape[:at], B, *t.shape[at:])
+    else:
+        t = t.movedim(d, at)
+    return t.reshape(*t.shape[:at], t.shape[at] * t.shape[at + 1], *t.shape[at + 2:])
+
+
+def _bsize(args, in_dims):
+    for a, d in zip(args, in_dims):
+        if d is not None:
+            return a.shape[d]
+    raise RuntimeError("vmap rule called without a batched argument")
+
+
+def _register_time_major_vmap(fwd, bwd, n_extra):
+    """fwd(x (T,N,V), targets (N,S), in_len (N,), tgt_len (N,), *extra) / bwd(x, ws, grad_loss (N,), S, flag)"""
+    @torch.library.register_vmap(fwd)
+    def _(info, in_dims, x, targets, in_len, tgt_len, *extra):
+        B = _bsize((x, targets, in_len, tgt_len), in_dims[:4])
+        loss, ws = fwd(_fold(x, in_dims[0], B, 1), _fold(targets, in_dims[1], B, 0), _fold(in_len, in_dims[2], B, 0),
+                       _fold(tgt_len, in_dims[3], B, 0), *extra)
+        return (loss.view(B, -1), ws), (0, None)
+
+    @torch.library.register_vmap(bwd)
+    def _(info, in_dims, x, ws, grad_loss, S, flag):
+        if in_dims[1] is not None:
+            raise RuntimeError("the workspace of a vmapped forward is shared by the whole batch")
+        B = _bsize((x, grad_loss), (in_dims[0], in_dims[2]))
+        gx = bwd(_fold(x, in_dims[0], B, 1), ws, _fold(grad_loss, in_dims[2], B, 0), S, flag)
+        T, BN, V = gx.shape
+        return gx.view(T, B, BN // B, V), 1
+
+
 # ----------------------------------------------------------------------------------------- RNN-T
 @torch.library.custom_op("ha_b200::rnnt_fwd", mutates_args=())
 def rnnt_fwd(joint: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, tgt_len: torch.Tensor,
@@ -394,3 +436,43 @@ def ctc_viterbi(lp, targets, in_len, tgt_len):
                               ali.data_ptr(), sc.data_ptr(), ws.data_ptr(), nbytes, _stream(lp))
     _lib.check(rc, "ha_ctc_viterbi")
     return ali, sc
+
+
+# ------------------------------------------------------------------------------- vmap rules
+_register_time_major_vmap(ctc_fwd, ctc_bwd, 1)
+_register_time_major_vmap(star_fwd, star_bwd, 2)
+
+
+@torch.library.register_vmap(rnnt_fwd)
+def _(info, in_dims, joint, targets, in_len, tgt_len, from_logits):
+    B = _bsize((joint, targets, in_len, tgt_len), in_dims[:4])
+    j = _fold(joint, in_dims[0], B, 0)
+    loss, ws = rnnt_fwd(j, _fold(targets, in_dims[1], B, 0), _fold(in_len, in_dims[2], B, 0),
+                        _fold(tgt_len, in_dims[3], B, 0), from_logits)
+    return (loss.view(B, -1), ws), (0, None)
+
+
+@torch.library.register_vmap(rnnt_bwd)
+def _(info, in_dims, joint, ws, grad_loss, from_logits):
+    if in_dims[1] is not None:
+        raise RuntimeError("the workspace of a vmapped forward is shared by the whole batch")
+    B = _bsize((joint, grad_loss), (in_dims[0], in_dims[2]))
+    gj = rnnt_bwd(_fold(joint, in_dims[0], B, 0), ws, _fold(grad_loss, in_dims[2], B, 0), from_logits)
+    return gj.view(B, gj.shape[0] // B, *gj.shape[1:]), 0
+
+
+@torch.library.register_vmap(rnnt_fg_fwd)
+def _(info, in_dims, f, g, targets, in_len, tgt_len):
+    B = _bsize((f, g, targets, in_len, tgt_len), in_dims)
+    loss, ws = rnnt_fg_fwd(_fold(f, in_dims[0], B, 0), _fold(g, in_dims[1], B, 0), _fold(targets, in_dims[2], B, 0),
+                           _fold(in_len, in_dims[3], B, 0), _fold(tgt_len, in_dims[4], B, 0))
+    return (loss.view(B, -1), ws), (0, None)
+
+
+@torch.library.register_vmap(rnnt_fg_bwd)
+def _(info, in_dims, f, g, ws, grad_loss):
+    if in_dims[2] is not None:
+        raise RuntimeError("the workspace of a vmapped forward is shared by the whole batch")
+    B = _bsize((f, g, grad_loss), (in_dims[0], in_dims[1], in_dims[3]))
+    gf, gg = rnnt_fg_bwd(_fold(f, in_dims[0], B, 0), _fold(g, in_dims[1], B, 0), ws, _fold(grad_loss, in_dims[3], B, 0))
+    return (gf.view(B, gf.shape[0] // B, *gf.shape[1:]), gg.view(B, gg.shape[0] // B, *gg.shape[1:])), (0, 0)

@@ -3,7 +3,7 @@
     transducer_forward_score(joint, targets, joint_lengths, target_lengths) -> (N,)   ha/transducer.py:175-205
     transducer_forward_score_fg(f, g, targets, joint_lengths, target_lengths) -> (N,)  joint-free variant
 """
-from . import ops
+from . import functional, ops
 
 
 def transducer_forward_score(joint, targets, joint_lengths, target_lengths, from_logits=False):
@@ -14,6 +14,8 @@ def transducer_forward_score(joint, targets, joint_lengths, target_lengths, from
     and written once in total).  targets (N,U); blank = 0.  Unlike the reference there is no
     power-of-two restriction on T (ha/transducer.py:194-195) and no -10000 scan seed (ha/scan.py:116).
     """
+    if functional.transforms_active():          # torch.func.grad / vmap: see functional.py
+        return functional.rnnt(joint, targets, joint_lengths, target_lengths, from_logits)
     loss, _ = ops.rnnt_fwd(joint, targets, joint_lengths, target_lengths, bool(from_logits))
     return loss
 
@@ -27,6 +29,8 @@ def transducer_forward_score_fg(f, g, targets, joint_lengths, target_lengths):
     d loss/d f = (d loss/d joint).sum(2), d loss/d g = (d loss/d joint).sum(1); the (N,T,U+1,K) tensor and
     its gradient (6.6 GB each at BASELINE config 4) never exist.
     """
+    if functional.transforms_active():          # torch.func.grad / vmap: see functional.py
+        return functional.rnnt_fg(f, g, targets, joint_lengths, target_lengths)
     loss, _ = ops.rnnt_fg_fwd(f, g, targets, joint_lengths, target_lengths)
     return loss
 

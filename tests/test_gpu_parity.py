@@ -683,3 +683,47 @@ def test_torch_compile_traces_through(hb):
     l2 = compiled(x2)
     l2.backward()
     assert torch.equal(step(x1.detach()), l2.detach()) and torch.equal(x1.grad, x2.grad)
+
+
+def test_vmap_per_sample_gradients(hb):
+    """torch.func.vmap(grad_and_value(...)) over utterances, the pattern of ha/grad_norm.py (which drops its CTC
+    term because the reference has no batching rule): one merged launch, same numbers as a Python loop"""
+    from torch.func import grad_and_value, vmap
+    g = torch.Generator().manual_seed(12)
+    B, T, V, S = 5, 30, 12, 6
+    x = torch.randn(B, T, V, generator=g).to(dev())                 # (B,T,V): one utterance per vmap slice
+    tg = torch.randint(1, V, (B, S), generator=g).to(dev())
+    il = torch.tensor([30, 28, 20, 25, 30]).to(dev()); tl = torch.tensor([6, 5, 3, 6, 1]).to(dev())
+
+    def one_ctc(xi, tgi, ili, tli):                                  # xi (T,V) -> scalar loss
+        return hb.ctc_forward_score3(xi[:, None, :], tgi[None], ili[None], tli[None], from_logits=True)[0]
+
+    def one_star(xi, tgi, ili, tli):
+        return hb.star_ctc_forward_score(xi[:, None, :], tgi[None], ili[None], tli[None], star_penalty=-0.5,
+                                         from_logits=True)[0]
+
+    for fn in (one_ctc, one_star):
+        grads, losses = vmap(grad_and_value(fn))(x, tg, il, tl)
+        for b in range(B):
+            gb, lb = grad_and_value(fn)(x[b], tg[b], il[b], tl[b])
+            assert torch.equal(losses[b], lb) and torch.equal(grads[b], gb)
+
+    U = 4
+    f = torch.randn(B, 7, V, generator=g).to(dev()); gg = torch.randn(B, U + 1, V, generator=g).to(dev())
+    tg2 = torch.randint(0, V, (B, U), generator=g).to(dev())
+    il2 = torch.tensor([7, 6, 5, 7, 3]).to(dev()); tl2 = torch.tensor([4, 3, 4, 1, 2]).to(dev())
+
+    def one_fg(fi, gi, tgi, ili, tli):
+        return hb.transducer_forward_score_fg(fi[None], gi[None], tgi[None], ili[None], tli[None])[0]
+
+    def one_joint(fi, gi, tgi, ili, tli):
+        return hb.transducer_forward_score((fi[:, None, :] + gi[None, :, :])[None], tgi[None], ili[None], tli[None],
+                                           from_logits=True)[0]
+
+    for fn in (one_fg, one_joint):
+        (gf, ggr), losses = vmap(grad_and_value(fn, argnums=(0, 1)))(f, gg, tg2, il2, tl2)
+        for b in range(B):
+            (gfb, ggb), lb = grad_and_value(fn, argnums=(0, 1))(f[b], gg[b], tg2[b], il2[b], tl2[b])
+            torch.testing.assert_close(losses[b], lb, rtol=1e-6, atol=1e-6)
+            torch.testing.assert_close(gf[b], gfb, rtol=1e-5, atol=2e-6)
+            torch.testing.assert_close(ggr[b], ggb, rtol=1e-5, atol=2e-6)
