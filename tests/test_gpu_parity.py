@@ -727,3 +727,36 @@ def test_vmap_per_sample_gradients(hb):
             torch.testing.assert_close(losses[b], lb, rtol=1e-6, atol=1e-6)
             torch.testing.assert_close(gf[b], gfb, rtol=1e-5, atol=2e-6)
             torch.testing.assert_close(ggr[b], ggb, rtol=1e-5, atol=2e-6)
+
+
+def test_stream_ordered_on_side_streams(hb):
+    """the ops launch on torch's current stream and never synchronise: two batches on two side streams, results
+    equal to the default-stream ones (ha/loop.py keeps the loss on the device until loss.item())"""
+    g = torch.Generator().manual_seed(21)
+    outs = []
+    data = []
+    for k in range(2):
+        x = torch.randn(300, 6, 64, generator=g).to(dev())
+        tg = torch.randint(1, 64, (6, 40), generator=g).to(dev())
+        il = torch.randint(150, 301, (6,), generator=g).to(dev()); tl = torch.randint(20, 41, (6,), generator=g).to(dev())
+        data.append((x, tg, il, tl))
+        xr = x.clone().requires_grad_(True)
+        l = hb.ctc_forward_score3(xr, tg, il, tl, from_logits=True)
+        l.sum().backward()
+        outs.append((l.detach().clone(), xr.grad.clone()))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    res = []
+    for k, st in enumerate(streams):
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            x, tg, il, tl = data[k]
+            xr = x.clone().requires_grad_(True)
+            l = hb.ctc_forward_score3(xr, tg, il, tl, from_logits=True)
+            l.sum().backward()
+            res.append((l, xr))
+    for st in streams:
+        torch.cuda.current_stream().wait_stream(st)
+    torch.cuda.synchronize()
+    for (l, xr), (l0, g0) in zip(res, outs):
+        assert torch.equal(l.detach(), l0) and torch.equal(xr.grad, g0)
