@@ -50,13 +50,16 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 struct RowCfg { int nwarps, nstage, rows_per_warp; size_t smem; bool ok; };
 
 template <typename F>
-RowCfg pick_row_cfg(int T, F smem_of /* (nstage, nwarps) -> bytes */, int ns_max = 4) {
-    // ns_max = 2 for the statistics ("rows") kernels: their per-row dependency chain (max, sum, log, gather) is
-    // long, so a third CTA per SM hides more latency than a deeper TMA ring does (measured: RNN-T rows 1.20 ->
-    // 0.98 ms, CTC rows 0.44 -> 0.38 ms); the gradient kernels keep the deeper ring.
+RowCfg pick_row_cfg(int T, F smem_of /* (nstage, nwarps) -> bytes */, int ns_max = 4, int nw_max = 8) {
+    // (ns_max, nw_max) = (2, 4) for the statistics ("rows") kernels and the CTC / star gradient kernels: a warp's
+    // per-row dependency chain (max, sum, log, gather / scatter) is long, so many small CTAs per SM (5-6 of four
+    // warps with a two-stage TMA ring each) hide more latency than a deep ring under few warps.  Measured on
+    // B200 (nw, ns sweep): RNN-T rows 1.20 -> 0.97 ms, CTC rows 0.44 -> 0.37 ms, CTC grad 0.62 -> 0.56 ms, star
+    // grad 0.22 -> 0.14 ms; the RNN-T gradient kernel (already at the copy peak) keeps 8 warps x 3 stages.
     RowCfg c{8, 4, 1, 0, false};
     if (const char* e = getenv("HA_B200_ROW_NSTAGE")) { int v = atoi(e); if (v >= 2 && v <= 4) ns_max = v; }   // tuning knob
-    for (int nw = 8; nw >= 1 && !c.ok; nw >>= 1) {
+    if (const char* e = getenv("HA_B200_ROW_NWARPS")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) nw_max = v; }
+    for (int nw = nw_max; nw >= 1 && !c.ok; nw >>= 1) {
         for (int ns = ns_max; ns >= 2; --ns) {
             size_t b = smem_of(ns, nw);
             if (b <= kRowSmemTarget || (ns == 2 && b <= kMaxSmem)) { c.nwarps = nw; c.nstage = ns; c.smem = b; c.ok = true; break; }
@@ -159,7 +162,7 @@ int ha_ctc_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
     rp.from_logits = from_logits;
     const bool vec = (V % 4 == 0) && aligned16(x) && (sx_t % 4 == 0) && (sx_n % 4 == 0);
     rp.use_bulk = vec ? 1 : 0;
-    RowCfg rc_ = pick_row_cfg(T, [&](int ns, int nw) { return rows_smem_bytes(w.Sp, V, ns, nw); }, 2);
+    RowCfg rc_ = pick_row_cfg(T, [&](int ns, int nw) { return rows_smem_bytes(w.Sp, V, ns, nw); }, 2, 4);
     if (!rc_.ok) return fail(HA_ERR_UNSUPPORTED_SHAPE, "V=%d too large for the row kernel", V);
     rp.nstage = rc_.nstage; rp.nwarps = rc_.nwarps; rp.rows_per_warp = rc_.rows_per_warp;
     {
@@ -204,7 +207,7 @@ int ha_ctc_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V, 
     const bool vec = (V % 4 == 0) && aligned16(gx) && (sg_t % 4 == 0) && (sg_n % 4 == 0) &&
                      (!from_logits || (aligned16(x) && (sx_t % 4 == 0) && (sx_n % 4 == 0)));
     gp.use_bulk = vec ? 1 : 0;
-    RowCfg rc_ = pick_row_cfg(T, [&](int ns, int nw) { return grad_smem_bytes(w.Sp, V, w.E, ns, nw); });
+    RowCfg rc_ = pick_row_cfg(T, [&](int ns, int nw) { return grad_smem_bytes(w.Sp, V, w.E, ns, nw); }, 2, 4);
     if (!rc_.ok) return fail(HA_ERR_UNSUPPORTED_SHAPE, "V=%d too large for the gradient kernel", V);
     gp.nstage = rc_.nstage; gp.nwarps = rc_.nwarps; gp.rows_per_warp = rc_.rows_per_warp;
     const dim3 grid((T + gp.nwarps * gp.rows_per_warp - 1) / (gp.nwarps * gp.rows_per_warp), N);
@@ -294,7 +297,7 @@ int ha_star_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
     rp.from_logits = from_logits;
     const bool vec = (V % 4 == 0) && aligned16(x) && (sx_t % 4 == 0) && (sx_n % 4 == 0);
     rp.use_bulk = vec ? 1 : 0;
-    RowCfg rc_ = pick_row_cfg(T, [&](int ns, int nw) { return rows_smem_bytes(w.Sp, V, ns, nw); }, 2);
+    RowCfg rc_ = pick_row_cfg(T, [&](int ns, int nw) { return rows_smem_bytes(w.Sp, V, ns, nw); }, 2, 4);
     if (!rc_.ok) return fail(HA_ERR_UNSUPPORTED_SHAPE, "V=%d too large for the row kernel", V);
     rp.nstage = rc_.nstage; rp.nwarps = rc_.nwarps; rp.rows_per_warp = rc_.rows_per_warp;
     {
@@ -338,7 +341,7 @@ int ha_star_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
     const bool vec = (V % 4 == 0) && aligned16(gx) && (sg_t % 4 == 0) && (sg_n % 4 == 0) &&
                      aligned16(x) && (sx_t % 4 == 0) && (sx_n % 4 == 0);
     gp.use_bulk = vec ? 1 : 0;
-    RowCfg rc_ = pick_row_cfg(T, [&](int ns, int nw) { return grad_smem_bytes(w.Sp, V, w.E, ns, nw); });
+    RowCfg rc_ = pick_row_cfg(T, [&](int ns, int nw) { return grad_smem_bytes(w.Sp, V, w.E, ns, nw); }, 2, 4);
     if (!rc_.ok) return fail(HA_ERR_UNSUPPORTED_SHAPE, "V=%d too large for the gradient kernel", V);
     gp.nstage = rc_.nstage; gp.nwarps = rc_.nwarps; gp.rows_per_warp = rc_.rows_per_warp;
     const dim3 grid((T + gp.nwarps * gp.rows_per_warp - 1) / (gp.nwarps * gp.rows_per_warp), N);
@@ -390,7 +393,7 @@ int ha_rnnt_fwd(const float* joint, int N, int T, int U1, int V,
     const bool vec = (V % 4 == 0) && aligned16(joint);
     rp.use_bulk = vec ? 1 : 0;
     const int nodes = T * U1;
-    RowCfg rc_ = pick_row_cfg(nodes, [&](int ns, int nw) { return rnnt_rows_smem_bytes(V, ns, nw); }, 2);
+    RowCfg rc_ = pick_row_cfg(nodes, [&](int ns, int nw) { return rnnt_rows_smem_bytes(V, ns, nw); }, 2, 4);
     if (!rc_.ok) return fail(HA_ERR_UNSUPPORTED_SHAPE, "V=%d too large for the row kernel", V);
     rp.nstage = rc_.nstage; rp.nwarps = rc_.nwarps; rp.rows_per_warp = rc_.rows_per_warp;
     {
