@@ -95,3 +95,33 @@ def test_reduce_loss_without_process_group():
     l = torch.tensor([2.0, 4.0], requires_grad=True)
     assert float(sharding.reduce_loss(l)) == 3.0
     assert abs(float(sharding.reduce_loss(l, torch.tensor([0.5, 0.25]))) - 1.0) < 1e-7
+
+
+def test_vmap_fold_helper_merges_the_vmapped_dimension():
+    """ops._fold: the batching rule's only tensor manipulation (CPU tensors suffice)"""
+    import torch
+    from haloop_b200 import ops
+    x = torch.arange(2 * 3 * 4 * 5.0).reshape(3, 2, 4, 5)           # vmap dim 0 (B=3) of (T=2, N=4, V=5)
+    f = ops._fold(x, 0, 3, 1)                                        # -> (T, B*N, V)
+    assert f.shape == (2, 12, 5)
+    for b in range(3):
+        assert torch.equal(f[:, 4 * b:4 * (b + 1)], x[b])
+    y = torch.arange(4.0)                                            # not batched: broadcast
+    g = ops._fold(y, None, 3, 0)
+    assert g.shape == (12,) and torch.equal(g, y.repeat(3))
+    assert ops._fold(None, None, 3, 0) is None
+
+
+def test_rnnt_buckets_cost_and_deal():
+    from haloop_b200 import sharding
+    import random
+    r = random.Random(1)
+    tl = [r.randint(100, 500) for _ in range(64)]; ul = [r.randint(20, 100) for _ in range(64)]
+    b = sharding.bucket_by_length(tl, ul, 1024, 1_000_000_000, "rnnt")
+    assert sorted(i for x in b for i in x.indices) == list(range(64))
+    for x in b:
+        assert x.t_max == max(tl[i] for i in x.indices) and x.u_max == max(ul[i] for i in x.indices)
+        assert x.cost == len(x.indices) * x.t_max * (x.u_max + 1) * 1024 * 4
+        assert x.cost <= 1_000_000_000 or len(x.indices) == 1
+    owned = sharding.deal_buckets(b, 4)
+    assert sorted(k for o in owned for k in o) == list(range(len(b)))
