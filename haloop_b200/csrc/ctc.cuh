@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) ctc_prep_kernel(PrepParams p) {
     if (threadIdx.x == 0) { s_bad = (Tn < 0 || Tn > p.T || Ln < 0 || Ln > p.S) ? 1 : 0; s_rank = 0; s_rep = 0; }
     __syncthreads();
     const int L = s_bad ? 0 : (int)Ln;
+    __syncthreads();           // every thread has read the length verdict before the label check below may flip s_bad
     for (int k = threadIdx.x; k < p.S; k += blockDim.x) {
         long long y = load_idx(p.targets, (long long)n * p.tgt_stride + k, p.tgt64);
         // labels beyond L_n are kept too: star-CTC reads targets[n, L_n] (ha/star.py:46)
