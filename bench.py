@@ -27,6 +27,9 @@ WORKLOADS = {
     "star": ("star", 128, 1000, 512, 200),
     "rnnt": ("rnnt", 32, 500, 1024, 100),
     "ctc_c1": ("ctc", 8, 200, 256, 50),
+    # config 2 with a batch that is a multiple of the 148 SMs (the trellis kernel runs one CTA per utterance, two per
+    # SM): shows how much of config 2's time is the 256-on-148 imbalance
+    "ctc_b296": ("ctc", 296, 1500, 1024, 300),
     # the same RNN-T batch given as its two factors f (N,T,V), g (N,U+1,V) instead of the
     # 6.6 GB joint f[:, :, None, :] + g[:, None, :, :] (ha/recognizer.py:114)
     "rnnt_fg": ("rnnt_fg", 32, 500, 1024, 100),
