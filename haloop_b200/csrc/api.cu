@@ -66,7 +66,9 @@ RowCfg pick_row_cfg(int T, F smem_of /* (nstage, nwarps) -> bytes */, int ns_max
         }
     }
     int rpw = (T + c.nwarps * 4 - 1) / (c.nwarps * 4);
-    c.rows_per_warp = rpw < 1 ? 1 : (rpw > 16 ? 16 : rpw);
+    int cap = 16;
+    if (const char* e = getenv("HA_B200_ROW_RPW")) { int v = atoi(e); if (v >= 1 && v <= 256) cap = v; }   // tuning knob
+    c.rows_per_warp = rpw < 1 ? 1 : (rpw > cap ? cap : rpw);
     return c;
 }
 
