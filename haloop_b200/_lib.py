@@ -30,13 +30,27 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/api.cu (one translation unit) for sm_100a into haloop_b200/libha_b200.so."""
+    """Compile every csrc/*.cu for sm_100a (one object each, in parallel) and link haloop_b200/libha_b200.so."""
     if not force and not needs_build():
         return SO_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", SO_PATH, os.path.join(CSRC, "api.cu")]
-    subprocess.check_call(cmd)
+    objdir = os.path.join(_HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    units = [f for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    deps = [os.path.getmtime(s) for s in _sources() if not s.endswith(".cu")]
+
+    def compile_one(f):
+        src, obj = os.path.join(CSRC, f), os.path.join(objdir, f[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max([os.path.getmtime(src)] + deps):
+            return obj
+        flags = [x for x in NVCC_FLAGS if x != "-shared"]
+        subprocess.check_call([nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(units))) as ex:
+        objs = list(ex.map(compile_one, units))
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO_PATH] + objs)
     return SO_PATH
 
 

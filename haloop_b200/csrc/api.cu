@@ -9,6 +9,7 @@
 #include "align.cuh"
 #include "common.cuh"
 #include "ctc.cuh"
+#include "host.h"
 #include "rnnt.cuh"
 #include "rnnt_fg.cuh"
 #include "star.cuh"
@@ -33,7 +34,7 @@ int check_launch(const char* what) {
     return HA_OK;
 }
 
-constexpr size_t kMaxSmem = 227 * 1024;       // opt-in dynamic shared memory per CTA on sm_100
+constexpr size_t kMaxSmem = hab::kMaxSmemOptin;
 constexpr size_t kRowSmemTarget = 100 * 1024; // two row-kernel CTAs per SM
 
 template <typename K>
@@ -44,7 +45,7 @@ int set_smem(K kernel, size_t bytes, const char* what) {
     return HA_OK;
 }
 
-bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+using hab::aligned16;
 
 // warps per CTA and ring depth for a warp-per-row streaming kernel with `row_floats` per stage
 struct RowCfg { int nwarps, nstage, rows_per_warp; size_t smem; bool ok; };
@@ -83,15 +84,29 @@ int common_checks(const void* x, int T, int N, int V, int S, const void* ws, siz
 
 }  // namespace
 
+namespace hab {
+int host_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int host_check_launch(const char* what) { return check_launch(what); }
+}  // namespace hab
+
 extern "C" {
 
 int ha_b200_version(void) { return 100; }
 const char* ha_b200_last_error(void) { return g_err; }
 
 // ------------------------------------------------------------------------------------- CTC ---
+// Two implementations share the entry points: the fused two-kernel path (ctc2.cu; V a multiple of 4 and rows that
+// fit the shared-memory rings) and the three-kernel path below (any V, unaligned views).  The choice depends on
+// (T, N, V, S) only, so the workspace query, the forward and the backward call agree on the layout.
 size_t ha_ctc_workspace_bytes(int T, int N, int V, int S) {
-    (void)V;
     if (T <= 0 || N <= 0 || S < 0) return 0;
+    if (ctc2_eligible(T, N, V, S)) return ctc2_workspace_bytes(T, N, S);
     return ctc_ws_layout(T, N, S).total;
 }
 
@@ -141,6 +156,13 @@ int ha_ctc_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
                const void* targets, int64_t tgt_stride, int S, int targets_i64,
                const void* in_len, const void* tgt_len, int lengths_i64,
                int from_logits, float* loss, void* ws, size_t ws_bytes, void* stream) {
+    if (ctc2_eligible(T, N, V, S)) {
+        int rc2 = common_checks(x, T, N, V, S, ws, ws_bytes, 0);
+        if (rc2) return rc2;
+        if (!in_len || !tgt_len || !loss || (S > 0 && !targets)) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+        return ctc2_fwd(x, sx_t, sx_n, T, N, V, targets, tgt_stride, S, targets_i64, in_len, tgt_len, lengths_i64,
+                        from_logits, loss, ws, ws_bytes, (cudaStream_t)stream);
+    }
     const CtcWs w = ctc_ws_layout(T, N, S);
     int rc = common_checks(x, T, N, V, S, ws, ws_bytes, w.total);
     if (rc) return rc;
@@ -193,6 +215,12 @@ int ha_ctc_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V, 
                const float* grad_loss, int from_logits,
                float* gx, int64_t sg_t, int64_t sg_n,
                void* ws, size_t ws_bytes, void* stream) {
+    if (ctc2_eligible(T, N, V, S)) {
+        int rc2 = common_checks(gx, T, N, V, S, ws, ws_bytes, 0);
+        if (rc2) return rc2;
+        if (!grad_loss) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+        return ctc2_bwd(x, sx_t, sx_n, T, N, V, S, grad_loss, from_logits, gx, sg_t, sg_n, ws, ws_bytes, (cudaStream_t)stream);
+    }
     const CtcWs w = ctc_ws_layout(T, N, S);
     int rc = common_checks(gx, T, N, V, S, ws, ws_bytes, w.total);
     if (rc) return rc;

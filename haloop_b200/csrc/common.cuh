@@ -193,7 +193,7 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
 // The phase-switch barrier of the trellis kernels: producer and compute warps come from different code
 // paths, so the barrier instruction lives in one non-inlined function and every thread of the CTA
 // executes the same instruction (bar.sync on a named barrier with an explicit thread count).
-__device__ __noinline__ void cta_phase_barrier(int id, int nthreads) {
+static __device__ __noinline__ void cta_phase_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 

@@ -1,0 +1,718 @@
+// ctc2.cuh — fused CTC loss + logit gradient for sm_100a, round 2.  Replaces ha/ctc.py:110-174
+// (ctc_forward_score3) and its autograd backward with TWO kernels that never write emissions or
+// occupancies to HBM:
+//
+//   ctc2_fwd_kernel  one CTA per (utterance, sweep direction).  Row warps stream the logit rows of
+//                    their side's half of the frames through a TMA ring, form the row log-sum-exp
+//                    and gather the blank + label probabilities straight into a shared-memory slot;
+//                    the trellis warps consume the slots, advance alpha (direction 0, forward in
+//                    time) or beta (direction 1, backward) and store only the LABEL states of each
+//                    frame (4 floats + one exponent per group of 4 labels).  The two sides meet in
+//                    the middle: whichever CTA finishes second forms Z from both boundaries.
+//   ctc2_bwd_kernel  same decomposition for the other half of each side's frames: row warps reload
+//                    the logit row (needed for the softmax anyway), gather the emissions from it,
+//                    the trellis warps advance the recursion, multiply the live pre-emission sums
+//                    with the rows the OTHER side stored in the forward pass and leave the label
+//                    occupancies in shared memory; the row warp that owns the frame turns its row
+//                    into (softmax - occupancy) * grad_out in place and bulk-stores it.
+//
+// HBM traffic per frame: logits read twice (4V + 4V), gradient written once (4V), stored label states
+// written once and read once (~5 L bytes each): 12.6 V at L = 0.3 V against 22 V for the three-kernel
+// path of round 1 (ctc.cuh: emission rows, packed alpha/beta rows of every state, occupancy rows).
+//
+// Numbers: "lane-normalised" linear domain.  A lane owns 4 consecutive (blank, label) pairs — 8
+// adjacent states — as plain fp32 values sharing one int32 exponent; after every step the lane rescales
+// so that its largest value sits in [2^32, 2^33).  The sum-product step of a pair is 2 FADD + 1 SEL +
+// 2 FMUL, the neighbour lane's label state is aligned with one exponent subtraction, and the only
+// values that can be lost are more than 2^158 (110 nats) below the largest of the same 8 adjacent states
+// (Limits).  tools/ctc2_proto.py is the numpy model of this file.
+#pragma once
+#include "common.cuh"
+
+namespace hab {
+
+constexpr int kJP = 4;            // pairs per lane
+constexpr int kR2 = 4;            // row warps per CTA
+constexpr int kNE = 8;            // emission / occupancy slots per CTA (multiple of kR2)
+constexpr int kNSR = 5;           // stored-row slots (backward)
+constexpr int kLaneExp = 32 + 127;        // biased exponent the lane maximum is normalised to
+constexpr int kAlignMax = 30;             // largest up-shift applied to the neighbour's label state
+constexpr float kFltMin = 1.1754943508222875e-38f;
+
+struct Ctc2Ws {                   // workspace layout (byte offsets)
+    size_t meta, order, tgt, dupnext, loss, zinfo, cnt, lse2, bound, tr, total;
+    int Sp, NLmax, SPL, BW;
+};
+__host__ inline Ctc2Ws ctc2_ws_layout(int T, int N, int S) {
+    Ctc2Ws w;
+    w.Sp = round_up(S > 0 ? S : 1, 4);
+    w.NLmax = w.Sp / 4 + 2;                     // lanes (groups of 4 label slots) per side
+    w.SPL = round_up(5 * w.NLmax, 4);           // stored row: [4 NL label values][NL exponents]
+    w.BW = round_up(9 * w.NLmax, 4);            // boundary: [4 NL blanks][4 NL labels][NL exponents]
+    size_t o = 256;
+    auto take = [&](size_t bytes) { size_t at = o; o = round_up_sz(o + bytes, 256); return at; };
+    w.meta = take(sizeof(int4) * (size_t)N);
+    w.order = take(sizeof(int) * (size_t)N);
+    w.tgt = take(sizeof(int) * (size_t)N * w.Sp);
+    w.dupnext = take(sizeof(int) * (size_t)N * w.Sp);
+    w.loss = take(sizeof(float) * (size_t)N);
+    w.zinfo = take(sizeof(int4) * (size_t)N);   // {exponent of Z, bits of 1 / mantissa of Z, -, -}
+    w.cnt = take(sizeof(int) * (size_t)N);      // arrivals at the meeting point
+    w.lse2 = take(sizeof(float) * (size_t)N * T);
+    w.bound = take(sizeof(int) * (size_t)N * 2 * w.BW);
+    w.tr = take(sizeof(int) * (size_t)N * T * w.SPL);
+    w.total = o;
+    return w;
+}
+
+struct Ctc2Params {
+    const float* x; long long sx_t, sx_n;
+    float* gx; long long sg_t, sg_n;
+    int T, N, V, Sp;
+    const int4* meta; const int* order; const int* tgt; const int* dupnext;
+    float* lse2; int* tr; int SPL; int* bound; int BW; int4* zinfo; int* cnt;
+    float* loss; float* loss_ws; const float* gout;
+    int from_logits, NS, NLmax, EMF;      // ring stages per row warp; lanes per side of the longest target; floats per emission slot (4 + 4 NLmax)
+};
+
+// shared memory (bytes): [mbarriers][mailboxes][Z reduction][targets (+ chains)][emission slots][stored slots][row ring]
+struct Ctc2Smem { int bars, mail, red, tgt, em, st, rows, total; };
+__host__ __device__ inline Ctc2Smem ctc2_smem(int W, int NS, int V, int Sp, int EMF, int SPL, bool bwd) {
+    Ctc2Smem s;
+    int o = 0;
+    auto take = [&](int bytes) { int at = o; o = round_up(o + bytes, 128); return at; };
+    s.bars = take(8 * (kR2 * NS + 2 * kNE + kNSR));
+    s.mail = take(8 * 2 * W);
+    s.red = take(16 * W + 16);
+    s.tgt = take(4 * Sp * (bwd ? 2 : 1));
+    s.em = take(4 * kNE * EMF);
+    s.st = take(bwd ? 4 * kNSR * SPL : 0);
+    s.rows = take(4 * kR2 * NS * V);
+    s.total = o;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------- emissions ---
+// p = 2^(x log2e - l2) for a logit x of a row whose log2-sum-exp2 is l2.  l2 is split into a multiple of
+// 2^-10 (l2q) and a remainder (dl) so that the integer part of the exponent can be removed BEFORE the one
+// rounding that matters: the fraction handed to ex2 is exact to 3e-8 whatever |log p| is.  The forward and
+// the backward kernel call this with bit-identical arguments, so both halves of a trellis see one model.
+struct RowNorm { float l2q, dl; };
+__device__ __forceinline__ RowNorm row_norm(float l2) {
+    RowNorm r;
+    r.l2q = rintf(l2 * 1024.0f) * (1.0f / 1024.0f);
+    r.dl = l2 - r.l2q;
+    return r;
+}
+__device__ __forceinline__ float emission2(float x, RowNorm rn) {
+    const float t = fminf(fmaxf(fmaf(x, kLog2e, -rn.l2q), -200.0f), 60.0f);
+    const float tk = t + kMagic;                                   // integer part in the low mantissa bits
+    const float kf = tk - kMagic;
+    const float f = fmaf(x, kLog2e, -(rn.l2q + kf)) - rn.dl;       // |f| <= 0.5 (+ the remainder)
+    const int k = __float_as_int(tk) - 0x4B400000;
+    const float p = ex2f(f);
+    return (k < -125) ? kFltMin : __int_as_float(__float_as_int(p) + (k << 23));
+}
+
+// -------------------------------------------------------------------------------- lane numbers ---
+struct Lane { float b[kJP], l[kJP]; int e; };
+
+__device__ __forceinline__ float pow2_clamped(int d) {             // 2^d, 0 below 2^-126; d <= 127
+    return __int_as_float(max(d + 127, 0) << 23);
+}
+
+// First half of a step: align the label state (cm, ce) of the pair below my lowest one to my exponent and
+// form the pre-emission sums  u = blank + label below,  v = label + (skip allowed ? u : blank)
+// [ha/ctc.py:155-167].  Their scale is s.e on return.
+__device__ __forceinline__ void lane_sums(Lane& s, unsigned allowed, float cm, int ce, float (&u)[kJP], float (&v)[kJP]) {
+    int d = ce - s.e;
+    if (d > kAlignMax) {                // the neighbour dwarfs this lane (the wavefront arrives): move my exponent up
+        const int sh = d - kAlignMax;
+        const float f = pow2_clamped(-sh);
+#pragma unroll
+        for (int j = 0; j < kJP; ++j) { s.b[j] *= f; s.l[j] *= f; }
+        s.e += sh;
+        d = kAlignMax;
+    }
+    const float c0 = cm * pow2_clamped(d);
+#pragma unroll
+    for (int j = 0; j < kJP; ++j) {
+        u[j] = s.b[j] + (j ? s.l[j ? j - 1 : 0] : c0);
+        v[j] = s.l[j] + (((allowed >> j) & 1u) ? u[j] : s.b[j]);
+    }
+}
+// Second half: multiply by the emissions and renormalise the lane.
+__device__ __forceinline__ void lane_emit(Lane& s, const float (&u)[kJP], const float (&v)[kJP], float pb, const float (&pl)[kJP]) {
+    float nb[kJP], nl[kJP];
+    float mx = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kJP; ++j) {
+        nb[j] = u[j] * pb;
+        nl[j] = v[j] * pl[j];
+        mx = fmaxf(mx, fmaxf(nb[j], nl[j]));
+    }
+    const int delta = min(kLaneExp - (__float_as_int(mx) >> 23), 120);
+    const float f = __int_as_float((delta + 127) << 23);
+#pragma unroll
+    for (int j = 0; j < kJP; ++j) { s.b[j] = nb[j] * f; s.l[j] = nl[j] * f; }
+    s.e = (mx > 0.0f) ? s.e - delta : kVoidE;
+}
+
+// Per-lane constants of a trellis thread.
+struct LaneCfg {
+    int gl;            // lane index within the side (32 w + lane)
+    int g;             // my position group (clamped into the slot): labels a = 4 g .. 4 g + 3
+    int a0, astep;     // label index a of my pair 0 and the step to pair 1 (+1 alpha, -1 beta)
+    unsigned allowed;  // skip-transition bits of my 4 pairs   [ha/ctc.py:140-142]
+    bool live;         // gl < NL: the lane owns a group of the stored rows
+};
+__device__ __forceinline__ LaneCfg lane_cfg(int gl, int dir, int L, int NL, int NLmax, const int* y) {
+    LaneCfg c;
+    const int A = 4 * NL;
+    c.gl = gl;
+    c.live = gl < NL;
+    const int g = dir ? NL - 1 - gl : gl;
+    c.g = min(max(g, 0), NLmax - 1);
+    c.a0 = dir ? A - 1 - 4 * gl : 4 * gl;
+    c.astep = dir ? -1 : 1;
+    c.allowed = 0;
+#pragma unroll
+    for (int j = 0; j < kJP; ++j) {
+        const int p = c.a0 + c.astep * j - 4;          // label position
+        bool al = false;
+        if (!dir) {
+            if (p == 0) al = true;
+            else if (p >= 1 && p < L) { const int yc = y[p] & kLabelMask, yp = y[p - 1] & kLabelMask; al = (yc != yp) && (yc != 0); }
+        } else {
+            if (p == L - 1 || p == -1) al = true;       // p == -1: the last pair's phantom label only ever collects Z
+            else if (p >= 0 && p + 1 < L) { const int yc = y[p] & kLabelMask, yn = y[p + 1] & kLabelMask; al = (yn != yc) && (yn != 0); }
+        }
+        if (al) c.allowed |= 1u << j;
+    }
+    return c;
+}
+
+__device__ __forceinline__ void side_barrier(int nthr) {
+    asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+}
+
+// the label state of the pair below my lowest one: lane - 1, or the mailbox the warp below filled last step
+__device__ __forceinline__ void fetch_below(const Lane& s, int w, int lane, const int2* mail_prev, float& cm, int& ce) {
+    cm = __shfl_up_sync(0xffffffffu, s.l[kJP - 1], 1);
+    ce = __shfl_up_sync(0xffffffffu, s.e, 1);
+    if (lane == 0) {
+        int2 in = make_int2(0, kVoidE);
+        if (w > 0) in = mail_prev[w - 1];
+        cm = __int_as_float(in.x); ce = in.y;
+    }
+}
+
+// --------------------------------------------------------------------------------------- prep ---
+struct Prep2Params {
+    const void* targets; long long tgt_stride; int tgt64;
+    const void* in_len; const void* tgt_len; int len64;
+    int T, N, V, S, Sp;
+    int4* meta; int* order; int* tgt; int* dupnext; int* cnt; int4* zinfo;
+};
+
+// grid N, block 256.  meta[n] = {T_n, L_n, invalid, frames an alignment needs beyond L_n}.
+__global__ void __launch_bounds__(256) ctc2_prep_kernel(Prep2Params p) {
+    extern __shared__ __align__(16) int s_y[];
+    __shared__ int s_bad, s_rank, s_rep;
+    const int n = blockIdx.x;
+    const long long Tn = load_idx(p.in_len, n, p.len64), Ln = load_idx(p.tgt_len, n, p.len64);
+    const bool lenbad = (Tn < 0 || Tn > p.T || Ln < 0 || Ln > p.S);
+    if (threadIdx.x == 0) { s_bad = lenbad ? 1 : 0; s_rank = 0; s_rep = 0; }
+    __syncthreads();
+    const int L = lenbad ? 0 : (int)Ln;
+    for (int k = threadIdx.x; k < p.S; k += blockDim.x) {
+        long long y = load_idx(p.targets, (long long)n * p.tgt_stride + k, p.tgt64);
+        if (y < 0 || y >= p.V) { if (k < L) s_bad = 1; y = 0; }
+        s_y[k] = (int)y;
+    }
+    for (int k = p.S + threadIdx.x; k < p.Sp; k += blockDim.x) s_y[k] = -1;
+    __syncthreads();
+    const int L4 = (L + 3) & ~3;
+    for (int k = threadIdx.x; k < p.Sp; k += blockDim.x) {
+        const int y = s_y[k];
+        int nxt = 0x7fffffff, notfirst = 0;
+        if (k < L) {
+            const int4* y4 = (const int4*)s_y;
+#pragma unroll 4
+            for (int j4 = 0; j4 < (L4 >> 2); ++j4) {
+                const int4 v = y4[j4];
+                const int j = 4 * j4;
+                const int m0 = (v.x == y) & (j < L), m1 = (v.y == y) & (j + 1 < L);
+                const int m2 = (v.z == y) & (j + 2 < L), m3 = (v.w == y) & (j + 3 < L);
+                notfirst |= (m0 & (j < k)) | (m1 & (j + 1 < k)) | (m2 & (j + 2 < k)) | (m3 & (j + 3 < k));
+                nxt = min(nxt, (m0 && j > k) ? j : 0x7fffffff);
+                nxt = min(nxt, (m1 && j + 1 > k) ? j + 1 : 0x7fffffff);
+                nxt = min(nxt, (m2 && j + 2 > k) ? j + 2 : 0x7fffffff);
+                nxt = min(nxt, (m3 && j + 3 > k) ? j + 3 : 0x7fffffff);
+            }
+        }
+        p.tgt[(size_t)n * p.Sp + k] = (y < 0 ? 0 : y) | (notfirst ? kNotFirst : 0);
+        p.dupnext[(size_t)n * p.Sp + k] = (nxt == 0x7fffffff) ? -1 : nxt;
+        // a blank must separate equal neighbours, and a label 0 can only be entered from the blank before
+        // it (ha/ctc.py:140: no skip into a blank-valued state): one extra frame each
+        if (k >= 1 && k < L && (s_y[k - 1] == y || y == 0)) atomicAdd(&s_rep, 1);
+    }
+    {   // longest-first work order (rank by counting; N is a batch size)
+        const long long mine = lenbad ? 0 : Tn * (Ln + 1);
+        int rank = 0;
+        for (int m = threadIdx.x; m < p.N; m += blockDim.x) {
+            const long long Tm = load_idx(p.in_len, m, p.len64), Lm = load_idx(p.tgt_len, m, p.len64);
+            const long long c = (Tm < 0 || Tm > p.T || Lm < 0 || Lm > p.S) ? 0 : Tm * (Lm + 1);
+            rank += (c > mine) || (c == mine && m < n);
+        }
+        if (rank) atomicAdd(&s_rank, rank);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        p.meta[n] = make_int4(s_bad ? 0 : (int)Tn, L, s_bad, s_rep);
+        p.order[s_rank] = n;
+        p.cnt[n] = 0;
+        p.zinfo[n] = make_int4(0, 0, 0, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------ forward ---
+// grid 2N (CTA c: utterance order[c / 2], direction c % 2), block 32 (W + kR2).
+template <int W, int MINB>
+__global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Params p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = p.order[blockIdx.x >> 1], dir = blockIdx.x & 1;
+    const int4 mt = p.meta[n];
+    const int Tn = mt.x, L = mt.y;
+    if (mt.z || Tn == 0 || Tn < L + mt.w) {       // invalid / empty / no alignment exists: decided combinatorially
+        if (dir == 0 && threadIdx.x == 0) {
+            const float v = mt.z ? CUDART_NAN_F : ((L == 0) ? 0.0f : CUDART_INF_F);
+            p.loss[n] = v; p.loss_ws[n] = v;
+        }
+        return;
+    }
+    const int NL = (L + 3) / 4 + 2;
+    const int Wn = (NL + 31) >> 5;                 // trellis warps this utterance needs
+    const int NS = p.NS, V = p.V, EMF = p.EMF;
+    const Ctc2Smem sm = ctc2_smem(W, NS, V, p.Sp, EMF, p.SPL, false);
+    uint64_t* row_full = (uint64_t*)(smem + sm.bars);            // [kR2][NS]
+    uint64_t* em_full = row_full + kR2 * NS;                     // [kNE]
+    uint64_t* em_empty = em_full + kNE;                          // [kNE]
+    int2* mail = (int2*)(smem + sm.mail);                        // [2][W]
+    double* redd = (double*)(smem + sm.red);                     // [W]
+    int* redi = (int*)(redd + W);                                // [W] + flag
+    int* s_tgt = (int*)(smem + sm.tgt);
+    float* s_em = (float*)(smem + sm.em);
+    float* s_rows = (float*)(smem + sm.rows);
+    const int tm = Tn >> 1;
+    const int steps1 = dir ? Tn - tm : tm;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kR2 * NS; ++i) mbar_init(&row_full[i], 1);
+        for (int i = 0; i < kNE; ++i) { mbar_init(&em_full[i], 32); mbar_init(&em_empty[i], 32 * Wn); }
+    }
+    for (int i = threadIdx.x; i < kNE * EMF; i += blockDim.x) s_em[i] = 0.0f;
+    for (int k = threadIdx.x; k < L; k += blockDim.x) s_tgt[k] = p.tgt[(size_t)n * p.Sp + k] & kLabelMask;
+    mbar_init_fence();
+    __syncthreads();
+
+    if (warp >= W) {
+        // ---------------------------------------------------------------------- row warps ---
+        const int r = warp - W;
+        float* wrows = s_rows + (size_t)r * NS * V;
+        uint64_t* wbar = row_full + r * NS;
+        const float* xb = p.x + (long long)n * p.sx_n;
+        const int nrows = (steps1 > r) ? (steps1 - 1 - r) / kR2 + 1 : 0;
+        auto issue = [&](int k) {
+            const int i = r + k * kR2, t = dir ? Tn - 1 - i : i;
+            if (lane == 0) {
+                mbar_expect_tx(&wbar[k % NS], (uint32_t)V * 4u);
+                bulk_g2s(wrows + (size_t)(k % NS) * V, xb + (long long)t * p.sx_t, (uint32_t)V * 4u, &wbar[k % NS]);
+            }
+        };
+        for (int k = 0; k < min(NS, nrows); ++k) issue(k);
+        const int V4 = V >> 2;
+        for (int k = 0; k < nrows; ++k) {
+            const int i = r + k * kR2, t = dir ? Tn - 1 - i : i;
+            const float* row = wrows + (size_t)(k % NS) * V;
+            mbar_wait(&wbar[k % NS], (uint32_t)(k / NS) & 1u);
+            float l2 = 0.0f;
+            if (p.from_logits) {
+                const float4* r4 = (const float4*)row;
+                float mx = -CUDART_INF_F;
+                for (int c = lane; c < V4; c += 32) {
+                    const float4 v = r4[c];
+                    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+                }
+                mx = warp_max(mx);
+                const float m2 = mx * kLog2e;
+                float s0 = 0.0f, s1 = 0.0f;
+                for (int c = lane; c < V4; c += 32) {
+                    const float4 v = r4[c];
+                    s0 += ex2f(fmaf(v.x, kLog2e, -m2)) + ex2f(fmaf(v.y, kLog2e, -m2));
+                    s1 += ex2f(fmaf(v.z, kLog2e, -m2)) + ex2f(fmaf(v.w, kLog2e, -m2));
+                }
+                l2 = m2 + log2f(warp_sum(s0 + s1));
+            }
+            if (lane == 0) p.lse2[(size_t)n * p.T + t] = l2;
+            const RowNorm rn = row_norm(l2);
+            const int slot = i % kNE, use = i / kNE;
+            if (use > 0) mbar_wait(&em_empty[slot], (uint32_t)(use - 1) & 1u);
+            float* em = s_em + slot * EMF;
+            if (lane == 0) em[0] = emission2(row[0], rn);
+            for (int kk = lane; kk < L; kk += 32) em[8 + kk] = emission2(row[s_tgt[kk]], rn);
+            mbar_arrive(&em_full[slot]);
+            __syncwarp();
+            if (k + NS < nrows) issue(k + NS);
+        }
+        return;
+    }
+    if (warp >= Wn) return;
+
+    // ------------------------------------------------------------------------ trellis warps ---
+    const int w = warp;
+    const int nthr = 32 * Wn;
+    const LaneCfg cfg = lane_cfg(32 * w + lane, dir, L, NL, p.NLmax, p.tgt + (size_t)n * p.Sp);
+    Lane s;
+#pragma unroll
+    for (int j = 0; j < kJP; ++j) { s.b[j] = 0.0f; s.l[j] = 0.0f; }
+    s.e = kVoidE;
+    const int k_inj = dir ? 4 * NL - 1 - (L + 4) : 3;       // the virtual source: mass 1 on the label below the first real pair
+    if (cfg.gl == (k_inj >> 2)) {
+#pragma unroll
+        for (int j = 0; j < kJP; ++j)
+            if (j == (k_inj & 3)) s.l[j] = 1.0f;
+        s.e = 0;
+    }
+    if (lane == 31) mail[1 * W + w] = make_int2(__float_as_int(s.l[kJP - 1]), s.e);
+    side_barrier(nthr);
+    // my pairs are all unreachable before step `first` and none can still complete after step `last`
+    const int q_lo = 128 * w - k_inj - 1, q_hi = 128 * w + 127 - k_inj - 1;     // real pair indices of this warp
+    const int first = max(q_lo, 0), last = Tn - L + q_hi;
+    int* trow = p.tr + ((size_t)n * p.T + (dir ? Tn - 1 : 0)) * p.SPL;
+    const long long tstep = dir ? -(long long)p.SPL : (long long)p.SPL;
+    const int emoff = 4 + 4 * cfg.g;
+    bool dead = false;
+    for (int i = 0; i < steps1; ++i) {
+        const int slot = i % kNE;
+        mbar_wait(&em_full[slot], (uint32_t)(i / kNE) & 1u);
+        const float* em = s_em + slot * EMF;
+        const float pb = em[0];
+        const float4 e4 = *(const float4*)(em + emoff);
+        mbar_arrive(&em_empty[slot]);
+        if (i >= first && i <= last) {
+            float pl[kJP];
+            pl[0] = dir ? e4.w : e4.x; pl[1] = dir ? e4.z : e4.y; pl[2] = dir ? e4.y : e4.z; pl[3] = dir ? e4.x : e4.w;
+            float cm; int ce;
+            fetch_below(s, w, lane, mail + ((i + 1) & 1) * W, cm, ce);
+            float u[kJP], v[kJP];
+            lane_sums(s, cfg.allowed, cm, ce, u, v);
+            lane_emit(s, u, v, pb, pl);
+        } else if (i > last && !dead) {
+            dead = true;
+#pragma unroll
+            for (int j = 0; j < kJP; ++j) { s.b[j] = 0.0f; s.l[j] = 0.0f; }
+            s.e = kVoidE;
+        }
+        if (lane == 31) mail[(i & 1) * W + w] = make_int2(__float_as_int(s.l[kJP - 1]), s.e);
+        if (cfg.live) {
+            const float4 o = dir ? make_float4(s.l[3], s.l[2], s.l[1], s.l[0]) : make_float4(s.l[0], s.l[1], s.l[2], s.l[3]);
+            *(float4*)(trow + 4 * cfg.g) = o;
+            trow[4 * NL + cfg.g] = s.e;
+        }
+        trow += tstep;
+        side_barrier(nthr);
+    }
+    // ---- the meeting: leave my boundary state; whoever arrives second forms Z from both ----
+    int* mybound = p.bound + ((size_t)n * 2 + dir) * p.BW;
+    if (cfg.live) {
+        const float4 ob = dir ? make_float4(s.b[3], s.b[2], s.b[1], s.b[0]) : make_float4(s.b[0], s.b[1], s.b[2], s.b[3]);
+        const float4 ol = dir ? make_float4(s.l[3], s.l[2], s.l[1], s.l[0]) : make_float4(s.l[0], s.l[1], s.l[2], s.l[3]);
+        *(float4*)(mybound + 4 * cfg.g) = ob;
+        *(float4*)(mybound + 4 * NL + 4 * cfg.g) = ol;
+        mybound[8 * NL + cfg.g] = s.e;
+    }
+    __threadfence();
+    side_barrier(nthr);
+    if (threadIdx.x == 0) { redi[W] = atomicAdd(&p.cnt[n], 1); __threadfence(); }
+    side_barrier(nthr);
+    if (redi[W] == 0) return;                                  // the other side is still sweeping: it will do it
+    {
+        const int* ob = p.bound + ((size_t)n * 2 + (1 - dir)) * p.BW;
+        float cm; int ce;
+        fetch_below(s, w, lane, mail + ((steps1 + 1) & 1) * W, cm, ce);
+        float u[kJP], v[kJP];
+        lane_sums(s, cfg.allowed, cm, ce, u, v);
+        // my blank of the pair with label index a is the other side's blank stored with label a -+ 1
+        const int A = 4 * NL;
+        float zm[2 * kJP]; int zx[2 * kJP];
+        int pm = 4 * kVoidE;
+#pragma unroll
+        for (int j = 0; j < kJP; ++j) {
+            const int a = cfg.a0 + cfg.astep * j, ab = a - cfg.astep;
+            float mb = 0.0f, ml = 0.0f; int xb = 0, xl = 0;
+            if (cfg.live) {
+                ml = v[j] * __int_as_float(__ldcg(ob + 4 * NL + a));
+                xl = s.e + __ldcg(ob + 8 * NL + (a >> 2));
+                if (ab >= 0 && ab < A) {
+                    mb = u[j] * __int_as_float(__ldcg(ob + ab));
+                    xb = s.e + __ldcg(ob + 8 * NL + (ab >> 2));
+                }
+            }
+            zm[2 * j] = mb; zx[2 * j] = (mb > 0.0f) ? xb + (__float_as_int(mb) >> 23) : 4 * kVoidE;
+            zm[2 * j + 1] = ml; zx[2 * j + 1] = (ml > 0.0f) ? xl + (__float_as_int(ml) >> 23) : 4 * kVoidE;
+            pm = max(pm, max(zx[2 * j], zx[2 * j + 1]));
+        }
+        // pm: the largest (scale + biased fp32 exponent) of any term; terms are summed relative to it in float64
+        pm = __reduce_max_sync(0xffffffffu, pm);
+        if (lane == 0) redi[w] = pm;
+        side_barrier(nthr);
+        for (int x = 0; x < Wn; ++x) pm = max(pm, redi[x]);
+        const bool feasible = pm > kVoidETest;
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < 2 * kJP; ++j) {
+            if (zm[j] > 0.0f) {
+                const int bexp = __float_as_int(zm[j]) >> 23;                     // biased exponent of the term's mantissa
+                const float mant = __int_as_float((__float_as_int(zm[j]) & 0x007fffff) | 0x3f800000);   // in [1, 2)
+                const int rel = zx[j] - pm;                                      // <= 0
+                (void)bexp;
+                if (rel > -1000) sum += scalbn((double)mant, rel);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) redd[w] = sum;
+        side_barrier(nthr);
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int x = 0; x < Wn; ++x) tot += redd[x];
+            // Z = tot * 2^(pm - 127): every term is mant * 2^(its scale + biased exponent - 127)
+            float v = CUDART_INF_F;
+            int4 zi = make_int4(1 << 29, __float_as_int(1.0f), 0, 0);
+            if (feasible && tot > 0.0) {
+                const int ex = ilogb(tot);
+                const double log2z = (double)(pm - 127) + log2(tot);
+                v = (float)(-log2z * kLn2);
+                zi.x = pm - 127 + ex;
+                zi.y = __float_as_int((float)(1.0 / scalbn(tot, -ex)));
+            }
+            p.loss[n] = v; p.loss_ws[n] = v;
+            p.zinfo[n] = zi;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------- backward ---
+// grid 2N, block 32 (W + kR2).  d loss / d logits = (softmax - occupancy) * gout (from_logits) or
+// -occupancy * gout (log-prob input, the reference's autograd boundary); rows t >= T_n and every row of an
+// infeasible or invalid utterance are zero.
+template <int W, int MINB>
+__global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Params p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = p.order[blockIdx.x >> 1], dir = blockIdx.x & 1;
+    const int4 mt = p.meta[n];
+    const int L = mt.y;
+    const float lossn = p.loss_ws[n];
+    const int Tn = (mt.z || !(lossn < CUDART_INF_F)) ? 0 : mt.x;      // NaN / inf loss: all-zero gradient
+    const int NS = p.NS, V = p.V, EMF = p.EMF, V4 = V >> 2;
+    float* gb = p.gx + (long long)n * p.sg_n;
+    const int tm = Tn >> 1;
+    const int steps1 = dir ? Tn - tm : tm;
+    const int nsteps2 = Tn - steps1;
+
+    if (warp >= W) {
+        // rows past the end of the utterance: zero, shared between the two sides' row warps
+        const int r = warp - W;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = Tn + dir + 2 * r; t < p.T; t += 2 * kR2) {
+            float4* dst = (float4*)(gb + (long long)t * p.sg_t);
+            for (int c = lane; c < V4; c += 32) dst[c] = z;
+        }
+    }
+    if (nsteps2 <= 0) return;
+
+    const int NL = (L + 3) / 4 + 2;
+    const int Wn = (NL + 31) >> 5;
+    const Ctc2Smem sm = ctc2_smem(W, NS, V, p.Sp, EMF, p.SPL, true);
+    uint64_t* row_full = (uint64_t*)(smem + sm.bars);            // [kR2][NS]
+    uint64_t* em_full = row_full + kR2 * NS;                     // [kNE]
+    uint64_t* occ_full = em_full + kNE;                          // [kNE]
+    uint64_t* st_full = occ_full + kNE;                          // [kNSR]
+    int2* mail = (int2*)(smem + sm.mail);
+    int* s_tgt = (int*)(smem + sm.tgt);
+    int* s_nxt = s_tgt + p.Sp;
+    float* s_em = (float*)(smem + sm.em);
+    int* s_st = (int*)(smem + sm.st);
+    float* s_rows = (float*)(smem + sm.rows);
+    const float g = p.gout[n];
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kR2 * NS; ++i) mbar_init(&row_full[i], 1);
+        for (int i = 0; i < kNE; ++i) { mbar_init(&em_full[i], 32); mbar_init(&occ_full[i], 32 * Wn); }
+        for (int i = 0; i < kNSR; ++i) mbar_init(&st_full[i], 1);
+    }
+    for (int i = threadIdx.x; i < kNE * EMF; i += blockDim.x) s_em[i] = 0.0f;
+    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+        s_tgt[k] = p.tgt[(size_t)n * p.Sp + k];
+        s_nxt[k] = p.dupnext[(size_t)n * p.Sp + k];
+    }
+    mbar_init_fence();
+    __syncthreads();
+
+    if (warp >= W) {
+        // ---------------------------------------------------------------------- row warps ---
+        const int r = warp - W;
+        float* wrows = s_rows + (size_t)r * NS * V;
+        uint64_t* wbar = row_full + r * NS;
+        const float* xb = p.x + (long long)n * p.sx_n;
+        const int nrows = (nsteps2 > r) ? (nsteps2 - 1 - r) / kR2 + 1 : 0;
+        auto frame = [&](int k) { const int i = steps1 + r + k * kR2; return dir ? Tn - 1 - i : i; };
+        auto issue = [&](int k) {
+            if (lane == 0) {
+                mbar_expect_tx(&wbar[k % NS], (uint32_t)V * 4u);
+                bulk_g2s(wrows + (size_t)(k % NS) * V, xb + (long long)frame(k) * p.sx_t, (uint32_t)V * 4u, &wbar[k % NS]);
+            }
+        };
+        // stage k % NS is refilled with row k + NS - 1 .. wait: rows k .. k + NS - 2 are in flight while row k is worked
+        // on; the stage that row k + NS - 1 goes to was stored from by row k - 1
+        for (int k = 0; k < min(NS - 1, nrows); ++k) issue(k);
+        for (int k = 0; k < nrows; ++k) {
+            if (k + NS - 1 < nrows) {
+                if (lane == 0) bulk_wait_read<0>();          // row k - 1's store has read its stage
+                __syncwarp();
+                issue(k + NS - 1);
+            }
+            const int i2 = r + k * kR2, t = frame(k);
+            float* row = wrows + (size_t)(k % NS) * V;
+            const float l2 = p.lse2[(size_t)n * p.T + t];
+            mbar_wait(&wbar[k % NS], (uint32_t)(k / NS) & 1u);
+            const RowNorm rn = row_norm(l2);
+            const int slot = i2 % kNE;
+            float* em = s_em + slot * EMF;
+            // (slot i2 % kNE was last used by my own row k - kNE / kR2: its occupancies were consumed in program order)
+            if (lane == 0) em[0] = emission2(row[0], rn);
+            for (int kk = lane; kk < L; kk += 32) em[8 + kk] = emission2(row[s_tgt[kk] & kLabelMask], rn);
+            mbar_arrive(&em_full[slot]);
+            __syncwarp();
+            // softmax * g in place while the trellis warps work on the frame
+            {
+                float4* r4 = (float4*)row;
+                if (p.from_logits) {
+                    for (int c = lane; c < V4; c += 32) {
+                        float4 v = r4[c];
+                        v.x = g * ex2f(fmaf(v.x, kLog2e, -l2)); v.y = g * ex2f(fmaf(v.y, kLog2e, -l2));
+                        v.z = g * ex2f(fmaf(v.z, kLog2e, -l2)); v.w = g * ex2f(fmaf(v.w, kLog2e, -l2));
+                        r4[c] = v;
+                    }
+                } else {
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int c = lane; c < V4; c += 32) r4[c] = z;
+                }
+            }
+            __syncwarp();
+            mbar_wait(&occ_full[slot], (uint32_t)(i2 / kNE) & 1u);
+            // occupancy of class y = sum over the positions that carry y, walked in position order by the first
+            // such position: one writer per class, no atomics, deterministic
+            float bs = 0.0f;
+            for (int kk = lane; kk < L; kk += 32) {
+                const int wd = s_tgt[kk];
+                bs += em[8 + kk];
+                if (!(wd & kNotFirst)) {
+                    float sacc = em[8 + kk];
+                    for (int j = s_nxt[kk]; j >= 0; j = s_nxt[j]) sacc += em[8 + j];
+                    row[wd & kLabelMask] -= g * sacc;
+                }
+            }
+            bs = warp_sum(bs);
+            __syncwarp();
+            if (lane == 0) row[0] -= g * (1.0f - bs);          // a frame's occupancies sum to one: the blank's share
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) { bulk_s2g(gb + (long long)t * p.sg_t, row, (uint32_t)V * 4u); bulk_commit(); }
+        }
+        if (lane == 0) bulk_wait_all<0>();
+        return;
+    }
+    if (warp >= Wn) return;
+
+    // ------------------------------------------------------------------------ trellis warps ---
+    const int w = warp;
+    const int nthr = 32 * Wn;
+    const LaneCfg cfg = lane_cfg(32 * w + lane, dir, L, NL, p.NLmax, p.tgt + (size_t)n * p.Sp);
+    Lane s;
+    {
+        const int* mybound = p.bound + ((size_t)n * 2 + dir) * p.BW;
+        float4 ob = make_float4(0.f, 0.f, 0.f, 0.f), ol = ob;
+        s.e = kVoidE;
+        if (cfg.live) {
+            ob = *(const float4*)(mybound + 4 * cfg.g);
+            ol = *(const float4*)(mybound + 4 * NL + 4 * cfg.g);
+            s.e = mybound[8 * NL + cfg.g];
+        }
+        s.b[0] = dir ? ob.w : ob.x; s.b[1] = dir ? ob.z : ob.y; s.b[2] = dir ? ob.y : ob.z; s.b[3] = dir ? ob.x : ob.w;
+        s.l[0] = dir ? ol.w : ol.x; s.l[1] = dir ? ol.z : ol.y; s.l[2] = dir ? ol.y : ol.z; s.l[3] = dir ? ol.x : ol.w;
+    }
+    const int4 zi = p.zinfo[n];
+    const int eZ = zi.x;
+    const float rZ = __int_as_float(zi.y);
+    if (lane == 31) mail[((steps1 + 1) & 1) * W + w] = make_int2(__float_as_int(s.l[kJP - 1]), s.e);
+    const int k_inj = dir ? 4 * NL - 1 - (L + 4) : 3;
+    const int q_lo = 128 * w - k_inj - 1, q_hi = 128 * w + 127 - k_inj - 1;
+    const int first = max(q_lo, 0), last = Tn - L + q_hi;
+    const int emoff = 4 + 4 * cfg.g;
+    const uint32_t st_bytes = (uint32_t)round_up(5 * NL, 4) * 4u;
+    const int* tr_n = p.tr + (size_t)n * p.T * p.SPL;
+    auto st_issue = [&](int i2) {          // the row the OTHER side stored for the frame of my phase-2 step i2
+        const int i = steps1 + i2, t = dir ? Tn - 1 - i : i;
+        mbar_expect_tx(&st_full[i2 % kNSR], st_bytes);
+        bulk_g2s(s_st + (i2 % kNSR) * p.SPL, tr_n + (size_t)t * p.SPL, st_bytes, &st_full[i2 % kNSR]);
+    };
+    if (threadIdx.x == 0)
+        for (int i2 = 0; i2 < min(kNSR - 1, nsteps2); ++i2) st_issue(i2);
+    side_barrier(nthr);
+    for (int i2 = 0; i2 < nsteps2; ++i2) {
+        const int i = steps1 + i2, t = dir ? Tn - 1 - i : i;
+        if (threadIdx.x == 0 && i2 + kNSR - 1 < nsteps2) st_issue(i2 + kNSR - 1);      // its slot was read in step i2 - 1
+        const int slot = i2 % kNE, ss = i2 % kNSR;
+        mbar_wait(&em_full[slot], (uint32_t)(i2 / kNE) & 1u);
+        float* em = s_em + slot * EMF;
+        const float pb = em[0];
+        const float4 e4 = *(const float4*)(em + emoff);
+        float4 occ = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i >= first && i <= last) {
+            mbar_wait(&st_full[ss], (uint32_t)(i2 / kNSR) & 1u);
+            const int* st = s_st + ss * p.SPL;
+            float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            int eb = kVoidE;
+            if (cfg.live) { o4 = *(const float4*)(st + 4 * cfg.g); eb = st[4 * NL + cfg.g]; }
+            float pl[kJP], ob[kJP];
+            pl[0] = dir ? e4.w : e4.x; pl[1] = dir ? e4.z : e4.y; pl[2] = dir ? e4.y : e4.z; pl[3] = dir ? e4.x : e4.w;
+            ob[0] = dir ? o4.w : o4.x; ob[1] = dir ? o4.z : o4.y; ob[2] = dir ? o4.y : o4.z; ob[3] = dir ? o4.x : o4.w;
+            float cm; int ce;
+            fetch_below(s, w, lane, mail + ((i + 1) & 1) * W, cm, ce);
+            float u[kJP], v[kJP];
+            lane_sums(s, cfg.allowed, cm, ce, u, v);
+            // occupancy of a label state = (my pre-emission sum) x (the other side's stored value) / Z
+            const int xs = s.e + eb - eZ;
+            const float sc = (xs < -126) ? 0.0f : __int_as_float(__float_as_int(rZ) + (min(xs, 90) << 23));
+            float gm[kJP];
+#pragma unroll
+            for (int j = 0; j < kJP; ++j) {
+                gm[j] = (v[j] * ob[j]) * sc;
+            }
+            occ = dir ? make_float4(gm[3], gm[2], gm[1], gm[0]) : make_float4(gm[0], gm[1], gm[2], gm[3]);
+            lane_emit(s, u, v, pb, pl);
+        } else {
+            mbar_wait(&st_full[ss], (uint32_t)(i2 / kNSR) & 1u);      // keep the ring's phases in step
+        }
+        if (lane == 31) mail[(i & 1) * W + w] = make_int2(__float_as_int(s.l[kJP - 1]), s.e);
+        if (cfg.live) *(float4*)(em + emoff) = occ;
+        mbar_arrive(&occ_full[slot]);
+        side_barrier(nthr);
+    }
+}
+
+}  // namespace hab

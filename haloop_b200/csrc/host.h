@@ -1,0 +1,28 @@
+// host.h — host-side helpers shared by the translation units of libha_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace hab {
+
+// records the thread-local message ha_b200_last_error() returns; returns `code`
+int host_fail(int code, const char* fmt, ...);
+int host_check_launch(const char* what);
+
+constexpr size_t kMaxSmemOptin = 227 * 1024;       // opt-in dynamic shared memory per CTA on sm_100
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- fused CTC path (ctc2.cu) ----
+bool ctc2_eligible(int T, int N, int V, int S);
+size_t ctc2_workspace_bytes(int T, int N, int S);
+int ctc2_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
+             const void* targets, int64_t tgt_stride, int S, int targets_i64,
+             const void* in_len, const void* tgt_len, int lengths_i64,
+             int from_logits, float* loss, void* ws, size_t ws_bytes, cudaStream_t st);
+int ctc2_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V, int S,
+             const float* grad_loss, int from_logits, float* gx, int64_t sg_t, int64_t sg_n,
+             void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace hab

@@ -40,6 +40,15 @@ def _unit_class_stride(x):
     return x if x.stride(-1) == 1 else x.contiguous()
 
 
+def _tma_view(x):
+    """Unit class stride and, when the class count allows the bulk-copy (TMA) path, rows that start on
+    16-byte boundaries; anything else (a sliced view) is copied once."""
+    x = _unit_class_stride(x)
+    if x.shape[-1] % 4 == 0 and (x.data_ptr() % 16 or any(st % 4 for st in x.stride()[:-1])):
+        x = x.contiguous()
+    return x
+
+
 def _empty_like_strided(x):
     """Fresh tensor with x's shape and strides (when x is dense), else contiguous."""
     if x.is_contiguous() or x.numel() == 0:
@@ -66,7 +75,7 @@ def _empty_like_strided(x):
 def ctc_fwd(x: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, tgt_len: torch.Tensor,
             from_logits: bool) -> tuple[torch.Tensor, torch.Tensor]:
     _check_cuda_f32(x, "emissions")
-    x = _unit_class_stride(x)
+    x = _tma_view(x)
     T, N, V = x.shape
     tg, tg64 = _idx(targets, x.device, "targets")
     il, il64 = _idx(in_len, x.device, "emission_lengths")
@@ -99,7 +108,7 @@ def _(x, targets, in_len, tgt_len, from_logits):
 @torch.library.custom_op("ha_b200::ctc_bwd", mutates_args=())
 def ctc_bwd(x: torch.Tensor, ws: torch.Tensor, grad_loss: torch.Tensor, S: int,
             from_logits: bool) -> torch.Tensor:
-    xs = _unit_class_stride(x)
+    xs = _tma_view(x)
     T, N, V = xs.shape
     gx = _empty_like_strided(xs)
     g = grad_loss.to(_F32).contiguous()
