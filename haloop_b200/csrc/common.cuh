@@ -144,6 +144,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (mbar_try_wait(bar, parity)) return;
     __trap();
 }
+// Wait of a warp that is not on the critical path (a row warp waiting for the trellis warps): sleep between
+// polls so that it leaves the issue slots to the warps that have work.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        __nanosleep(128);
+        if (mbar_try_wait(bar, parity)) return;
+    }
+    __trap();
+}
 // Producer-side wait: back off between polls so a spinning producer lane does not take issue slots
 // from the compute warps of its scheduler.
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {

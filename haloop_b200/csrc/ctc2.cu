@@ -45,7 +45,7 @@ Ctc2Params base_params(const Ctc2Ws& w, unsigned char* base, int T, int N, int V
     Ctc2Params p{};
     p.T = T; p.N = N; p.V = V; p.Sp = w.Sp;
     p.meta = (const int4*)(base + w.meta); p.order = (const int*)(base + w.order);
-    p.tgt = (const int*)(base + w.tgt); p.dupnext = (const int*)(base + w.dupnext);
+    p.tgt = (const int*)(base + w.tgt); p.nflist = (const int*)(base + w.nflist); p.nfhdr = (const int2*)(base + w.nfhdr); p.NF = w.NF;
     p.lse2 = (float*)(base + w.lse2); p.tr = (int*)(base + w.tr); p.SPL = w.SPL;
     p.bound = (int*)(base + w.bound); p.BW = w.BW; p.zinfo = (int4*)(base + w.zinfo); p.cnt = (int*)(base + w.cnt);
     p.loss_ws = (float*)(base + w.loss);
@@ -80,9 +80,9 @@ int ctc2_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
     pp.in_len = in_len; pp.tgt_len = tgt_len; pp.len64 = lengths_i64;
     pp.T = T; pp.N = N; pp.V = V; pp.S = S; pp.Sp = w.Sp;
     pp.meta = (int4*)(base + w.meta); pp.order = (int*)(base + w.order);
-    pp.tgt = (int*)(base + w.tgt); pp.dupnext = (int*)(base + w.dupnext);
+    pp.tgt = (int*)(base + w.tgt); pp.nflist = (int*)(base + w.nflist); pp.nfhdr = (int2*)(base + w.nfhdr); pp.NF = w.NF;
     pp.cnt = (int*)(base + w.cnt); pp.zinfo = (int4*)(base + w.zinfo);
-    ctc2_prep_kernel<<<N, 256, (size_t)w.Sp * 4, st>>>(pp);
+    ctc2_prep_kernel<<<N, 256, (size_t)w.Sp * 8, st>>>(pp);
     if ((rc = host_check_launch("ctc2_prep_kernel"))) return rc;
 
     Ctc2Params p = base_params(w, base, T, N, V, c);

@@ -35,13 +35,14 @@ constexpr int kJP = 4;            // pairs per lane
 constexpr int kR2 = 4;            // row warps per CTA
 constexpr int kNE = 8;            // emission / occupancy slots per CTA (multiple of kR2)
 constexpr int kNSR = 5;           // stored-row slots (backward)
+constexpr int kRcap = 8;          // later occurrences of a class are scattered in parallel up to this occurrence rank
 constexpr int kLaneExp = 32 + 127;        // biased exponent the lane maximum is normalised to
 constexpr int kAlignMax = 30;             // largest up-shift applied to the neighbour's label state
 constexpr float kFltMin = 1.1754943508222875e-38f;
 
 struct Ctc2Ws {                   // workspace layout (byte offsets)
-    size_t meta, order, tgt, dupnext, loss, zinfo, cnt, lse2, bound, tr, total;
-    int Sp, NLmax, SPL, BW;
+    size_t meta, order, tgt, nflist, nfhdr, loss, zinfo, cnt, lse2, bound, tr, total;
+    int Sp, NLmax, SPL, BW, NF;
 };
 __host__ inline Ctc2Ws ctc2_ws_layout(int T, int N, int S) {
     Ctc2Ws w;
@@ -54,7 +55,9 @@ __host__ inline Ctc2Ws ctc2_ws_layout(int T, int N, int S) {
     w.meta = take(sizeof(int4) * (size_t)N);
     w.order = take(sizeof(int) * (size_t)N);
     w.tgt = take(sizeof(int) * (size_t)N * w.Sp);
-    w.dupnext = take(sizeof(int) * (size_t)N * w.Sp);
+    w.NF = w.Sp + 32 * kRcap;                   // later occurrences of a class, padded per occurrence rank
+    w.nflist = take(sizeof(int) * (size_t)N * w.NF);
+    w.nfhdr = take(sizeof(int2) * (size_t)N);
     w.loss = take(sizeof(float) * (size_t)N);
     w.zinfo = take(sizeof(int4) * (size_t)N);   // {exponent of Z, bits of 1 / mantissa of Z, -, -}
     w.cnt = take(sizeof(int) * (size_t)N);      // arrivals at the meeting point
@@ -69,7 +72,7 @@ struct Ctc2Params {
     const float* x; long long sx_t, sx_n;
     float* gx; long long sg_t, sg_n;
     int T, N, V, Sp;
-    const int4* meta; const int* order; const int* tgt; const int* dupnext;
+    const int4* meta; const int* order; const int* tgt; const int* nflist; const int2* nfhdr; int NF;
     float* lse2; int* tr; int SPL; int* bound; int BW; int4* zinfo; int* cnt;
     float* loss; float* loss_ws; const float* gout;
     int from_logits, NS, NLmax, EMF;      // ring stages per row warp; lanes per side of the longest target; floats per emission slot (4 + 4 NLmax)
@@ -84,7 +87,7 @@ __host__ __device__ inline Ctc2Smem ctc2_smem(int W, int NS, int V, int Sp, int 
     s.bars = take(8 * (kR2 * NS + 2 * kNE + kNSR));
     s.mail = take(8 * 2 * W);
     s.red = take(16 * W + 16);
-    s.tgt = take(4 * Sp * (bwd ? 2 : 1));
+    s.tgt = take(bwd ? 4 * (2 * Sp + 32 * kRcap) : 4 * Sp);
     s.em = take(4 * kNE * EMF);
     s.st = take(bwd ? 4 * kNSR * SPL : 0);
     s.rows = take(4 * kR2 * NS * V);
@@ -112,6 +115,51 @@ __device__ __forceinline__ float emission2(float x, RowNorm rn) {
     const int k = __float_as_int(tk) - 0x4B400000;
     const float p = ex2f(f);
     return (k < -125) ? kFltMin : __int_as_float(__float_as_int(p) + (k << 23));
+}
+
+// Blank + label emissions of one row into an emission slot: four independent labels per lane and iteration,
+// so the LDS -> LDS -> FFMA -> MUFU -> STS chains of a row overlap instead of queueing behind each other.
+__device__ __forceinline__ void gather_row(float* em, const float* row, const int* s_tgt, int L, int lane, RowNorm rn) {
+    if (lane == 0) em[0] = emission2(row[0], rn);
+    for (int k0 = lane; k0 < L; k0 += 128) {
+        float xv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xv[q] = row[s_tgt[min(k0 + 32 * q, L - 1)] & kLabelMask];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xv[q] = emission2(xv[q], rn);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (k0 + 32 * q < L) em[8 + k0 + 32 * q] = xv[q];
+    }
+}
+
+// log2-sum-exp2 of a row of V logits (V % 4 == 0) held in shared memory.  One pass without the usual maximum
+// when the plain sum stays inside the fp32 range (|logit| < ~85); otherwise the shifted two-pass form.
+__device__ __forceinline__ float row_lse2(const float* row, int V4, int lane) {
+    const float4* r4 = (const float4*)row;
+    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll 4
+    for (int c = lane; c < V4; c += 32) {
+        const float4 v = r4[c];
+        s0 += ex2f(v.x * kLog2e) + ex2f(v.y * kLog2e);
+        s1 += ex2f(v.z * kLog2e) + ex2f(v.w * kLog2e);
+    }
+    const float s = warp_sum(s0 + s1);
+    if (s > 1e-30f && s < 1e30f) return log2f(s);
+    float mx = -CUDART_INF_F;
+    for (int c = lane; c < V4; c += 32) {
+        const float4 v = r4[c];
+        mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+    mx = warp_max(mx);
+    const float m2 = mx * kLog2e;
+    s0 = 0.0f; s1 = 0.0f;
+    for (int c = lane; c < V4; c += 32) {
+        const float4 v = r4[c];
+        s0 += ex2f(fmaf(v.x, kLog2e, -m2)) + ex2f(fmaf(v.y, kLog2e, -m2));
+        s1 += ex2f(fmaf(v.z, kLog2e, -m2)) + ex2f(fmaf(v.w, kLog2e, -m2));
+    }
+    return m2 + log2f(warp_sum(s0 + s1));
 }
 
 // -------------------------------------------------------------------------------- lane numbers ---
@@ -211,18 +259,23 @@ __device__ __forceinline__ void fetch_below(const Lane& s, int w, int lane, cons
 struct Prep2Params {
     const void* targets; long long tgt_stride; int tgt64;
     const void* in_len; const void* tgt_len; int len64;
-    int T, N, V, S, Sp;
-    int4* meta; int* order; int* tgt; int* dupnext; int* cnt; int4* zinfo;
+    int T, N, V, S, Sp, NF;
+    int4* meta; int* order; int* tgt; int* nflist; int2* nfhdr; int* cnt; int4* zinfo;
 };
 
-// grid N, block 256.  meta[n] = {T_n, L_n, invalid, frames an alignment needs beyond L_n}.
+// grid N, block 256.  meta[n] = {T_n, L_n, invalid, frames an alignment needs beyond L_n}; tgt[n][k] = label |
+// kNotFirst; nflist[n] = the positions whose label occurred before, as (label << 10 | position): occurrence ranks
+// 1 .. kRcap-1 in groups padded to 32 entries (-1) — the classes of a group are distinct, so the gradient kernel
+// updates one group per instruction — then any higher ranks in position order (a serial tail).
 __global__ void __launch_bounds__(256) ctc2_prep_kernel(Prep2Params p) {
-    extern __shared__ __align__(16) int s_y[];
-    __shared__ int s_bad, s_rank, s_rep;
+    extern __shared__ __align__(16) int s_y[];          // [Sp] labels, [Sp] occurrence ranks
+    __shared__ int s_bad, s_rank, s_rep, s_cnt[kRcap], s_off[kRcap], s_fill[kRcap], s_tail;
+    int* s_rk = s_y + p.Sp;
     const int n = blockIdx.x;
     const long long Tn = load_idx(p.in_len, n, p.len64), Ln = load_idx(p.tgt_len, n, p.len64);
     const bool lenbad = (Tn < 0 || Tn > p.T || Ln < 0 || Ln > p.S);
-    if (threadIdx.x == 0) { s_bad = lenbad ? 1 : 0; s_rank = 0; s_rep = 0; }
+    if (threadIdx.x == 0) { s_bad = lenbad ? 1 : 0; s_rank = 0; s_rep = 0; s_tail = 0; }
+    if (threadIdx.x < kRcap) { s_cnt[threadIdx.x] = 0; s_fill[threadIdx.x] = 0; }
     __syncthreads();
     const int L = lenbad ? 0 : (int)Ln;
     for (int k = threadIdx.x; k < p.S; k += blockDim.x) {
@@ -231,28 +284,25 @@ __global__ void __launch_bounds__(256) ctc2_prep_kernel(Prep2Params p) {
         s_y[k] = (int)y;
     }
     for (int k = p.S + threadIdx.x; k < p.Sp; k += blockDim.x) s_y[k] = -1;
+    int* nfl = p.nflist + (size_t)n * p.NF;
+    for (int k = threadIdx.x; k < p.NF; k += blockDim.x) nfl[k] = -1;
     __syncthreads();
     const int L4 = (L + 3) & ~3;
     for (int k = threadIdx.x; k < p.Sp; k += blockDim.x) {
         const int y = s_y[k];
-        int nxt = 0x7fffffff, notfirst = 0;
+        int rk = 0;                                     // earlier positions with my label (branch-free vector scan)
         if (k < L) {
             const int4* y4 = (const int4*)s_y;
 #pragma unroll 4
             for (int j4 = 0; j4 < (L4 >> 2); ++j4) {
                 const int4 v = y4[j4];
                 const int j = 4 * j4;
-                const int m0 = (v.x == y) & (j < L), m1 = (v.y == y) & (j + 1 < L);
-                const int m2 = (v.z == y) & (j + 2 < L), m3 = (v.w == y) & (j + 3 < L);
-                notfirst |= (m0 & (j < k)) | (m1 & (j + 1 < k)) | (m2 & (j + 2 < k)) | (m3 & (j + 3 < k));
-                nxt = min(nxt, (m0 && j > k) ? j : 0x7fffffff);
-                nxt = min(nxt, (m1 && j + 1 > k) ? j + 1 : 0x7fffffff);
-                nxt = min(nxt, (m2 && j + 2 > k) ? j + 2 : 0x7fffffff);
-                nxt = min(nxt, (m3 && j + 3 > k) ? j + 3 : 0x7fffffff);
+                rk += ((v.x == y) & (j < k)) + ((v.y == y) & (j + 1 < k)) + ((v.z == y) & (j + 2 < k)) + ((v.w == y) & (j + 3 < k));
             }
+            if (rk > 0) atomicAdd(&s_cnt[min(rk, kRcap) - 1], 1);      // s_cnt[kRcap - 1]: the serial tail
         }
-        p.tgt[(size_t)n * p.Sp + k] = (y < 0 ? 0 : y) | (notfirst ? kNotFirst : 0);
-        p.dupnext[(size_t)n * p.Sp + k] = (nxt == 0x7fffffff) ? -1 : nxt;
+        s_rk[k] = rk;
+        p.tgt[(size_t)n * p.Sp + k] = (y < 0 ? 0 : y) | (rk ? kNotFirst : 0);
         // a blank must separate equal neighbours, and a label 0 can only be entered from the blank before
         // it (ha/ctc.py:140: no skip into a blank-valued state): one extra frame each
         if (k >= 1 && k < L && (s_y[k - 1] == y || y == 0)) atomicAdd(&s_rep, 1);
@@ -269,10 +319,24 @@ __global__ void __launch_bounds__(256) ctc2_prep_kernel(Prep2Params p) {
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        int o = 0;
+        for (int r = 0; r < kRcap - 1; ++r) { s_off[r] = o; o += (s_cnt[r] + 31) & ~31; }
+        s_off[kRcap - 1] = o;
         p.meta[n] = make_int4(s_bad ? 0 : (int)Tn, L, s_bad, s_rep);
+        p.nfhdr[n] = make_int2(o, s_cnt[kRcap - 1]);
         p.order[s_rank] = n;
         p.cnt[n] = 0;
         p.zinfo[n] = make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+        const int rk = s_rk[k];
+        if (rk >= 1 && rk < kRcap) nfl[s_off[rk - 1] + atomicAdd(&s_fill[rk - 1], 1)] = (s_y[k] << 10) | k;
+    }
+    if (threadIdx.x == 0 && s_cnt[kRcap - 1] > 0) {     // rare: a label occurring more than kRcap times
+        int o = s_off[kRcap - 1];
+        for (int k = 0; k < L; ++k)
+            if (s_rk[k] >= kRcap) nfl[o++] = (s_y[k] << 10) | k;
     }
 }
 
@@ -337,31 +401,12 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
             const int i = r + k * kR2, t = dir ? Tn - 1 - i : i;
             const float* row = wrows + (size_t)(k % NS) * V;
             mbar_wait(&wbar[k % NS], (uint32_t)(k / NS) & 1u);
-            float l2 = 0.0f;
-            if (p.from_logits) {
-                const float4* r4 = (const float4*)row;
-                float mx = -CUDART_INF_F;
-                for (int c = lane; c < V4; c += 32) {
-                    const float4 v = r4[c];
-                    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-                }
-                mx = warp_max(mx);
-                const float m2 = mx * kLog2e;
-                float s0 = 0.0f, s1 = 0.0f;
-                for (int c = lane; c < V4; c += 32) {
-                    const float4 v = r4[c];
-                    s0 += ex2f(fmaf(v.x, kLog2e, -m2)) + ex2f(fmaf(v.y, kLog2e, -m2));
-                    s1 += ex2f(fmaf(v.z, kLog2e, -m2)) + ex2f(fmaf(v.w, kLog2e, -m2));
-                }
-                l2 = m2 + log2f(warp_sum(s0 + s1));
-            }
+            const float l2 = p.from_logits ? row_lse2(row, V4, lane) : 0.0f;
             if (lane == 0) p.lse2[(size_t)n * p.T + t] = l2;
             const RowNorm rn = row_norm(l2);
             const int slot = i % kNE, use = i / kNE;
-            if (use > 0) mbar_wait(&em_empty[slot], (uint32_t)(use - 1) & 1u);
-            float* em = s_em + slot * EMF;
-            if (lane == 0) em[0] = emission2(row[0], rn);
-            for (int kk = lane; kk < L; kk += 32) em[8 + kk] = emission2(row[s_tgt[kk]], rn);
+            if (use > 0) mbar_wait_relaxed(&em_empty[slot], (uint32_t)(use - 1) & 1u);
+            gather_row(s_em + slot * EMF, row, s_tgt, L, lane, rn);
             mbar_arrive(&em_full[slot]);
             __syncwarp();
             if (k + NS < nrows) issue(k + NS);
@@ -543,7 +588,7 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
     uint64_t* st_full = occ_full + kNE;                          // [kNSR]
     int2* mail = (int2*)(smem + sm.mail);
     int* s_tgt = (int*)(smem + sm.tgt);
-    int* s_nxt = s_tgt + p.Sp;
+    int* s_nf = s_tgt + p.Sp;                                    // later occurrences of a class (ctc2_prep_kernel)
     float* s_em = (float*)(smem + sm.em);
     int* s_st = (int*)(smem + sm.st);
     float* s_rows = (float*)(smem + sm.rows);
@@ -555,10 +600,9 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
         for (int i = 0; i < kNSR; ++i) mbar_init(&st_full[i], 1);
     }
     for (int i = threadIdx.x; i < kNE * EMF; i += blockDim.x) s_em[i] = 0.0f;
-    for (int k = threadIdx.x; k < L; k += blockDim.x) {
-        s_tgt[k] = p.tgt[(size_t)n * p.Sp + k];
-        s_nxt[k] = p.dupnext[(size_t)n * p.Sp + k];
-    }
+    const int2 nf = p.nfhdr[n];                                  // {entries in rank groups of 32, serial tail}
+    for (int k = threadIdx.x; k < L; k += blockDim.x) s_tgt[k] = p.tgt[(size_t)n * p.Sp + k];
+    for (int k = threadIdx.x; k < nf.x + nf.y; k += blockDim.x) s_nf[k] = p.nflist[(size_t)n * p.NF + k];
     mbar_init_fence();
     __syncthreads();
 
@@ -576,62 +620,92 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
                 bulk_g2s(wrows + (size_t)(k % NS) * V, xb + (long long)frame(k) * p.sx_t, (uint32_t)V * 4u, &wbar[k % NS]);
             }
         };
-        // stage k % NS is refilled with row k + NS - 1 .. wait: rows k .. k + NS - 2 are in flight while row k is worked
-        // on; the stage that row k + NS - 1 goes to was stored from by row k - 1
-        for (int k = 0; k < min(NS - 1, nrows); ++k) issue(k);
-        for (int k = 0; k < nrows; ++k) {
-            if (k + NS - 1 < nrows) {
-                if (lane == 0) bulk_wait_read<0>();          // row k - 1's store has read its stage
-                __syncwarp();
-                issue(k + NS - 1);
-            }
+        // pre(k): gather the emissions of row k for the trellis warps, then turn the row into softmax * g in place.
+        auto pre = [&](int k) {
             const int i2 = r + k * kR2, t = frame(k);
             float* row = wrows + (size_t)(k % NS) * V;
             const float l2 = p.lse2[(size_t)n * p.T + t];
             mbar_wait(&wbar[k % NS], (uint32_t)(k / NS) & 1u);
-            const RowNorm rn = row_norm(l2);
-            const int slot = i2 % kNE;
-            float* em = s_em + slot * EMF;
-            // (slot i2 % kNE was last used by my own row k - kNE / kR2: its occupancies were consumed in program order)
-            if (lane == 0) em[0] = emission2(row[0], rn);
-            for (int kk = lane; kk < L; kk += 32) em[8 + kk] = emission2(row[s_tgt[kk] & kLabelMask], rn);
-            mbar_arrive(&em_full[slot]);
+            // (slot i2 % kNE was last used by my own row k - kNE / kR2, whose occupancies I consumed in program order)
+            gather_row(s_em + (i2 % kNE) * EMF, row, s_tgt, L, lane, row_norm(l2));
+            mbar_arrive(&em_full[i2 % kNE]);
             __syncwarp();
-            // softmax * g in place while the trellis warps work on the frame
-            {
-                float4* r4 = (float4*)row;
-                if (p.from_logits) {
-                    for (int c = lane; c < V4; c += 32) {
-                        float4 v = r4[c];
-                        v.x = g * ex2f(fmaf(v.x, kLog2e, -l2)); v.y = g * ex2f(fmaf(v.y, kLog2e, -l2));
-                        v.z = g * ex2f(fmaf(v.z, kLog2e, -l2)); v.w = g * ex2f(fmaf(v.w, kLog2e, -l2));
-                        r4[c] = v;
-                    }
-                } else {
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int c = lane; c < V4; c += 32) r4[c] = z;
+            float4* r4 = (float4*)row;
+            if (p.from_logits) {
+#pragma unroll 4
+                for (int c = lane; c < V4; c += 32) {
+                    float4 v = r4[c];
+                    v.x = g * ex2f(fmaf(v.x, kLog2e, -l2)); v.y = g * ex2f(fmaf(v.y, kLog2e, -l2));
+                    v.z = g * ex2f(fmaf(v.z, kLog2e, -l2)); v.w = g * ex2f(fmaf(v.w, kLog2e, -l2));
+                    r4[c] = v;
                 }
+            } else {
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = lane; c < V4; c += 32) r4[c] = z;
             }
             __syncwarp();
-            mbar_wait(&occ_full[slot], (uint32_t)(i2 / kNE) & 1u);
-            // occupancy of class y = sum over the positions that carry y, walked in position order by the first
-            // such position: one writer per class, no atomics, deterministic
+        };
+        // post(k): subtract the occupancies the trellis warps left in the slot and store the row.
+        auto post = [&](int k) {
+            const int i2 = r + k * kR2, t = frame(k);
+            float* row = wrows + (size_t)(k % NS) * V;
+            const float* em = s_em + (i2 % kNE) * EMF;
+            mbar_wait_relaxed(&occ_full[i2 % kNE], (uint32_t)(i2 / kNE) & 1u);
+            // first occurrences of a class: all distinct, four per lane and iteration
             float bs = 0.0f;
-            for (int kk = lane; kk < L; kk += 32) {
-                const int wd = s_tgt[kk];
-                bs += em[8 + kk];
-                if (!(wd & kNotFirst)) {
-                    float sacc = em[8 + kk];
-                    for (int j = s_nxt[kk]; j >= 0; j = s_nxt[j]) sacc += em[8 + j];
-                    row[wd & kLabelMask] -= g * sacc;
+            for (int k0 = lane; k0 < L; k0 += 128) {
+                int wd[4]; float oc[4], rv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int kk = min(k0 + 32 * q, L - 1);
+                    wd[q] = s_tgt[kk];
+                    oc[q] = (k0 + 32 * q < L) ? em[8 + kk] : 0.0f;
                 }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { rv[q] = row[wd[q] & kLabelMask]; bs += oc[q]; }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (k0 + 32 * q < L && !(wd[q] & kNotFirst)) row[wd[q] & kLabelMask] = fmaf(-g, oc[q], rv[q]);
             }
+            __syncwarp();
+            // later occurrences: the list holds them by occurrence rank, one rank (distinct classes) per 32 entries,
+            // so a class is updated in position order by one lane at a time: deterministic, no atomics
+            for (int e0 = 0; e0 < nf.x; e0 += 32) {
+                const int e = s_nf[e0 + lane];
+                if (e >= 0) row[e >> 10] = fmaf(-g, em[8 + (e & 1023)], row[e >> 10]);
+                __syncwarp();
+            }
+            if (nf.y > 0 && lane == 0)
+                for (int x = nf.x; x < nf.x + nf.y; ++x) { const int e = s_nf[x]; row[e >> 10] = fmaf(-g, em[8 + (e & 1023)], row[e >> 10]); }
             bs = warp_sum(bs);
             __syncwarp();
             if (lane == 0) row[0] -= g * (1.0f - bs);          // a frame's occupancies sum to one: the blank's share
             fence_async_smem();
             __syncwarp();
             if (lane == 0) { bulk_s2g(gb + (long long)t * p.sg_t, row, (uint32_t)V * 4u); bulk_commit(); }
+        };
+        if (NS >= 2) {
+            // two stages: row k + 1 is gathered (its emissions are what the trellis warps wait for) before row k's
+            // occupancies are awaited; row k + 2 is fetched into row k's stage once row k's store has read it
+            for (int k = 0; k < min(2, nrows); ++k) issue(k);
+            if (nrows > 0) pre(0);
+            for (int k = 0; k < nrows; ++k) {
+                if (k + 1 < nrows) pre(k + 1);
+                post(k);
+                if (k + 2 < nrows) {
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                    issue(k + 2);
+                }
+            }
+        } else {
+            for (int k = 0; k < nrows; ++k) {
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+                issue(k);
+                pre(k);
+                post(k);
+            }
         }
         if (lane == 0) bulk_wait_all<0>();
         return;
