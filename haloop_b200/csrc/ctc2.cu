@@ -20,9 +20,9 @@ Cfg2 pick_cfg2(int V, int S) {
     static const int kW[] = {1, 2, 3, 5, 9};
     for (int w : kW) if (!c.W && w >= Wn) c.W = w;
     if (!c.W || V % 4 != 0 || V < 4) return c;
-    const int EMF = 4 + 4 * NLmax, SPL = round_up(5 * NLmax, 4);
+    const int SPL = round_up(5 * NLmax, 4);
     for (int ns = 2; ns >= 1 && !c.ok; --ns) {
-        const size_t f = ctc2_smem(c.W, ns, V, Sp, EMF, SPL, false).total, b = ctc2_smem(c.W, ns, V, Sp, EMF, SPL, true).total;
+        const size_t f = ctc2_smem(c.W, ns, V, Sp, SPL, false).total, b = ctc2_smem(c.W, ns, V, Sp, SPL, true).total;
         const size_t cap = (ns == 2) ? 56 * 1024 : 110 * 1024;       // 4 CTAs per SM with two stages, 2 with one
         if (b <= cap) { c.NS = ns; c.smem_fwd = f; c.smem_bwd = b; c.ok = true; }
     }
@@ -49,7 +49,7 @@ Ctc2Params base_params(const Ctc2Ws& w, unsigned char* base, int T, int N, int V
     p.lse2 = (float*)(base + w.lse2); p.tr = (int*)(base + w.tr); p.SPL = w.SPL;
     p.bound = (int*)(base + w.bound); p.BW = w.BW; p.zinfo = (int4*)(base + w.zinfo); p.cnt = (int*)(base + w.cnt);
     p.loss_ws = (float*)(base + w.loss);
-    p.NS = c.NS; p.NLmax = w.NLmax; p.EMF = 4 + 4 * w.NLmax;
+    p.NS = c.NS; p.NLmax = w.NLmax; p.EMF = ctc2_em_floats(w.Sp);
     return p;
 }
 

@@ -27,18 +27,19 @@
 // values that can be lost are more than 2^158 (110 nats) below the largest of the same 8 adjacent states
 // (Limits).  tools/ctc2_proto.py is the numpy model of this file.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace hab {
 
 constexpr int kJP = 4;            // pairs per lane
 constexpr int kR2 = 4;            // row warps per CTA
-constexpr int kNE = 8;            // emission / occupancy slots per CTA (multiple of kR2)
-constexpr int kNSR = 5;           // stored-row slots (backward)
+constexpr int kNE = 8;            // emission / occupancy slots per CTA (a power of two, multiple of kR2)
+constexpr int kNSR = 4;           // stored-row slots (backward; a power of two)
 constexpr int kRcap = 8;          // later occurrences of a class are scattered in parallel up to this occurrence rank
 constexpr int kLaneExp = 32 + 127;        // biased exponent the lane maximum is normalised to
 constexpr int kAlignMax = 30;             // largest up-shift applied to the neighbour's label state
-constexpr float kFltMin = 1.1754943508222875e-38f;
 
 struct Ctc2Ws {                   // workspace layout (byte offsets)
     size_t meta, order, tgt, nflist, nfhdr, loss, zinfo, cnt, lse2, bound, tr, total;
@@ -75,20 +76,25 @@ struct Ctc2Params {
     const int4* meta; const int* order; const int* tgt; const int* nflist; const int2* nfhdr; int NF;
     float* lse2; int* tr; int SPL; int* bound; int BW; int4* zinfo; int* cnt;
     float* loss; float* loss_ws; const float* gout;
-    int from_logits, NS, NLmax, EMF;      // ring stages per row warp; lanes per side of the longest target; floats per emission slot (4 + 4 NLmax)
+    int from_logits, NS, NLmax, EMF;      // ring stages per row warp (1 or 2); lanes per side of the longest target;
+                                          // floats per emission slot (ctc2_em_floats)
 };
 
-// shared memory (bytes): [mbarriers][mailboxes][Z reduction][targets (+ chains)][emission slots][stored slots][row ring]
+// An emission slot: [0] blank, [4 + a] label index a = position + 4 (a < 4 and a >= L + 4 are phantoms that stay 0).
+// Sized so that the lanes of the longest target and a row warp's four-labels-per-lane batches stay inside it.
+__host__ __device__ inline int ctc2_em_floats(int Sp) { return 16 + round_up(Sp, 128); }
+
+// shared memory (bytes): [mbarriers][mailboxes][Z reduction][targets (+ later occurrences)][emission slots][stored slots][row ring]
 struct Ctc2Smem { int bars, mail, red, tgt, em, st, rows, total; };
-__host__ __device__ inline Ctc2Smem ctc2_smem(int W, int NS, int V, int Sp, int EMF, int SPL, bool bwd) {
+__host__ __device__ inline Ctc2Smem ctc2_smem(int W, int NS, int V, int Sp, int SPL, bool bwd) {
     Ctc2Smem s;
     int o = 0;
     auto take = [&](int bytes) { int at = o; o = round_up(o + bytes, 128); return at; };
     s.bars = take(8 * (kR2 * NS + 2 * kNE + kNSR));
     s.mail = take(8 * 2 * W);
     s.red = take(16 * W + 16);
-    s.tgt = take(bwd ? 4 * (2 * Sp + 32 * kRcap) : 4 * Sp);
-    s.em = take(4 * kNE * EMF);
+    s.tgt = take(4 * (round_up(Sp, 128) + (bwd ? Sp + 32 * kRcap : 0)));
+    s.em = take(4 * kNE * ctc2_em_floats(Sp));
     s.st = take(bwd ? 4 * kNSR * SPL : 0);
     s.rows = take(4 * kR2 * NS * V);
     s.total = o;
@@ -100,6 +106,7 @@ __host__ __device__ inline Ctc2Smem ctc2_smem(int W, int NS, int V, int Sp, int 
 // 2^-10 (l2q) and a remainder (dl) so that the integer part of the exponent can be removed BEFORE the one
 // rounding that matters: the fraction handed to ex2 is exact to 3e-8 whatever |log p| is.  The forward and
 // the backward kernel call this with bit-identical arguments, so both halves of a trellis see one model.
+// Floor: 2^-125.75 (a class more than 87 nats below probability one), so every emission is a positive normal.
 struct RowNorm { float l2q, dl; };
 __device__ __forceinline__ RowNorm row_norm(float l2) {
     RowNorm r;
@@ -108,23 +115,23 @@ __device__ __forceinline__ RowNorm row_norm(float l2) {
     return r;
 }
 __device__ __forceinline__ float emission2(float x, RowNorm rn) {
-    const float t = fminf(fmaxf(fmaf(x, kLog2e, -rn.l2q), -200.0f), 60.0f);
-    const float tk = t + kMagic;                                   // integer part in the low mantissa bits
+    const float t = fmaxf(fmaf(x, kLog2e, -rn.l2q), -125.0f);
+    const float tk = t + kMagic;                                   // integer part k in the low mantissa bits
     const float kf = tk - kMagic;
-    const float f = fmaf(x, kLog2e, -(rn.l2q + kf)) - rn.dl;       // |f| <= 0.5 (+ the remainder)
-    const int k = __float_as_int(tk) - 0x4B400000;
-    const float p = ex2f(f);
-    return (k < -125) ? kFltMin : __int_as_float(__float_as_int(p) + (k << 23));
+    const float f = fmaxf(fmaf(x, kLog2e, -(rn.l2q + kf)) - rn.dl, -0.75f);    // |f| <= 0.5 + |dl|; the clamp only acts below the floor
+    // p * 2^k by exponent-field arithmetic: bits(tk) = 0x4B400000 + k and 0x4B400000 << 23 == 0 (mod 2^32)
+    return __int_as_float(__float_as_int(ex2f(f)) + (__float_as_int(tk) << 23));
 }
 
-// Blank + label emissions of one row into an emission slot: four independent labels per lane and iteration,
-// so the LDS -> LDS -> FFMA -> MUFU -> STS chains of a row overlap instead of queueing behind each other.
-__device__ __forceinline__ void gather_row(float* em, const float* row, const int* s_tgt, int L, int lane, RowNorm rn) {
+// Blank + label emissions of one row into an emission slot: four independent labels per lane and iteration, so
+// the LDS -> LDS -> FFMA -> MUFU -> STS chains of a row overlap.  s_off: byte offset of the label's logit in the
+// row (label * 4, flag bits below), padded with zeros to a multiple of 128 entries.
+__device__ __forceinline__ void gather_row(float* em, const float* row, const int* s_off, int L, int lane, RowNorm rn) {
     if (lane == 0) em[0] = emission2(row[0], rn);
     for (int k0 = lane; k0 < L; k0 += 128) {
         float xv[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) xv[q] = row[s_tgt[min(k0 + 32 * q, L - 1)] & kLabelMask];
+        for (int q = 0; q < 4; ++q) xv[q] = *(const float*)((const char*)row + (s_off[k0 + 32 * q] & ~3));
 #pragma unroll
         for (int q = 0; q < 4; ++q) xv[q] = emission2(xv[q], rn);
 #pragma unroll
@@ -163,6 +170,9 @@ __device__ __forceinline__ float row_lse2(const float* row, int V4, int lane) {
 }
 
 // -------------------------------------------------------------------------------- lane numbers ---
+// A lane's 4 pairs are kept in POSITION order for both directions: component c is the pair whose label index is
+// a = 4 g + c.  Direction 1 (beta) walks them downwards, so "the pair below" is c + 1 and the value entering
+// from the previous lane of the side lands at c = 3; nothing is reversed when rows are loaded or stored.
 struct Lane { float b[kJP], l[kJP]; int e; };
 
 __device__ __forceinline__ float pow2_clamped(int d) {             // 2^d, 0 below 2^-126; d <= 127
@@ -172,61 +182,59 @@ __device__ __forceinline__ float pow2_clamped(int d) {             // 2^d, 0 bel
 // First half of a step: align the label state (cm, ce) of the pair below my lowest one to my exponent and
 // form the pre-emission sums  u = blank + label below,  v = label + (skip allowed ? u : blank)
 // [ha/ctc.py:155-167].  Their scale is s.e on return.
+template <int DIR>
 __device__ __forceinline__ void lane_sums(Lane& s, unsigned allowed, float cm, int ce, float (&u)[kJP], float (&v)[kJP]) {
     int d = ce - s.e;
     if (d > kAlignMax) {                // the neighbour dwarfs this lane (the wavefront arrives): move my exponent up
         const int sh = d - kAlignMax;
         const float f = pow2_clamped(-sh);
 #pragma unroll
-        for (int j = 0; j < kJP; ++j) { s.b[j] *= f; s.l[j] *= f; }
+        for (int c = 0; c < kJP; ++c) { s.b[c] *= f; s.l[c] *= f; }
         s.e += sh;
         d = kAlignMax;
     }
     const float c0 = cm * pow2_clamped(d);
 #pragma unroll
-    for (int j = 0; j < kJP; ++j) {
-        u[j] = s.b[j] + (j ? s.l[j ? j - 1 : 0] : c0);
-        v[j] = s.l[j] + (((allowed >> j) & 1u) ? u[j] : s.b[j]);
+    for (int c = 0; c < kJP; ++c) {
+        const float below = DIR ? (c == kJP - 1 ? c0 : s.l[c < kJP - 1 ? c + 1 : c]) : (c == 0 ? c0 : s.l[c ? c - 1 : 0]);
+        u[c] = s.b[c] + below;
+        v[c] = s.l[c] + (((allowed >> c) & 1u) ? u[c] : s.b[c]);
     }
 }
 // Second half: multiply by the emissions and renormalise the lane.
-__device__ __forceinline__ void lane_emit(Lane& s, const float (&u)[kJP], const float (&v)[kJP], float pb, const float (&pl)[kJP]) {
+__device__ __forceinline__ void lane_emit(Lane& s, const float (&u)[kJP], const float (&v)[kJP], float pb, float4 pl) {
     float nb[kJP], nl[kJP];
+    nl[0] = v[0] * pl.x; nl[1] = v[1] * pl.y; nl[2] = v[2] * pl.z; nl[3] = v[3] * pl.w;
     float mx = 0.0f;
 #pragma unroll
-    for (int j = 0; j < kJP; ++j) {
-        nb[j] = u[j] * pb;
-        nl[j] = v[j] * pl[j];
-        mx = fmaxf(mx, fmaxf(nb[j], nl[j]));
+    for (int c = 0; c < kJP; ++c) {
+        nb[c] = u[c] * pb;
+        mx = fmaxf(mx, fmaxf(nb[c], nl[c]));
     }
     const int delta = min(kLaneExp - (__float_as_int(mx) >> 23), 120);
     const float f = __int_as_float((delta + 127) << 23);
 #pragma unroll
-    for (int j = 0; j < kJP; ++j) { s.b[j] = nb[j] * f; s.l[j] = nl[j] * f; }
+    for (int c = 0; c < kJP; ++c) { s.b[c] = nb[c] * f; s.l[c] = nl[c] * f; }
     s.e = (mx > 0.0f) ? s.e - delta : kVoidE;
 }
 
 // Per-lane constants of a trellis thread.
 struct LaneCfg {
-    int gl;            // lane index within the side (32 w + lane)
+    int gl;            // lane index within the side (32 w + lane); direction 1 counts the groups downwards
     int g;             // my position group (clamped into the slot): labels a = 4 g .. 4 g + 3
-    int a0, astep;     // label index a of my pair 0 and the step to pair 1 (+1 alpha, -1 beta)
-    unsigned allowed;  // skip-transition bits of my 4 pairs   [ha/ctc.py:140-142]
+    unsigned allowed;  // skip-transition bits of my 4 pairs, by component   [ha/ctc.py:140-142]
     bool live;         // gl < NL: the lane owns a group of the stored rows
 };
 __device__ __forceinline__ LaneCfg lane_cfg(int gl, int dir, int L, int NL, int NLmax, const int* y) {
-    LaneCfg c;
-    const int A = 4 * NL;
-    c.gl = gl;
-    c.live = gl < NL;
+    LaneCfg cf;
+    cf.gl = gl;
+    cf.live = gl < NL;
     const int g = dir ? NL - 1 - gl : gl;
-    c.g = min(max(g, 0), NLmax - 1);
-    c.a0 = dir ? A - 1 - 4 * gl : 4 * gl;
-    c.astep = dir ? -1 : 1;
-    c.allowed = 0;
+    cf.g = min(max(g, 0), NLmax - 1);
+    cf.allowed = 0;
 #pragma unroll
-    for (int j = 0; j < kJP; ++j) {
-        const int p = c.a0 + c.astep * j - 4;          // label position
+    for (int c = 0; c < kJP; ++c) {
+        const int p = 4 * g + c - 4;                    // label position
         bool al = false;
         if (!dir) {
             if (p == 0) al = true;
@@ -235,24 +243,37 @@ __device__ __forceinline__ LaneCfg lane_cfg(int gl, int dir, int L, int NL, int 
             if (p == L - 1 || p == -1) al = true;       // p == -1: the last pair's phantom label only ever collects Z
             else if (p >= 0 && p + 1 < L) { const int yc = y[p] & kLabelMask, yn = y[p + 1] & kLabelMask; al = (yn != yc) && (yn != 0); }
         }
-        if (al) c.allowed |= 1u << j;
+        if (al) cf.allowed |= 1u << c;
     }
-    return c;
+    return cf;
 }
 
 __device__ __forceinline__ void side_barrier(int nthr) {
     asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
 }
 
-// the label state of the pair below my lowest one: lane - 1, or the mailbox the warp below filled last step
+// the label state of the pair below my lowest one: the previous lane of the side, or the mailbox the warp below
+// filled last step
+template <int DIR>
 __device__ __forceinline__ void fetch_below(const Lane& s, int w, int lane, const int2* mail_prev, float& cm, int& ce) {
-    cm = __shfl_up_sync(0xffffffffu, s.l[kJP - 1], 1);
+    cm = __shfl_up_sync(0xffffffffu, s.l[DIR ? 0 : kJP - 1], 1);
     ce = __shfl_up_sync(0xffffffffu, s.e, 1);
     if (lane == 0) {
         int2 in = make_int2(0, kVoidE);
         if (w > 0) in = mail_prev[w - 1];
         cm = __int_as_float(in.x); ce = in.y;
     }
+}
+
+// waits of warps that poll often: a short sleep between polls leaves the issue slots to the warps that have work
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+    if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        __nanosleep(ns);
+        if (mbar_try_wait(bar, parity)) return;
+    }
+    __trap();
 }
 
 // --------------------------------------------------------------------------------------- prep ---
@@ -269,12 +290,12 @@ struct Prep2Params {
 // updates one group per instruction — then any higher ranks in position order (a serial tail).
 __global__ void __launch_bounds__(256) ctc2_prep_kernel(Prep2Params p) {
     extern __shared__ __align__(16) int s_y[];          // [Sp] labels, [Sp] occurrence ranks
-    __shared__ int s_bad, s_rank, s_rep, s_cnt[kRcap], s_off[kRcap], s_fill[kRcap], s_tail;
+    __shared__ int s_bad, s_rank, s_rep, s_cnt[kRcap], s_off[kRcap], s_fill[kRcap];
     int* s_rk = s_y + p.Sp;
     const int n = blockIdx.x;
     const long long Tn = load_idx(p.in_len, n, p.len64), Ln = load_idx(p.tgt_len, n, p.len64);
     const bool lenbad = (Tn < 0 || Tn > p.T || Ln < 0 || Ln > p.S);
-    if (threadIdx.x == 0) { s_bad = lenbad ? 1 : 0; s_rank = 0; s_rep = 0; s_tail = 0; }
+    if (threadIdx.x == 0) { s_bad = lenbad ? 1 : 0; s_rank = 0; s_rep = 0; }
     if (threadIdx.x < kRcap) { s_cnt[threadIdx.x] = 0; s_fill[threadIdx.x] = 0; }
     __syncthreads();
     const int L = lenbad ? 0 : (int)Ln;
@@ -358,15 +379,15 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
     }
     const int NL = (L + 3) / 4 + 2;
     const int Wn = (NL + 31) >> 5;                 // trellis warps this utterance needs
-    const int NS = p.NS, V = p.V, EMF = p.EMF;
-    const Ctc2Smem sm = ctc2_smem(W, NS, V, p.Sp, EMF, p.SPL, false);
+    const int NS = p.NS, nsm = NS - 1, V = p.V, EMF = p.EMF;
+    const Ctc2Smem sm = ctc2_smem(W, NS, V, p.Sp, p.SPL, false);
     uint64_t* row_full = (uint64_t*)(smem + sm.bars);            // [kR2][NS]
     uint64_t* em_full = row_full + kR2 * NS;                     // [kNE]
     uint64_t* em_empty = em_full + kNE;                          // [kNE]
     int2* mail = (int2*)(smem + sm.mail);                        // [2][W]
     double* redd = (double*)(smem + sm.red);                     // [W]
     int* redi = (int*)(redd + W);                                // [W] + flag
-    int* s_tgt = (int*)(smem + sm.tgt);
+    int* s_off = (int*)(smem + sm.tgt);
     float* s_em = (float*)(smem + sm.em);
     float* s_rows = (float*)(smem + sm.rows);
     const int tm = Tn >> 1;
@@ -377,7 +398,8 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
         for (int i = 0; i < kNE; ++i) { mbar_init(&em_full[i], 32); mbar_init(&em_empty[i], 32 * Wn); }
     }
     for (int i = threadIdx.x; i < kNE * EMF; i += blockDim.x) s_em[i] = 0.0f;
-    for (int k = threadIdx.x; k < L; k += blockDim.x) s_tgt[k] = p.tgt[(size_t)n * p.Sp + k] & kLabelMask;
+    for (int k = threadIdx.x; k < round_up(L, 128); k += blockDim.x)
+        s_off[k] = (k < L) ? (p.tgt[(size_t)n * p.Sp + k] & kLabelMask) << 2 : 0;
     mbar_init_fence();
     __syncthreads();
 
@@ -388,25 +410,24 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
         uint64_t* wbar = row_full + r * NS;
         const float* xb = p.x + (long long)n * p.sx_n;
         const int nrows = (steps1 > r) ? (steps1 - 1 - r) / kR2 + 1 : 0;
+        const int V4 = V >> 2;
         auto issue = [&](int k) {
             const int i = r + k * kR2, t = dir ? Tn - 1 - i : i;
             if (lane == 0) {
-                mbar_expect_tx(&wbar[k % NS], (uint32_t)V * 4u);
-                bulk_g2s(wrows + (size_t)(k % NS) * V, xb + (long long)t * p.sx_t, (uint32_t)V * 4u, &wbar[k % NS]);
+                mbar_expect_tx(&wbar[k & nsm], (uint32_t)V * 4u);
+                bulk_g2s(wrows + (k & nsm) * V, xb + (long long)t * p.sx_t, (uint32_t)V * 4u, &wbar[k & nsm]);
             }
         };
         for (int k = 0; k < min(NS, nrows); ++k) issue(k);
-        const int V4 = V >> 2;
         for (int k = 0; k < nrows; ++k) {
             const int i = r + k * kR2, t = dir ? Tn - 1 - i : i;
-            const float* row = wrows + (size_t)(k % NS) * V;
-            mbar_wait(&wbar[k % NS], (uint32_t)(k / NS) & 1u);
+            const float* row = wrows + (k & nsm) * V;
+            mbar_wait(&wbar[k & nsm], (uint32_t)(k >> nsm) & 1u);
             const float l2 = p.from_logits ? row_lse2(row, V4, lane) : 0.0f;
             if (lane == 0) p.lse2[(size_t)n * p.T + t] = l2;
-            const RowNorm rn = row_norm(l2);
-            const int slot = i % kNE, use = i / kNE;
-            if (use > 0) mbar_wait_relaxed(&em_empty[slot], (uint32_t)(use - 1) & 1u);
-            gather_row(s_em + slot * EMF, row, s_tgt, L, lane, rn);
+            const int slot = i & (kNE - 1), use = i / kNE;
+            if (use > 0) mbar_wait_sleep(&em_empty[slot], (uint32_t)(use - 1) & 1u, 128);
+            gather_row(s_em + slot * EMF, row, s_off, L, lane, row_norm(l2));
             mbar_arrive(&em_full[slot]);
             __syncwarp();
             if (k + NS < nrows) issue(k + NS);
@@ -421,61 +442,63 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
     const LaneCfg cfg = lane_cfg(32 * w + lane, dir, L, NL, p.NLmax, p.tgt + (size_t)n * p.Sp);
     Lane s;
 #pragma unroll
-    for (int j = 0; j < kJP; ++j) { s.b[j] = 0.0f; s.l[j] = 0.0f; }
+    for (int c = 0; c < kJP; ++c) { s.b[c] = 0.0f; s.l[c] = 0.0f; }
     s.e = kVoidE;
     const int k_inj = dir ? 4 * NL - 1 - (L + 4) : 3;       // the virtual source: mass 1 on the label below the first real pair
     if (cfg.gl == (k_inj >> 2)) {
+        const int cj = dir ? 3 - (k_inj & 3) : (k_inj & 3);
 #pragma unroll
-        for (int j = 0; j < kJP; ++j)
-            if (j == (k_inj & 3)) s.l[j] = 1.0f;
+        for (int c = 0; c < kJP; ++c)
+            if (c == cj) s.l[c] = 1.0f;
         s.e = 0;
     }
-    if (lane == 31) mail[1 * W + w] = make_int2(__float_as_int(s.l[kJP - 1]), s.e);
+    if (lane == 31) mail[1 * W + w] = make_int2(__float_as_int(s.l[dir ? 0 : kJP - 1]), s.e);
     side_barrier(nthr);
     // my pairs are all unreachable before step `first` and none can still complete after step `last`
     const int q_lo = 128 * w - k_inj - 1, q_hi = 128 * w + 127 - k_inj - 1;     // real pair indices of this warp
     const int first = max(q_lo, 0), last = Tn - L + q_hi;
-    int* trow = p.tr + ((size_t)n * p.T + (dir ? Tn - 1 : 0)) * p.SPL;
-    const long long tstep = dir ? -(long long)p.SPL : (long long)p.SPL;
-    const int emoff = 4 + 4 * cfg.g;
-    bool dead = false;
-    for (int i = 0; i < steps1; ++i) {
-        const int slot = i % kNE;
-        mbar_wait(&em_full[slot], (uint32_t)(i / kNE) & 1u);
-        const float* em = s_em + slot * EMF;
-        const float pb = em[0];
-        const float4 e4 = *(const float4*)(em + emoff);
-        mbar_arrive(&em_empty[slot]);
-        if (i >= first && i <= last) {
-            float pl[kJP];
-            pl[0] = dir ? e4.w : e4.x; pl[1] = dir ? e4.z : e4.y; pl[2] = dir ? e4.y : e4.z; pl[3] = dir ? e4.x : e4.w;
-            float cm; int ce;
-            fetch_below(s, w, lane, mail + ((i + 1) & 1) * W, cm, ce);
-            float u[kJP], v[kJP];
-            lane_sums(s, cfg.allowed, cm, ce, u, v);
-            lane_emit(s, u, v, pb, pl);
-        } else if (i > last && !dead) {
-            dead = true;
+    const float* emp = s_em + 4 + 4 * cfg.g;                // my four label emissions in slot 0
+
+    auto sweep = [&](auto dirc) {
+        constexpr int DIR = decltype(dirc)::value;
+        int* trow = p.tr + ((size_t)n * p.T + (DIR ? Tn - 1 : 0)) * p.SPL + 4 * cfg.g;
+        const int eoff = 4 * NL - 3 * cfg.g;                 // from my label group to my exponent word
+        const long long tstep = DIR ? -(long long)p.SPL : (long long)p.SPL;
+        bool dead = false;
+        for (int i = 0; i < steps1; ++i) {
+            const int slot = i & (kNE - 1);
+            mbar_wait_sleep(&em_full[slot], (uint32_t)(i / kNE) & 1u, 32);
+            const float pb = s_em[slot * EMF];
+            const float4 pl = *(const float4*)(emp + slot * EMF);
+            mbar_arrive(&em_empty[slot]);
+            if (i >= first && i <= last) {
+                float cm; int ce;
+                fetch_below<DIR>(s, w, lane, mail + ((i + 1) & 1) * W, cm, ce);
+                float u[kJP], v[kJP];
+                lane_sums<DIR>(s, cfg.allowed, cm, ce, u, v);
+                lane_emit(s, u, v, pb, pl);
+            } else if (i > last && !dead) {
+                dead = true;
 #pragma unroll
-            for (int j = 0; j < kJP; ++j) { s.b[j] = 0.0f; s.l[j] = 0.0f; }
-            s.e = kVoidE;
+                for (int c = 0; c < kJP; ++c) { s.b[c] = 0.0f; s.l[c] = 0.0f; }
+                s.e = kVoidE;
+            }
+            if (lane == 31) mail[(i & 1) * W + w] = make_int2(__float_as_int(s.l[DIR ? 0 : kJP - 1]), s.e);
+            if (cfg.live) {
+                *(float4*)trow = make_float4(s.l[0], s.l[1], s.l[2], s.l[3]);
+                trow[eoff] = s.e;
+            }
+            trow += tstep;
+            side_barrier(nthr);
         }
-        if (lane == 31) mail[(i & 1) * W + w] = make_int2(__float_as_int(s.l[kJP - 1]), s.e);
-        if (cfg.live) {
-            const float4 o = dir ? make_float4(s.l[3], s.l[2], s.l[1], s.l[0]) : make_float4(s.l[0], s.l[1], s.l[2], s.l[3]);
-            *(float4*)(trow + 4 * cfg.g) = o;
-            trow[4 * NL + cfg.g] = s.e;
-        }
-        trow += tstep;
-        side_barrier(nthr);
-    }
+    };
+    if (dir) sweep(std::integral_constant<int, 1>{}); else sweep(std::integral_constant<int, 0>{});
+
     // ---- the meeting: leave my boundary state; whoever arrives second forms Z from both ----
     int* mybound = p.bound + ((size_t)n * 2 + dir) * p.BW;
     if (cfg.live) {
-        const float4 ob = dir ? make_float4(s.b[3], s.b[2], s.b[1], s.b[0]) : make_float4(s.b[0], s.b[1], s.b[2], s.b[3]);
-        const float4 ol = dir ? make_float4(s.l[3], s.l[2], s.l[1], s.l[0]) : make_float4(s.l[0], s.l[1], s.l[2], s.l[3]);
-        *(float4*)(mybound + 4 * cfg.g) = ob;
-        *(float4*)(mybound + 4 * NL + 4 * cfg.g) = ol;
+        *(float4*)(mybound + 4 * cfg.g) = make_float4(s.b[0], s.b[1], s.b[2], s.b[3]);
+        *(float4*)(mybound + 4 * NL + 4 * cfg.g) = make_float4(s.l[0], s.l[1], s.l[2], s.l[3]);
         mybound[8 * NL + cfg.g] = s.e;
     }
     __threadfence();
@@ -486,28 +509,28 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
     {
         const int* ob = p.bound + ((size_t)n * 2 + (1 - dir)) * p.BW;
         float cm; int ce;
-        fetch_below(s, w, lane, mail + ((steps1 + 1) & 1) * W, cm, ce);
         float u[kJP], v[kJP];
-        lane_sums(s, cfg.allowed, cm, ce, u, v);
+        if (dir) { fetch_below<1>(s, w, lane, mail + ((steps1 + 1) & 1) * W, cm, ce); lane_sums<1>(s, cfg.allowed, cm, ce, u, v); }
+        else { fetch_below<0>(s, w, lane, mail + ((steps1 + 1) & 1) * W, cm, ce); lane_sums<0>(s, cfg.allowed, cm, ce, u, v); }
         // my blank of the pair with label index a is the other side's blank stored with label a -+ 1
         const int A = 4 * NL;
         float zm[2 * kJP]; int zx[2 * kJP];
         int pm = 4 * kVoidE;
 #pragma unroll
-        for (int j = 0; j < kJP; ++j) {
-            const int a = cfg.a0 + cfg.astep * j, ab = a - cfg.astep;
+        for (int c = 0; c < kJP; ++c) {
+            const int a = 4 * cfg.g + c, ab = dir ? a + 1 : a - 1;
             float mb = 0.0f, ml = 0.0f; int xb = 0, xl = 0;
             if (cfg.live) {
-                ml = v[j] * __int_as_float(__ldcg(ob + 4 * NL + a));
+                ml = v[c] * __int_as_float(__ldcg(ob + 4 * NL + a));
                 xl = s.e + __ldcg(ob + 8 * NL + (a >> 2));
                 if (ab >= 0 && ab < A) {
-                    mb = u[j] * __int_as_float(__ldcg(ob + ab));
+                    mb = u[c] * __int_as_float(__ldcg(ob + ab));
                     xb = s.e + __ldcg(ob + 8 * NL + (ab >> 2));
                 }
             }
-            zm[2 * j] = mb; zx[2 * j] = (mb > 0.0f) ? xb + (__float_as_int(mb) >> 23) : 4 * kVoidE;
-            zm[2 * j + 1] = ml; zx[2 * j + 1] = (ml > 0.0f) ? xl + (__float_as_int(ml) >> 23) : 4 * kVoidE;
-            pm = max(pm, max(zx[2 * j], zx[2 * j + 1]));
+            zm[2 * c] = mb; zx[2 * c] = (mb > 0.0f) ? xb + (__float_as_int(mb) >> 23) : 4 * kVoidE;
+            zm[2 * c + 1] = ml; zx[2 * c + 1] = (ml > 0.0f) ? xl + (__float_as_int(ml) >> 23) : 4 * kVoidE;
+            pm = max(pm, max(zx[2 * c], zx[2 * c + 1]));
         }
         // pm: the largest (scale + biased fp32 exponent) of any term; terms are summed relative to it in float64
         pm = __reduce_max_sync(0xffffffffu, pm);
@@ -519,10 +542,8 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
 #pragma unroll
         for (int j = 0; j < 2 * kJP; ++j) {
             if (zm[j] > 0.0f) {
-                const int bexp = __float_as_int(zm[j]) >> 23;                     // biased exponent of the term's mantissa
                 const float mant = __int_as_float((__float_as_int(zm[j]) & 0x007fffff) | 0x3f800000);   // in [1, 2)
                 const int rel = zx[j] - pm;                                      // <= 0
-                (void)bexp;
                 if (rel > -1000) sum += scalbn((double)mant, rel);
             }
         }
@@ -562,7 +583,7 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
     const int L = mt.y;
     const float lossn = p.loss_ws[n];
     const int Tn = (mt.z || !(lossn < CUDART_INF_F)) ? 0 : mt.x;      // NaN / inf loss: all-zero gradient
-    const int NS = p.NS, V = p.V, EMF = p.EMF, V4 = V >> 2;
+    const int NS = p.NS, nsm = NS - 1, V = p.V, EMF = p.EMF, V4 = V >> 2;
     float* gb = p.gx + (long long)n * p.sg_n;
     const int tm = Tn >> 1;
     const int steps1 = dir ? Tn - tm : tm;
@@ -581,14 +602,14 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
 
     const int NL = (L + 3) / 4 + 2;
     const int Wn = (NL + 31) >> 5;
-    const Ctc2Smem sm = ctc2_smem(W, NS, V, p.Sp, EMF, p.SPL, true);
+    const Ctc2Smem sm = ctc2_smem(W, NS, V, p.Sp, p.SPL, true);
     uint64_t* row_full = (uint64_t*)(smem + sm.bars);            // [kR2][NS]
     uint64_t* em_full = row_full + kR2 * NS;                     // [kNE]
     uint64_t* occ_full = em_full + kNE;                          // [kNE]
     uint64_t* st_full = occ_full + kNE;                          // [kNSR]
     int2* mail = (int2*)(smem + sm.mail);
-    int* s_tgt = (int*)(smem + sm.tgt);
-    int* s_nf = s_tgt + p.Sp;                                    // later occurrences of a class (ctc2_prep_kernel)
+    int* s_off = (int*)(smem + sm.tgt);                          // label * 4 | "occurred before", padded to 128 entries
+    int* s_nf = s_off + round_up(p.Sp, 128);                     // later occurrences of a class (ctc2_prep_kernel)
     float* s_em = (float*)(smem + sm.em);
     int* s_st = (int*)(smem + sm.st);
     float* s_rows = (float*)(smem + sm.rows);
@@ -601,7 +622,10 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
     }
     for (int i = threadIdx.x; i < kNE * EMF; i += blockDim.x) s_em[i] = 0.0f;
     const int2 nf = p.nfhdr[n];                                  // {entries in rank groups of 32, serial tail}
-    for (int k = threadIdx.x; k < L; k += blockDim.x) s_tgt[k] = p.tgt[(size_t)n * p.Sp + k];
+    for (int k = threadIdx.x; k < round_up(L, 128); k += blockDim.x) {
+        const int wd = (k < L) ? p.tgt[(size_t)n * p.Sp + k] : kNotFirst;
+        s_off[k] = ((wd & kLabelMask) << 2) | ((wd & kNotFirst) ? 1 : 0);
+    }
     for (int k = threadIdx.x; k < nf.x + nf.y; k += blockDim.x) s_nf[k] = p.nflist[(size_t)n * p.NF + k];
     mbar_init_fence();
     __syncthreads();
@@ -616,19 +640,19 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
         auto frame = [&](int k) { const int i = steps1 + r + k * kR2; return dir ? Tn - 1 - i : i; };
         auto issue = [&](int k) {
             if (lane == 0) {
-                mbar_expect_tx(&wbar[k % NS], (uint32_t)V * 4u);
-                bulk_g2s(wrows + (size_t)(k % NS) * V, xb + (long long)frame(k) * p.sx_t, (uint32_t)V * 4u, &wbar[k % NS]);
+                mbar_expect_tx(&wbar[k & nsm], (uint32_t)V * 4u);
+                bulk_g2s(wrows + (k & nsm) * V, xb + (long long)frame(k) * p.sx_t, (uint32_t)V * 4u, &wbar[k & nsm]);
             }
         };
         // pre(k): gather the emissions of row k for the trellis warps, then turn the row into softmax * g in place.
         auto pre = [&](int k) {
             const int i2 = r + k * kR2, t = frame(k);
-            float* row = wrows + (size_t)(k % NS) * V;
+            float* row = wrows + (k & nsm) * V;
             const float l2 = p.lse2[(size_t)n * p.T + t];
-            mbar_wait(&wbar[k % NS], (uint32_t)(k / NS) & 1u);
+            mbar_wait(&wbar[k & nsm], (uint32_t)(k >> nsm) & 1u);
             // (slot i2 % kNE was last used by my own row k - kNE / kR2, whose occupancies I consumed in program order)
-            gather_row(s_em + (i2 % kNE) * EMF, row, s_tgt, L, lane, row_norm(l2));
-            mbar_arrive(&em_full[i2 % kNE]);
+            gather_row(s_em + (i2 & (kNE - 1)) * EMF, row, s_off, L, lane, row_norm(l2));
+            mbar_arrive(&em_full[i2 & (kNE - 1)]);
             __syncwarp();
             float4* r4 = (float4*)row;
             if (p.from_logits) {
@@ -648,24 +672,21 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
         // post(k): subtract the occupancies the trellis warps left in the slot and store the row.
         auto post = [&](int k) {
             const int i2 = r + k * kR2, t = frame(k);
-            float* row = wrows + (size_t)(k % NS) * V;
-            const float* em = s_em + (i2 % kNE) * EMF;
-            mbar_wait_relaxed(&occ_full[i2 % kNE], (uint32_t)(i2 / kNE) & 1u);
-            // first occurrences of a class: all distinct, four per lane and iteration
+            float* row = wrows + (k & nsm) * V;
+            const float* em = s_em + (i2 & (kNE - 1)) * EMF;
+            mbar_wait_sleep(&occ_full[i2 & (kNE - 1)], (uint32_t)(i2 / kNE) & 1u, 128);
+            // first occurrences of a class: all distinct, four per lane and iteration (the padding is "not first" with
+            // occupancy zero, so no bounds are checked)
             float bs = 0.0f;
             for (int k0 = lane; k0 < L; k0 += 128) {
                 int wd[4]; float oc[4], rv[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int kk = min(k0 + 32 * q, L - 1);
-                    wd[q] = s_tgt[kk];
-                    oc[q] = (k0 + 32 * q < L) ? em[8 + kk] : 0.0f;
-                }
+                for (int q = 0; q < 4; ++q) { wd[q] = s_off[k0 + 32 * q]; oc[q] = em[8 + k0 + 32 * q]; }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { rv[q] = row[wd[q] & kLabelMask]; bs += oc[q]; }
+                for (int q = 0; q < 4; ++q) { rv[q] = *(const float*)((const char*)row + (wd[q] & ~3)); bs += oc[q]; }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    if (k0 + 32 * q < L && !(wd[q] & kNotFirst)) row[wd[q] & kLabelMask] = fmaf(-g, oc[q], rv[q]);
+                    if (!(wd[q] & 1)) *(float*)((char*)row + wd[q]) = fmaf(-g, oc[q], rv[q]);
             }
             __syncwarp();
             // later occurrences: the list holds them by occurrence rank, one rank (distinct classes) per 32 entries,
@@ -726,67 +747,62 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
             ol = *(const float4*)(mybound + 4 * NL + 4 * cfg.g);
             s.e = mybound[8 * NL + cfg.g];
         }
-        s.b[0] = dir ? ob.w : ob.x; s.b[1] = dir ? ob.z : ob.y; s.b[2] = dir ? ob.y : ob.z; s.b[3] = dir ? ob.x : ob.w;
-        s.l[0] = dir ? ol.w : ol.x; s.l[1] = dir ? ol.z : ol.y; s.l[2] = dir ? ol.y : ol.z; s.l[3] = dir ? ol.x : ol.w;
+        s.b[0] = ob.x; s.b[1] = ob.y; s.b[2] = ob.z; s.b[3] = ob.w;
+        s.l[0] = ol.x; s.l[1] = ol.y; s.l[2] = ol.z; s.l[3] = ol.w;
     }
     const int4 zi = p.zinfo[n];
     const int eZ = zi.x;
     const float rZ = __int_as_float(zi.y);
-    if (lane == 31) mail[((steps1 + 1) & 1) * W + w] = make_int2(__float_as_int(s.l[kJP - 1]), s.e);
+    if (lane == 31) mail[((steps1 + 1) & 1) * W + w] = make_int2(__float_as_int(s.l[dir ? 0 : kJP - 1]), s.e);
     const int k_inj = dir ? 4 * NL - 1 - (L + 4) : 3;
     const int q_lo = 128 * w - k_inj - 1, q_hi = 128 * w + 127 - k_inj - 1;
     const int first = max(q_lo, 0), last = Tn - L + q_hi;
-    const int emoff = 4 + 4 * cfg.g;
+    float* emp = s_em + 4 + 4 * cfg.g;                      // my four label emissions / occupancies in slot 0
+    const int* stp = s_st + 4 * cfg.g;                      // the other side's four label states of my group in slot 0
+    const int eoff = 4 * NL - 3 * cfg.g;
     const uint32_t st_bytes = (uint32_t)round_up(5 * NL, 4) * 4u;
     const int* tr_n = p.tr + (size_t)n * p.T * p.SPL;
     auto st_issue = [&](int i2) {          // the row the OTHER side stored for the frame of my phase-2 step i2
         const int i = steps1 + i2, t = dir ? Tn - 1 - i : i;
-        mbar_expect_tx(&st_full[i2 % kNSR], st_bytes);
-        bulk_g2s(s_st + (i2 % kNSR) * p.SPL, tr_n + (size_t)t * p.SPL, st_bytes, &st_full[i2 % kNSR]);
+        mbar_expect_tx(&st_full[i2 & (kNSR - 1)], st_bytes);
+        bulk_g2s(s_st + (i2 & (kNSR - 1)) * p.SPL, tr_n + (size_t)t * p.SPL, st_bytes, &st_full[i2 & (kNSR - 1)]);
     };
     if (threadIdx.x == 0)
         for (int i2 = 0; i2 < min(kNSR - 1, nsteps2); ++i2) st_issue(i2);
     side_barrier(nthr);
-    for (int i2 = 0; i2 < nsteps2; ++i2) {
-        const int i = steps1 + i2, t = dir ? Tn - 1 - i : i;
-        if (threadIdx.x == 0 && i2 + kNSR - 1 < nsteps2) st_issue(i2 + kNSR - 1);      // its slot was read in step i2 - 1
-        const int slot = i2 % kNE, ss = i2 % kNSR;
-        mbar_wait(&em_full[slot], (uint32_t)(i2 / kNE) & 1u);
-        float* em = s_em + slot * EMF;
-        const float pb = em[0];
-        const float4 e4 = *(const float4*)(em + emoff);
-        float4 occ = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i >= first && i <= last) {
+
+    auto sweep = [&](auto dirc) {
+        constexpr int DIR = decltype(dirc)::value;
+        for (int i2 = 0; i2 < nsteps2; ++i2) {
+            const int i = steps1 + i2;
+            if (threadIdx.x == 0 && i2 + kNSR - 1 < nsteps2) st_issue(i2 + kNSR - 1);      // its slot was read in step i2 - 1
+            const int slot = i2 & (kNE - 1), ss = i2 & (kNSR - 1);
+            mbar_wait_sleep(&em_full[slot], (uint32_t)(i2 / kNE) & 1u, 32);
+            const float pb = s_em[slot * EMF];
+            const float4 pl = *(const float4*)(emp + slot * EMF);
+            float4 occ = make_float4(0.f, 0.f, 0.f, 0.f);
             mbar_wait(&st_full[ss], (uint32_t)(i2 / kNSR) & 1u);
-            const int* st = s_st + ss * p.SPL;
-            float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            int eb = kVoidE;
-            if (cfg.live) { o4 = *(const float4*)(st + 4 * cfg.g); eb = st[4 * NL + cfg.g]; }
-            float pl[kJP], ob[kJP];
-            pl[0] = dir ? e4.w : e4.x; pl[1] = dir ? e4.z : e4.y; pl[2] = dir ? e4.y : e4.z; pl[3] = dir ? e4.x : e4.w;
-            ob[0] = dir ? o4.w : o4.x; ob[1] = dir ? o4.z : o4.y; ob[2] = dir ? o4.y : o4.z; ob[3] = dir ? o4.x : o4.w;
-            float cm; int ce;
-            fetch_below(s, w, lane, mail + ((i + 1) & 1) * W, cm, ce);
-            float u[kJP], v[kJP];
-            lane_sums(s, cfg.allowed, cm, ce, u, v);
-            // occupancy of a label state = (my pre-emission sum) x (the other side's stored value) / Z
-            const int xs = s.e + eb - eZ;
-            const float sc = (xs < -126) ? 0.0f : __int_as_float(__float_as_int(rZ) + (min(xs, 90) << 23));
-            float gm[kJP];
-#pragma unroll
-            for (int j = 0; j < kJP; ++j) {
-                gm[j] = (v[j] * ob[j]) * sc;
+            if (i >= first && i <= last) {
+                float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                int eb = kVoidE;
+                if (cfg.live) { o4 = *(const float4*)(stp + ss * p.SPL); eb = stp[ss * p.SPL + eoff]; }
+                float cm; int ce;
+                fetch_below<DIR>(s, w, lane, mail + ((i + 1) & 1) * W, cm, ce);
+                float u[kJP], v[kJP];
+                lane_sums<DIR>(s, cfg.allowed, cm, ce, u, v);
+                // occupancy of a label state = (my pre-emission sum) x (the other side's stored value) / Z
+                const int xs = s.e + eb - eZ;
+                const float sc = (xs < -126) ? 0.0f : __int_as_float(__float_as_int(rZ) + (min(xs, 90) << 23));
+                occ = make_float4((v[0] * o4.x) * sc, (v[1] * o4.y) * sc, (v[2] * o4.z) * sc, (v[3] * o4.w) * sc);
+                lane_emit(s, u, v, pb, pl);
             }
-            occ = dir ? make_float4(gm[3], gm[2], gm[1], gm[0]) : make_float4(gm[0], gm[1], gm[2], gm[3]);
-            lane_emit(s, u, v, pb, pl);
-        } else {
-            mbar_wait(&st_full[ss], (uint32_t)(i2 / kNSR) & 1u);      // keep the ring's phases in step
+            if (lane == 31) mail[(i & 1) * W + w] = make_int2(__float_as_int(s.l[DIR ? 0 : kJP - 1]), s.e);
+            if (cfg.live) *(float4*)(emp + slot * EMF) = occ;
+            mbar_arrive(&occ_full[slot]);
+            side_barrier(nthr);
         }
-        if (lane == 31) mail[(i & 1) * W + w] = make_int2(__float_as_int(s.l[kJP - 1]), s.e);
-        if (cfg.live) *(float4*)(em + emoff) = occ;
-        mbar_arrive(&occ_full[slot]);
-        side_barrier(nthr);
-    }
+    };
+    if (dir) sweep(std::integral_constant<int, 1>{}); else sweep(std::integral_constant<int, 0>{});
 }
 
 }  // namespace hab
