@@ -507,25 +507,39 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
     side_barrier(nthr);
     if (redi[W] == 0) return;                                  // the other side is still sweeping: it will do it
     {
-        const int* ob = p.bound + ((size_t)n * 2 + (1 - dir)) * p.BW;
+        // Z = sum over the states of (alpha's pre-emission sums of the meeting frame) x (beta's boundary).  Whichever
+        // side gets here runs the SAME arithmetic on the two stored boundaries, so the result does not depend on
+        // which CTA finished last (bit-identical repeats).
+        const int* ba = p.bound + ((size_t)n * 2 + 0) * p.BW;
+        const int* ob = p.bound + ((size_t)n * 2 + 1) * p.BW;
+        const LaneCfg ca = lane_cfg(32 * w + lane, 0, L, NL, p.NLmax, p.tgt + (size_t)n * p.Sp);
+        Lane sa;
+#pragma unroll
+        for (int c = 0; c < kJP; ++c) {
+            sa.b[c] = ca.live ? __int_as_float(__ldcg(ba + 4 * ca.g + c)) : 0.0f;
+            sa.l[c] = ca.live ? __int_as_float(__ldcg(ba + 4 * NL + 4 * ca.g + c)) : 0.0f;
+        }
+        sa.e = ca.live ? __ldcg(ba + 8 * NL + ca.g) : kVoidE;
+        if (lane == 31) mail[w] = make_int2(__float_as_int(sa.l[kJP - 1]), sa.e);
+        side_barrier(nthr);
         float cm; int ce;
         float u[kJP], v[kJP];
-        if (dir) { fetch_below<1>(s, w, lane, mail + ((steps1 + 1) & 1) * W, cm, ce); lane_sums<1>(s, cfg.allowed, cm, ce, u, v); }
-        else { fetch_below<0>(s, w, lane, mail + ((steps1 + 1) & 1) * W, cm, ce); lane_sums<0>(s, cfg.allowed, cm, ce, u, v); }
-        // my blank of the pair with label index a is the other side's blank stored with label a -+ 1
+        fetch_below<0>(sa, w, lane, mail, cm, ce);
+        lane_sums<0>(sa, ca.allowed, cm, ce, u, v);
+        // alpha's blank of the pair with label index a is beta's blank stored with label a - 1
         const int A = 4 * NL;
         float zm[2 * kJP]; int zx[2 * kJP];
         int pm = 4 * kVoidE;
 #pragma unroll
         for (int c = 0; c < kJP; ++c) {
-            const int a = 4 * cfg.g + c, ab = dir ? a + 1 : a - 1;
+            const int a = 4 * ca.g + c, ab = a - 1;
             float mb = 0.0f, ml = 0.0f; int xb = 0, xl = 0;
-            if (cfg.live) {
+            if (ca.live) {
                 ml = v[c] * __int_as_float(__ldcg(ob + 4 * NL + a));
-                xl = s.e + __ldcg(ob + 8 * NL + (a >> 2));
+                xl = sa.e + __ldcg(ob + 8 * NL + (a >> 2));
                 if (ab >= 0 && ab < A) {
                     mb = u[c] * __int_as_float(__ldcg(ob + ab));
-                    xb = s.e + __ldcg(ob + 8 * NL + (ab >> 2));
+                    xb = sa.e + __ldcg(ob + 8 * NL + (ab >> 2));
                 }
             }
             zm[2 * c] = mb; zx[2 * c] = (mb > 0.0f) ? xb + (__float_as_int(mb) >> 23) : 4 * kVoidE;
