@@ -20,7 +20,7 @@ Cfg2 pick_cfg2(int V, int S) {
     static const int kW[] = {1, 2, 3, 5, 9};
     for (int w : kW) if (!c.W && w >= Wn) c.W = w;
     if (!c.W || V % 4 != 0 || V < 4) return c;
-    const int SPL = round_up(5 * NLmax, 4);
+    const int SPL = 8 * NLmax;
     for (int ns = 2; ns >= 1 && !c.ok; --ns) {
         const size_t f = ctc2_smem(c.W, ns, V, Sp, SPL, false).total, b = ctc2_smem(c.W, ns, V, Sp, SPL, true).total;
         const size_t cap = (ns == 2) ? 56 * 1024 : 110 * 1024;       // 4 CTAs per SM with two stages, 2 with one

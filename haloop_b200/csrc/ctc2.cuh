@@ -20,12 +20,14 @@
 // written once and read once (~5 L bytes each): 12.6 V at L = 0.3 V against 22 V for the three-kernel
 // path of round 1 (ctc.cuh: emission rows, packed alpha/beta rows of every state, occupancy rows).
 //
-// Numbers: "lane-normalised" linear domain.  A lane owns 4 consecutive (blank, label) pairs — 8
-// adjacent states — as plain fp32 values sharing one int32 exponent; after every step the lane rescales
-// so that its largest value sits in [2^32, 2^33).  The sum-product step of a pair is 2 FADD + 1 SEL +
-// 2 FMUL, the neighbour lane's label state is aligned with one exponent subtraction, and the only
-// values that can be lost are more than 2^158 (110 nats) below the largest of the same 8 adjacent states
-// (Limits).  tools/ctc2_proto.py is the numpy model of this file.
+// Numbers: "pair-normalised" linear domain.  A lane owns 4 consecutive (blank, label) pairs; the two states
+// of a pair are plain fp32 values sharing one int32 exponent, rescaled after every step so that the larger of
+// the two sits in [2^32, 2^33).  The sum-product step of a pair is 2 FADD + 1 SEL + 2 FMUL plus one exponent
+// alignment of the label state below, every rounding is 6e-8 relative whatever T and log V are, and the only
+// value that can be lost is a state more than 2^158 (110 nats) below the OTHER state of its own pair.  (One
+// exponent per lane — 8 adjacent states — is not enough: with T >> L the alpha of adjacent states differs by
+// tens of nats per label and the low states still carry posterior mass through a large beta; tools/ctc2_proto.py,
+// the numpy model of this file, shows it at T = 3000, L = 4.)
 #pragma once
 #include <type_traits>
 
@@ -49,8 +51,8 @@ __host__ inline Ctc2Ws ctc2_ws_layout(int T, int N, int S) {
     Ctc2Ws w;
     w.Sp = round_up(S > 0 ? S : 1, 4);
     w.NLmax = w.Sp / 4 + 2;                     // lanes (groups of 4 label slots) per side
-    w.SPL = round_up(5 * w.NLmax, 4);           // stored row: [4 NL label values][NL exponents]
-    w.BW = round_up(9 * w.NLmax, 4);            // boundary: [4 NL blanks][4 NL labels][NL exponents]
+    w.SPL = 8 * w.NLmax;                        // stored row: [4 NL label values][4 NL pair exponents]
+    w.BW = 12 * w.NLmax;                        // boundary: [4 NL blanks][4 NL labels][4 NL pair exponents]
     size_t o = 256;
     auto take = [&](size_t bytes) { size_t at = o; o = round_up_sz(o + bytes, 256); return at; };
     w.meta = take(sizeof(int4) * (size_t)N);
@@ -82,7 +84,7 @@ struct Ctc2Params {
 
 // An emission slot: [0] blank, [4 + a] label index a = position + 4 (a < 4 and a >= L + 4 are phantoms that stay 0).
 // Sized so that the lanes of the longest target and a row warp's four-labels-per-lane batches stay inside it.
-__host__ __device__ inline int ctc2_em_floats(int Sp) { return 16 + round_up(Sp, 128); }
+__host__ __device__ inline int ctc2_em_floats(int Sp) { return max(Sp + 12, 8 + round_up(Sp, 128)); }
 
 // shared memory (bytes): [mbarriers][mailboxes][Z reduction][targets (+ later occurrences)][emission slots][stored slots][row ring]
 struct Ctc2Smem { int bars, mail, red, tgt, em, st, rows, total; };
@@ -93,7 +95,7 @@ __host__ __device__ inline Ctc2Smem ctc2_smem(int W, int NS, int V, int Sp, int 
     s.bars = take(8 * (kR2 * NS + 2 * kNE + kNSR));
     s.mail = take(8 * 2 * W);
     s.red = take(16 * W + 16);
-    s.tgt = take(4 * (round_up(Sp, 128) + (bwd ? Sp + 32 * kRcap : 0)));
+    s.tgt = take(4 * round_up(Sp, 128));
     s.em = take(4 * kNE * ctc2_em_floats(Sp));
     s.st = take(bwd ? 4 * kNSR * SPL : 0);
     s.rows = take(4 * kR2 * NS * V);
@@ -173,49 +175,57 @@ __device__ __forceinline__ float row_lse2(const float* row, int V4, int lane) {
 // A lane's 4 pairs are kept in POSITION order for both directions: component c is the pair whose label index is
 // a = 4 g + c.  Direction 1 (beta) walks them downwards, so "the pair below" is c + 1 and the value entering
 // from the previous lane of the side lands at c = 3; nothing is reversed when rows are loaded or stored.
-struct Lane { float b[kJP], l[kJP]; int e; };
+struct Lane { float b[kJP], l[kJP]; int e[kJP]; };
 
-__device__ __forceinline__ float pow2_clamped(int d) {             // 2^d, 0 below 2^-126; d <= 127
-    return __int_as_float(max(d + 127, 0) << 23);
+// x * 2^d for x >= 0 by exponent-field arithmetic: exact while the result is a normal number, 0 below 2^-126
+// (a factor 2^d formed on its own would already be 0 at d < -126, although x * 2^d is not).  d <= 64.
+__device__ __forceinline__ float scale_pow2(float x, int d) {
+    const int b = __float_as_int(x);
+    return ((b >> 23) + d > 0) ? __int_as_float(b + (d << 23)) : 0.0f;
 }
 
-// First half of a step: align the label state (cm, ce) of the pair below my lowest one to my exponent and
-// form the pre-emission sums  u = blank + label below,  v = label + (skip allowed ? u : blank)
-// [ha/ctc.py:155-167].  Their scale is s.e on return.
+// First half of a step: align the label state of the pair below each of my pairs (cm, ce: the one entering from
+// the previous lane) to the pair's exponent and form the pre-emission sums
+//     u = blank + label below,  v = label + (skip allowed ? u : blank)                 [ha/ctc.py:155-167]
+// Their scale is s.e[c] on return.
 template <int DIR>
 __device__ __forceinline__ void lane_sums(Lane& s, unsigned allowed, float cm, int ce, float (&u)[kJP], float (&v)[kJP]) {
-    int d = ce - s.e;
-    if (d > kAlignMax) {                // the neighbour dwarfs this lane (the wavefront arrives): move my exponent up
-        const int sh = d - kAlignMax;
-        const float f = pow2_clamped(-sh);
-#pragma unroll
-        for (int c = 0; c < kJP; ++c) { s.b[c] *= f; s.l[c] *= f; }
-        s.e += sh;
-        d = kAlignMax;
-    }
-    const float c0 = cm * pow2_clamped(d);
+    float lb[kJP]; int d[kJP];
 #pragma unroll
     for (int c = 0; c < kJP; ++c) {
-        const float below = DIR ? (c == kJP - 1 ? c0 : s.l[c < kJP - 1 ? c + 1 : c]) : (c == 0 ? c0 : s.l[c ? c - 1 : 0]);
-        u[c] = s.b[c] + below;
+        const bool edge = DIR ? (c == kJP - 1) : (c == 0);
+        const int cb = DIR ? (c < kJP - 1 ? c + 1 : c) : (c ? c - 1 : 0);
+        lb[c] = edge ? cm : s.l[cb];
+        d[c] = (edge ? ce : s.e[cb]) - s.e[c];
+    }
+    if (max(max(d[0], d[1]), max(d[2], d[3])) > kAlignMax) {        // a pair dwarfed by the one below it (the wavefront
+#pragma unroll                                                      // arrives): move its exponent up
+        for (int c = 0; c < kJP; ++c) {
+            if (d[c] > kAlignMax) {
+                const int sh = d[c] - kAlignMax;
+                s.b[c] = scale_pow2(s.b[c], -min(sh, 512)); s.l[c] = scale_pow2(s.l[c], -min(sh, 512)); s.e[c] += sh;
+                d[c] = kAlignMax;
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kJP; ++c) {
+        u[c] = s.b[c] + scale_pow2(lb[c], max(d[c], -512));
         v[c] = s.l[c] + (((allowed >> c) & 1u) ? u[c] : s.b[c]);
     }
 }
-// Second half: multiply by the emissions and renormalise the lane.
+// Second half: multiply by the emissions and renormalise each pair.
 __device__ __forceinline__ void lane_emit(Lane& s, const float (&u)[kJP], const float (&v)[kJP], float pb, float4 pl) {
-    float nb[kJP], nl[kJP];
-    nl[0] = v[0] * pl.x; nl[1] = v[1] * pl.y; nl[2] = v[2] * pl.z; nl[3] = v[3] * pl.w;
-    float mx = 0.0f;
+    const float plc[kJP] = {pl.x, pl.y, pl.z, pl.w};
 #pragma unroll
     for (int c = 0; c < kJP; ++c) {
-        nb[c] = u[c] * pb;
-        mx = fmaxf(mx, fmaxf(nb[c], nl[c]));
+        const float nb = u[c] * pb, nl = v[c] * plc[c];
+        const float mx = fmaxf(nb, nl);
+        const int delta = min(kLaneExp - (__float_as_int(mx) >> 23), 120);
+        const float f = __int_as_float((delta + 127) << 23);
+        s.b[c] = nb * f; s.l[c] = nl * f;
+        s.e[c] = (mx > 0.0f) ? s.e[c] - delta : kVoidE;
     }
-    const int delta = min(kLaneExp - (__float_as_int(mx) >> 23), 120);
-    const float f = __int_as_float((delta + 127) << 23);
-#pragma unroll
-    for (int c = 0; c < kJP; ++c) { s.b[c] = nb[c] * f; s.l[c] = nl[c] * f; }
-    s.e = (mx > 0.0f) ? s.e - delta : kVoidE;
 }
 
 // Per-lane constants of a trellis thread.
@@ -257,7 +267,7 @@ __device__ __forceinline__ void side_barrier(int nthr) {
 template <int DIR>
 __device__ __forceinline__ void fetch_below(const Lane& s, int w, int lane, const int2* mail_prev, float& cm, int& ce) {
     cm = __shfl_up_sync(0xffffffffu, s.l[DIR ? 0 : kJP - 1], 1);
-    ce = __shfl_up_sync(0xffffffffu, s.e, 1);
+    ce = __shfl_up_sync(0xffffffffu, s.e[DIR ? 0 : kJP - 1], 1);
     if (lane == 0) {
         int2 in = make_int2(0, kVoidE);
         if (w > 0) in = mail_prev[w - 1];
@@ -442,17 +452,15 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
     const LaneCfg cfg = lane_cfg(32 * w + lane, dir, L, NL, p.NLmax, p.tgt + (size_t)n * p.Sp);
     Lane s;
 #pragma unroll
-    for (int c = 0; c < kJP; ++c) { s.b[c] = 0.0f; s.l[c] = 0.0f; }
-    s.e = kVoidE;
+    for (int c = 0; c < kJP; ++c) { s.b[c] = 0.0f; s.l[c] = 0.0f; s.e[c] = kVoidE; }
     const int k_inj = dir ? 4 * NL - 1 - (L + 4) : 3;       // the virtual source: mass 1 on the label below the first real pair
     if (cfg.gl == (k_inj >> 2)) {
         const int cj = dir ? 3 - (k_inj & 3) : (k_inj & 3);
 #pragma unroll
         for (int c = 0; c < kJP; ++c)
-            if (c == cj) s.l[c] = 1.0f;
-        s.e = 0;
+            if (c == cj) { s.l[c] = 1.0f; s.e[c] = 0; }
     }
-    if (lane == 31) mail[1 * W + w] = make_int2(__float_as_int(s.l[dir ? 0 : kJP - 1]), s.e);
+    if (lane == 31) mail[1 * W + w] = make_int2(__float_as_int(s.l[dir ? 0 : kJP - 1]), s.e[dir ? 0 : kJP - 1]);
     side_barrier(nthr);
     // my pairs are all unreachable before step `first` and none can still complete after step `last`
     const int q_lo = 128 * w - k_inj - 1, q_hi = 128 * w + 127 - k_inj - 1;     // real pair indices of this warp
@@ -462,7 +470,7 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
     auto sweep = [&](auto dirc) {
         constexpr int DIR = decltype(dirc)::value;
         int* trow = p.tr + ((size_t)n * p.T + (DIR ? Tn - 1 : 0)) * p.SPL + 4 * cfg.g;
-        const int eoff = 4 * NL - 3 * cfg.g;                 // from my label group to my exponent word
+        const int eoff = 4 * NL;                             // from my label group to my exponent group
         const long long tstep = DIR ? -(long long)p.SPL : (long long)p.SPL;
         bool dead = false;
         for (int i = 0; i < steps1; ++i) {
@@ -480,13 +488,12 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
             } else if (i > last && !dead) {
                 dead = true;
 #pragma unroll
-                for (int c = 0; c < kJP; ++c) { s.b[c] = 0.0f; s.l[c] = 0.0f; }
-                s.e = kVoidE;
+                for (int c = 0; c < kJP; ++c) { s.b[c] = 0.0f; s.l[c] = 0.0f; s.e[c] = kVoidE; }
             }
-            if (lane == 31) mail[(i & 1) * W + w] = make_int2(__float_as_int(s.l[DIR ? 0 : kJP - 1]), s.e);
+            if (lane == 31) mail[(i & 1) * W + w] = make_int2(__float_as_int(s.l[DIR ? 0 : kJP - 1]), s.e[DIR ? 0 : kJP - 1]);
             if (cfg.live) {
                 *(float4*)trow = make_float4(s.l[0], s.l[1], s.l[2], s.l[3]);
-                trow[eoff] = s.e;
+                *(int4*)(trow + eoff) = make_int4(s.e[0], s.e[1], s.e[2], s.e[3]);
             }
             trow += tstep;
             side_barrier(nthr);
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
     if (cfg.live) {
         *(float4*)(mybound + 4 * cfg.g) = make_float4(s.b[0], s.b[1], s.b[2], s.b[3]);
         *(float4*)(mybound + 4 * NL + 4 * cfg.g) = make_float4(s.l[0], s.l[1], s.l[2], s.l[3]);
-        mybound[8 * NL + cfg.g] = s.e;
+        *(int4*)(mybound + 8 * NL + 4 * cfg.g) = make_int4(s.e[0], s.e[1], s.e[2], s.e[3]);
     }
     __threadfence();
     side_barrier(nthr);
@@ -518,9 +525,9 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
         for (int c = 0; c < kJP; ++c) {
             sa.b[c] = ca.live ? __int_as_float(__ldcg(ba + 4 * ca.g + c)) : 0.0f;
             sa.l[c] = ca.live ? __int_as_float(__ldcg(ba + 4 * NL + 4 * ca.g + c)) : 0.0f;
+            sa.e[c] = ca.live ? __ldcg(ba + 8 * NL + 4 * ca.g + c) : kVoidE;
         }
-        sa.e = ca.live ? __ldcg(ba + 8 * NL + ca.g) : kVoidE;
-        if (lane == 31) mail[w] = make_int2(__float_as_int(sa.l[kJP - 1]), sa.e);
+        if (lane == 31) mail[w] = make_int2(__float_as_int(sa.l[kJP - 1]), sa.e[kJP - 1]);
         side_barrier(nthr);
         float cm; int ce;
         float u[kJP], v[kJP];
@@ -536,10 +543,10 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_fwd_kernel(Ctc2Para
             float mb = 0.0f, ml = 0.0f; int xb = 0, xl = 0;
             if (ca.live) {
                 ml = v[c] * __int_as_float(__ldcg(ob + 4 * NL + a));
-                xl = sa.e + __ldcg(ob + 8 * NL + (a >> 2));
+                xl = sa.e[c] + __ldcg(ob + 8 * NL + a);
                 if (ab >= 0 && ab < A) {
                     mb = u[c] * __int_as_float(__ldcg(ob + ab));
-                    xb = sa.e + __ldcg(ob + 8 * NL + (ab >> 2));
+                    xb = sa.e[c] + __ldcg(ob + 8 * NL + ab);
                 }
             }
             zm[2 * c] = mb; zx[2 * c] = (mb > 0.0f) ? xb + (__float_as_int(mb) >> 23) : 4 * kVoidE;
@@ -623,7 +630,7 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
     uint64_t* st_full = occ_full + kNE;                          // [kNSR]
     int2* mail = (int2*)(smem + sm.mail);
     int* s_off = (int*)(smem + sm.tgt);                          // label * 4 | "occurred before", padded to 128 entries
-    int* s_nf = s_off + round_up(p.Sp, 128);                     // later occurrences of a class (ctc2_prep_kernel)
+    const int* nfl = p.nflist + (size_t)n * p.NF;                // later occurrences of a class (ctc2_prep_kernel)
     float* s_em = (float*)(smem + sm.em);
     int* s_st = (int*)(smem + sm.st);
     float* s_rows = (float*)(smem + sm.rows);
@@ -640,7 +647,6 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
         const int wd = (k < L) ? p.tgt[(size_t)n * p.Sp + k] : kNotFirst;
         s_off[k] = ((wd & kLabelMask) << 2) | ((wd & kNotFirst) ? 1 : 0);
     }
-    for (int k = threadIdx.x; k < nf.x + nf.y; k += blockDim.x) s_nf[k] = p.nflist[(size_t)n * p.NF + k];
     mbar_init_fence();
     __syncthreads();
 
@@ -706,12 +712,12 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
             // later occurrences: the list holds them by occurrence rank, one rank (distinct classes) per 32 entries,
             // so a class is updated in position order by one lane at a time: deterministic, no atomics
             for (int e0 = 0; e0 < nf.x; e0 += 32) {
-                const int e = s_nf[e0 + lane];
+                const int e = __ldg(nfl + e0 + lane);
                 if (e >= 0) row[e >> 10] = fmaf(-g, em[8 + (e & 1023)], row[e >> 10]);
                 __syncwarp();
             }
             if (nf.y > 0 && lane == 0)
-                for (int x = nf.x; x < nf.x + nf.y; ++x) { const int e = s_nf[x]; row[e >> 10] = fmaf(-g, em[8 + (e & 1023)], row[e >> 10]); }
+                for (int x = nf.x; x < nf.x + nf.y; ++x) { const int e = __ldg(nfl + x); row[e >> 10] = fmaf(-g, em[8 + (e & 1023)], row[e >> 10]); }
             bs = warp_sum(bs);
             __syncwarp();
             if (lane == 0) row[0] -= g * (1.0f - bs);          // a frame's occupancies sum to one: the blank's share
@@ -755,26 +761,27 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
     {
         const int* mybound = p.bound + ((size_t)n * 2 + dir) * p.BW;
         float4 ob = make_float4(0.f, 0.f, 0.f, 0.f), ol = ob;
-        s.e = kVoidE;
+        int4 oe = make_int4(kVoidE, kVoidE, kVoidE, kVoidE);
         if (cfg.live) {
             ob = *(const float4*)(mybound + 4 * cfg.g);
             ol = *(const float4*)(mybound + 4 * NL + 4 * cfg.g);
-            s.e = mybound[8 * NL + cfg.g];
+            oe = *(const int4*)(mybound + 8 * NL + 4 * cfg.g);
         }
+        s.e[0] = oe.x; s.e[1] = oe.y; s.e[2] = oe.z; s.e[3] = oe.w;
         s.b[0] = ob.x; s.b[1] = ob.y; s.b[2] = ob.z; s.b[3] = ob.w;
         s.l[0] = ol.x; s.l[1] = ol.y; s.l[2] = ol.z; s.l[3] = ol.w;
     }
     const int4 zi = p.zinfo[n];
     const int eZ = zi.x;
     const float rZ = __int_as_float(zi.y);
-    if (lane == 31) mail[((steps1 + 1) & 1) * W + w] = make_int2(__float_as_int(s.l[dir ? 0 : kJP - 1]), s.e);
+    if (lane == 31) mail[((steps1 + 1) & 1) * W + w] = make_int2(__float_as_int(s.l[dir ? 0 : kJP - 1]), s.e[dir ? 0 : kJP - 1]);
     const int k_inj = dir ? 4 * NL - 1 - (L + 4) : 3;
     const int q_lo = 128 * w - k_inj - 1, q_hi = 128 * w + 127 - k_inj - 1;
     const int first = max(q_lo, 0), last = Tn - L + q_hi;
     float* emp = s_em + 4 + 4 * cfg.g;                      // my four label emissions / occupancies in slot 0
     const int* stp = s_st + 4 * cfg.g;                      // the other side's four label states of my group in slot 0
-    const int eoff = 4 * NL - 3 * cfg.g;
-    const uint32_t st_bytes = (uint32_t)round_up(5 * NL, 4) * 4u;
+    const int eoff = 4 * NL;
+    const uint32_t st_bytes = (uint32_t)(8 * NL) * 4u;
     const int* tr_n = p.tr + (size_t)n * p.T * p.SPL;
     auto st_issue = [&](int i2) {          // the row the OTHER side stored for the frame of my phase-2 step i2
         const int i = steps1 + i2, t = dir ? Tn - 1 - i : i;
@@ -798,19 +805,21 @@ __global__ void __launch_bounds__(32 * (W + kR2), MINB) ctc2_bwd_kernel(Ctc2Para
             mbar_wait(&st_full[ss], (uint32_t)(i2 / kNSR) & 1u);
             if (i >= first && i <= last) {
                 float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                int eb = kVoidE;
-                if (cfg.live) { o4 = *(const float4*)(stp + ss * p.SPL); eb = stp[ss * p.SPL + eoff]; }
+                int4 eb = make_int4(kVoidE, kVoidE, kVoidE, kVoidE);
+                if (cfg.live) { o4 = *(const float4*)(stp + ss * p.SPL); eb = *(const int4*)(stp + ss * p.SPL + eoff); }
                 float cm; int ce;
                 fetch_below<DIR>(s, w, lane, mail + ((i + 1) & 1) * W, cm, ce);
                 float u[kJP], v[kJP];
                 lane_sums<DIR>(s, cfg.allowed, cm, ce, u, v);
                 // occupancy of a label state = (my pre-emission sum) x (the other side's stored value) / Z
-                const int xs = s.e + eb - eZ;
-                const float sc = (xs < -126) ? 0.0f : __int_as_float(__float_as_int(rZ) + (min(xs, 90) << 23));
-                occ = make_float4((v[0] * o4.x) * sc, (v[1] * o4.y) * sc, (v[2] * o4.z) * sc, (v[3] * o4.w) * sc);
+                auto scale = [&](int xs) {       // 2^xs / mantissa of Z, flushing below 2^-126
+                    return (xs < -126) ? 0.0f : __int_as_float(__float_as_int(rZ) + (min(xs, 90) << 23));
+                };
+                occ = make_float4((v[0] * o4.x) * scale(s.e[0] + eb.x - eZ), (v[1] * o4.y) * scale(s.e[1] + eb.y - eZ),
+                                  (v[2] * o4.z) * scale(s.e[2] + eb.z - eZ), (v[3] * o4.w) * scale(s.e[3] + eb.w - eZ));
                 lane_emit(s, u, v, pb, pl);
             }
-            if (lane == 31) mail[(i & 1) * W + w] = make_int2(__float_as_int(s.l[DIR ? 0 : kJP - 1]), s.e);
+            if (lane == 31) mail[(i & 1) * W + w] = make_int2(__float_as_int(s.l[DIR ? 0 : kJP - 1]), s.e[DIR ? 0 : kJP - 1]);
             if (cfg.live) *(float4*)(emp + slot * EMF) = occ;
             mbar_arrive(&occ_full[slot]);
             side_barrier(nthr);

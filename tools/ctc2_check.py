@@ -81,6 +81,8 @@ def main():
         dict(T=400, N=4, V=64, S=60, scale=5.0),
         dict(T=400, N=4, V=64, S=60, scale=6.0, from_logits=False),
         dict(T=1500, N=6, V=1024, S=300),
+        dict(T=16000, N=2, V=16, S=4, var=False, special=False),      # T >> L: adjacent states 30+ nats apart
+        dict(T=30000, N=1, V=16, S=40, var=False),
         dict(T=1500, N=6, V=1024, S=300, scale=3.0),
     ]
     bad = 0

@@ -37,7 +37,7 @@ class Side:
         NL = self.NL
         self.bm = np.zeros((NL, JP), f32)
         self.lm = np.zeros((NL, JP), f32)
-        self.e = np.full(NL, VOID_E, np.int64)
+        self.e = np.full((NL, JP), VOID_E, np.int64)         # one exponent per (blank, label) pair
         self.A = 4 * NL                       # a-space size
         # pair k of this side <-> label index a
         k = np.arange(self.A)
@@ -45,7 +45,7 @@ class Side:
         a_inj = 3 if dirn == 0 else L + 4
         k_inj = a_inj if dirn == 0 else self.A - 1 - a_inj
         self.lm[k_inj // 4, k_inj % 4] = 1.0
-        self.e[k_inj // 4] = 0
+        self.e[k_inj // 4, k_inj % 4] = 0
         # allowed mask per pair
         al = np.zeros(self.A, bool)
         for kk in range(self.A):
@@ -74,30 +74,29 @@ class Side:
 def lane_step(s, pb, pl):
     """One recursion step of side s.  pl[NL,JP]: label emission of each pair.  Returns (u, v, e_pre)."""
     NL = s.NL
-    cm = np.concatenate([[f32(0)], s.lm[:-1, JP - 1]]).astype(f32)
-    ce = np.concatenate([[VOID_E], s.e[:-1]])
+    lm_flat = s.lm.reshape(-1); e_flat = s.e.reshape(-1)
+    cm = np.concatenate([[f32(0)], lm_flat[:-1]]).astype(f32).reshape(NL, JP)      # label state of the pair below
+    ce = np.concatenate([[VOID_E], e_flat[:-1]]).reshape(NL, JP)
     d = ce - s.e
     big = d > 30
     sh = np.where(big, d - 30, 0)
-    fac = pow2(-np.minimum(sh, 200))
-    s.bm = (s.bm * fac[:, None]).astype(f32)
-    s.lm = (s.lm * fac[:, None]).astype(f32)
+    s.bm = np.ldexp(s.bm, -np.minimum(sh, 300).astype(np.int32)).astype(f32)
+    s.lm = np.ldexp(s.lm, -np.minimum(sh, 300).astype(np.int32)).astype(f32)
     s.e = s.e + sh
     d = np.where(big, 30, d)
-    c0 = (cm * pow2(np.maximum(d, -127))).astype(f32)
-    c = np.concatenate([c0[:, None], s.lm[:, :JP - 1]], axis=1).astype(f32)
+    c = np.ldexp(cm, np.maximum(d, -300).astype(np.int32)).astype(f32)     # exponent-field shift: exact while representable
     u = (s.bm + c).astype(f32)
     v = (s.lm + np.where(s.al, u, s.bm)).astype(f32)
     e_pre = s.e.copy()
     nb = (u * f32(pb)).astype(f32)
     nl = (v * pl).astype(f32)
-    mx = np.maximum(nb.max(axis=1), nl.max(axis=1))
+    mx = np.maximum(nb, nl)
     ex = (mx.view(np.int32) >> 23).astype(np.int64)
     delta = np.minimum((TARGET + 127) - ex, 120)
     f = pow2(delta)
     zero = mx == 0
-    s.bm = np.where(zero[:, None], f32(0), nb * f[:, None]).astype(f32)
-    s.lm = np.where(zero[:, None], f32(0), nl * f[:, None]).astype(f32)
+    s.bm = np.where(zero, f32(0), nb * f).astype(f32)
+    s.lm = np.where(zero, f32(0), nl * f).astype(f32)
     s.e = np.where(zero, VOID_E, s.e - delta)
     return u, v, e_pre
 
@@ -139,7 +138,7 @@ def run_utt(x, y, L, Tn, from_logits=True, gout=1.0):
     tm = Tn // 2
     steps1 = [tm, Tn - tm]
     stored_l = np.zeros((Tn, A), f32)        # post-emission label values by a
-    stored_e = np.zeros((Tn, NL), np.int64)  # by group g' = a // 4
+    stored_e = np.zeros((Tn, A), np.int64)   # exponent of the pair, by a
     bound = []
     for s in sides:
         for i in range(steps1[s.dir]):
@@ -148,33 +147,11 @@ def run_utt(x, y, L, Tn, from_logits=True, gout=1.0):
             pl = em[s.a_of].reshape(NL, JP)
             lane_step(s, pb, pl)
             stored_l[t, s.a_of] = s.lm.reshape(-1)
-            gi = np.arange(NL) if s.dir == 0 else (NL - 1 - np.arange(NL))
-            stored_e[t, gi] = s.e
-        bB = np.zeros(A, f32); lB = np.zeros(A, f32); eB = np.zeros(NL, np.int64)
+            stored_e[t, s.a_of] = s.e.reshape(-1)
+        bB = np.zeros(A, f32); lB = np.zeros(A, f32); eB = np.zeros(A, np.int64)
         bB[s.a_of] = s.bm.reshape(-1); lB[s.a_of] = s.lm.reshape(-1)
-        gi = np.arange(NL) if s.dir == 0 else (NL - 1 - np.arange(NL))
-        eB[gi] = s.e
+        eB[s.a_of] = s.e.reshape(-1)
         bound.append((bB, lB, eB))
-
-    def z_from(d):
-        """Z as the side that arrives second would form it: my pre-emission sums x the other's boundary."""
-        import copy
-        s = copy.deepcopy(sides[d])
-        u, v, e_pre = lane_step(s, f32(1), np.ones((NL, JP), f32))
-        oB, oL, oE = bound[1 - d]
-        a = s.a_of.reshape(NL, JP)
-        ab = a - 1 if d == 0 else a + 1
-        okb = (ab >= 0) & (ab < A)
-        abc = np.clip(ab, 0, A - 1)
-        tot = 0.0
-        for ln in range(NL):
-            for j in range(JP):
-                if okb[ln, j] and u[ln, j] > 0 and oB[abc[ln, j]] > 0:
-                    tot += float(u[ln, j]) * float(oB[abc[ln, j]]) * 2.0 ** float(e_pre[ln] + oE[abc[ln, j] // 4] - 0) if abs(e_pre[ln] + oE[abc[ln, j] // 4]) < 900 else 0.0
-                if v[ln, j] > 0 and oL[a[ln, j]] > 0:
-                    ee = e_pre[ln] + oE[a[ln, j] // 4]
-                    tot += float(v[ln, j]) * float(oL[a[ln, j]]) * 2.0 ** float(ee) if abs(ee) < 900 else 0.0
-        return tot
 
     # Z in a safe way: collect (mantissa, exponent) terms and sum relative to the max exponent
     def z_terms(d):
@@ -190,10 +167,10 @@ def run_utt(x, y, L, Tn, from_logits=True, gout=1.0):
                 if 0 <= ab[ln, j] < A:
                     m = float(u[ln, j]) * float(oB[ab[ln, j]])
                     if m > 0:
-                        terms.append((m, int(e_pre[ln] + oE[ab[ln, j] // 4])))
+                        terms.append((m, int(e_pre[ln, j] + oE[ab[ln, j]])))
                 m = float(v[ln, j]) * float(oL[a[ln, j]])
                 if m > 0:
-                    terms.append((m, int(e_pre[ln] + oE[a[ln, j] // 4])))
+                    terms.append((m, int(e_pre[ln, j] + oE[a[ln, j]])))
         if not terms:
             return None
         pm = max(np.log2(m) + e for m, e in terms)
@@ -220,9 +197,9 @@ def run_utt(x, y, L, Tn, from_logits=True, gout=1.0):
             u, v, e_pre = lane_step(s, pb, pl)
             a = s.a_of.reshape(NL, JP)
             ob = stored_l[t][a]
-            eb = stored_e[t][a // 4]
-            xexp = e_pre[:, None] + eb - eZ
-            sc = (rZ * pow2(np.clip(xexp, -200, 90))).astype(f32)
+            eb = stored_e[t][a]
+            xexp = e_pre + eb - eZ
+            sc = (rZ * pow2(np.clip(xexp, -127, 90))).astype(f32)
             g = ((v * ob).astype(f32) * sc).astype(f32)
             occ[t, a.reshape(-1)] = g.reshape(-1)
     grad = np.zeros((T, V), np.float64)
