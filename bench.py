@@ -236,34 +236,31 @@ def cpu_reference_run(kind, B, T, V, U, seconds_target, threads):
     return b * T / t, f"B_cpu={b} of B={B}, same T={T} V={V} U={U}, float64, loss+grad", b, t
 
 
-def run_sweep(args, rank, world, local_rank):
+def measure_sweep(kind, rank, world, dev, steps, warm):
     """BASELINE.json configs[4] / SURVEY 8(d) C5: a pool of variable-length utterances, sorted by length, cut
-    into buckets by padded byte cost (the DurationBatchSampler rule, ha/sampler.py:13-29), dealt to the ranks
-    greedily by cost; a step is one pass over the pool (loss + gradient of every bucket) and one all-reduce of
-    [sum loss, count].  Strong scaling: the pool is fixed as the number of GPUs grows."""
+    into buckets by padded byte cost (the DurationBatchSampler rule, ha/sampler.py:13-29; RNN-T: in strips of
+    similar T, then by U, so that both paddings stay small), dealt to the ranks greedily by cost; a step is one
+    pass over the pool (loss + gradient of every bucket) and one all-reduce of [sum loss, count].  Strong
+    scaling: the pool is fixed as the number of GPUs grows.  Needs an initialised process group when world > 1.
+    Returns the result dict on rank 0 (None elsewhere)."""
     import random
     import torch
     import torch.distributed as dist
     from haloop_b200 import ops, sharding
-    kind = "rnnt" if args.workload == "sweep_rnnt" else "ctc"
     V = 1024
     rnd = random.Random(0)
     if kind == "ctc":
         n_pool = 4096
         tl_ = [10 * rnd.randint(20, 150) for _ in range(n_pool)]
         ul_ = [max(1, min((t - 1) // 2, round(t / 5 * rnd.uniform(0.6, 1.0)))) for t in tl_]
-        budget = 393_216_000                         # a quarter of BASELINE config 2's padded logits: 38 buckets
+        budget = 196_608_000                         # an eighth of BASELINE config 2's padded logits: ~76 buckets
     else:
         n_pool = 256                                 # 4096 RNN-T joints (~300 GB) do not fit one GPU: 256 do
         tl_ = [rnd.randint(100, 500) for _ in range(n_pool)]
         ul_ = [rnd.randint(20, 100) for _ in range(n_pool)]
-        budget = 1_654_784_000                       # a quarter of BASELINE config 4's padded joint: 20 buckets
+XX
     buckets = sharding.bucket_by_length(tl_, ul_, V, budget, kind)
     mine = sharding.deal_buckets(buckets, world)[rank]
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     data = []
     for bi in mine:
@@ -278,10 +275,10 @@ def run_sweep(args, rank, world, local_rank):
         data.append((x, tg, il, tl, torch.ones(Bk, device=dev)))
     red = torch.zeros(2, device=dev, dtype=torch.float64)
 
-    # buckets alternate over two streams: a short bucket's trellis kernel (one CTA per utterance) does not fill
-    # the GPU on its own, the next bucket's streaming kernels run beside it
+    # buckets rotate over four streams: a short bucket's kernels (one CTA per utterance and sweep direction) do
+    # not fill the GPU on their own, the neighbouring buckets' kernels run beside them
     main_stream = torch.cuda.current_stream()
-    side = [torch.cuda.Stream(), torch.cuda.Stream()]
+    side = [torch.cuda.Stream() for _ in range(4)]
     partial = [torch.zeros(2, device=dev, dtype=torch.float64) for _ in side]
 
     def step():
@@ -290,7 +287,8 @@ def run_sweep(args, rank, world, local_rank):
             with torch.cuda.stream(st):
                 partial[k].zero_()
         for j, (x, tg, il, tl, go) in enumerate(data):
-            with torch.cuda.stream(side[j & 1]):
+            k = j % len(side)
+            with torch.cuda.stream(side[k]):
                 if kind == "ctc":
                     xv = x.permute(1, 0, 2)
                     loss, ws = ops.ctc_fwd(xv, tg, il, tl, True)
@@ -298,10 +296,10 @@ def run_sweep(args, rank, world, local_rank):
                 else:
                     loss, ws = ops.rnnt_fwd(x, tg, il, tl, True)
                     ops.rnnt_bwd(x, ws, go, True)
-                partial[j & 1][0] += loss.sum(); partial[j & 1][1] += loss.numel()
+                partial[k][0] += loss.sum(); partial[k][1] += loss.numel()
         for st in side:
             main_stream.wait_stream(st)
-        red.copy_(partial[0] + partial[1])
+        red.copy_(sum(partial[1:], partial[0]))
         if world > 1:
             dist.all_reduce(red)
 
@@ -310,11 +308,10 @@ def run_sweep(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
     for _ in range(warm):
         step()
     barrier()
-    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
+    sampler = ClockSampler(dev.index or 0, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -328,39 +325,117 @@ def run_sweep(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t) / steps
+    del data
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    frames = sum(tl_)
+    if kind == "ctc":
+        ab = 8 * V * frames
+        padded = sum(len(b.indices) * b.t_max for b in buckets)
+        true_units = frames
+    else:
+        true_units = sum(t * (u + 1) for t, u in zip(tl_, ul_))
+        ab = 8 * V * true_units
+        padded = sum(len(b.indices) * b.t_max * (b.u_max + 1) for b in buckets)
+    peak, peak_src = measured_peak()
+    gbs = ab / (ms_step * 1e-3) / 1e9
+    loads = [sum(buckets[k].cost for k in o) for o in sharding.deal_buckets(buckets, world)]
+    return {
+        "metric": "utterance-frames/sec (loss + logit gradient)", "value": frames / (ms_step * 1e-3),
+        "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"sweep_{kind}: {kind} pool of {n_pool} variable-length utterances, V={V}, "
+                               f"{len(buckets)} length buckets of <= {budget / 1e9:.2f} GB padded logits, dealt to "
+                               f"{world} rank(s) by cost; one pass over the pool per step, four buckets in flight",
+                   "frames": frames, "buckets": len(buckets),
+                   "padding_overhead": padded / true_units,
+                   "rank_load_imbalance": max(loads) / (sum(loads) / len(loads)),
+                   "l2": "every bucket's logits are larger than L2"},
+        "mean_loss": float(red[0] / red[1]),
+        "gpu_launches": (3 if kind == "ctc" else 5) * len(mine) * steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "scope": "whole step (all buckets, all ranks), algorithmic bytes of the TRUE "
+                                              "lengths, against world x the single-GPU peak", "achieved": gbs,
+                     "peak": peak * world, "unit": "GB/s", "frac": gbs / peak / world, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_step": ab},
+    }
+
+
+def run_sweep(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    kind = "rnnt" if args.workload == "sweep_rnnt" else "ctc"
+    out = measure_sweep(kind, rank, world, dev, max(1, min(args.steps, 10)), max(1, min(args.warmup, 3)))
     if rank == 0:
-        frames = sum(tl_)
-        if kind == "ctc":
-            ab = 8 * V * frames
-            padded = sum(len(b.indices) * b.t_max for b in buckets)
-        else:
-            ab = 8 * V * sum(t * (u + 1) for t, u in zip(tl_, ul_))
-            padded = sum(len(b.indices) * b.t_max * (b.u_max + 1) for b in buckets)
-        peak, peak_src = measured_peak()
-        gbs = ab / (ms_step * 1e-3) / 1e9
-        loads = [sum(buckets[k].cost for k in o) for o in sharding.deal_buckets(buckets, world)]
-        print(json.dumps({
-            "metric": "utterance-frames/sec (loss + logit gradient)", "value": frames / (ms_step * 1e-3),
-            "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {kind} pool of {n_pool} variable-length utterances, V={V}, "
-                                   f"{len(buckets)} length buckets of <= {budget / 1e9:.2f} GB padded logits, dealt to "
-                                   f"{world} rank(s) by cost; one pass over the pool per step",
-                       "frames": frames, "buckets": len(buckets),
-                       "padding_overhead": padded / (frames if kind == "ctc" else sum(t * (u + 1) for t, u in zip(tl_, ul_))),
-                       "rank_load_imbalance": max(loads) / (sum(loads) / len(loads)),
-                       "l2": "every bucket's logits are larger than L2"},
-            "mean_loss": float(red[0] / red[1]),
-            "gpu_launches": (4 if kind == "ctc" else 5) * len(mine) * steps,
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "scope": "whole step (all buckets of rank 0's share), algorithmic bytes of the "
-                                                  "TRUE lengths", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                         "frac": gbs / peak / world, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_step": ab},
-            "e2e": None, "cpu_baseline": None,
-        }))
+        out["e2e"] = None; out["cpu_baseline"] = None
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_quick(kind, B, T, V, U, dev, scale=1.0, steps=20, warm=3):
+    """A short single-GPU measurement of one more workload (device-generated inputs, CUDA events around `steps`
+    steps after `warm`): the sub-records of the default run's "workloads"."""
+    import torch
+    from haloop_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(5)
+    nbytes_x = alg_bytes(kind, B, T, V, U) // 2
+    nsets = 1 if nbytes_x > 2 * 126e6 else max(2, int(4 * 126e6 // nbytes_x) + 1)
+    tg = torch.randint(1, V, (B, U), device=dev, generator=g)
+    il = torch.full((B,), T, dtype=torch.int64, device=dev); tl = torch.full((B,), U, dtype=torch.int64, device=dev)
+    if kind == "rnnt_fg":
+        xs = [(torch.randn(B, T, V, device=dev, generator=g) * scale, torch.randn(B, U + 1, V, device=dev, generator=g) * scale)
+              for _ in range(nsets)]
+    else:
+        shape = (B, T, V) if kind != "rnnt" else (B, T, U + 1, V)
+        xs = [torch.randn(shape, device=dev, generator=g) * scale for _ in range(nsets)]
+    gout = torch.ones(B, device=dev)
+
+    def step(i):
+        x = xs[i % nsets]
+        if kind == "ctc":
+            xv = x.permute(1, 0, 2); loss, ws = ops.ctc_fwd(xv, tg, il, tl, True); ops.ctc_bwd(xv, ws, gout, U, True)
+        elif kind == "star":
+            xv = x.permute(1, 0, 2); loss, ws = ops.star_fwd(xv, tg, il, tl, -0.5, True); ops.star_bwd(xv, ws, gout, U, True)
+        elif kind == "rnnt_fg":
+            loss, ws = ops.rnnt_fg_fwd(x[0], x[1], tg, il, tl); ops.rnnt_fg_bwd(x[0], x[1], ws, gout)
+        else:
+            loss, ws = ops.rnnt_fwd(x, tg, il, tl, True); ops.rnnt_bwd(x, ws, gout, True)
+        return loss
+
+    for i in range(warm):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / steps
+    peak, _ = measured_peak()
+    ab = alg_bytes(kind, B, T, V, U)
+    out = {"config": f"{kind} B={B} T={T} V={V} U={U} fp32, logits x{scale:g}, full lengths, from logits",
+           "ms_per_step": ms, "value": B * T / (ms * 1e-3), "unit": "frames/s", "steps": steps, "warmup": warm,
+           "mean_loss": float(loss.double().mean()),
+           "roofline": {"bound": "hbm", "achieved": ab / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": ab / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": ab},
+           "clocks": clocks}
+    if kind == "rnnt_fg":
+        flops = 6.0 * B * T * (U + 1) * V
+        out["roofline"]["note"] = "bound by its GEMMs and the lattice sweep, not by HBM"
+        out["gemm_tflops_over_whole_step"] = flops / (ms * 1e-3) / 1e12
+    del xs
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -378,6 +453,9 @@ def main():
                          "rotating inputs are copied into the captured buffer every step")
     ap.add_argument("--no-library-baseline", action="store_true",
                     help="skip timing F.ctc_loss / torchaudio.rnnt_loss on the same GPU (SURVEY 8d)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline workload only: skip the \"workloads\" sub-records (star, rnnt, rnnt_fg, ctc with x3 "
+                         "logits and the length-bucketed sweeps; with N > 1 the sweeps are the strong-scaling curve)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -617,7 +695,31 @@ def main():
         h2d = sum(t.numel() for t in (hx if fg else (hx,))) * 4 + htg.numel() * 8 + 16 * B
         e2e = {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4 * B, "ms_per_step": e2e_ms, "steps": n_e2e,
-               "note": "pinned host logits -> device every step (double-buffered on a copy stream), loss read back"}
+               "h2d_gbs": h2d / (e2e_ms * 1e-3) / 1e9,
+               "note": "pinned host logits -> device every step (double-buffered on a copy stream), per-utterance loss "
+                       "read back; the logit gradient stays on the device, where the model's backward consumes it. "
+                       "This number is bound by the host-to-device copy (h2d_gbs, PCIe), not by the kernels"}
+
+    # ---- the other workloads of BASELINE.json, as sub-records of the same line.  One GPU: configs 3, 4, the
+    #      joint-free RNN-T, config 2 with x3 logits (peaky posteriors) and both length-bucketed sweeps (config 5).
+    #      N GPUs: the sweeps, which are the STRONG-scaling curve of config 5 (the headline above is weak scaling).
+    extras = None
+    if not args.no_extras and args.workload == "ctc" and not args.graph:
+        del sets
+        torch.cuda.empty_cache()
+        extras = {}
+        try:
+            if world == 1:
+                for name, (k2, B2, T2, V2, U2) in (("star", WORKLOADS["star"]), ("rnnt", WORKLOADS["rnnt"]),
+                                                    ("rnnt_fg", WORKLOADS["rnnt_fg"])):
+                    extras[name] = measure_quick(k2, B2, T2, V2, U2, dev)
+                extras["ctc_x3"] = measure_quick("ctc", B, T, V, U, dev, scale=3.0)
+            for k2 in ("ctc", "rnnt"):
+                r = measure_sweep(k2, rank, world, dev, 5, 2)
+                if rank == 0:
+                    extras["sweep_" + k2] = r
+        except Exception as e:                      # a sub-record must never take the headline down with it
+            extras["error"] = repr(e)[:300]
 
     if rank != 0:
         if world > 1:
@@ -628,11 +730,16 @@ def main():
     ab = alg_bytes(kind, B, T, V, U)
     mid = "lattice" if kind.startswith("rnnt") else "trellis"
     names = [f"{kind}_rows_kernel", f"{kind}_{mid}_kernel", f"{kind}_grad_kernel"]
+    if kind == "ctc":
+        # fused path (csrc/ctc2.cuh): the forward call is ctc2_prep + ctc2_fwd (row statistics, emission gather and
+        # the first half of both sweeps in one kernel), the backward call is ctc2_bwd (second half of the sweeps,
+        # occupancies and the gradient rows in one kernel); emissions and occupancies never reach HBM
+        names = ["ctc2_prep_kernel", "ctc2_fwd_kernel", "ctc2_bwd_kernel"]
     if kind == "rnnt_fg":
         names = ["rnnt_fg_stats_kernel + rnnt_fg_gemm_kernel<E>", "rnnt_lattice_kernel",
                  "rnnt_fg_gemm_kernel<DF> + rnnt_fg_gemm_kernel<DG> + rnnt_fg_fix_kernel"]
     tr = [ncu_traffic(k) if args.workload in ("ctc", "star", "rnnt") else None for k in names]
-    launches_per_step = {"ctc": 4, "star": 4, "rnnt": 5, "rnnt_fg": 8}[kind]
+    launches_per_step = {"ctc": 3, "star": 4, "rnnt": 5, "rnnt_fg": 8}[kind]
     step_gbs = ab / (ms_step * 1e-3) / 1e9
     grad_gbs = ab / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else None      # --graph: forward and backward are one replay
     out = {
@@ -648,16 +755,20 @@ def main():
         "roofline": {
             "bound": "hbm", "scope": "whole step: " + " + ".join(names),
             "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
-            "traffic": (sum(tr) if all(t is not None for t in tr) else None),
+            "traffic": (sum(t for t in tr if t is not None) if tr[1] is not None and tr[2] is not None else None),
             "peak_source": peak_src, "algorithmic_bytes_per_step": ab,
             "kernels": {
                 names[2]: {"ms": bwd_ms, "achieved": grad_gbs, "frac": (grad_gbs / peak) if grad_gbs else None, "traffic": tr[2],
                            "note": "the backward call = this one kernel (timed live by CUDA events): reads the logits, "
-                                   "writes the gradient; its algorithmic bytes are the step's"},
+                                   "writes the gradient; its algorithmic bytes are the step's"
+                                   + ("; it also runs the second half of both sweeps" if kind == "ctc" else "")},
                 "forward (" + names[0] + " + " + names[1] + ")": {
-                    "ms": fwd_ms, "traffic": (tr[0] + tr[1]) if tr[0] is not None and tr[1] is not None else None,
-                    "note": "rows kernel is HBM-bound; the " + mid + " kernel is instruction-issue / latency bound "
-                            "(profiles/, DESIGN.md section 5)"},
+                    "ms": fwd_ms, "traffic": ((tr[0] or 0) + tr[1]) if tr[1] is not None else None,
+                    "note": ("one fused kernel: logit rows in through TMA, row statistics + emission gather by the row "
+                             "warps, first half of the alpha and beta sweeps by the trellis warps (profiles/, DESIGN.md)"
+                             if kind == "ctc" else
+                             "rows kernel is HBM-bound; the " + mid + " kernel is instruction-issue / latency bound "
+                             "(profiles/, DESIGN.md section 5)")},
             },
         },
     }
@@ -673,6 +784,8 @@ def main():
                                         "joint_bytes": 4 * B * T * (U + 1) * V}
     if e2e:
         out["e2e"] = e2e
+    if extras is not None:
+        out["workloads"] = extras
     if not args.no_library_baseline and world == 1 and kind == "rnnt_fg":
         try:
             from torchaudio.functional import rnnt_loss

@@ -28,11 +28,29 @@ def padded_cost(n, t_max, u_max, vocab, kind):
     return n * per
 
 
+def _length_order(in_lens, tgt_lens, vocab, budget_bytes, kind):
+    """CTC / star: by input length.  RNN-T pads BOTH T and U+1, so sorting by T alone leaves U random inside a
+    bucket (1.6x padded lattice nodes on a uniform pool): cut the T-sorted list into strips of about
+    sqrt(utterances per bucket) buckets each and sort every strip by U, so a bucket is compact in both."""
+    order = sorted(range(len(in_lens)), key=lambda i: (in_lens[i], tgt_lens[i]))
+    if kind != "rnnt" or len(order) < 4:
+        return order
+    mean_cost = sum(padded_cost(1, in_lens[i], tgt_lens[i], vocab, kind) for i in order) / len(order)
+    per_bucket = max(1.0, budget_bytes / mean_cost)
+    n_buckets = max(1.0, len(order) / per_bucket)
+    strips = max(1, round(n_buckets ** 0.5))
+    size = -(-len(order) // strips)
+    out = []
+    for k in range(0, len(order), size):
+        out += sorted(order[k:k + size], key=lambda i: (tgt_lens[i], in_lens[i]))
+    return out
+
+
 def bucket_by_length(in_lens: Sequence[int], tgt_lens: Sequence[int], vocab: int, budget_bytes: int,
                      kind: str = "ctc") -> List[Bucket]:
-    """Sort by input length, then cut greedily: a bucket closes when adding the next utterance would
-    push its padded cost past `budget_bytes` (the DurationBatchSampler rule, ha/sampler.py:13-29)."""
-    order = sorted(range(len(in_lens)), key=lambda i: (in_lens[i], tgt_lens[i]))
+    """Sort by length (see _length_order), then cut greedily: a bucket closes when adding the next utterance
+    would push its padded cost past `budget_bytes` (the DurationBatchSampler rule, ha/sampler.py:13-29)."""
+    order = _length_order(in_lens, tgt_lens, vocab, budget_bytes, kind)
     buckets, cur, t_max, u_max = [], [], 0, 0
     for i in order:
         nt, nu = max(t_max, in_lens[i]), max(u_max, tgt_lens[i])
