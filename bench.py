@@ -258,7 +258,7 @@ def measure_sweep(kind, rank, world, dev, steps, warm):
         n_pool = 256                                 # 4096 RNN-T joints (~300 GB) do not fit one GPU: 256 do
         tl_ = [rnd.randint(100, 500) for _ in range(n_pool)]
         ul_ = [rnd.randint(20, 100) for _ in range(n_pool)]
-XX
+        budget = 300_000_000                         # ~88 buckets of 2-4 joints: 1.11x padded lattice nodes
     buckets = sharding.bucket_by_length(tl_, ul_, V, budget, kind)
     mine = sharding.deal_buckets(buckets, world)[rank]
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
