@@ -236,7 +236,7 @@ def cpu_reference_run(kind, B, T, V, U, seconds_target, threads):
     return b * T / t, f"B_cpu={b} of B={B}, same T={T} V={V} U={U}, float64, loss+grad", b, t
 
 
-def measure_sweep(kind, rank, world, dev, steps, warm):
+def measure_sweep(kind, rank, world, dev, steps, warm, n_streams=None, budget_mb=None):
     """BASELINE.json configs[4] / SURVEY 8(d) C5: a pool of variable-length utterances, sorted by length, cut
     into buckets by padded byte cost (the DurationBatchSampler rule, ha/sampler.py:13-29; RNN-T: in strips of
     similar T, then by U, so that both paddings stay small), dealt to the ranks greedily by cost; a step is one
@@ -253,18 +253,29 @@ def measure_sweep(kind, rank, world, dev, steps, warm):
         n_pool = 4096
         tl_ = [10 * rnd.randint(20, 150) for _ in range(n_pool)]
         ul_ = [max(1, min((t - 1) // 2, round(t / 5 * rnd.uniform(0.6, 1.0)))) for t in tl_]
-        budget = 196_608_000                         # an eighth of BASELINE config 2's padded logits: ~76 buckets
+        budget = 786_432_000                         # half of BASELINE config 2's padded logits
     else:
         n_pool = 256                                 # 4096 RNN-T joints (~300 GB) do not fit one GPU: 256 do
         tl_ = [rnd.randint(100, 500) for _ in range(n_pool)]
         ul_ = [rnd.randint(20, 100) for _ in range(n_pool)]
-        budget = 300_000_000                         # ~88 buckets of 2-4 joints: 1.11x padded lattice nodes
-    buckets = sharding.bucket_by_length(tl_, ul_, V, budget, kind)
-    mine = sharding.deal_buckets(buckets, world)[rank]
+        budget = 827_392_000                         # an eighth of BASELINE config 4's padded joint
+    if budget_mb:
+        budget = int(budget_mb * 1e6)
+    n_streams = n_streams or (3 if kind == "ctc" else 8)
+    # utterances are dealt to the ranks by their own cost, then every rank buckets its share by length: the ranks'
+    # loads agree to a fraction of a percent and the buckets stay large at any number of ranks
+    shares = sharding.deal_utterances(tl_, ul_, V, world, kind)
+    all_buckets = []
+    for r in range(world):
+        bs = sharding.bucket_by_length([tl_[i] for i in shares[r]], [ul_[i] for i in shares[r]], V, budget, kind)
+        for b in bs:
+            b.indices = [shares[r][i] for i in b.indices]
+        all_buckets.append(bs)
+    buckets = [b for bs in all_buckets for b in bs]
+    mine_b = all_buckets[rank]
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     data = []
-    for bi in mine:
-        b = buckets[bi]
+    for b in mine_b:
         Bk = len(b.indices)
         shape = (Bk, b.t_max, V) if kind == "ctc" else (Bk, b.t_max, b.u_max + 1, V)
         x = torch.randn(shape, device=dev, generator=g)
@@ -278,7 +289,7 @@ def measure_sweep(kind, rank, world, dev, steps, warm):
     # buckets rotate over four streams: a short bucket's kernels (one CTA per utterance and sweep direction) do
     # not fill the GPU on their own, the neighbouring buckets' kernels run beside them
     main_stream = torch.cuda.current_stream()
-    side = [torch.cuda.Stream() for _ in range(4)]
+    side = [torch.cuda.Stream() for _ in range(n_streams)]
     partial = [torch.zeros(2, device=dev, dtype=torch.float64) for _ in side]
 
     def step():
@@ -340,20 +351,21 @@ def measure_sweep(kind, rank, world, dev, steps, warm):
         padded = sum(len(b.indices) * b.t_max * (b.u_max + 1) for b in buckets)
     peak, peak_src = measured_peak()
     gbs = ab / (ms_step * 1e-3) / 1e9
-    loads = [sum(buckets[k].cost for k in o) for o in sharding.deal_buckets(buckets, world)]
+    loads = [sum(b.cost for b in bs) for bs in all_buckets]
     return {
         "metric": "utterance-frames/sec (loss + logit gradient)", "value": frames / (ms_step * 1e-3),
         "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"sweep_{kind}: {kind} pool of {n_pool} variable-length utterances, V={V}, "
-                               f"{len(buckets)} length buckets of <= {budget / 1e9:.2f} GB padded logits, dealt to "
-                               f"{world} rank(s) by cost; one pass over the pool per step, four buckets in flight",
+                               f"dealt to {world} rank(s) by cost, each share cut into length buckets of <= "
+                               f"{budget / 1e9:.2f} GB padded logits ({len(buckets)} in all); one pass over the pool per step, "
+                               f"{n_streams} buckets in flight",
                    "frames": frames, "buckets": len(buckets),
                    "padding_overhead": padded / true_units,
                    "rank_load_imbalance": max(loads) / (sum(loads) / len(loads)),
                    "l2": "every bucket's logits are larger than L2"},
         "mean_loss": float(red[0] / red[1]),
-        "gpu_launches": (3 if kind == "ctc" else 5) * len(mine) * steps,
+        "gpu_launches": (3 if kind == "ctc" else 5) * len(mine_b) * steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "scope": "whole step (all buckets, all ranks), algorithmic bytes of the TRUE "
                                               "lengths, against world x the single-GPU peak", "achieved": gbs,
@@ -370,7 +382,8 @@ def run_sweep(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     kind = "rnnt" if args.workload == "sweep_rnnt" else "ctc"
-    out = measure_sweep(kind, rank, world, dev, max(1, min(args.steps, 10)), max(1, min(args.warmup, 3)))
+    out = measure_sweep(kind, rank, world, dev, max(1, min(args.steps, 10)), max(1, min(args.warmup, 3)),
+                        args.sweep_streams, args.sweep_budget_mb)
     if rank == 0:
         out["e2e"] = None; out["cpu_baseline"] = None
         print(json.dumps(out))
@@ -453,6 +466,8 @@ def main():
                          "rotating inputs are copied into the captured buffer every step")
     ap.add_argument("--no-library-baseline", action="store_true",
                     help="skip timing F.ctc_loss / torchaudio.rnnt_loss on the same GPU (SURVEY 8d)")
+    ap.add_argument("--sweep-streams", type=int, default=None, help="sweep workloads: buckets in flight")
+    ap.add_argument("--sweep-budget-mb", type=float, default=None, help="sweep workloads: padded logit bytes per bucket")
     ap.add_argument("--no-extras", action="store_true",
                     help="headline workload only: skip the \"workloads\" sub-records (star, rnnt, rnnt_fg, ctc with x3 "
                          "logits and the length-bucketed sweeps; with N > 1 the sweeps are the strong-scaling curve)")

@@ -78,6 +78,26 @@ def deal_buckets(buckets: Sequence[Bucket], world_size: int) -> List[List[int]]:
     return owned
 
 
+def deal_utterances(in_lens: Sequence[int], tgt_lens: Sequence[int], vocab: int, world_size: int,
+                    kind: str = "ctc") -> List[List[int]]:
+    """Deal UTTERANCES (not buckets) to the ranks, heaviest first to the currently lightest rank, by their own
+    (unpadded) logit bytes.  Each rank then cuts its share into length buckets itself (bucket_by_length): with
+    thousands of utterances the ranks' loads agree to a fraction of a percent whatever the bucket size is, so the
+    buckets can stay large (a launch per bucket fills the GPU) at any number of ranks.  Deterministic."""
+    cost = [padded_cost(1, in_lens[i], tgt_lens[i], vocab, kind) for i in range(len(in_lens))]
+    loads = [0] * world_size
+    owned = [[] for _ in range(world_size)]
+    import heapq
+    heap = [(0, r) for r in range(world_size)]
+    for i in sorted(range(len(cost)), key=lambda k: (-cost[k], k)):
+        load, r = heapq.heappop(heap)
+        owned[r].append(i)
+        heapq.heappush(heap, (load + cost[i], r))
+    for o in owned:
+        o.sort()
+    return owned
+
+
 def shard_batch(n_utts: int, rank: int, world_size: int) -> range:
     """Contiguous split of one already-formed batch: utterances [lo, hi) belong to `rank`."""
     per, rem = divmod(n_utts, world_size)
