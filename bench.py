@@ -290,27 +290,11 @@ def measure_sweep(kind, rank, world, dev, steps, warm, n_streams=None, budget_mb
     # not fill the GPU on their own, the neighbouring buckets' kernels run beside them
     main_stream = torch.cuda.current_stream()
     side = [torch.cuda.Stream() for _ in range(n_streams)]
-    partial = [torch.zeros(2, device=dev, dtype=torch.float64) for _ in side]
 
     def step():
-        for k, st in enumerate(side):
-            st.wait_stream(main_stream)
-            with torch.cuda.stream(st):
-                partial[k].zero_()
-        for j, (x, tg, il, tl, go) in enumerate(data):
-            k = j % len(side)
-            with torch.cuda.stream(side[k]):
-                if kind == "ctc":
-                    xv = x.permute(1, 0, 2)
-                    loss, ws = ops.ctc_fwd(xv, tg, il, tl, True)
-                    ops.ctc_bwd(xv, ws, go, tg.shape[1], True)
-                else:
-                    loss, ws = ops.rnnt_fwd(x, tg, il, tl, True)
-                    ops.rnnt_bwd(x, ws, go, True)
-                partial[k][0] += loss.sum(); partial[k][1] += loss.numel()
-        for st in side:
-            main_stream.wait_stream(st)
-        red.copy_(sum(partial[1:], partial[0]))
+        res = sharding.bucketed_pass(kind, data, side)
+        red[0] = sum(l.sum(dtype=torch.float64) for l, _ in res)
+        red[1] = float(sum(l.numel() for l, _ in res))
         if world > 1:
             dist.all_reduce(red)
 

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(256) ctc_viterbi_kernel(ViterbiParams p) {
         if (S_ > 1 && fv[S_ - 2] > fv[S_ - 1]) s = S_ - 2;
         p.score[n] = fv[s];
         __threadfence_block();
+        if (!(fv[s] > -CUDART_INF_F)) return;        // no alignment exists: the score is -inf and the path stays all -1
         for (int t = Tn - 1; t >= 0; --t) {
             ali[t] = cls[s];
             if (t > 0) s -= bp[(size_t)t * p.S_ + s];

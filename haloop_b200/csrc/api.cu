@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unordered_set>
 
 #include "../../include/ha_b200.h"
 #include "align.cuh"
@@ -37,11 +38,19 @@ int check_launch(const char* what) {
 constexpr size_t kMaxSmem = hab::kMaxSmemOptin;
 constexpr size_t kRowSmemTarget = 100 * 1024; // two row-kernel CTAs per SM
 
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute is sticky per (kernel, device): it is raised
+// to the opt-in maximum the first time this thread launches the kernel on a device and not touched again.
 template <typename K>
 int set_smem(K kernel, size_t bytes, const char* what) {
     if (bytes > kMaxSmem) return fail(HA_ERR_UNSUPPORTED_SHAPE, "%s needs %zu B of shared memory", what, bytes);
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    thread_local std::unordered_set<unsigned long long> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long key = (unsigned long long)(uintptr_t)(const void*)kernel * 64ull + (unsigned)(dev & 63);
+    if (done.count(key)) return HA_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     if (e != cudaSuccess) return fail(HA_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    done.insert(key);
     return HA_OK;
 }
 
@@ -58,8 +67,6 @@ RowCfg pick_row_cfg(int T, F smem_of /* (nstage, nwarps) -> bytes */, int ns_max
     // B200 (nw, ns sweep): RNN-T rows 1.20 -> 0.97 ms, CTC rows 0.44 -> 0.37 ms, CTC grad 0.62 -> 0.56 ms, star
     // grad 0.22 -> 0.14 ms; the RNN-T gradient kernel (already at the copy peak) keeps 8 warps x 3 stages.
     RowCfg c{8, 4, 1, 0, false};
-    if (const char* e = getenv("HA_B200_ROW_NSTAGE")) { int v = atoi(e); if (v >= 2 && v <= 4) ns_max = v; }   // tuning knob
-    if (const char* e = getenv("HA_B200_ROW_NWARPS")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) nw_max = v; }
     for (int nw = nw_max; nw >= 1 && !c.ok; nw >>= 1) {
         for (int ns = ns_max; ns >= 2; --ns) {
             size_t b = smem_of(ns, nw);
@@ -68,7 +75,6 @@ RowCfg pick_row_cfg(int T, F smem_of /* (nstage, nwarps) -> bytes */, int ns_max
     }
     int rpw = (T + c.nwarps * 4 - 1) / (c.nwarps * 4);
     int cap = 16;
-    if (const char* e = getenv("HA_B200_ROW_RPW")) { int v = atoi(e); if (v >= 1 && v <= 256) cap = v; }   // tuning knob
     c.rows_per_warp = rpw < 1 ? 1 : (rpw > cap ? cap : rpw);
     return c;
 }
@@ -116,10 +122,7 @@ static int ctc_trellis_launch(const TrellisParams& tp, int nslot, int N, cudaStr
     // pairs, plus one producer warp per direction.  (J, W) are template parameters (the per-step
     // barriers and mailbox indices become immediates); two slots per warp up to 5 warps measured best.
     if (nslot > 32) return fail(HA_ERR_UNSUPPORTED_SHAPE, "target length > 1023 is not supported");
-    int env_w = 0;
-    if (const char* e = getenv("HA_B200_TRELLIS_W")) env_w = atoi(e);
     int W = nslot < 2 ? 1 : ((nslot + 1) / 2 < 5 ? (nslot + 1) / 2 : 5);
-    if (env_w >= 1 && env_w <= 5) W = env_w < nslot ? env_w : nslot;
     int J = (nslot + W - 1) / W;
     if (J == 7) J = 8;
     if (J > 8) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: J=%d", J);
@@ -262,10 +265,7 @@ size_t ha_star_workspace_bytes(int T, int N, int V, int S) {
 static int star_trellis_launch(const StarTrellisParams& tp, int nslot, int N, cudaStream_t st) {
     StarTrellisParams p = tp;
     if (nslot > 16) return fail(HA_ERR_UNSUPPORTED_SHAPE, "star-CTC target length > 511 is not supported");
-    int env_w = 0;
-    if (const char* e = getenv("HA_B200_TRELLIS_W")) env_w = atoi(e);
     int W = nslot < 2 ? 1 : (nslot < 4 ? 2 : 4);
-    if (env_w >= 1 && env_w <= 5) W = env_w < nslot ? env_w : nslot;
     const int J = (nslot + W - 1) / W;
     if (J > 4) return fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: star J=%d", J);
     W = (nslot + J - 1) / J;

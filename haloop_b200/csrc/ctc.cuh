@@ -109,7 +109,9 @@ __global__ void __launch_bounds__(256) ctc_prep_kernel(PrepParams p) {
         }
         p.tgt[(size_t)n * p.Sp + k] = y | (notfirst ? kNotFirst : 0);
         p.dupnext[(size_t)n * p.Sp + k] = (nxt == 0x7fffffff) ? -1 : nxt;
-        if (k >= 1 && k < L && s_y[k - 1] == y) atomicAdd(&s_rep, 1);
+        // a blank must separate equal neighbours; in CTC a label 0 can only be entered from the blank before it
+        // (ha/ctc.py:140: no skip into a blank-valued state): one extra frame each
+        if (k >= 1 && k < L && (s_y[k - 1] == y || (!p.star && y == 0))) atomicAdd(&s_rep, 1);
     }
     __syncthreads();
     {   // longest-first work order (rank by counting; N is a batch size)

@@ -25,7 +25,9 @@ def ctc_forward_score3(emissions, targets, emission_lengths, target_lengths, fro
 
 
 def ctc_reduce_mean(losses, target_lengths):
-    """(losses / target_lengths).mean(-1), identical to F.ctc_loss(reduction='mean')."""
+    """(losses / target_lengths).mean(-1), exactly as ha/ctc.py:177-178: like the reference it divides by the raw
+    target length, so an empty transcript gives inf (F.ctc_loss(reduction='mean') clamps the length at 1 instead;
+    use ctc_loss(..., reduction='mean') or the patched TemporalClassifier.forward for that behaviour)."""
     return (losses / target_lengths.to(losses.device)).mean(-1)
 
 

@@ -57,6 +57,7 @@ class _TimeMajor(torch.autograd.Function):
         ctx.mark_non_differentiable(output[1])
 
     @staticmethod
+    @torch.autograd.function.once_differentiable     # no second derivative: double backward raises
     def backward(ctx, grad_loss, _grad_ws):
         x, ws = ctx.saved_tensors
         bwd = ops.ctc_bwd if ctx.kind == 0 else ops.star_bwd
@@ -86,6 +87,7 @@ class _Joint(torch.autograd.Function):
         ctx.mark_non_differentiable(output[1])
 
     @staticmethod
+    @torch.autograd.function.once_differentiable     # no second derivative: double backward raises
     def backward(ctx, grad_loss, _grad_ws):
         joint, ws = ctx.saved_tensors
         return ops.rnnt_bwd(_plain(joint), _plain(ws), _plain(grad_loss), ctx.from_logits), None, None, None, None
@@ -112,6 +114,7 @@ class _Factored(torch.autograd.Function):
         ctx.mark_non_differentiable(output[1])
 
     @staticmethod
+    @torch.autograd.function.once_differentiable     # no second derivative: double backward raises
     def backward(ctx, grad_loss, _grad_ws):
         f, g, ws = ctx.saved_tensors
         gf, gg = ops.rnnt_fg_bwd(_plain(f), _plain(g), _plain(ws), _plain(grad_loss))

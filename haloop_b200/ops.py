@@ -214,6 +214,17 @@ def _star_backward(ctx, grad_loss, _grad_ws):
 star_fwd.register_autograd(_star_backward, setup_context=_star_setup)
 
 
+# ------------------------------------------------------------------------- no second derivative
+def _no_double_backward(op, name):
+    """The backward ops return a first-order gradient computed by a kernel; nothing differentiates through it.
+    The reference's pure-PyTorch losses support double backward (gradient penalties, create_graph=True): make
+    that use fail loudly here instead of silently treating the gradient as a constant."""
+    def _raise(ctx, *grads):
+        raise NotImplementedError(f"haloop_b200: {name} has no second derivative (double backward / "
+                                  "create_graph=True through the alignment losses is not supported)")
+    op.register_autograd(_raise)
+
+
 # ------------------------------------------------------------------------------------------ vmap
 # Utterances are independent, so the batching rule of every op is "fold the vmapped dimension into the
 # utterance dimension and run once" (the reference has to drop its CTC term under torch.func.vmap for lack
@@ -446,6 +457,11 @@ def ctc_viterbi(lp, targets, in_len, tgt_len):
     _lib.check(rc, "ha_ctc_viterbi")
     return ali, sc
 
+
+_no_double_backward(ctc_bwd, "ctc_bwd")
+_no_double_backward(star_bwd, "star_bwd")
+_no_double_backward(rnnt_bwd, "rnnt_bwd")
+_no_double_backward(rnnt_fg_bwd, "rnnt_fg_bwd")
 
 # ------------------------------------------------------------------------------- vmap rules
 _register_time_major_vmap(ctc_fwd, ctc_bwd, 1)

@@ -32,7 +32,9 @@ def temporal_classifier_forward(self, features, targets, input_lengths=None, tar
         else:
             losses = star_ctc_forward_score(logits, targets, input_lengths, target_lengths,
                                             star_penalty=star_penalty, from_logits=True)
-        return ctc_reduce_mean(losses, target_lengths), {}
+        # the live call site is F.ctc_loss(reduction='mean') (ha/recognizer.py:71), which divides by
+        # target_lengths.clamp_min(1): an empty transcript must not turn the batch loss into inf
+        return (losses / target_lengths.to(losses.device).clamp_min(1)).mean(), {}
 
 
 def transducer_forward(self, features, targets, input_lengths=None, target_lengths=None,

@@ -12,6 +12,7 @@ from dataclasses import dataclass
 from typing import List, Sequence
 
 import torch
+import torch.utils.data
 
 
 @dataclass
@@ -96,6 +97,91 @@ def deal_utterances(in_lens: Sequence[int], tgt_lens: Sequence[int], vocab: int,
     for o in owned:
         o.sort()
     return owned
+
+
+def bucketed_pass(kind: str, data, streams, want_grad: bool = True):
+    """Loss (+ logit gradient) of every bucket a rank owns, the buckets rotating over `streams` so that a short
+    bucket's kernels (one CTA per utterance and sweep direction) run beside its neighbours' instead of leaving SMs
+    idle.  data: list of (x, targets, in_len, tgt_len, grad_out) with x (B,T,V) batch-major logits (ctc, star:
+    handed to the op as the permuted (T,B,V) view, the way ha/recognizer.py:70 does) or the (B,T,U+1,V) joint
+    (rnnt).  Returns [(loss (B,), grad like x or None)] in bucket order; the current stream waits for all of it."""
+    from . import ops
+    main = torch.cuda.current_stream()
+    for st in streams:
+        st.wait_stream(main)
+    out = []
+    for j, (x, tg, il, tl, go) in enumerate(data):
+        with torch.cuda.stream(streams[j % len(streams)]):
+            if kind == "ctc":
+                xv = x.permute(1, 0, 2)
+                loss, ws = ops.ctc_fwd(xv, tg, il, tl, True)
+                g = ops.ctc_bwd(xv, ws, go, tg.shape[1], True).permute(1, 0, 2) if want_grad else None
+            elif kind == "star":
+                xv = x.permute(1, 0, 2)
+                loss, ws = ops.star_fwd(xv, tg, il, tl, -0.5, True)
+                g = ops.star_bwd(xv, ws, go, tg.shape[1], True).permute(1, 0, 2) if want_grad else None
+            else:
+                loss, ws = ops.rnnt_fwd(x, tg, il, tl, True)
+                g = ops.rnnt_bwd(x, ws, go, True) if want_grad else None
+            out.append((loss, g))
+    for st in streams:
+        main.wait_stream(st)
+    return out
+
+
+class LengthBucketBatchSampler(torch.utils.data.Sampler):
+    """Drop-in for the reference's DurationBatchSampler (ha/sampler.py:7-29) as the `batch_sampler` of the hac
+    training DataLoader (ha/loop.py:502-509): same interface (`data_source.duration(i)`, `max_duration`), same
+    growth rule ((len(batch) + 1) * max duration of the batch <= max_duration), but over a LENGTH-SORTED order so the
+    padding inside a batch stays small, and sharded: the utterances are first dealt to `world_size` ranks by
+    duration (heaviest first to the lightest rank), every rank batches its own share, and the order of the batches
+    is reshuffled every epoch from `seed + epoch` (set_epoch, as torch's DistributedSampler).  Every rank yields the
+    same NUMBER of batches (the shortest share's count; its leftover batches are dropped like drop_last=True),
+    so DDP ranks step in lockstep."""
+
+    def __init__(self, data_source, max_duration=240, rank=0, world_size=1, shuffle=True, seed=0):
+        self.data_source = data_source
+        self.max_duration = max_duration
+        self.rank, self.world_size, self.shuffle, self.seed, self.epoch = rank, world_size, shuffle, seed, 0
+        dur = [float(data_source.duration(i)) for i in range(len(data_source))]
+        import heapq
+        heap = [(0.0, r) for r in range(world_size)]
+        shares = [[] for _ in range(world_size)]
+        for i in sorted(range(len(dur)), key=lambda k: (-dur[k], k)):
+            load, r = heapq.heappop(heap)
+            shares[r].append(i)
+            heapq.heappush(heap, (load + dur[i], r))
+        self._batches = [self._cut(sorted(sh, key=lambda k: (dur[k], k)), dur) for sh in shares]
+        self._len = min(len(b) for b in self._batches)
+
+    def _cut(self, order, dur):
+        batches, batch, mx = [], [], 0.0
+        for i in order:
+            new_mx = max(mx, dur[i])
+            if batch and (len(batch) + 1) * new_mx > self.max_duration:
+                batches.append(batch)
+                batch, mx = [i], dur[i]
+            else:
+                batch.append(i)
+                mx = new_mx
+        if batch:
+            batches.append(batch)
+        return batches
+
+    def set_epoch(self, epoch):
+        self.epoch = epoch
+
+    def __len__(self):
+        return self._len
+
+    def __iter__(self):
+        mine = self._batches[self.rank]
+        order = list(range(len(mine)))
+        if self.shuffle:
+            g = torch.Generator().manual_seed(self.seed + self.epoch)
+            order = torch.randperm(len(mine), generator=g).tolist()
+        for k in order[:self._len]:
+            yield list(mine[k])
 
 
 def shard_batch(n_utts: int, rank: int, world_size: int) -> range:

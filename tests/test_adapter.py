@@ -1,6 +1,8 @@
 """patch_haloop() on a stand-in for ha.recognizer (the real module imports kaldialign / g2p_en / wandb,
 absent here and on the GPU box; SURVEY 8f rank 3 asks for a stub).  The stand-in mirrors the attribute
 structure of TemporalClassifier (ha/recognizer.py:35-46) and Transducer (ha/recognizer.py:84-89)."""
+import os
+import sys
 import types
 
 import pytest
@@ -112,5 +114,90 @@ def test_patched_forwards_match_the_live_call_sites():
         assert abs(float(loss) / float(ref) - 1) < 1e-4
         for a, p in zip(got, tr.parameters()):
             assert close(a, p.grad)
+    finally:
+        adapter.unpatch_haloop(saved)
+
+
+# ------------------------------------------------------------------ the REAL reference modules ---
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "ha")), reason="the reference tree only exists in the build container")
+def test_patch_the_real_ha_recognizer_module():
+    """patch_haloop() on the actual ha.recognizer (imported from /root/reference, never edited): the four names
+    imported at ha/recognizer.py:6-8 are rebound, both forward()s are replaced by the adapter's, which accept the
+    keyword arguments ha/loop.py:130-135 passes (the reference's own forwards do not), the attributes the adapter
+    relies on exist on the real classes, CTCAttentionDecoder (ha/transformer.py:34-54) reaches the patched forward
+    through its `recognizer`, and unpatching restores everything.  No kernel runs here (CPU container)."""
+    import inspect
+    sys.path.insert(0, REF)
+    try:
+        import ha.recognizer as R
+        import ha.transformer as Tm
+    finally:
+        sys.path.remove(REF)
+    orig = (R.ctc_forward_score3, R.ctc_reduce_mean, R.star_ctc_forward_score, R.transducer_forward_score,
+            R.TemporalClassifier.forward, R.Transducer.forward)
+    saved = hb.patch_haloop(R)
+    try:
+        assert R.ctc_forward_score3 is hb.ctc_forward_score3 and R.star_ctc_forward_score is hb.star_ctc_forward_score
+        assert R.transducer_forward_score is hb.transducer_forward_score and R.ctc_reduce_mean is hb.ctc_reduce_mean
+        assert R.TemporalClassifier.forward is adapter.temporal_classifier_forward
+        assert R.Transducer.forward is adapter.transducer_forward
+        for fn in (R.TemporalClassifier.forward, R.Transducer.forward):
+            params = inspect.signature(fn).parameters
+            assert {"features", "targets", "input_lengths", "target_lengths", "star_penalty", "measure_entropy",
+                    "drop_labels"} <= set(params)
+        tc = R.TemporalClassifier(12, 9)
+        assert isinstance(tc.classifier, nn.Linear) and isinstance(tc.dropout, nn.Dropout)
+        tr = R.Transducer(12, 9)
+        assert callable(tr.lm.init_hidden) and callable(tr.lm.forward_batch_first)
+        lm_out, _ = tr.lm.forward_batch_first(torch.zeros(2, 4, dtype=torch.long), tr.lm.init_hidden(2))
+        assert lm_out.shape == (2, 4, 9), "g (N,U+1,C) as transducer_forward_score_fg expects it"
+        assert Tm.TemporalClassifier is R.TemporalClassifier, "CTCAttentionDecoder.recognizer is the patched class"
+        with pytest.raises(ValueError, match="CUDA"):            # the patched forward reaches the kernels' front door
+            tc(torch.zeros(2, 5, 12), torch.ones(2, 2, dtype=torch.long), torch.tensor([5, 5]), torch.tensor([2, 2]))
+    finally:
+        adapter.unpatch_haloop(saved)
+    assert orig == (R.ctc_forward_score3, R.ctc_reduce_mean, R.star_ctc_forward_score, R.transducer_forward_score,
+                    R.TemporalClassifier.forward, R.Transducer.forward)
+
+
+@pytest.mark.gpu
+def test_patched_temporal_classifier_matches_the_real_module_goldens():
+    """tests/golden/adapter_temporal_classifier.npz holds losses and parameter gradients of the REAL
+    ha.recognizer.TemporalClassifier (oracle/make_adapter_golden.py): the live F.ctc_loss call site with an empty
+    transcript in the batch (the clamp), the star branch as the call site means it, and the CTC term of
+    CTCAttentionDecoder (prompt stripped, x 0.3).  A module with the same parameters, patched, must reproduce them."""
+    import numpy as np
+    from conftest import golden_path
+    d = np.load(golden_path("adapter_temporal_classifier"))
+    dev = torch.device("cuda")
+    m = _stub_module()
+    saved = hb.patch_haloop(m)
+    try:
+        tc = m.TemporalClassifier(12, 9).to(dev)
+        with torch.no_grad():
+            tc.classifier.weight.copy_(torch.from_numpy(d["weight"]).float())
+            tc.classifier.bias.copy_(torch.from_numpy(d["bias"]).float())
+        feats = torch.from_numpy(d["feats"]).float().to(dev)
+        tg = torch.from_numpy(d["targets"]).to(dev); il = torch.from_numpy(d["in_len"]).to(dev)
+        tl = torch.from_numpy(d["tgt_len"]).to(dev)
+
+        def check(loss, ref_loss, gw, gb=None):
+            loss.backward()
+            assert torch.isfinite(loss) and abs(float(loss.detach()) / float(ref_loss) - 1) < 1e-4
+            assert np.abs(tc.classifier.weight.grad.double().cpu().numpy() - gw).max() < 1e-4 * max(1.0, np.abs(gw).max())
+            if gb is not None:
+                assert np.abs(tc.classifier.bias.grad.double().cpu().numpy() - gb).max() < 1e-4 * max(1.0, np.abs(gb).max())
+            tc.zero_grad()
+
+        loss, _ = tc(feats, tg, il, tl)                                   # one utterance has L = 0
+        check(loss, d["ctc_loss"], d["ctc_gw"], d["ctc_gb"])
+        loss, _ = tc(feats, tg, il, torch.from_numpy(d["star_tgt_len"]).to(dev), star_penalty=float(d["star_penalty"]))
+        check(loss, d["star_loss"], d["star_gw"], d["star_gb"])
+        cond = torch.from_numpy(d["att_condtargets"]).to(dev); cl = torch.from_numpy(d["att_cond_len"]).to(dev)
+        loss, _ = tc(feats, cond[:, 1:], il, cl - 1, None)                # ha/transformer.py:49-53
+        check(0.3 * loss, d["att_loss"], d["att_gw"])
     finally:
         adapter.unpatch_haloop(saved)

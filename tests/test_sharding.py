@@ -125,3 +125,65 @@ def test_rnnt_buckets_cost_and_deal():
         assert x.cost <= 1_000_000_000 or len(x.indices) == 1
     owned = sharding.deal_buckets(b, 4)
     assert sorted(k for o in owned for k in o) == list(range(len(b)))
+
+
+def test_deal_utterances_then_bucket_per_rank():
+    """bench.py's config-5 dealing: utterances go to ranks by their own cost (loads agree to a fraction of a percent),
+    every rank buckets its share; the 2-D order keeps RNN-T padding small."""
+    import random
+    r = random.Random(0)
+    tl = [10 * r.randint(20, 150) for _ in range(4096)]
+    ul = [max(1, min((t - 1) // 2, round(t / 5 * r.uniform(0.6, 1.0)))) for t in tl]
+    for world in (1, 2, 4, 8):
+        shares = sharding.deal_utterances(tl, ul, 1024, world, "ctc")
+        assert sorted(i for s in shares for i in s) == list(range(4096))
+        loads = [sum(tl[i] for i in s) for s in shares]
+        assert max(loads) / (sum(loads) / world) < 1.002
+        assert shares == sharding.deal_utterances(tl, ul, 1024, world, "ctc")
+    tl = [r.randint(100, 500) for _ in range(256)]; ul = [r.randint(20, 100) for _ in range(256)]
+    b1 = sharding.bucket_by_length(tl, ul, 1024, 300_000_000, "rnnt")
+    true = sum(t * (u + 1) for t, u in zip(tl, ul))
+    assert sum(len(b.indices) * b.t_max * (b.u_max + 1) for b in b1) / true < 1.15
+    assert sorted(i for b in b1 for i in b.indices) == list(range(256))
+
+
+class _ToyAudio(torch.utils.data.Dataset):
+    def __init__(self, n):
+        g = torch.Generator().manual_seed(3)
+        self.d = (torch.rand(n, generator=g) * 14 + 1).tolist()
+
+    def __len__(self):
+        return len(self.d)
+
+    def duration(self, i):
+        return self.d[i]
+
+    def __getitem__(self, i):
+        return i, torch.zeros(int(self.d[i] * 10), 4), "x"
+
+
+def test_length_bucket_batch_sampler_is_a_duration_batch_sampler_dropin():
+    """Same interface and growth rule as ha/sampler.py:7-29, usable as DataLoader(batch_sampler=...) in
+    ha/loop.py:502-509; length-sorted, sharded over ranks, same number of batches on every rank."""
+    ds = _ToyAudio(500)
+    seen, counts = [], []
+    for rank in range(4):
+        s = sharding.LengthBucketBatchSampler(ds, max_duration=120, rank=rank, world_size=4, seed=1)
+        batches = list(s)
+        counts.append(len(batches))
+        assert len(batches) == len(s)
+        for b in batches:
+            assert len(b) * max(ds.duration(i) for i in b) <= 120 or len(b) == 1
+        seen += [i for b in batches for i in b]
+        s.set_epoch(1)
+        assert sorted(map(tuple, s)) == sorted(map(tuple, batches)) and list(s) != batches, "reshuffled per epoch"
+    assert len(set(counts)) == 1, "DDP ranks take the same number of steps"
+    full = list(sharding.LengthBucketBatchSampler(ds, max_duration=120, shuffle=False))
+    padded = sum(len(b) * max(ds.duration(i) for i in b) for b in full)
+    assert padded / sum(ds.duration(i) for b in full for i in b) < 1.15, "length-sorted: little padding inside a batch"
+    assert len(seen) == len(set(seen)) and len(seen) > 0.93 * 500, "ranks own disjoint utterances; at most the tail is dropped"
+    loader = torch.utils.data.DataLoader(ds, batch_sampler=sharding.LengthBucketBatchSampler(ds, max_duration=120),
+                                         collate_fn=lambda b: (torch.tensor([x[0] for x in b]),
+                                                               torch.nn.utils.rnn.pad_sequence([x[1] for x in b], batch_first=True)))
+    idx, x = next(iter(loader))
+    assert x.shape[0] == len(idx) and x.shape[2] == 4
