@@ -13,6 +13,7 @@
 #include "host.h"
 #include "rnnt.cuh"
 #include "rnnt_fg.cuh"
+#include "rnnt_fg_umma.cuh"
 #include "star.cuh"
 
 using namespace hab;
@@ -490,10 +491,33 @@ int ha_rnnt_bwd(const float* joint, int N, int T, int U1, int V,
 }
 
 // ------------------------------------------------------------- joint-free (factored) RNN-T ---
+// The three contractions run on the tensor cores (rnnt_fg_umma.cuh) when the class count tiles evenly; the fp32 SIMT
+// kernels of rnnt_fg.cuh remain for every other shape.
+static int fg_umma_nt(int V) {            // accumulator columns per CTA for the two gradient GEMMs (0: not eligible)
+    if (V % 16 != 0) return 0;
+    for (int nt = 64; nt >= 16; nt >>= 1) if (V % nt == 0) return nt;      // 3 x 64 TMEM columns: two CTAs per SM
+    return 0;
+}
+
 size_t ha_rnnt_fg_workspace_bytes(int N, int T, int U1, int V) {
-    (void)V;
     if (T <= 0 || N <= 0 || U1 <= 0) return 0;
-    return rnnt_fg_ws_layout(N, T, U1).total;
+    size_t total = rnnt_fg_ws_layout(N, T, U1).total;
+    if (fg_umma_nt(V)) total += fg_umma_ws_layout(N, T, U1, V).total;
+    return total;
+}
+
+static FgUmmaParams fg_umma_params(const RnntFgParams& r, const FgUmmaWs& u, unsigned char* ubase) {
+    FgUmmaParams q{};
+    q.f = r.f; q.g = r.g; q.gf = r.gf; q.gg = r.gg;
+    q.N = r.N; q.T = r.T; q.U1 = r.U1; q.V = r.V; q.Up = r.Up; q.D = r.D;
+    q.meta = r.meta; q.tgt = r.tgt;
+    q.mf = r.mf; q.mg = r.mg; q.lf0 = r.lf0; q.lg0 = r.lg0; q.lgy = r.lgy; q.E = r.E;
+    q.bl = r.bl; q.lb = r.lb; q.occ = r.occ; q.gout = r.gout; q.loss = r.loss;
+    q.Fh = (float*)(ubase + u.Fh); q.Fl = (float*)(ubase + u.Fl); q.Gh = (float*)(ubase + u.Gh); q.Gl = (float*)(ubase + u.Gl);
+    q.Fth = (float*)(ubase + u.Fth); q.Ftl = (float*)(ubase + u.Ftl); q.Gth = (float*)(ubase + u.Gth); q.Gtl = (float*)(ubase + u.Gtl);
+    q.Wh = (float*)(ubase + u.Wh); q.Wl = (float*)(ubase + u.Wl); q.Wth = (float*)(ubase + u.Wth); q.Wtl = (float*)(ubase + u.Wtl);
+    q.Tp = u.Tp; q.Tk = u.Tk; q.Uk = u.Uk; q.Um = u.Um;
+    return q;
 }
 
 static RnntFgParams rnnt_fg_params(const float* f, const float* g, int N, int T, int U1, int V,
@@ -515,7 +539,7 @@ int ha_rnnt_fg_fwd(const float* f, const float* g, int N, int T, int U1, int V,
                    float* loss, void* ws, size_t ws_bytes, void* stream) {
     if (U1 <= 0) return fail(HA_ERR_INVALID_ARGUMENT, "U1 must be >= 1");
     const RnntFgWs w = rnnt_fg_ws_layout(N, T, U1);
-    int rc = common_checks(f, T, N, V, U1 - 1, ws, ws_bytes, w.total);
+    int rc = common_checks(f, T, N, V, U1 - 1, ws, ws_bytes, ha_rnnt_fg_workspace_bytes(N, T, U1, V));
     if (rc) return rc;
     if (!g || !in_len || !tgt_len || !loss || (U1 > 1 && !targets)) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
     if (U1 > 1024) return fail(HA_ERR_UNSUPPORTED_SHAPE, "U+1 > 1024 is not supported");
@@ -534,10 +558,25 @@ int ha_rnnt_fg_fwd(const float* f, const float* g, int N, int T, int U1, int V,
     RnntFgParams p = rnnt_fg_params(f, g, N, T, U1, V, w, base);
     rnnt_fg_chain_kernel<<<N, 128, (size_t)w.Up * 4, st>>>(p);
     if ((rc = check_launch("rnnt_fg_chain_kernel"))) return rc;
-    rnnt_fg_stats_kernel<<<dim3((T + U1 + 7) / 8, N), 256, 0, st>>>(p);
-    if ((rc = check_launch("rnnt_fg_stats_kernel"))) return rc;
-    rnnt_fg_gemm_kernel<kE><<<dim3((T + kGM - 1) / kGM, (U1 + kGN - 1) / kGN, N), 256, 0, st>>>(p);
-    if ((rc = check_launch("rnnt_fg_gemm_kernel<E>"))) return rc;
+    if (fg_umma_nt(V) && aligned16(f) && aligned16(g)) {
+        const FgUmmaWs uw = fg_umma_ws_layout(N, T, U1, V);
+        const FgUmmaParams q = fg_umma_params(p, uw, base + w.total);
+        fg_rows_kernel<<<dim3((uw.Tp + uw.Um + 7) / 8, N), 256, 0, st>>>(q);
+        if ((rc = check_launch("fg_rows_kernel"))) return rc;
+        FgGemmParams gp{};
+        gp.Ah = q.Fh; gp.Al = q.Fl; gp.lda = V; gp.a_batch = (size_t)uw.Tp * V;
+        gp.Bh = q.Gh; gp.Bl = q.Gl; gp.ldb = V; gp.b_batch = (size_t)uw.Um * V;
+        gp.K = V; gp.NT = uw.Uk <= 160 ? uw.Uk : 128; gp.q = q;
+        const size_t smem = fg_gemm_smem(gp.NT);
+        if ((rc = set_smem(fg_umma_gemm_kernel<kUmmaE>, smem, "fg_umma_gemm<E>"))) return rc;
+        fg_umma_gemm_kernel<kUmmaE><<<dim3(uw.Tp / kUM, uw.Uk / gp.NT, N), 128, smem, st>>>(gp);
+        if ((rc = check_launch("fg_umma_gemm_kernel<E>"))) return rc;
+    } else {
+        rnnt_fg_stats_kernel<<<dim3((T + U1 + 7) / 8, N), 256, 0, st>>>(p);
+        if ((rc = check_launch("rnnt_fg_stats_kernel"))) return rc;
+        rnnt_fg_gemm_kernel<kE><<<dim3((T + kGM - 1) / kGM, (U1 + kGN - 1) / kGN, N), 256, 0, st>>>(p);
+        if ((rc = check_launch("rnnt_fg_gemm_kernel<E>"))) return rc;
+    }
 
     RnntLatticeParams lp{};
     lp.N = N; lp.T = T; lp.U1 = U1; lp.D = w.D; lp.meta = p.meta;
@@ -557,17 +596,47 @@ int ha_rnnt_fg_bwd(const float* f, const float* g, int N, int T, int U1, int V,
                    void* ws, size_t ws_bytes, void* stream) {
     if (U1 <= 0) return fail(HA_ERR_INVALID_ARGUMENT, "U1 must be >= 1");
     const RnntFgWs w = rnnt_fg_ws_layout(N, T, U1);
-    int rc = common_checks(f, T, N, V, U1 - 1, ws, ws_bytes, w.total);
+    int rc = common_checks(f, T, N, V, U1 - 1, ws, ws_bytes, ha_rnnt_fg_workspace_bytes(N, T, U1, V));
     if (rc) return rc;
     if (!g || !grad_loss || !gf || !gg) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* base = (unsigned char*)ws;
     RnntFgParams p = rnnt_fg_params(f, g, N, T, U1, V, w, base);
     p.gf = gf; p.gg = gg; p.gout = grad_loss;
-    rnnt_fg_gemm_kernel<kDF><<<dim3((T + kGM - 1) / kGM, (V + kGN - 1) / kGN, N), 256, 0, st>>>(p);
-    if ((rc = check_launch("rnnt_fg_gemm_kernel<DF>"))) return rc;
-    rnnt_fg_gemm_kernel<kDG><<<dim3((U1 + kGM - 1) / kGM, (V + kGN - 1) / kGN, N), 256, 0, st>>>(p);
-    if ((rc = check_launch("rnnt_fg_gemm_kernel<DG>"))) return rc;
+    const int nt = fg_umma_nt(V);
+    if (nt && aligned16(f) && aligned16(g) && aligned16(gf) && aligned16(gg)) {
+        // (the forward call took the same branch: it depends on V and on the alignment of f and g only)
+        const FgUmmaWs uw = fg_umma_ws_layout(N, T, U1, V);
+        const FgUmmaParams q = fg_umma_params(p, uw, base + w.total);
+        FgTransposeParams tp{q.Fh, q.Fl, q.Fth, q.Ftl, uw.Tp, V, uw.Tk, uw.Tp};
+        fg_transpose_kernel<<<dim3((V + 31) / 32, (uw.Tk + 31) / 32, 2 * N), dim3(32, 8), 0, st>>>(tp);
+        if ((rc = check_launch("fg_transpose_kernel<F>"))) return rc;
+        FgTransposeParams tg{q.Gh, q.Gl, q.Gth, q.Gtl, uw.Um, V, uw.Uk, uw.Um};
+        fg_transpose_kernel<<<dim3((V + 31) / 32, (uw.Uk + 31) / 32, 2 * N), dim3(32, 8), 0, st>>>(tg);
+        if ((rc = check_launch("fg_transpose_kernel<G>"))) return rc;
+        fg_w_kernel<<<dim3((uw.Tp + 7) / 8, N), 256, 0, st>>>(q);
+        if ((rc = check_launch("fg_w_kernel"))) return rc;
+        const size_t smem = fg_gemm_smem(nt);
+        FgGemmParams df{};
+        df.Ah = q.Wh; df.Al = q.Wl; df.lda = uw.Uk; df.a_batch = (size_t)uw.Tp * uw.Uk;
+        df.Bh = q.Gth; df.Bl = q.Gtl; df.ldb = uw.Uk; df.b_batch = (size_t)V * uw.Uk;
+        df.K = uw.Uk; df.NT = nt; df.q = q;
+        if ((rc = set_smem(fg_umma_gemm_kernel<kUmmaDF>, smem, "fg_umma_gemm<DF>"))) return rc;
+        fg_umma_gemm_kernel<kUmmaDF><<<dim3(uw.Tp / kUM, V / nt, N), 128, smem, st>>>(df);
+        if ((rc = check_launch("fg_umma_gemm_kernel<DF>"))) return rc;
+        FgGemmParams dg{};
+        dg.Ah = q.Wth; dg.Al = q.Wtl; dg.lda = uw.Tk; dg.a_batch = (size_t)uw.Um * uw.Tk;
+        dg.Bh = q.Fth; dg.Bl = q.Ftl; dg.ldb = uw.Tk; dg.b_batch = (size_t)V * uw.Tk;
+        dg.K = uw.Tk; dg.NT = nt; dg.q = q;
+        if ((rc = set_smem(fg_umma_gemm_kernel<kUmmaDG>, smem, "fg_umma_gemm<DG>"))) return rc;
+        fg_umma_gemm_kernel<kUmmaDG><<<dim3(uw.Um / kUM, V / nt, N), 128, smem, st>>>(dg);
+        if ((rc = check_launch("fg_umma_gemm_kernel<DG>"))) return rc;
+    } else {
+        rnnt_fg_gemm_kernel<kDF><<<dim3((T + kGM - 1) / kGM, (V + kGN - 1) / kGN, N), 256, 0, st>>>(p);
+        if ((rc = check_launch("rnnt_fg_gemm_kernel<DF>"))) return rc;
+        rnnt_fg_gemm_kernel<kDG><<<dim3((U1 + kGM - 1) / kGM, (V + kGN - 1) / kGN, N), 256, 0, st>>>(p);
+        if ((rc = check_launch("rnnt_fg_gemm_kernel<DG>"))) return rc;
+    }
     rnnt_fg_fix_kernel<<<dim3((T + U1 + 7) / 8, N), 256, 0, st>>>(p);
     return check_launch("rnnt_fg_fix_kernel");
 }

@@ -285,6 +285,9 @@ def test_rnnt_joint_free_golden(hb, name):
     dict(N=2, T=130, U=70, V=33),                  # several tiles in every GEMM, V % 4 != 0
     dict(N=4, T=61, U=9, V=200, zero=True),        # label 0 in the targets
     dict(N=2, T=200, U=100, V=96, scale=3.0),      # the C4 lattice width, peaky
+    dict(N=2, T=300, U=100, V=256),                # tensor-core path: 128-column gradient tiles, 3 row tiles
+    dict(N=2, T=40, U=300, V=48, scale=2.0),       # tensor-core path: U+1 > 256 (two E tiles), 16-column gradient tiles
+    dict(N=3, T=129, U=15, V=1024, zero=True),     # tensor-core path: K = V = 1024, label 0
 ])
 def test_rnnt_joint_free_vs_oracle(hb, oracle, cfg):
     N, T, U, V = cfg["N"], cfg["T"], cfg["U"], cfg["V"]
