@@ -236,6 +236,44 @@ def cpu_reference_run(kind, B, T, V, U, seconds_target, threads):
     return b * T / t, f"B_cpu={b} of B={B}, same T={T} V={V} U={U}, float64, loss+grad", b, t
 
 
+def python_reference_run(kind, T, V, U, b_cpu):
+    """Time the REAL reference (oracle/_ref/ha, copied unmodified from /root/reference by oracle/build_ref.py) on
+    the host cores: fp32, log_softmax + ha.ctc.ctc_forward_score3 / ha.star.star_ctc_forward_score /
+    ha.transducer.transducer_forward_score + .sum().backward(), on `b_cpu` utterances of the same T, V, U
+    (the full batches need ~42 / 8 / 7 minutes).  Returns None when oracle/_ref is absent."""
+    from oracle import build_ref
+    if not build_ref.available() or kind == "rnnt_fg":
+        return None
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    try:
+        from ha.ctc import ctc_forward_score3
+        from ha.star import star_ctc_forward_score
+        from ha.transducer import transducer_forward_score
+    finally:
+        sys.path.pop(0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    shape = (T, b_cpu, V) if kind != "rnnt" else (b_cpu, T, U + 1, V)
+    x = torch.randn(shape, generator=g, requires_grad=True)
+    tg = torch.randint(1, V, (b_cpu, U), generator=g)
+    il = torch.full((b_cpu,), T); tl = torch.full((b_cpu,), U)
+    t0 = time.perf_counter()
+    lp = x.log_softmax(-1)
+    if kind == "ctc":
+        loss = ctc_forward_score3(lp, tg, il, tl)
+    elif kind == "star":
+        loss = star_ctc_forward_score(lp, tg, il, tl, star_penalty=-0.5)
+    else:
+        loss = transducer_forward_score(lp, tg, il, tl)
+    loss.sum().backward()
+    dt = time.perf_counter() - t0
+    return {"value": b_cpu * T / dt, "unit": "frames/s", "cores": os.cpu_count() or 1, "torch_threads": torch.get_num_threads(),
+            "kind": "reference", "seconds": dt,
+            "sample": f"the reference's own Python (ha/{'transducer' if kind == 'rnnt' else kind}.py, fp32, autograd backward) "
+                      f"on B_cpu={b_cpu} utterances of the same T={T} V={V} U={U}"}
+
+
 def measure_sweep(kind, rank, world, dev, steps, warm, n_streams=None, budget_mb=None):
     """BASELINE.json configs[4] / SURVEY 8(d) C5: a pool of variable-length utterances, sorted by length, cut
     into buckets by padded byte cost (the DurationBatchSampler rule, ha/sampler.py:13-29; RNN-T: in strips of
@@ -851,6 +889,14 @@ def main():
         fps, sample, b, tcpu = cpu_reference_run(kind, B, T, V, U, args.cpu_seconds, threads)
         out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                                "sample": sample, "seconds": tcpu}
+        try:
+            ref = python_reference_run(kind, T, V, U, {"ctc": 2, "star": 4, "rnnt": 1}.get(kind, 1))
+        except Exception as e:
+            ref = {"unavailable": repr(e)[:200]}
+        if ref is not None:
+            # the C port above is the conservative CPU arm (it is ~1000x faster than the code it restates);
+            # this is the reference itself, same box, same run
+            out["cpu_baseline_reference"] = ref
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
