@@ -7,11 +7,12 @@ and registered as PyTorch custom ops with autograd.  There is no CPU fallback.
 from .ctc import ctc_forward_score3, ctc_reduce_mean, ctc_loss
 from .star import star_ctc_forward_score
 from .transducer import transducer_forward_score, transducer_forward_score_fg, rnnt_loss
-from .align import greedy_decode, ctc_viterbi_align
+from .align import greedy_decode, greedy_decode_nested, ctc_viterbi_align, ctc_beam_search_decode_logits
 from .recognizer import patch_haloop
 
 __all__ = [
     "ctc_forward_score3", "ctc_reduce_mean", "ctc_loss", "star_ctc_forward_score",
-    "transducer_forward_score", "transducer_forward_score_fg", "rnnt_loss", "greedy_decode", "ctc_viterbi_align", "patch_haloop",
+    "transducer_forward_score", "transducer_forward_score_fg", "rnnt_loss", "greedy_decode", "greedy_decode_nested",
+    "ctc_viterbi_align", "ctc_beam_search_decode_logits", "patch_haloop",
 ]
 __version__ = "0.1.0"

@@ -8,6 +8,7 @@
 
 #include "../../include/ha_b200.h"
 #include "align.cuh"
+#include "beam.cuh"
 #include "common.cuh"
 #include "ctc.cuh"
 #include "host.h"
@@ -657,6 +658,30 @@ int ha_greedy_decode(const float* x, int64_t sx_n, int64_t sx_t, int N, int T, i
     if (rc) return rc;
     greedy_collapse_kernel<<<N, 256, 0, st>>>(p);
     return check_launch("greedy_collapse_kernel");
+}
+
+size_t ha_ctc_beam_search_workspace_bytes(int N, int T, int V, int beam) {
+    if (N <= 0 || T <= 0 || V <= 0 || beam <= 0 || beam > kMaxBeam) return 0;
+    return beam_ws_bytes(N, T, V, beam);
+}
+
+int ha_ctc_beam_search(const float* lp, int64_t sx_n, int64_t sx_t, int N, int T, int V,
+                       const void* in_len, int lengths_i64, int beam, int reference_ext_blank,
+                       int64_t* hyp, int64_t* hyp_len, float* score, void* ws, size_t ws_bytes, void* stream) {
+    if (!lp || !hyp || !hyp_len || !score || !ws) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+    if (N <= 0 || T <= 0 || V <= 0 || N > 65535) return fail(HA_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (beam < 1 || beam > kMaxBeam) return fail(HA_ERR_UNSUPPORTED_SHAPE, "beam size must be 1..%d", kMaxBeam);
+    if (V > 65534) return fail(HA_ERR_UNSUPPORTED_SHAPE, "V > 65534 is not supported by the beam search");
+    if (ws_bytes < beam_ws_bytes(N, T, V, beam)) return fail(HA_ERR_WORKSPACE_TOO_SMALL, "workspace %zu < %zu", ws_bytes, beam_ws_bytes(N, T, V, beam));
+    BeamParams p{};
+    p.lp = lp; p.sx_n = sx_n; p.sx_t = sx_t; p.N = N; p.T = T; p.V = V; p.beam = beam;
+    p.in_len = in_len; p.len64 = lengths_i64;
+    p.ext_blank = reference_ext_blank ? 0.0f : -HUGE_VALF;
+    p.bp = (int*)ws;
+    p.cand = (float*)((unsigned char*)ws + round_up_sz((size_t)N * T * beam * 4, 256));
+    p.hyp = (long long*)hyp; p.hyp_len = (long long*)hyp_len; p.score = score;
+    ctc_beam_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("ctc_beam_kernel");
 }
 
 size_t ha_ctc_viterbi_workspace_bytes(int T, int N, int V, int S) {

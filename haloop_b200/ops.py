@@ -432,6 +432,29 @@ def greedy_decode(x, in_len=None):
     return ali, sc, hyp, hl
 
 
+def ctc_beam_search(x, in_len=None, beam_size=3, reference_ext_blank=True):
+    """x (N,T,V) log-probs -> hyp (N,beam,T) i64 padded with -1 (best first), hyp_len (N,beam), score (N,beam)."""
+    _check_cuda_f32(x, "log_probs")
+    x = _unit_class_stride(x)
+    N, T, V = x.shape
+    dev = x.device
+    hyp = torch.empty(N, beam_size, T, dtype=torch.int64, device=dev)
+    hl = torch.empty(N, beam_size, dtype=torch.int64, device=dev)
+    sc = torch.empty(N, beam_size, dtype=_F32, device=dev)
+    il, il64 = (None, 0) if in_len is None else _idx(in_len, dev, "input_lengths")
+    L = _lib.lib()
+    nbytes = L.ha_ctc_beam_search_workspace_bytes(N, T, V, beam_size)
+    if nbytes == 0:
+        raise ValueError("beam_size must be between 1 and 16")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.ha_ctc_beam_search(x.data_ptr(), x.stride(0), x.stride(1), N, T, V,
+                                  il.data_ptr() if il is not None else None, il64, int(beam_size), int(bool(reference_ext_blank)),
+                                  hyp.data_ptr(), hl.data_ptr(), sc.data_ptr(), ws.data_ptr(), nbytes, _stream(x))
+    _lib.check(rc, "ha_ctc_beam_search")
+    return hyp, hl, sc
+
+
 def ctc_viterbi(lp, targets, in_len, tgt_len):
     """lp (T,N,V) log-probs -> alignment (N,T) i64 (class per frame, -1 padded), score (N,) f32."""
     _check_cuda_f32(lp, "log_probs")

@@ -99,6 +99,18 @@ int ha_greedy_decode(const float* x, int64_t sx_n, int64_t sx_t, int N, int T, i
                      const void* in_len, int lengths_i64,
                      int64_t* alignment, float* score, int64_t* hyp, int64_t* hyp_len, void* stream);
 
+/* ---- CTC prefix beam search: ha/beam.py:71-137 ctc_beam_search_decode_logits (the decode the reference leaves
+ * commented out at ha/recognizer.py:58 with "FIXME: speed it up"), hypothesis for hypothesis, including its in-place
+ * update order, its un-merged duplicate prefixes and the 0.0 blank score of extension candidates.
+ * lp (N,T,V) log-probs viewed through (sx_n, sx_t, 1); in_len may be NULL (every frame); beam <= 16.
+ * reference_ext_blank = 1: extension candidates enter with blank score 0.0 (log 1) exactly as ha/beam.py:124 does;
+ * 0: with -inf (log 0), the algorithm of the reference's probability-domain twin (ha/beam.py:4-68) and of [Graves14].
+ * hyp (N,beam,T) int64 padded with -1, best first; hyp_len (N,beam); score (N,beam) = the reference's seq_logits. */
+size_t ha_ctc_beam_search_workspace_bytes(int N, int T, int V, int beam);
+int ha_ctc_beam_search(const float* lp, int64_t sx_n, int64_t sx_t, int N, int T, int V,
+                       const void* in_len, int lengths_i64, int beam, int reference_ext_blank,
+                       int64_t* hyp, int64_t* hyp_len, float* score, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- CTC Viterbi forced alignment (max-semiring of ha/ctc.py:144-167; not in the reference) - */
 size_t ha_ctc_viterbi_workspace_bytes(int T, int N, int V, int S);
 /* lp (T,N,V) log-probs through (sx_t, sx_n, 1); alignment (N,T) int64 class per frame (-1 beyond

@@ -235,3 +235,27 @@ def test_viterbi_consistency(oracle):
         s = sum(float(lp[t, n, path[t]]) for t in range(il[n]))
         assert abs(s - sc[n]) < 1e-3
         assert sc[n] <= -loss[n] + 1e-4     # best path <= total
+
+
+# ------------------------------------------------------------------ prefix beam search (ha/beam.py:71-137) ---
+BEAM_GOLDENS = ["beam_small", "beam_short", "beam_peaky", "beam_blanky",
+                "graves_small", "graves_medium", "graves_peaky", "graves_blanky", "graves_wide"]
+
+
+@pytest.mark.parametrize("name", BEAM_GOLDENS)
+def test_beam_oracle_vs_reference_golden(name):
+    """The numpy restatement reproduces the unmodified reference hypothesis for hypothesis (both modes)."""
+    from oracle import beam_oracle
+    from conftest import golden_path
+    d = np.load(golden_path(name))
+    assert int(d["n"]) >= 1
+    ext_blank = -np.inf if name.startswith("graves") else 0.0
+    for i in range(int(d["n"])):
+        for b in d["beams"]:
+            seqs, sc = beam_oracle.ctc_beam_search(d[f"lp_{i}"], int(b), ext_blank)
+            hl = d[f"len_{i}_{b}"]
+            assert [len(s) for s in seqs] == hl.tolist()
+            for j, s in enumerate(seqs):
+                assert s == d[f"hyp_{i}_{b}"][j, :hl[j]].tolist()
+            np.testing.assert_allclose(sc, d[f"score_{i}_{b}"], rtol=1e-5 if name.startswith("graves") else 1e-10,
+                                       atol=1e-6 if name.startswith("graves") else 1e-12)
