@@ -8,11 +8,12 @@ from .ctc import ctc_forward_score3, ctc_reduce_mean, ctc_loss
 from .star import star_ctc_forward_score
 from .transducer import transducer_forward_score, transducer_forward_score_fg, rnnt_loss
 from .align import greedy_decode, greedy_decode_nested, ctc_viterbi_align, ctc_beam_search_decode_logits
+from .head import linear_ctc_forward_score, linear_ctc_loss
 from .recognizer import patch_haloop
 
 __all__ = [
     "ctc_forward_score3", "ctc_reduce_mean", "ctc_loss", "star_ctc_forward_score",
     "transducer_forward_score", "transducer_forward_score_fg", "rnnt_loss", "greedy_decode", "greedy_decode_nested",
-    "ctc_viterbi_align", "ctc_beam_search_decode_logits", "patch_haloop",
+    "ctc_viterbi_align", "ctc_beam_search_decode_logits", "linear_ctc_forward_score", "linear_ctc_loss", "patch_haloop",
 ]
 __version__ = "0.1.0"

@@ -77,6 +77,11 @@ SIGNATURES = {
     "ha_rnnt_fg_fwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "ha_rnnt_fg_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ha_greedy_decode": (_i32, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "ha_head_ctc_workspace_bytes": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "ha_head_ctc_fwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _i32,
+                               _vp, _vp, _sz, _vp, _sz, _vp]),
+    "ha_head_ctc_bwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp,
+                               _vp, _sz, _vp, _sz, _vp]),
     "ha_ctc_beam_search_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ha_ctc_beam_search": (_i32, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ha_ctc_viterbi_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),

@@ -157,6 +157,35 @@ static int ctc_trellis_launch(const TrellisParams& tp, int nslot, int N, cudaStr
     return check_launch("ctc_trellis_kernel");
 }
 
+}  // extern "C"
+
+namespace hab {
+void ctc_head_dims(int S, int* Sp, int* E, int* JWp, int* SPX) {
+    const CtcWs w = ctc_ws_layout(1, 1, S);
+    *Sp = w.Sp; *E = w.E; *JWp = w.JWp; *SPX = w.SPX;
+}
+int ctc_prep_for_head(const void* targets, int64_t tgt_stride, int S, int targets_i64,
+                      const void* in_len, const void* tgt_len, int lengths_i64, int T, int N, int V, int Sp,
+                      void* meta, int* order, int* tgt, int* dupnext, cudaStream_t st) {
+    PrepParams pp{};
+    pp.targets = targets; pp.tgt_stride = tgt_stride; pp.tgt64 = targets_i64;
+    pp.in_len = in_len; pp.tgt_len = tgt_len; pp.len64 = lengths_i64;
+    pp.T = T; pp.N = N; pp.V = V; pp.S = S; pp.Sp = Sp;
+    pp.meta = (int4*)meta; pp.order = order; pp.tgt = tgt; pp.dupnext = dupnext; pp.star = 0;
+    ctc_prep_kernel<<<N, 256, (size_t)round_up(S > 0 ? S : 1, 4) * 4, st>>>(pp);
+    return check_launch("ctc_prep_kernel");
+}
+int ctc_trellis_for_head(int T, int N, int S, int Sp, int E, int SPX, int JWp, const void* meta, const int* order,
+                         const int* tgt, float* em, float* tr, float* loss, float* loss_ws, cudaStream_t st) {
+    TrellisParams tp{};
+    tp.T = T; tp.N = N; tp.meta = (const int4*)meta; tp.order = order; tp.tgt = tgt; tp.Sp = Sp;
+    tp.em = em; tp.E = E; tp.tr = tr; tp.SPX = SPX; tp.JWp = JWp; tp.loss = loss; tp.loss_ws = loss_ws;
+    return ctc_trellis_launch(tp, (S + 1 + 31) / 32, N, st);
+}
+}  // namespace hab
+
+extern "C" {
+
 int ha_ctc_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
                const void* targets, int64_t tgt_stride, int S, int targets_i64,
                const void* in_len, const void* tgt_len, int lengths_i64,

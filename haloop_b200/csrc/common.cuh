@@ -89,6 +89,13 @@ __device__ __forceinline__ float exp2_poly(float f) {
     return fmaf(r, f, 1.0f);
 }
 
+// 2^(K + f) for an integer-valued K in [-127, 1] and |f| <= 0.5 (exp2_poly: relative error ~1e-7, no
+// MUFU), exponent added into the bit pattern
+__device__ __forceinline__ float emission_linear(float K, float f) {
+    const int k = __float_as_int(K + kMagic) - 0x4B400000;          // K is integer valued: exact, no F2I
+    return (k < -125) ? 1.1754943508222875e-38f : xf_scale(exp2_poly(f), k);
+}
+
 // stored trellis word: [12 bits: exponent distance below the slot base, saturating][20 mantissa bits]
 constexpr unsigned kPackVoid = 0xfff00000u;
 __device__ __forceinline__ int xf_pack(float m, int below) {     // m in [1,2), below >= 0

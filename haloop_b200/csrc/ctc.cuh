@@ -30,12 +30,6 @@ struct CtcWs {                 // workspace layout (byte offsets), filled by ctc
 // the linear domain on extended-range numbers (common.cuh, XF).  The occupancy row written in place:
 // [1] sum of the label occupancies (the blank's is one minus it), [4+k] label occupancy.
 __host__ __device__ inline int ctc_em_floats(int Sp) { return 4 + Sp; }
-// 2^(K + f) for an integer-valued K in [-127, 1] and |f| <= 0.5 (exp2_poly: relative error ~1e-7, no
-// MUFU), exponent added into the bit pattern
-__device__ __forceinline__ float emission_linear(float K, float f) {
-    const int k = __float_as_int(K + kMagic) - 0x4B400000;          // K is integer valued: exact, no F2I
-    return (k < -125) ? 1.1754943508222875e-38f : xf_scale(exp2_poly(f), k);
-}
 __host__ inline CtcWs ctc_ws_layout(int T, int N, int S) {
     CtcWs w;
     w.Sp = round_up(S > 0 ? S : 1, 4);

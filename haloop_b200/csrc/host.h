@@ -25,4 +25,12 @@ int ctc2_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V, in
              const float* grad_loss, int from_logits, float* gx, int64_t sg_t, int64_t sg_n,
              void* ws, size_t ws_bytes, cudaStream_t st);
 
+// ---- classifier head + CTC (head.cu) reuses the CTC prep and trellis kernels instantiated in api.cu ----
+void ctc_head_dims(int S, int* Sp, int* E, int* JWp, int* SPX);
+int ctc_prep_for_head(const void* targets, int64_t tgt_stride, int S, int targets_i64,
+                      const void* in_len, const void* tgt_len, int lengths_i64, int T, int N, int V, int Sp,
+                      void* meta, int* order, int* tgt, int* dupnext, cudaStream_t st);
+int ctc_trellis_for_head(int T, int N, int S, int Sp, int E, int SPX, int JWp, const void* meta, const int* order,
+                         const int* tgt, float* em, float* tr, float* loss, float* loss_ws, cudaStream_t st);
+
 }  // namespace hab

@@ -432,6 +432,105 @@ def greedy_decode(x, in_len=None):
     return ali, sc, hyp, hl
 
 
+# --------------------------------------------------------------------- fused classifier head + CTC
+_PRECISION = {"tf32x3": 3, "tf32": 1}
+
+
+def _head_sizes(N, T, D, V, S):
+    import ctypes
+    a, b, c = ctypes.c_size_t(0), ctypes.c_size_t(0), ctypes.c_size_t(0)
+    rc = _lib.lib().ha_head_ctc_workspace_bytes(N, T, D, V, S, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    _lib.check(rc, "ha_head_ctc_workspace_bytes")
+    return a.value, b.value, c.value
+
+
+@torch.library.custom_op("ha_b200::head_ctc_fwd", mutates_args=())
+def head_ctc_fwd(h: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, targets: torch.Tensor,
+                 in_len: torch.Tensor, tgt_len: torch.Tensor, precision: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """h (N,T,D), weight (V,D), bias (V) -> per-utterance CTC loss (N,) of log_softmax(h W^T + b), saved state."""
+    _check_cuda_f32(h, "features")
+    _check_cuda_f32(weight, "weight")
+    h, weight = h.contiguous(), weight.contiguous()
+    N, T, D = h.shape
+    V = weight.shape[0]
+    if weight.shape[1] != D:
+        raise ValueError("weight must be (V, D)")
+    b = None if bias is None else bias.to(_F32).contiguous()
+    tg, tg64 = _idx(targets, h.device, "targets")
+    il, il64 = _idx(in_len, h.device, "input_lengths")
+    tl, tl64 = _idx(tgt_len, h.device, "target_lengths")
+    if il64 != tl64:
+        il, tl, il64 = il.to(torch.int64), tl.to(torch.int64), 1
+    if tg.dim() != 2 or tg.shape[0] != N or il.shape != (N,) or tl.shape != (N,):
+        raise ValueError("expected targets (N,S), input_lengths (N,), target_lengths (N,)")
+    S = tg.shape[1]
+    saved_b, fwd_b, _ = _head_sizes(N, T, D, V, S)
+    saved = torch.empty(saved_b, dtype=torch.uint8, device=h.device)
+    scratch = torch.empty(fwd_b, dtype=torch.uint8, device=h.device)
+    loss = torch.empty(N, dtype=_F32, device=h.device)
+    with torch.cuda.device(h.device):
+        rc = _lib.lib().ha_head_ctc_fwd(h.data_ptr(), weight.data_ptr(), b.data_ptr() if b is not None else None,
+                                        N, T, D, V, tg.data_ptr() if S else None, tg.stride(0) if S else 0, S, tg64,
+                                        il.data_ptr(), tl.data_ptr(), il64, int(precision), loss.data_ptr(),
+                                        saved.data_ptr(), saved_b, scratch.data_ptr(), fwd_b, _stream(h))
+    _lib.check(rc, "ha_head_ctc_fwd")
+    return loss, saved
+
+
+@head_ctc_fwd.register_fake
+def _(h, weight, bias, targets, in_len, tgt_len, precision):
+    N, T, D = h.shape
+    saved_b, _, _ = _head_sizes(int(N), int(T), int(D), int(weight.shape[0]), int(targets.shape[1]))
+    return h.new_empty(N), h.new_empty(saved_b, dtype=torch.uint8)
+
+
+@torch.library.custom_op("ha_b200::head_ctc_bwd", mutates_args=())
+def head_ctc_bwd(h: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, saved: torch.Tensor,
+                 grad_loss: torch.Tensor, S: int, precision: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    h, weight = h.contiguous(), weight.contiguous()
+    N, T, D = h.shape
+    V = weight.shape[0]
+    b = None if bias is None else bias.to(_F32).contiguous()
+    g = grad_loss.to(_F32).contiguous()
+    _, _, bwd_b = _head_sizes(N, T, D, V, S)
+    scratch = torch.empty(bwd_b, dtype=torch.uint8, device=h.device)
+    dh = torch.empty_like(h)
+    dW = torch.empty_like(weight)
+    db = torch.empty(V, dtype=_F32, device=h.device)
+    with torch.cuda.device(h.device):
+        rc = _lib.lib().ha_head_ctc_bwd(h.data_ptr(), weight.data_ptr(), b.data_ptr() if b is not None else None,
+                                        N, T, D, V, S, g.data_ptr(), int(precision), dh.data_ptr(), dW.data_ptr(),
+                                        db.data_ptr(), saved.data_ptr(), saved.numel(), scratch.data_ptr(), bwd_b,
+                                        _stream(h))
+    _lib.check(rc, "ha_head_ctc_bwd")
+    return dh, dW, db
+
+
+@head_ctc_bwd.register_fake
+def _(h, weight, bias, saved, grad_loss, S, precision):
+    return torch.empty_like(h), torch.empty_like(weight), weight.new_empty(weight.shape[0])
+
+
+def _head_setup(ctx, inputs, output):
+    h, weight, bias, targets, _, _, precision = inputs
+    _, saved = output
+    ctx.save_for_backward(h, weight, bias, saved)
+    ctx.S = targets.shape[1]
+    ctx.precision = precision
+    ctx.has_bias = bias is not None
+
+
+def _head_backward(ctx, grad_loss, _grad_saved):
+    h, weight, bias, saved = ctx.saved_tensors
+    if grad_loss is None:
+        grad_loss = torch.zeros(h.shape[0], dtype=_F32, device=h.device)
+    dh, dW, db = head_ctc_bwd(h, weight, bias, saved, grad_loss, ctx.S, ctx.precision)
+    return dh, dW, (db if ctx.has_bias else None), None, None, None, None
+
+
+head_ctc_fwd.register_autograd(_head_backward, setup_context=_head_setup)
+
+
 def ctc_beam_search(x, in_len=None, beam_size=3, reference_ext_blank=True):
     """x (N,T,V) log-probs -> hyp (N,beam,T) i64 padded with -1 (best first), hyp_len (N,beam), score (N,beam)."""
     _check_cuda_f32(x, "log_probs")

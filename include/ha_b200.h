@@ -111,6 +111,26 @@ int ha_ctc_beam_search(const float* lp, int64_t sx_n, int64_t sx_t, int N, int T
                        const void* in_len, int lengths_i64, int beam, int reference_ext_blank,
                        int64_t* hyp, int64_t* hyp_len, float* score, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- fused classifier head + CTC: replaces, at ha/recognizer.py:43-46 + 61-82,
+ *   log_probs = classifier(features).log_softmax(-1);  loss = ctc(log_probs.permute(1,0,2), ...)
+ * with one op on the features: h (N,T,D) fp32 contiguous (dropout already applied by the caller), W (V,D) and bias (V)
+ * (nn.Linear layout; bias may be NULL).  The (N,T,V) logits, log-probs and their gradient are never written: the
+ * GEMM h W^T runs on the tensor cores (tcgen05 kind::tf32) with the log-softmax statistics and the gather of the blank
+ * and label logits as its epilogue; the backward recomputes the logits tile by tile and emits dh, dW, db from
+ * g (softmax - occupancy) through an L2-sized ring of rows.  precision: 3 = error-compensated tf32 x 3 (fp32-grade,
+ * what nn.Linear computes under torch.autocast(dtype=float32)), 1 = plain tf32 (torch's allow_tf32 = True).
+ * D and V must be multiples of 4.  `saved` is written by the forward and read by the backward; the scratch buffers
+ * are free again when the call's kernels have run.  loss (N), per utterance, as ha_ctc_fwd. */
+int ha_head_ctc_workspace_bytes(int N, int T, int D, int V, int S, size_t* saved, size_t* fwd_scratch, size_t* bwd_scratch);
+int ha_head_ctc_fwd(const float* h, const float* W, const float* bias, int N, int T, int D, int V,
+                    const void* targets, int64_t tgt_stride, int S, int targets_i64,
+                    const void* in_len, const void* tgt_len, int lengths_i64, int precision,
+                    float* loss, void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes, void* stream);
+/* dh (N,T,D), dW (V,D), db (V, may be NULL) = gradients of sum_n grad_loss[n] * loss[n] */
+int ha_head_ctc_bwd(const float* h, const float* W, const float* bias, int N, int T, int D, int V, int S,
+                    const float* grad_loss, int precision, float* dh, float* dW, float* db,
+                    void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---- CTC Viterbi forced alignment (max-semiring of ha/ctc.py:144-167; not in the reference) - */
 size_t ha_ctc_viterbi_workspace_bytes(int T, int N, int V, int S);
 /* lp (T,N,V) log-probs through (sx_t, sx_n, 1); alignment (N,T) int64 class per frame (-1 beyond
