@@ -59,10 +59,11 @@ HeadWs head_ws_layout(int N, int T, int D, int V, int S) {
     const int tiles_dw = ((V + kHM - 1) / kHM) * ((D + kHN - 1) / kHN);
     w.splits_max = tiles_dw >= 148 ? 1 : (148 / tiles_dw);
     o = 256;
-    w.d = take(sizeof(float) * (size_t)w.R * V);
+    const int Vp = round_up(V, 4);                                   // leading dimension of the class-contiguous scratch matrices
+    w.d = take(sizeof(float) * (size_t)w.R * Vp);
     w.dT = take(sizeof(float) * (size_t)V * w.R);
     w.hT = take(sizeof(float) * (size_t)D * w.R);
-    w.Wt = take(sizeof(float) * (size_t)D * V);
+    w.Wt = take(sizeof(float) * (size_t)D * Vp);
     w.part = take(sizeof(float) * (size_t)w.splits_max * V * D);
     w.bwd_total = o;
     return w;
@@ -120,7 +121,7 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, HeadGemmParams p, cu
 int check_shapes(int N, int T, int D, int V, int S) {
     if (N <= 0 || T <= 0 || D <= 0 || V <= 0 || S < 0) return host_fail(HA_ERR_INVALID_ARGUMENT, "bad sizes N=%d T=%d D=%d V=%d S=%d", N, T, D, V, S);
     if (N > 65535) return host_fail(HA_ERR_UNSUPPORTED_SHAPE, "N=%d > 65535", N);
-    if (D % 4 || V % 4) return host_fail(HA_ERR_UNSUPPORTED_SHAPE, "feature and class counts must be multiples of 4 (D=%d, V=%d)", D, V);
+    if (D % 4) return host_fail(HA_ERR_UNSUPPORTED_SHAPE, "the feature dimension must be a multiple of 4 (D=%d): rows are copied by TMA", D);
     if ((long long)N * T > 0x7fffff00ll) return host_fail(HA_ERR_UNSUPPORTED_SHAPE, "N*T too large");
     if (S > 1023) return host_fail(HA_ERR_UNSUPPORTED_SHAPE, "target length > 1023 is not supported");
     return HA_OK;
@@ -204,18 +205,18 @@ int ha_head_ctc_bwd(const float* h, const float* W, const float* bias, int N, in
     float* hT = (float*)(cb + w.hT);
     float* Wt = (float*)(cb + w.Wt);
     float* part = (float*)(cb + w.part);
-    const int R = w.R;
+    const int R = w.R, Vp = round_up(V, 4);
 
     {   // W^T (D x V): the B operand of dh = d W, contraction index (classes) contiguous
         const dim3 grid((D + 31) / 32, (V + 31) / 32), block(32, 8);
-        head_transpose_kernel<<<grid, block, 0, st>>>(W, 0, V, D, Wt, V);
+        head_transpose_kernel<<<grid, block, 0, st>>>(W, 0, V, D, Wt, Vp);
         if ((rc = host_check_launch("head_transpose_kernel(W)"))) return rc;
     }
     CUtensorMap m_h, m_W, m_d, m_Wt, m_dT, m_hT;
     if ((rc = make_map(&m_h, h, (size_t)rows, (size_t)D, (size_t)D))) return rc;
     if ((rc = make_map(&m_W, W, (size_t)V, (size_t)D, (size_t)D))) return rc;
-    if ((rc = make_map(&m_d, d, (size_t)R, (size_t)V, (size_t)V))) return rc;
-    if ((rc = make_map(&m_Wt, Wt, (size_t)D, (size_t)V, (size_t)V))) return rc;
+    if ((rc = make_map(&m_d, d, (size_t)R, (size_t)V, (size_t)Vp))) return rc;
+    if ((rc = make_map(&m_Wt, Wt, (size_t)D, (size_t)V, (size_t)Vp))) return rc;
     if ((rc = make_map(&m_dT, dT, (size_t)V, (size_t)R, (size_t)R))) return rc;
     if ((rc = make_map(&m_hT, hT, (size_t)D, (size_t)R, (size_t)R))) return rc;
 
@@ -229,7 +230,7 @@ int ha_head_ctc_bwd(const float* h, const float* W, const float* bias, int N, in
         p.meta = (const int4*)(sb + w.meta); p.cls2pos = (const int*)(sb + w.cls2pos); p.dupnext = (const int*)(sb + w.dupnext);
         p.Sp = w.Sp; p.V = V; p.em = (float*)(sb + w.em); p.E = w.E;
         p.lse2 = (const float*)(sb + w.lse2); p.loss = (const float*)(sb + w.loss); p.gout = grad_loss;
-        p.out = d; p.ldo = V; p.outT = dT; p.ldt = R;
+        p.out = d; p.ldo = Vp; p.outT = dT; p.ldt = R;
         if ((rc = launch_gemm<kEpiBwdD>(m_h, m_W, p, st, "head_gemm_kernel<bwd d>"))) return rc;
         {
             const dim3 grid((D + 31) / 32, (crp + 31) / 32), block(32, 8);

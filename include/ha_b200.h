@@ -119,7 +119,7 @@ int ha_ctc_beam_search(const float* lp, int64_t sx_n, int64_t sx_t, int N, int T
  * and label logits as its epilogue; the backward recomputes the logits tile by tile and emits dh, dW, db from
  * g (softmax - occupancy) through an L2-sized ring of rows.  precision: 3 = error-compensated tf32 x 3 (fp32-grade,
  * what nn.Linear computes under torch.autocast(dtype=float32)), 1 = plain tf32 (torch's allow_tf32 = True).
- * D and V must be multiples of 4.  `saved` is written by the forward and read by the backward; the scratch buffers
+ * D must be a multiple of 4 (feature rows are copied by TMA).  `saved` is written by the forward and read by the backward; the scratch buffers
  * are free again when the call's kernels have run.  loss (N), per utterance, as ha_ctc_fwd. */
 int ha_head_ctc_workspace_bytes(int N, int T, int D, int V, int S, size_t* saved, size_t* fwd_scratch, size_t* bwd_scratch);
 int ha_head_ctc_fwd(const float* h, const float* W, const float* bias, int N, int T, int D, int V,

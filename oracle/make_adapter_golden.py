@@ -25,6 +25,31 @@ from ha.star import star_ctc_forward_score    # noqa: E402
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
+def head_golden():
+    """The fused head's own fixture: a wider TemporalClassifier (several 128-class / 32-feature tiles, ragged
+    lengths, repeated labels), loss per utterance through the module's log_probs (ha/recognizer.py:43-46) and the
+    reference's ctc_forward_score3, gradients w.r.t. features, weight and bias for a non-uniform grad_output."""
+    from ha.ctc import ctc_forward_score3
+    torch.manual_seed(99)
+    N, T, D, V, U = 4, 150, 72, 300, 24
+    g = torch.Generator().manual_seed(23)
+    feats = torch.randn(N, T, D, generator=g, dtype=torch.float64).requires_grad_(True)
+    tg = torch.randint(1, V, (N, U), generator=g)
+    tg[1, 3:9] = tg[1, 3]                                   # repeated labels
+    il = torch.tensor([150, 120, 97, 150]); tl = torch.tensor([24, 20, 11, 1])
+    go = torch.tensor([1.0, 0.5, 2.0, 0.25], dtype=torch.float64)
+    tc = R.TemporalClassifier(D, V).double()
+    tc.dropout.p = 0.0
+    losses = ctc_forward_score3(tc.log_probs(feats).permute(1, 0, 2), tg, il, tl)
+    (losses * go).sum().backward()
+    out = {"feats": feats.detach().numpy(), "targets": tg.numpy(), "in_len": il.numpy(), "tgt_len": tl.numpy(),
+           "weight": tc.classifier.weight.detach().numpy(), "bias": tc.classifier.bias.detach().numpy(),
+           "grad_out": go.numpy(), "loss": losses.detach().numpy(), "dh": feats.grad.numpy(),
+           "dW": tc.classifier.weight.grad.numpy(), "db": tc.classifier.bias.grad.numpy()}
+    np.savez_compressed(os.path.join(OUT, "head_temporal_classifier.npz"), **out)
+    print("wrote head_temporal_classifier.npz", {k: v.shape for k, v in out.items()})
+
+
 def main():
     torch.manual_seed(4321)
     N, T, D, V, U = 5, 40, 12, 9, 6
@@ -66,6 +91,7 @@ def main():
     out["att_condtargets"] = cond.numpy(); out["att_cond_len"] = cl.numpy()
     out["att_loss"] = loss.item(); out["att_gw"] = tc.classifier.weight.grad.numpy().copy()
     np.savez_compressed(os.path.join(OUT, "adapter_temporal_classifier.npz"), **out)
+    head_golden()
     print("wrote adapter_temporal_classifier.npz", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 
 

@@ -72,6 +72,19 @@ def ctc_reduce_mean(losses, tgt_len):
     return float(np.mean(np.asarray(losses, np.float64) / np.asarray(tgt_len, np.float64)))
 
 
+def head_ctc(h, W, b, targets, in_len, tgt_len, grad_out=None):
+    """Classifier head + CTC in float64: ha/recognizer.py:43-46 (`classifier(features).log_softmax(-1)`, dropout
+    already applied) followed by ha/ctc.py:110-174, with the gradients of sum_n grad_out[n] loss[n] w.r.t. the
+    features h (N,T,D), the weight W (V,D) and the bias b (V) (chain rule through the linear layer).
+    -> (loss (N,), dh, dW, db)."""
+    h = _f64(h); W = _f64(W)
+    b = _f64(b) if b is not None else np.zeros(W.shape[0])
+    logits = h @ W.T + b                                     # (N,T,V)
+    loss, g = ctc(np.ascontiguousarray(logits.transpose(1, 0, 2)), targets, in_len, tgt_len, True, grad_out)
+    g = np.nan_to_num(g.transpose(1, 0, 2), nan=0.0, posinf=0.0, neginf=0.0)      # (N,T,V)
+    return loss, g @ W, np.einsum("ntv,ntd->vd", g, h), g.sum((0, 1))
+
+
 def star(x, targets, in_len, tgt_len, star_penalty=-0.5, from_logits=True, grad_out=None,
          want_grad=True):
     """x (T,N,V) -> (loss (N,), grad).  ha/star.py:65-163."""

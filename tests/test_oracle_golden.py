@@ -259,3 +259,15 @@ def test_beam_oracle_vs_reference_golden(name):
                 assert s == d[f"hyp_{i}_{b}"][j, :hl[j]].tolist()
             np.testing.assert_allclose(sc, d[f"score_{i}_{b}"], rtol=1e-5 if name.startswith("graves") else 1e-10,
                                        atol=1e-6 if name.startswith("graves") else 1e-12)
+
+
+# ------------------------------------------------------------ classifier head + CTC (ha/recognizer.py:43-46) ---
+def test_head_oracle_vs_reference_module_golden(oracle):
+    """oracle.head_ctc against the unmodified TemporalClassifier.log_probs + ctc_forward_score3 in float64."""
+    from conftest import golden_path
+    d = np.load(golden_path("head_temporal_classifier"))
+    loss, dh, dW, db = oracle.head_ctc(d["feats"], d["weight"], d["bias"], d["targets"], d["in_len"], d["tgt_len"], d["grad_out"])
+    np.testing.assert_allclose(loss, d["loss"], rtol=1e-11)
+    np.testing.assert_allclose(dh, d["dh"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(dW, d["dW"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(db, d["db"], rtol=1e-9, atol=1e-11)
