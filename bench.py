@@ -473,6 +473,82 @@ def measure_quick(kind, B, T, V, U, dev, scale=1.0, steps=20, warm=3):
     return out
 
 
+def measure_head(dev, B=256, T=1500, D=1024, V=1024, U=300, steps=5, warm=2):
+    """Linear -> log_softmax -> CTC as one op (haloop_b200.linear_ctc_forward_score, tcgen05 tf32 x 3)
+    on BASELINE config 2 with the reference's feat_dim (ha/recognizer.py:38), loss + gradients w.r.t. features, weight
+    and bias; beside it the unfused path on the same GPU (cuBLAS fp32 logits, allow_tf32 off as under the reference's
+    autocast(float32) -> the fused CTC kernels -> cuBLAS dW, dh).  Tensor-core bound: the roofline is in TFLOP/s."""
+    import torch
+    import torch.nn.functional as F
+    from haloop_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(7)
+    h = torch.randn(B, T, D, device=dev, generator=g)
+    W = torch.randn(V, D, device=dev, generator=g) / D ** 0.5
+    b = torch.randn(V, device=dev, generator=g) * 0.1
+    tg = torch.randint(1, V, (B, U), device=dev, generator=g)
+    il = torch.full((B,), T, dtype=torch.int64, device=dev); tl = torch.full((B,), U, dtype=torch.int64, device=dev)
+    gout = torch.ones(B, device=dev)
+
+    def fused(prec):
+        loss, saved = ops.head_ctc_fwd(h, W, b, tg, il, tl, prec)
+        ops.head_ctc_bwd(h, W, b, saved, gout, U, prec)
+        return loss
+
+    def unfused():
+        logits = F.linear(h, W, b)
+        xv = logits.permute(1, 0, 2)
+        loss, ws = ops.ctc_fwd(xv, tg, il, tl, True)
+        gl = ops.ctc_bwd(xv, ws, gout, U, True).permute(1, 0, 2).reshape(B * T, V)
+        dh = gl @ W; dW = gl.t() @ h.reshape(B * T, D); db = gl.sum(0)       # noqa: F841
+        return loss
+
+    def timed(fn):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats(dev)
+        base = torch.cuda.memory_allocated(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, float(loss.double().mean()), (torch.cuda.max_memory_allocated(dev) - base) / 1e9
+
+    sampler = ClockSampler(dev.index or 0, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
+    sampler.start()
+    ms3, loss3, mem3 = timed(lambda: fused(3))
+    clocks = sampler.stop()
+    ms1, loss1, mem1 = timed(lambda: fused(1))
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        msu, lossu, memu = timed(unfused)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        msu_tf32, _, _ = timed(unfused)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_tf32, src = float(peaks["bf16_tflops_sustained"]) / 2, "measured bf16_tflops_sustained / 2 (kind::tf32 runs at half the bf16 rate)"
+    except Exception:
+        peak_tf32, src = 2250.0 / 2, "fallback: nominal dense bf16 2250 TFLOP/s / 2"
+    gemm = 2.0 * B * T * D * V                       # one h W^T-sized contraction
+    mma3 = 4 * 3 * gemm                              # forward, recomputation, dh, dW; three tf32 products each
+    return {"config": f"head_ctc B={B} T={T} D={D} V={V} U={U} fp32 features/weights, full lengths; loss + d/dh, d/dW, d/db",
+            "ms_per_step": ms3, "value": B * T / (ms3 * 1e-3), "unit": "frames/s", "steps": steps, "warmup": warm,
+            "mean_loss": loss3, "dtype": "tf32 x 3 (fp32-grade), fp32 accumulate", "peak_extra_memory_gb": mem3,
+            "roofline": {"bound": "tensor", "achieved": mma3 / (ms3 * 1e-3) / 1e12, "peak": peak_tf32, "unit": "TFLOP/s",
+                         "frac": mma3 / (ms3 * 1e-3) / 1e12 / peak_tf32, "peak_source": src,
+                         "flops_per_step": mma3, "note": "tf32 tensor-core flops actually issued (4 contractions x 3 split "
+                         "products); the useful fp32 flops are a third of it"},
+            "single_product_tf32": {"ms_per_step": ms1, "mean_loss": loss1},
+            "unfused_same_gpu": {"what": "F.linear (cuBLAS fp32) -> ha_ctc_fwd/bwd -> cuBLAS dh, dW, db", "ms_per_step": msu,
+                                 "ms_per_step_allow_tf32": msu_tf32, "mean_loss": lossu, "peak_extra_memory_gb": memu},
+            "clocks": clocks}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -742,7 +818,7 @@ def main():
     #      N GPUs: the sweeps, which are the STRONG-scaling curve of config 5 (the headline above is weak scaling).
     extras = None
     if not args.no_extras and args.workload == "ctc" and not args.graph:
-        del sets
+        sets = sets[:1]                 # the library baseline below still needs one input set
         torch.cuda.empty_cache()
         extras = {}
         try:
@@ -751,6 +827,11 @@ def main():
                                                     ("rnnt_fg", WORKLOADS["rnnt_fg"])):
                     extras[name] = measure_quick(k2, B2, T2, V2, U2, dev)
                 extras["ctc_x3"] = measure_quick("ctc", B, T, V, U, dev, scale=3.0)
+                try:
+                    extras["head_ctc"] = measure_head(dev)
+                except Exception as e:
+                    extras["head_ctc"] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
             for k2 in ("ctc", "rnnt"):
                 r = measure_sweep(k2, rank, world, dev, 5, 2)
                 if rank == 0:

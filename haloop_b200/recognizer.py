@@ -10,14 +10,18 @@ them, fixing the two call sites that are broken or disabled at HEAD:
 import torch
 
 from .ctc import ctc_forward_score3, ctc_reduce_mean
+from .head import linear_ctc_forward_score
 from .star import star_ctc_forward_score
 from .transducer import transducer_forward_score, transducer_forward_score_fg, rnnt_loss
 
 
 def temporal_classifier_forward(self, features, targets, input_lengths=None, target_lengths=None,
                                 star_penalty=None, measure_entropy=False, drop_labels=False):
-    """TemporalClassifier.forward (ha/recognizer.py:61-82) on the fused kernels: the classifier's
-    raw logits go straight into the loss (log-softmax fused, from_logits=True)."""
+    """TemporalClassifier.forward (ha/recognizer.py:61-82) on the fused kernels.  CTC branch: the classifier itself is
+    part of the op (haloop_b200.linear_ctc_forward_score: Linear -> log_softmax -> CTC on the tensor cores, the (N,T,C)
+    logits never written) whenever the feature dimension is a multiple of 4 (`self.fused_head = False` turns it off);
+    otherwise, and on the star branch, the classifier's raw logits go straight into the loss (log-softmax fused,
+    from_logits=True)."""
     N, T = features.shape[0], features.shape[1]
     dev = features.device
     if input_lengths is None:
@@ -25,7 +29,14 @@ def temporal_classifier_forward(self, features, targets, input_lengths=None, tar
     if target_lengths is None:
         target_lengths = torch.full((N,), targets.shape[-1], dtype=torch.long, device=dev)
     with torch.autocast(device_type="cuda", enabled=False):
-        logits = self.classifier(self.dropout(features).float()).float()      # (N,T,C)
+        feats = self.dropout(features).float()
+        lin = self.classifier
+        if (star_penalty is None and getattr(self, "fused_head", True) and type(lin) is torch.nn.Linear
+                and feats.dim() == 3 and feats.shape[-1] % 4 == 0 and feats.is_cuda and targets.dim() == 2):
+            losses = linear_ctc_forward_score(feats, lin.weight.float(), None if lin.bias is None else lin.bias.float(),
+                                              targets, input_lengths, target_lengths)
+            return (losses / target_lengths.to(losses.device).clamp_min(1)).mean(), {}
+        logits = lin(feats).float()                                            # (N,T,C)
         logits = logits.permute(1, 0, 2)                                       # (T,N,C) view, no copy
         if star_penalty is None:
             losses = ctc_forward_score3(logits, targets, input_lengths, target_lengths, from_logits=True)
