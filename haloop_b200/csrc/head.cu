@@ -49,15 +49,34 @@ HeadWs head_ws_layout(int N, int T, int D, int V, int S) {
     w.stats = take(sizeof(float2) * rows * w.tiles_n);
     w.tr = take(sizeof(float) * rows * w.SPX);
     w.fwd_total = o;
-    // backward: rows are processed in chunks of R so that d, d^T and h^T of a chunk stay in L2 (32 MB each at most)
+    // backward: rows are processed in chunks of R so that d, d^T and h^T of a chunk stay in L2 (~40 MB each at most).
+    // A chunk's GEMMs are separate launches of persistent CTAs, so R is chosen to make their tile counts whole
+    // multiples of the SM count (a 512-tile launch on 148 SMs idles 13 % of the machine in its last wave).
+    const int nsm = sm_count();
     const size_t widest = (size_t)(V > D ? V : D);
-    long long R = (long long)((32u << 20) / (4 * widest)) / kHM * kHM;
-    if (R < kHM) R = kHM;
+    long long blocks = (long long)((40u << 20) / (4 * widest)) / kHM;          // row blocks of 128 that fit the budget
+    if (blocks < 1) blocks = 1;
+    {
+        auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+        const int unit = nsm / gcd(nsm, w.tiles_n);                             // row blocks per whole wave pattern
+        if (blocks >= unit) blocks = blocks / unit * unit;
+    }
+    long long R = blocks * kHM;
     const long long rows_up = (long long)round_up_sz(rows, kHM);
     if (R > rows_up) R = rows_up;
     w.R = (int)R;
+    // split-K of dW = d^T h over the chunk's rows: the split count that wastes the least of the last wave, each split
+    // keeping at least 16 k-blocks
     const int tiles_dw = ((V + kHM - 1) / kHM) * ((D + kHN - 1) / kHN);
-    w.splits_max = tiles_dw >= 148 ? 1 : (148 / tiles_dw);
+    const int nkb = (int)(R / kHK);
+    int best = 1;
+    double best_eff = 0.0;
+    for (int sp = 1; sp <= 16 && (sp == 1 || nkb / sp >= 16); ++sp) {
+        const long long t = (long long)tiles_dw * sp;
+        const double eff = (double)t / (double)(((t + nsm - 1) / nsm) * nsm);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }
+    }
+    w.splits_max = best;
     o = 256;
     const int Vp = round_up(V, 4);                                   // leading dimension of the class-contiguous scratch matrices
     w.d = take(sizeof(float) * (size_t)w.R * Vp);
@@ -162,7 +181,7 @@ int ha_head_ctc_fwd(const float* h, const float* W, const float* bias, int N, in
 
     if ((rc = ctc_prep_for_head(targets, tgt_stride, S, targets_i64, in_len, tgt_len, lengths_i64, T, N, V, w.Sp,
                                 sb + w.meta, (int*)(sb + w.order), (int*)(sb + w.tgt), (int*)(sb + w.dupnext), st))) return rc;
-    head_cls2pos_kernel<<<N, 256, 0, st>>>((const int4*)(sb + w.meta), (const int*)(sb + w.tgt), w.Sp, V, (int*)(sb + w.cls2pos));
+    head_cls2pos_kernel<<<N, 256, 0, st>>>((const int4*)(sb + w.meta), (const int*)(sb + w.tgt), (const int*)(sb + w.dupnext), w.Sp, V, (int*)(sb + w.cls2pos));
     if ((rc = host_check_launch("head_cls2pos_kernel"))) return rc;
 
     CUtensorMap ma, mb;

@@ -37,6 +37,7 @@ constexpr int kHThreads = 320;
 constexpr size_t kHSmem = 1024 + (size_t)kHStages * kHStageBytes + 256;
 
 enum { kEpiFwd = 0, kEpiBwdD = 1, kEpiStore = 2, kEpiAccum = 3 };
+constexpr int kHasDup = 0x40000000;           // cls2pos flag: the class occurs again later in the target
 
 struct HeadGemmParams {
     int M, N, K;                 // rows of A this launch covers, rows of B (= output columns), contraction length
@@ -223,23 +224,33 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                 const int col = n0 + c0 + j;
                                 if (col < p.N) {
                                     if (col == 0) erow[1] = v[j];
-                                    for (int k = __ldg(c2p + col); k >= 0; k = __ldg(nxt + k)) erow[4 + k] = v[j];
+                                    const int kf = __ldg(c2p + col);
+                                    if (kf >= 0) {
+                                        erow[4 + (kf & ~kHasDup)] = v[j];
+                                        if (kf & kHasDup)
+                                            for (int k = __ldg(nxt + (kf & ~kHasDup)); k >= 0; k = __ldg(nxt + k)) erow[4 + k] = v[j];
+                                    }
                                 }
                             }
                         }
                     } else {
-                        float dv[16];
+                        // occupancy of class col = sum over the positions that hold it.  All sixteen first-position loads of
+                        // the chunk are issued before any is used (they are scattered 4-byte reads of this thread's own
+                        // occupancy row: one at a time they cost an L2 round trip each); later occurrences are rare
+                        int kf[16];
+                        float o[16], dv[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int col = n0 + c0 + j;
-                            float d = 0.0f;
-                            if (live && col < p.N) {
-                                float o = (col == 0) ? 1.0f - erow[1] : 0.0f;
-                                for (int k = __ldg(c2p + col); k >= 0; k = __ldg(nxt + k)) o += erow[4 + k];
-                                d = g * (ex2f(fmaf(v[j], kLog2e, -l2)) - o);
-                            }
-                            dv[j] = d;
-                        }
+                        for (int j = 0; j < 16; ++j) kf[j] = (live && n0 + c0 + j < p.N) ? __ldg(c2p + n0 + c0 + j) : -1;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = (kf[j] >= 0) ? erow[4 + (kf[j] & ~kHasDup)] : 0.0f;
+                        if (live && n0 + c0 == 0) o[0] += 1.0f - erow[1];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (kf[j] >= 0 && (kf[j] & kHasDup))
+                                for (int k = __ldg(nxt + (kf[j] & ~kHasDup)); k >= 0; k = __ldg(nxt + k)) o[j] += erow[4 + k];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            dv[j] = (live && n0 + c0 + j < p.N) ? g * (ex2f(fmaf(v[j], kLog2e, -l2)) - o[j]) : 0.0f;
                         if (rl < p.M) {
                             float* drow = p.out + (size_t)rl * p.ldo + n0 + c0;
 #pragma unroll
@@ -293,8 +304,9 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------- small kernels ---
-// grid N, block 256: cls2pos[n][c] = first target position of utterance n that holds class c, else -1
-__global__ void __launch_bounds__(256) head_cls2pos_kernel(const int4* meta, const int* tgt, int Sp, int V, int* cls2pos) {
+// grid N, block 256: cls2pos[n][c] = first target position of utterance n that holds class c (| kHasDup when a later
+// position holds it too: only then is the dupnext chain walked), else -1
+__global__ void __launch_bounds__(256) head_cls2pos_kernel(const int4* meta, const int* tgt, const int* dupnext, int Sp, int V, int* cls2pos) {
     const int n = blockIdx.x;
     int* row = cls2pos + (size_t)n * V;
     for (int c = threadIdx.x; c < V; c += 256) row[c] = -1;
@@ -303,7 +315,7 @@ __global__ void __launch_bounds__(256) head_cls2pos_kernel(const int4* meta, con
     const int L = mt.z ? 0 : mt.y;
     for (int k = threadIdx.x; k < L; k += 256) {
         const int w = tgt[(size_t)n * Sp + k];
-        if (!(w & kNotFirst)) row[w & kLabelMask] = k;
+        if (!(w & kNotFirst)) row[w & kLabelMask] = k | (dupnext[(size_t)n * Sp + k] >= 0 ? kHasDup : 0);
     }
 }
 
