@@ -50,6 +50,19 @@ def run(N, T, D, V, S, seed=0, precision="tf32x3", scale=1.0, time_it=False, che
         ev[2].record()
         torch.cuda.synchronize()
         print(f"   fwd {ev[0].elapsed_time(ev[1]):.3f} ms  bwd {ev[1].elapsed_time(ev[2]):.3f} ms", flush=True)
+        from haloop_b200 import ops
+        loss, saved = ops.head_ctc_fwd(h, W, b, tg, il, tl, ops._PRECISION[precision])
+        gout = torch.ones(N, device="cuda")
+        for i in range(8):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            ops.head_ctc_bwd(h, W, b, saved, gout, S, ops._PRECISION[precision])
+            e1.record()
+            t1 = time.perf_counter()
+            torch.cuda.synchronize()
+            print(f"   bwd op {i}: gpu {e0.elapsed_time(e1):.2f} ms, host call {1e3 * (t1 - t0):.2f} ms", flush=True)
 
 
 if __name__ == "__main__":
