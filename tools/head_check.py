@@ -80,5 +80,7 @@ if __name__ == "__main__":
         run(256, 1500, 1024, 1024, 300, time_it=True)
     elif which == "perf":
         run(256, 1500, 1024, 1024, 300, time_it=True, check=False)
+    elif which == "prof":          # one forward + backward of a quarter batch (1 + 3 x 21 GEMM launches; ncu takes the first six)
+        run(64, 1500, 1024, 1024, 300, check=False)
     elif which == "perf1":
         run(256, 1500, 1024, 1024, 300, time_it=True, check=False, precision="tf32")

@@ -5,7 +5,7 @@ import json, os, re, sys
 R = sys.argv[1] if len(sys.argv) > 1 else "r01"
 root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles")
 out = {}
-for w in ("ctc", "star", "rnnt", "rnnt_fg"):
+for w in ("ctc", "star", "rnnt", "rnnt_fg", "head"):
     path = os.path.join(root, f"ncu_{w}_{R}.txt")
     if not os.path.exists(path):
         continue

@@ -19,6 +19,11 @@ want = [
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu_pct"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu_pct"),
     ("smsp__inst_executed.sum", "warp_insts"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pct"),
+    ("sm__pipe_tensor_subpipe_tmem_cycles_active.avg.pct_of_peak_sustained_active", "tensor_tmem_pct"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem_wavefront_pct"),
+    ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
     ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall_barrier"),
     ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_sb"),
     ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_sb"),
