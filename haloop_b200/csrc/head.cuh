@@ -18,9 +18,12 @@
 //   warps 2-5   split warps: kind::tf32 reads only the top 19 bits of an fp32 word, so the raw tile IS the high half;
 //               these warps write the low half  x - tf32(x)  of both operand tiles (same swizzled positions, so the
 //               pass is layout-blind) for the error-compensated 3-product  a b ~ ah bh + al bh + ah bl
-//   warps 6-9   epilogue: tcgen05.ld of the finished accumulator (double-buffered in TMEM: 2 x [MAIN 128 | SMALL 128]
-//               columns, so the epilogue of tile i runs under the MMAs of tile i+1)
-// ah bh goes to MAIN, the two cross products (2^-11 of the magnitude) to SMALL; the epilogue adds them in fp32.
+//   warps 6-9   epilogue.  TMEM holds [MAIN0 | MAIN1 | SMALL | SUM] x 128 columns: ah bh accumulates into MAIN[c & 1] for
+//               chunk c of 8 k-blocks, the two cross products (2^-11 of the magnitude) into SMALL for the whole tile; the
+//               epilogue warps fold each finished chunk into SUM with round-to-nearest fp32 adds (the tensor core adds
+//               into its accumulator by truncation: one accumulator over K = 1024 .. 10^4 drifts by ~half an ulp per
+//               MMA), add SMALL at the last chunk, release the buffers and run the contraction's epilogue from SUM
+//               while the MMA warp is already two chunks into the next tile.
 #pragma once
 #include <cuda.h>
 
@@ -34,6 +37,7 @@ constexpr int kHStages = 3;
 constexpr int kHTile = kHM * kHK * 4;               // bytes of one operand tile (16 KB)
 constexpr int kHStageBytes = 4 * kHTile;            // [A raw | B raw | A low | B low]
 constexpr int kHThreads = 320;
+constexpr int kHChunkKb = 8;                        // k-blocks per accumulation chunk (K = 256: 32 accumulating MMAs)
 constexpr size_t kHSmem = 1024 + (size_t)kHStages * kHStageBytes + 256;
 
 enum { kEpiFwd = 0, kEpiBwdD = 1, kEpiStore = 2, kEpiAccum = 3 };
@@ -78,14 +82,16 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint64_t* raw_full = bars;                      // [kHStages] TMA -> split warps, MMA
     uint64_t* lo_full = bars + kHStages;            // [kHStages] split warps -> MMA
     uint64_t* empty = bars + 2 * kHStages;          // [kHStages] MMA -> TMA
-    uint64_t* acc_full = bars + 3 * kHStages;       // [2] MMA -> epilogue
-    uint64_t* acc_empty = acc_full + 2;             // [2] epilogue -> MMA
-    uint32_t* s_tmem = (uint32_t*)(acc_empty + 2);
+    uint64_t* acc_full = bars + 3 * kHStages;       // [2] MMA -> epilogue: chunk finished in MAIN[b]
+    uint64_t* acc_empty = acc_full + 2;             // [2] epilogue -> MMA: MAIN[b] folded into SUM
+    uint64_t* small_empty = acc_empty + 2;          // [1] epilogue -> MMA: SMALL folded into SUM (once per tile)
+    uint32_t* s_tmem = (uint32_t*)(small_empty + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         for (int s = 0; s < kHStages; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&lo_full[s], 128); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+        mbar_init(small_empty, 128);
     }
     if (warp == 1) tmem_alloc(s_tmem, 512);
     mbar_init_fence();
@@ -115,35 +121,40 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(kHM, kHN);
-            uint32_t it = 0, lt = 0;
+            uint32_t it = 0, lt = 0, gc = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
                 const int sp = tile / (p.tiles_n * p.tiles_m);
                 const int kb0 = sp * p.kb_per_split, kb1 = min(nkb_all, kb0 + p.kb_per_split);
-                const uint32_t buf = lt & 1u;
-                mbar_wait(&acc_empty[buf], ((lt >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t d_main = tmem + buf * 256u, d_small = d_main + 128u;
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % kHStages;
-                    const uint32_t ph = (it / kHStages) & 1u;
-                    mbar_wait(&raw_full[s], ph);
-                    if (p.nprod == 3) mbar_wait(&lo_full[s], ph);
+                const uint32_t d_small = tmem + 256u;
+                for (int kc = kb0; kc < kb1; kc += kHChunkKb, ++gc) {
+                    // a chunk of kHChunkKb k-blocks accumulates into MAIN[gc & 1]; the epilogue warps fold it into SUM
+                    const uint32_t b = gc & 1u;
+                    mbar_wait(&acc_empty[b], ((gc >> 1) & 1u) ^ 1u);
+                    if (kc == kb0 && p.nprod == 3) mbar_wait(small_empty, (lt & 1u) ^ 1u);
                     tc_fence_after();
-                    const uint32_t st = base + (uint32_t)s * kHStageBytes;
+                    const uint32_t d_main = tmem + b * 128u;
+                    const int kce = min(kb1, kc + kHChunkKb);
+                    for (int kb = kc; kb < kce; ++kb, ++it) {
+                        const int s = it % kHStages;
+                        const uint32_t ph = (it / kHStages) & 1u;
+                        mbar_wait(&raw_full[s], ph);
+                        if (p.nprod == 3) mbar_wait(&lo_full[s], ph);
+                        tc_fence_after();
+                        const uint32_t st = base + (uint32_t)s * kHStageBytes;
 #pragma unroll
-                    for (int ks = 0; ks < kHK / 8; ++ks) {
-                        const uint64_t ah = umma_desc_sw128(st + ks * 32), bh = umma_desc_sw128(st + kHTile + ks * 32);
-                        const uint32_t acc = (kb > kb0 || ks > 0) ? 1u : 0u;
-                        umma_tf32(d_main, ah, bh, idesc, acc);
-                        if (p.nprod == 3) {
-                            const uint64_t al = umma_desc_sw128(st + 2 * kHTile + ks * 32), bl = umma_desc_sw128(st + 3 * kHTile + ks * 32);
-                            umma_tf32(d_small, al, bh, idesc, acc);
-                            umma_tf32(d_small, ah, bl, idesc, 1u);
+                        for (int ks = 0; ks < kHK / 8; ++ks) {
+                            const uint64_t ah = umma_desc_sw128(st + ks * 32), bh = umma_desc_sw128(st + kHTile + ks * 32);
+                            umma_tf32(d_main, ah, bh, idesc, (kb > kc || ks > 0) ? 1u : 0u);
+                            if (p.nprod == 3) {
+                                const uint64_t al = umma_desc_sw128(st + 2 * kHTile + ks * 32), bl = umma_desc_sw128(st + 3 * kHTile + ks * 32);
+                                umma_tf32(d_small, al, bh, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+                                umma_tf32(d_small, ah, bl, idesc, 1u);
+                            }
                         }
+                        umma_commit(&empty[s]);
                     }
-                    umma_commit(&empty[s]);
+                    umma_commit(&acc_full[b]);
                 }
-                umma_commit(&acc_full[buf]);
             }
         }
     } else if (warp < 6) {
@@ -170,13 +181,42 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     } else {
         const int q = warp & 3;                                  // TMEM lanes [32 q, 32 q + 32) belong to this warp
-        uint32_t lt = 0;
+        uint32_t lt = 0, gc = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
             const int nb = tile % p.tiles_n, mb = (tile / p.tiles_n) % p.tiles_m, sp = tile / (p.tiles_n * p.tiles_m);
-            const uint32_t buf = lt & 1u;
-            mbar_wait(&acc_full[buf], (lt >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t trow = tmem + buf * 256u + ((uint32_t)(32 * q) << 16);
+            const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+            const uint32_t trow = tlane + 384u;                   // SUM: what the epilogue below reads
+            {
+                // fold every finished chunk into SUM with round-to-nearest fp32 adds (the tensor core accumulates by
+                // truncation: one accumulator over a long K drifts by ~half an ulp per MMA); SMALL joins at the last one
+                const int kb0 = sp * p.kb_per_split, kb1 = min(nkb_all, kb0 + p.kb_per_split);
+                for (int kc = kb0; kc < kb1; kc += kHChunkKb, ++gc) {
+                    const uint32_t b = gc & 1u;
+                    const bool first = kc == kb0, last = kc + kHChunkKb >= kb1;
+                    if (lane == 0) mbar_wait(&acc_full[b], (gc >> 1) & 1u);
+                    __syncwarp();
+                    tc_fence_after();
+                    for (int c0 = 0; c0 < kHN && nb * kHN + c0 < p.N; c0 += 16) {
+                        float a[16], su[16], sm[16];
+                        tmem_ld16_nowait(tlane + b * 128u + c0, a);
+                        if (!first) tmem_ld16_nowait(trow + c0, su);
+                        if (last && p.nprod == 3) tmem_ld16_nowait(tlane + 256u + c0, sm);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float r = a[j];
+                            if (last && p.nprod == 3) r += sm[j];
+                            if (!first) r += su[j];
+                            a[j] = r;
+                        }
+                        tmem_st16_nowait(trow + c0, a);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[b]);
+                    if (last && p.nprod == 3) mbar_arrive(small_empty);
+                }
+            }
             const int rl = mb * kHM + 32 * q + lane;             // row inside this launch's A range
             const int n0 = nb * kHN;
 
@@ -197,16 +237,15 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 float* erow = p.em + (size_t)row * p.E;
                 float m = -CUDART_INF_F, ssum = 0.0f;
                 for (int c0 = 0; c0 < kHN && n0 + c0 < p.N; c0 += 16) {
-                    float a[16], b[16];
+                    float a[16];
                     tmem_ld16_nowait(trow + c0, a);
-                    if (p.nprod == 3) tmem_ld16_nowait(trow + 128 + c0, b);
                     tmem_ld_wait();
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int col = n0 + c0 + j;
                         const float bj = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.0f;
-                        v[j] = (p.nprod == 3 ? a[j] + b[j] : a[j]) + bj;
+                        v[j] = a[j] + bj;
                     }
                     if (EPI == kEpiFwd) {
                         float cm = -CUDART_INF_F;
@@ -271,19 +310,15 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 float* orow = (EPI == kEpiAccum) ? p.out + ((size_t)sp * p.M + rl) * p.ldo + n0
                                                  : p.out + ((size_t)p.a_row0 + rl) * p.ldo + n0;
                 for (int c0 = 0; c0 < kHN && n0 + c0 < p.N; c0 += 16) {
-                    float a[16], b[16];
+                    float a[16];
                     tmem_ld16_nowait(trow + c0, a);
-                    if (p.nprod == 3) tmem_ld16_nowait(trow + 128 + c0, b);
                     tmem_ld_wait();
                     if (rl < p.M && (EPI == kEpiAccum || p.a_row0 + rl < p.rows_total)) {
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
                             if (n0 + c0 + 4 * j4 >= p.N) continue;
                             float4 o;
-                            o.x = p.nprod == 3 ? a[4 * j4] + b[4 * j4] : a[4 * j4];
-                            o.y = p.nprod == 3 ? a[4 * j4 + 1] + b[4 * j4 + 1] : a[4 * j4 + 1];
-                            o.z = p.nprod == 3 ? a[4 * j4 + 2] + b[4 * j4 + 2] : a[4 * j4 + 2];
-                            o.w = p.nprod == 3 ? a[4 * j4 + 3] + b[4 * j4 + 3] : a[4 * j4 + 3];
+                            o.x = a[4 * j4]; o.y = a[4 * j4 + 1]; o.z = a[4 * j4 + 2]; o.w = a[4 * j4 + 3];
                             float4* dst = (float4*)(orow + c0 + 4 * j4);
                             if (EPI == kEpiAccum && p.accumulate) {
                                 const float4 old = *dst;
@@ -294,8 +329,6 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);
         }
     }
     tc_fence_before();
