@@ -19,7 +19,7 @@
 //               these warps write the low half  x - tf32(x)  of both operand tiles (same swizzled positions, so the
 //               pass is layout-blind) for the error-compensated 3-product  a b ~ ah bh + al bh + ah bl
 //   warps 6-9   epilogue.  TMEM holds [MAIN0 | MAIN1 | SMALL | SUM] x 128 columns: ah bh accumulates into MAIN[c & 1] for
-//               chunk c of 8 k-blocks, the two cross products (2^-11 of the magnitude) into SMALL for the whole tile; the
+//               chunk c of 16 k-blocks, the two cross products (2^-11 of the magnitude) into SMALL for the whole tile; the
 //               epilogue warps fold each finished chunk into SUM with round-to-nearest fp32 adds (the tensor core adds
 //               into its accumulator by truncation: one accumulator over K = 1024 .. 10^4 drifts by ~half an ulp per
 //               MMA), add SMALL at the last chunk, release the buffers and run the contraction's epilogue from SUM
@@ -37,7 +37,7 @@ constexpr int kHStages = 3;
 constexpr int kHTile = kHM * kHK * 4;               // bytes of one operand tile (16 KB)
 constexpr int kHStageBytes = 4 * kHTile;            // [A raw | B raw | A low | B low]
 constexpr int kHThreads = 320;
-constexpr int kHChunkKb = 8;                        // k-blocks per accumulation chunk (K = 256: 32 accumulating MMAs)
+constexpr int kHChunkKb = 16;                       // k-blocks per accumulation chunk (K = 512: 64 accumulating MMAs)
 constexpr size_t kHSmem = 1024 + (size_t)kHStages * kHStageBytes + 256;
 
 enum { kEpiFwd = 0, kEpiBwdD = 1, kEpiStore = 2, kEpiAccum = 3 };
