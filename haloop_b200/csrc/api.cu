@@ -1,5 +1,7 @@
 // api.cu — the C ABI of libha_b200.so (include/ha_b200.h): argument checks, workspace carving,
 // kernel selection and launches.  No allocation, no synchronisation, no global state.
+#include <cuda.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -88,6 +90,26 @@ int common_checks(const void* x, int T, int N, int V, int S, const void* ws, siz
     if (!aligned16(ws)) return fail(HA_ERR_INVALID_ARGUMENT, "workspace must be 16-byte aligned");
     if (ws_bytes < need) return fail(HA_ERR_WORKSPACE_TOO_SMALL, "workspace %zu < %zu", ws_bytes, need);
     return HA_OK;
+}
+
+// one contraction of the joint-free RNN-T on the GEMM engine: every utterance is a batch entry of the same two tensor maps
+template <int MODE>
+int fg_engine_launch(const float* A, size_t a_rows, size_t a_cols, const float* B, size_t b_rows, size_t b_cols,
+                            int batches, int tiles_m, int ncols, int K, const FgUmmaParams& q, cudaStream_t st, const char* what) {
+    alignas(64) CUtensorMap ma, mb;
+    int rc;
+    if ((rc = host_make_map(&ma, A, (size_t)batches * a_rows, a_cols, a_cols))) return rc;
+    if ((rc = host_make_map(&mb, B, (size_t)batches * b_rows, b_cols, b_cols))) return rc;
+    if ((rc = set_smem(umma_gemm_kernel<FgEpi<MODE>>, kHSmem, what))) return rc;
+    GemmCore c{};
+    c.N = ncols; c.K = K; c.a_row0 = 0; c.nprod = 3; c.chunk_kb = kFgChunkKb;
+    c.tiles_m = tiles_m; c.tiles_n = (ncols + kHN - 1) / kHN; c.splits = 1; c.kb_per_split = (K + kHK - 1) / kHK;
+    c.batches = batches; c.a_batch_rows = (int)a_rows; c.b_batch_rows = (int)b_rows;
+    const int ntiles = c.tiles_m * c.tiles_n * batches;
+    const int grid = ntiles < host_sm_count() ? ntiles : host_sm_count();
+    FgEpi<MODE> epi{q};
+    umma_gemm_kernel<FgEpi<MODE>><<<grid, kHThreads, kHSmem, st>>>(ma, mb, c, epi);
+    return check_launch(what);
 }
 
 }  // namespace
@@ -523,10 +545,8 @@ int ha_rnnt_bwd(const float* joint, int N, int T, int U1, int V,
 // ------------------------------------------------------------- joint-free (factored) RNN-T ---
 // The three contractions run on the tensor cores (rnnt_fg_umma.cuh) when the class count tiles evenly; the fp32 SIMT
 // kernels of rnnt_fg.cuh remain for every other shape.
-static int fg_umma_nt(int V) {            // accumulator columns per CTA for the two gradient GEMMs (0: not eligible)
-    if (V % 16 != 0) return 0;
-    for (int nt = 64; nt >= 16; nt >>= 1) if (V % nt == 0) return nt;      // 3 x 64 TMEM columns: two CTAs per SM
-    return 0;
+static int fg_umma_nt(int V) {            // tensor-core path of the joint-free RNN-T: rows of F / G must be TMA-copyable
+    return (V % 16 == 0) ? 128 : 0;       // (16-byte aligned rows; a multiple of 16 keeps every padded extent aligned too)
 }
 
 size_t ha_rnnt_fg_workspace_bytes(int N, int T, int U1, int V) {
@@ -593,14 +613,10 @@ int ha_rnnt_fg_fwd(const float* f, const float* g, int N, int T, int U1, int V,
         const FgUmmaParams q = fg_umma_params(p, uw, base + w.total);
         fg_rows_kernel<<<dim3((uw.Tp + uw.Um + 7) / 8, N), 256, 0, st>>>(q);
         if ((rc = check_launch("fg_rows_kernel"))) return rc;
-        FgGemmParams gp{};
-        gp.Ah = q.Fh; gp.Al = q.Fl; gp.lda = V; gp.a_batch = (size_t)uw.Tp * V;
-        gp.Bh = q.Gh; gp.Bl = q.Gl; gp.ldb = V; gp.b_batch = (size_t)uw.Um * V;
-        gp.K = V; gp.NT = uw.Uk <= 160 ? uw.Uk : 128; gp.q = q;
-        const size_t smem = fg_gemm_smem(gp.NT);
-        if ((rc = set_smem(fg_umma_gemm_kernel<kUmmaE>, smem, "fg_umma_gemm<E>"))) return rc;
-        fg_umma_gemm_kernel<kUmmaE><<<dim3(uw.Tp / kUM, uw.Uk / gp.NT, N), 128, smem, st>>>(gp);
-        if ((rc = check_launch("fg_umma_gemm_kernel<E>"))) return rc;
+        // E = F G^T: rows of F (Tp per utterance) x rows of G (Um per utterance, Uk columns of E used), K = V
+        if ((rc = fg_engine_launch<kUmmaE>(q.Fh, uw.Tp, V, q.Gh, uw.Um, V, N, uw.Tp / kHM, uw.Uk, V, q, st, "umma_gemm_kernel<fg E>"))) return rc;
+        fg_arc_kernel<<<dim3((T + 7) / 8, N), 256, 0, st>>>(q);
+        if ((rc = check_launch("fg_arc_kernel"))) return rc;
     } else {
         rnnt_fg_stats_kernel<<<dim3((T + U1 + 7) / 8, N), 256, 0, st>>>(p);
         if ((rc = check_launch("rnnt_fg_stats_kernel"))) return rc;
@@ -638,29 +654,18 @@ int ha_rnnt_fg_bwd(const float* f, const float* g, int N, int T, int U1, int V,
         // (the forward call took the same branch: it depends on V and on the alignment of f and g only)
         const FgUmmaWs uw = fg_umma_ws_layout(N, T, U1, V);
         const FgUmmaParams q = fg_umma_params(p, uw, base + w.total);
-        FgTransposeParams tp{q.Fh, q.Fl, q.Fth, q.Ftl, uw.Tp, V, uw.Tk, uw.Tp};
-        fg_transpose_kernel<<<dim3((V + 31) / 32, (uw.Tk + 31) / 32, 2 * N), dim3(32, 8), 0, st>>>(tp);
+        FgTransposeParams tp{q.Fh, q.Fth, uw.Tp, V, uw.Tk, uw.Tp};
+        fg_transpose_kernel<<<dim3((V + 31) / 32, (uw.Tk + 31) / 32, N), dim3(32, 8), 0, st>>>(tp);
         if ((rc = check_launch("fg_transpose_kernel<F>"))) return rc;
-        FgTransposeParams tg{q.Gh, q.Gl, q.Gth, q.Gtl, uw.Um, V, uw.Uk, uw.Um};
-        fg_transpose_kernel<<<dim3((V + 31) / 32, (uw.Uk + 31) / 32, 2 * N), dim3(32, 8), 0, st>>>(tg);
+        FgTransposeParams tg{q.Gh, q.Gth, uw.Um, V, uw.Uk, uw.Um};
+        fg_transpose_kernel<<<dim3((V + 31) / 32, (uw.Uk + 31) / 32, N), dim3(32, 8), 0, st>>>(tg);
         if ((rc = check_launch("fg_transpose_kernel<G>"))) return rc;
         fg_w_kernel<<<dim3((uw.Tp + 7) / 8, N), 256, 0, st>>>(q);
         if ((rc = check_launch("fg_w_kernel"))) return rc;
-        const size_t smem = fg_gemm_smem(nt);
-        FgGemmParams df{};
-        df.Ah = q.Wh; df.Al = q.Wl; df.lda = uw.Uk; df.a_batch = (size_t)uw.Tp * uw.Uk;
-        df.Bh = q.Gth; df.Bl = q.Gtl; df.ldb = uw.Uk; df.b_batch = (size_t)V * uw.Uk;
-        df.K = uw.Uk; df.NT = nt; df.q = q;
-        if ((rc = set_smem(fg_umma_gemm_kernel<kUmmaDF>, smem, "fg_umma_gemm<DF>"))) return rc;
-        fg_umma_gemm_kernel<kUmmaDF><<<dim3(uw.Tp / kUM, V / nt, N), 128, smem, st>>>(df);
-        if ((rc = check_launch("fg_umma_gemm_kernel<DF>"))) return rc;
-        FgGemmParams dg{};
-        dg.Ah = q.Wth; dg.Al = q.Wtl; dg.lda = uw.Tk; dg.a_batch = (size_t)uw.Um * uw.Tk;
-        dg.Bh = q.Fth; dg.Bl = q.Ftl; dg.ldb = uw.Tk; dg.b_batch = (size_t)V * uw.Tk;
-        dg.K = uw.Tk; dg.NT = nt; dg.q = q;
-        if ((rc = set_smem(fg_umma_gemm_kernel<kUmmaDG>, smem, "fg_umma_gemm<DG>"))) return rc;
-        fg_umma_gemm_kernel<kUmmaDG><<<dim3(uw.Um / kUM, V / nt, N), 128, smem, st>>>(dg);
-        if ((rc = check_launch("fg_umma_gemm_kernel<DG>"))) return rc;
+        // DF = (W G) (.) F: rows of W (Tp x Uk) x rows of G^T (V x Uk), K = Uk;  DG = (W^T F) (.) G: rows of W^T (Um x Tk) x
+        // rows of F^T (V x Tk), K = Tk
+        if ((rc = fg_engine_launch<kUmmaDF>(q.Wh, uw.Tp, uw.Uk, q.Gth, V, uw.Uk, N, uw.Tp / kHM, V, uw.Uk, q, st, "umma_gemm_kernel<fg DF>"))) return rc;
+        if ((rc = fg_engine_launch<kUmmaDG>(q.Wth, uw.Um, uw.Tk, q.Fth, V, uw.Tk, N, uw.Um / kHM, V, uw.Tk, q, st, "umma_gemm_kernel<fg DG>"))) return rc;
     } else {
         rnnt_fg_gemm_kernel<kDF><<<dim3((T + kGM - 1) / kGM, (V + kGN - 1) / kGN, N), 256, 0, st>>>(p);
         if ((rc = check_launch("rnnt_fg_gemm_kernel<DF>"))) return rc;

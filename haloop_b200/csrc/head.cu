@@ -120,20 +120,23 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, HeadGemmParams p, cu
     int dev = 0;
     cudaGetDevice(&dev);
     if (!done[dev & 7]) {
-        cudaError_t e = cudaFuncSetAttribute(head_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmem);
+        cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<HeadEpi<EPI>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmem);
         if (e != cudaSuccess) return host_fail(HA_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
         done[dev & 7] = true;
     }
-    p.tiles_m = (p.M + kHM - 1) / kHM;
-    p.tiles_n = (p.N + kHN - 1) / kHN;
+    GemmCore c{};
+    c.N = p.N; c.K = p.K; c.a_row0 = p.a_row0; c.nprod = p.nprod; c.chunk_kb = kHChunkKb;
+    c.batches = 1; c.a_batch_rows = 0; c.b_batch_rows = 0;
+    c.tiles_m = (p.M + kHM - 1) / kHM;
+    c.tiles_n = (p.N + kHN - 1) / kHN;
     const int nkb = (p.K + kHK - 1) / kHK;
-    if (p.splits < 1) p.splits = 1;
-    if (p.splits > nkb) p.splits = nkb;
-    p.kb_per_split = (nkb + p.splits - 1) / p.splits;
-    p.splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;          // no empty split
-    const int ntiles = p.tiles_m * p.tiles_n * p.splits;
+    c.splits = p.splits < 1 ? 1 : (p.splits > nkb ? nkb : p.splits);
+    c.kb_per_split = (nkb + c.splits - 1) / c.splits;
+    c.splits = (nkb + c.kb_per_split - 1) / c.kb_per_split;          // no empty split
+    const int ntiles = c.tiles_m * c.tiles_n * c.splits;
     const int grid = ntiles < sm_count() ? ntiles : sm_count();
-    head_gemm_kernel<EPI><<<grid, kHThreads, kHSmem, st>>>(a, b, p);
+    HeadEpi<EPI> epi{p};
+    umma_gemm_kernel<HeadEpi<EPI>><<<grid, kHThreads, kHSmem, st>>>(a, b, c, epi);
     return host_check_launch(what);
 }
 
@@ -147,6 +150,10 @@ int check_shapes(int N, int T, int D, int V, int S) {
 }
 
 }  // namespace
+
+int host_make_map(void* map, const float* ptr, size_t rows, size_t cols, size_t ld) { return make_map((CUtensorMap*)map, ptr, rows, cols, ld); }
+int host_sm_count() { return sm_count(); }
+
 }  // namespace hab
 
 using namespace hab;

@@ -33,4 +33,10 @@ int ctc_prep_for_head(const void* targets, int64_t tgt_stride, int S, int target
 int ctc_trellis_for_head(int T, int N, int S, int Sp, int E, int SPX, int JWp, const void* meta, const int* order,
                          const int* tgt, float* em, float* tr, float* loss, float* loss_ws, cudaStream_t st);
 
+// ---- tensor maps for the GEMM engine (head.cu) ----
+// (rows x cols) fp32 matrix, cols contiguous (the contraction index), leading dimension ld floats; box 128 rows x 32 cols,
+// SWIZZLE_128B.  `map` points at a CUtensorMap.
+int host_make_map(void* map, const float* ptr, size_t rows, size_t cols, size_t ld);
+int host_sm_count();
+
 }  // namespace hab
