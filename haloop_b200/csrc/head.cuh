@@ -65,16 +65,18 @@ struct HeadEpi {
             const int* nxt = p.dupnext + (size_t)n * p.Sp;
             float* erow = p.em + (size_t)row * p.E;
             float m = -CUDART_INF_F, ssum = 0.0f;
-            if (EPI == kEpiFwd) {
-                for (int c0 = 0; c0 < kHN && n0 + c0 < p.N; c0 += 16) {
-                    float v[16];
-                    tmem_ld16_nowait(trow + c0, v);
-                    tmem_ld_wait();
+            for (int c0 = 0; c0 < kHN && n0 + c0 < p.N; c0 += 16) {
+                float a[16];
+                tmem_ld16_nowait(trow + c0, a);
+                tmem_ld_wait();
+                float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int col = n0 + c0 + j;
-                        v[j] += (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.0f;
-                    }
+                for (int j = 0; j < 16; ++j) {
+                    const int col = n0 + c0 + j;
+                    const float bj = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+                    v[j] = a[j] + bj;
+                }
+                if (EPI == kEpiFwd) {
                     float cm = -CUDART_INF_F;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) if (n0 + c0 + j < p.N) cm = fmaxf(cm, v[j]);
@@ -99,35 +101,24 @@ struct HeadEpi {
                             }
                         }
                     }
-                }
-            } else {
-                // occupancy of class col = sum over the positions that hold it: scattered 4-byte reads of this thread's own
-                // occupancy row.  The sixteen first-position loads of a chunk are issued together, and one chunk AHEAD of
-                // the accumulators they are combined with, so their latency (an L2 / DRAM round trip) hides behind the
-                // TMEM load, the exponentials and the stores of the current chunk; later occurrences of a class are rare.
-                auto gather = [&](int c0, float (&o)[16]) {
+                } else {
+                    // occupancy of class col = sum over the positions that hold it.  All sixteen first-position loads of
+                    // the chunk are issued before any is used (they are scattered 4-byte reads of this thread's own
+                    // occupancy row: one at a time they cost an L2 round trip each); later occurrences are rare
                     int kf[16];
-                    const bool on = live && c0 < kHN;
+                    float o[16], dv[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) kf[j] = (on && n0 + c0 + j < p.N) ? __ldg(c2p + n0 + c0 + j) : -1;
+                    for (int j = 0; j < 16; ++j) kf[j] = (live && n0 + c0 + j < p.N) ? __ldg(c2p + n0 + c0 + j) : -1;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) o[j] = (kf[j] >= 0) ? erow[4 + (kf[j] & ~kHasDup)] : 0.0f;
-                    if (on && n0 + c0 == 0) o[0] += 1.0f - erow[1];
+                    if (live && n0 + c0 == 0) o[0] += 1.0f - erow[1];
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if (kf[j] >= 0 && (kf[j] & kHasDup))
                             for (int k = __ldg(nxt + (kf[j] & ~kHasDup)); k >= 0; k = __ldg(nxt + k)) o[j] += erow[4 + k];
-                };
-                auto emit = [&](int c0, const float (&o)[16]) {
-                    float v[16], dv[16];
-                    tmem_ld16_nowait(trow + c0, v);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int col = n0 + c0 + j;
-                        const float bj = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.0f;
-                        dv[j] = (live && col < p.N) ? g * (ex2f(fmaf(v[j] + bj, kLog2e, -l2)) - o[j]) : 0.0f;
-                    }
+                    for (int j = 0; j < 16; ++j)
+                        dv[j] = (live && n0 + c0 + j < p.N) ? g * (ex2f(fmaf(v[j], kLog2e, -l2)) - o[j]) : 0.0f;
                     if (rl < p.M) {
                         float* drow = p.out + (size_t)rl * p.ldo + n0 + c0;
 #pragma unroll
@@ -140,16 +131,6 @@ struct HeadEpi {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (n0 + c0 + j < p.N) p.outT[(size_t)(n0 + c0 + j) * p.ldt + rl] = dv[j];
-                    }
-                };
-                float oA[16], oB[16];
-                gather(0, oA);
-                for (int c0 = 0; c0 < kHN && n0 + c0 < p.N; c0 += 32) {
-                    gather(c0 + 16, oB);
-                    emit(c0, oA);
-                    if (c0 + 16 < kHN && n0 + c0 + 16 < p.N) {
-                        gather(c0 + 32, oA);
-                        emit(c0 + 16, oB);
                     }
                 }
             }
