@@ -25,5 +25,20 @@ hb.transducer_forward_score(j, torch.randint(0, 8, (1, 199), generator=g).to(dev
 lp = torch.randn(3, 50, 20, generator=g).log_softmax(-1).to(dev)
 hb.greedy_decode(lp, torch.tensor([50, 40, 3]).to(dev))
 hb.ctc_viterbi_align(lp.permute(1, 0, 2), torch.randint(1, 20, (3, 8), generator=g).to(dev), torch.tensor([50, 40, 30]).to(dev), torch.tensor([8, 5, 2]).to(dev))
+hb.ctc_beam_search_decode_logits(lp, 4, torch.tensor([50, 40, 3]).to(dev), graves=True)
+hb.ctc_beam_search_decode_logits(lp[0, :9], 3)
+# fused classifier head + CTC (tensor-core GEMM engine; V = 40 also takes the joint-free RNN-T through it above when V % 16 == 0)
+for (N, T, D, V, S) in [(3, 70, 64, 40, 7), (2, 130, 100, 260, 11)]:
+    h = torch.randn(N, T, D, generator=g).to(dev).requires_grad_(True)
+    W = (torch.randn(V, D, generator=g) / D ** 0.5).to(dev).requires_grad_(True)
+    b = torch.randn(V, generator=g).to(dev).requires_grad_(True)
+    tg = torch.randint(1, V, (N, S), generator=g).to(dev)
+    il = torch.tensor([T, T - 9, T // 2][:N]).to(dev); tl = torch.tensor([S, S // 2, 1][:N]).to(dev)
+    hb.linear_ctc_forward_score(h, W, b, tg, il, tl).sum().backward()
+for (N, T, U, V) in [(2, 140, 9, 32)]:                                                 # joint-free RNN-T on the engine (V % 16 == 0)
+    f = torch.randn(N, T, V, generator=g).to(dev).requires_grad_(True)
+    gg = torch.randn(N, U + 1, V, generator=g).to(dev).requires_grad_(True)
+    tg = torch.randint(1, V, (N, U), generator=g).to(dev)
+    hb.transducer_forward_score_fg(f, gg, tg, torch.tensor([T, T - 30]).to(dev), torch.tensor([U, U // 2]).to(dev)).sum().backward()
 torch.cuda.synchronize()
 print("done")
