@@ -10,6 +10,7 @@ from .transducer import transducer_forward_score, transducer_forward_score_fg, r
 from .align import greedy_decode, greedy_decode_nested, ctc_viterbi_align, ctc_beam_search_decode_logits
 from .head import linear_ctc_forward_score, linear_ctc_loss
 from .recognizer import patch_haloop
+from . import loop, sharding
 
 __all__ = [
     "ctc_forward_score3", "ctc_reduce_mean", "ctc_loss", "star_ctc_forward_score",

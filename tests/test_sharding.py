@@ -187,3 +187,83 @@ def test_length_bucket_batch_sampler_is_a_duration_batch_sampler_dropin():
                                                                torch.nn.utils.rnn.pad_sequence([x[1] for x in b], batch_first=True)))
     idx, x = next(iter(loader))
     assert x.shape[0] == len(idx) and x.shape[2] == 4
+
+
+# ------------------------------------------------------------- hac loop wiring (haloop_b200/loop.py) ---
+class _ToySet(torch.utils.data.Dataset):
+    """Stand-in for the reference's datasets: items + duration(i) (ha/sampler.py:17)."""
+    def __init__(self, n):
+        g = torch.Generator().manual_seed(3)
+        self.len = torch.randint(5, 40, (n,), generator=g).tolist()
+        self.x = [torch.randn(l, 6, generator=g) for l in self.len]
+        self.y = [torch.randint(1, 5, (max(1, l // 5),), generator=g) for l in self.len]
+    def __len__(self): return len(self.len)
+    def duration(self, i): return float(self.len[i])
+    def __getitem__(self, i): return self.x[i], self.y[i]
+
+
+def _collate(items):
+    xs, ys = zip(*items)
+    il = torch.tensor([len(x) for x in xs]); tl = torch.tensor([len(y) for y in ys])
+    return (torch.nn.utils.rnn.pad_sequence(xs, batch_first=True), torch.nn.utils.rnn.pad_sequence(ys, batch_first=True), il, tl)
+
+
+class _ToySystem:
+    """encoder + recognizer called through __call__, as ha/loop.py:125-134 does."""
+    def __init__(self):
+        torch.manual_seed(0)
+        self.encoder = torch.nn.Linear(6, 8)
+        self.recognizer = torch.nn.Linear(8, 5)
+    def forward(self, x, y, il, tl):
+        lp = self.recognizer(torch.tanh(self.encoder(x))).log_softmax(-1).permute(1, 0, 2)
+        return torch.nn.functional.ctc_loss(lp, y, il, tl)
+
+
+def _loop_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from haloop_b200 import loop
+        ds = _ToySet(64)
+        system = loop.distribute(_ToySystem())
+        loader = loop.sharded_loader(ds, _collate, max_duration=200, seed=1)
+        loader.batch_sampler.set_epoch(0)
+        seen, nb = [], 0
+        for x, y, il, tl in loader:
+            system.encoder.zero_grad(); system.recognizer.zero_grad()
+            system.forward(x, y, il, tl).backward()
+            nb += 1
+            seen.append(int(il.sum()))
+        enc, rec = loop.state_modules(system)
+        grads = torch.cat([p.grad.flatten() for p in list(enc.parameters()) + list(rec.parameters())])
+        gathered = [torch.zeros_like(grads) for _ in range(world)]
+        dist.all_gather(gathered, grads)
+        idx = sorted(i for b in loader.batch_sampler for i in b)
+        all_idx = [None] * world
+        dist.all_gather_object(all_idx, idx)
+        nbs = [None] * world
+        dist.all_gather_object(nbs, nb)
+        out[rank] = dict(same_grads=bool(torch.allclose(gathered[0], gathered[1])), nb=nbs,
+                         disjoint=len(set(all_idx[0]) & set(all_idx[1])) == 0, covered=len(set(all_idx[0]) | set(all_idx[1])),
+                         wrapped=isinstance(system.encoder, torch.nn.parallel.DistributedDataParallel))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_loop_distribute_and_sharded_loader_world2_gloo():
+    """DDP around encoder + recognizer and the rank-sharded length-bucketed loader: both ranks step the same number of
+    batches over disjoint utterances and end every step with identical (all-reduced) gradients."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    procs = [ctx.Process(target=_loop_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    for r in range(world):
+        o = out[r]
+        assert o["wrapped"] and o["same_grads"] and o["disjoint"]
+        assert o["nb"][0] == o["nb"][1] and o["nb"][0] >= 2
+        assert o["covered"] >= 56            # at most the leftover batches of the longer share are dropped
