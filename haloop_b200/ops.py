@@ -584,6 +584,7 @@ _no_double_backward(ctc_bwd, "ctc_bwd")
 _no_double_backward(star_bwd, "star_bwd")
 _no_double_backward(rnnt_bwd, "rnnt_bwd")
 _no_double_backward(rnnt_fg_bwd, "rnnt_fg_bwd")
+_no_double_backward(head_ctc_bwd, "head_ctc_bwd")
 
 # ------------------------------------------------------------------------------- vmap rules
 _register_time_major_vmap(ctc_fwd, ctc_bwd, 1)

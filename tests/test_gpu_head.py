@@ -183,3 +183,55 @@ def test_head_rejects_what_it_cannot_do(hb):
     with pytest.raises(ValueError):
         hb.linear_ctc_forward_score(torch.randn(2, 10, 8, device="cuda"), torch.randn(8, 8, device="cuda"), None, tg, il, tl,
                                     precision="bf16")
+
+
+def test_head_custom_op_registration_and_double_backward(hb):
+    """torch.library.opcheck on the forward op (schema, fake kernel, autograd registration) and a loud failure for
+    second-order use (the backward op has no derivative)."""
+    from haloop_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    h = torch.randn(2, 20, 16, generator=g).cuda().requires_grad_(True)
+    W = torch.randn(12, 16, generator=g).cuda().requires_grad_(True)
+    b = torch.randn(12, generator=g).cuda().requires_grad_(True)
+    tg = torch.randint(1, 12, (2, 4), generator=g).cuda()
+    il = torch.tensor([20, 15]).cuda(); tl = torch.tensor([4, 2]).cuda()
+    torch.library.opcheck(ops.head_ctc_fwd, (h, W, b, tg, il, tl, 3),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    loss = hb.linear_ctc_forward_score(h, W, b, tg, il, tl).sum()
+    (gh,) = torch.autograd.grad(loss, h, create_graph=True)      # first order works; the op is once-differentiable:
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        gh.sum().backward()
+
+
+def test_head_cuda_graph_capture_and_replay(hb):
+    """The op builds its tensor maps on the host and launches on the current stream without synchronising: a forward +
+    backward pair captures into a CUDA graph and replays bit-identically on new features written into the captured
+    buffer."""
+    from haloop_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    N, T, D, V, S = 4, 200, 128, 256, 30
+    hs = [torch.randn(N, T, D, generator=g).cuda() for _ in range(3)]
+    W = (torch.randn(V, D, generator=g) / D ** 0.5).cuda(); b = torch.randn(V, generator=g).cuda()
+    tg = torch.randint(1, V, (N, S), generator=g).cuda()
+    il = torch.tensor([200, 180, 150, 200]).cuda(); tl = torch.tensor([30, 25, 10, 30]).cuda()
+    go = torch.ones(N, device="cuda")
+    eager = []
+    for h in hs:
+        loss, saved = ops.head_ctc_fwd(h, W, b, tg, il, tl, 3)
+        eager.append((loss.clone(),) + tuple(t.clone() for t in ops.head_ctc_bwd(h, W, b, saved, go, S, 3)))
+    hbuf = hs[0].clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        loss, saved = ops.head_ctc_fwd(hbuf, W, b, tg, il, tl, 3)
+        ops.head_ctc_bwd(hbuf, W, b, saved, go, S, 3)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        gl, gsaved = ops.head_ctc_fwd(hbuf, W, b, tg, il, tl, 3)
+        gdh, gdW, gdb = ops.head_ctc_bwd(hbuf, W, b, gsaved, go, S, 3)
+    for h, (el, edh, edW, edb) in zip(hs, eager):
+        hbuf.copy_(h)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(gl, el) and torch.equal(gdh, edh) and torch.equal(gdW, edW) and torch.equal(gdb, edb)
