@@ -16,7 +16,7 @@ struct HeadWs {
     // forward scratch
     size_t stats, tr, fwd_total;
     // backward scratch
-    size_t d, dT, hT, Wt, part, bwd_total;
+    size_t d, Wt, part, colpart, bwd_total;
     int Sp, E, JWp, SPX, tiles_n, R, splits_max;
 };
 
@@ -49,7 +49,7 @@ HeadWs head_ws_layout(int N, int T, int D, int V, int S) {
     w.stats = take(sizeof(float2) * rows * w.tiles_n);
     w.tr = take(sizeof(float) * rows * w.SPX);
     w.fwd_total = o;
-    // backward: rows are processed in chunks of R so that d, d^T and h^T of a chunk stay in L2 (~40 MB each at most).
+    // backward: rows are processed in chunks of R so that d of a chunk (and the h rows it pairs with) stay in L2 (~40 MB).
     // A chunk's GEMMs are separate launches of persistent CTAs, so R is chosen to make their tile counts whole
     // multiples of the SM count (a 512-tile launch on 148 SMs idles 13 % of the machine in its last wave).
     const int nsm = sm_count();
@@ -80,10 +80,9 @@ HeadWs head_ws_layout(int N, int T, int D, int V, int S) {
     o = 256;
     const int Vp = round_up(V, 4);                                   // leading dimension of the class-contiguous scratch matrices
     w.d = take(sizeof(float) * (size_t)w.R * Vp);
-    w.dT = take(sizeof(float) * (size_t)V * w.R);
-    w.hT = take(sizeof(float) * (size_t)D * w.R);
     w.Wt = take(sizeof(float) * (size_t)D * Vp);
     w.part = take(sizeof(float) * (size_t)w.splits_max * V * D);
+    w.colpart = take(sizeof(float) * (size_t)kColSplits * V);
     w.bwd_total = o;
     return w;
 }
@@ -101,15 +100,15 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 // (rows x cols) fp32 matrix, cols contiguous (the contraction index), leading dimension ld floats; box 128 rows x 32 cols
-int make_map(CUtensorMap* m, const float* ptr, size_t rows, size_t cols, size_t ld) {
+int make_map(CUtensorMap* m, const float* ptr, size_t rows, size_t cols, size_t ld, int mn = 0) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return host_fail(HA_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)kHK, (cuuint32_t)kHM};
+    const cuuint32_t box[2] = {(cuuint32_t)kHK, (cuuint32_t)(mn ? 32 : kHM)};
     const cuuint32_t es[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return host_fail(HA_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%zu cols=%zu ld=%zu", (int)r, rows, cols, ld);
     return HA_OK;
 }
@@ -127,6 +126,7 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, HeadGemmParams p, cu
     GemmCore c{};
     c.N = p.N; c.K = p.K; c.a_row0 = p.a_row0; c.nprod = p.nprod; c.chunk_kb = kHChunkKb;
     c.batches = 1; c.a_batch_rows = 0; c.b_batch_rows = 0;
+    c.a_mn = p.a_mn; c.b_mn = p.b_mn; c.a_k0 = p.a_k0; c.b_k0 = p.b_k0; c.a_batch_k = 0; c.b_batch_k = 0; c.b_row0 = 0;
     c.tiles_m = (p.M + kHM - 1) / kHM;
     c.tiles_n = (p.N + kHN - 1) / kHN;
     const int nkb = (p.K + kHK - 1) / kHK;
@@ -151,7 +151,7 @@ int check_shapes(int N, int T, int D, int V, int S) {
 
 }  // namespace
 
-int host_make_map(void* map, const float* ptr, size_t rows, size_t cols, size_t ld) { return make_map((CUtensorMap*)map, ptr, rows, cols, ld); }
+int host_make_map(void* map, const float* ptr, size_t rows, size_t cols, size_t ld, int mn) { return make_map((CUtensorMap*)map, ptr, rows, cols, ld, mn); }
 int host_sm_count() { return sm_count(); }
 
 }  // namespace hab
@@ -227,10 +227,9 @@ int ha_head_ctc_bwd(const float* h, const float* W, const float* bias, int N, in
     unsigned char* cb = (unsigned char*)scratch;
     const int rows = N * T;
     float* d = (float*)(cb + w.d);
-    float* dT = (float*)(cb + w.dT);
-    float* hT = (float*)(cb + w.hT);
     float* Wt = (float*)(cb + w.Wt);
     float* part = (float*)(cb + w.part);
+    float* colpart = (float*)(cb + w.colpart);
     const int R = w.R, Vp = round_up(V, 4);
 
     {   // W^T (D x V): the B operand of dh = d W, contraction index (classes) contiguous
@@ -238,13 +237,14 @@ int ha_head_ctc_bwd(const float* h, const float* W, const float* bias, int N, in
         head_transpose_kernel<<<grid, block, 0, st>>>(W, 0, V, D, Wt, Vp);
         if ((rc = host_check_launch("head_transpose_kernel(W)"))) return rc;
     }
-    CUtensorMap m_h, m_W, m_d, m_Wt, m_dT, m_hT;
+    CUtensorMap m_h, m_W, m_d, m_Wt, m_d_mn, m_h_mn;
     if ((rc = make_map(&m_h, h, (size_t)rows, (size_t)D, (size_t)D))) return rc;
     if ((rc = make_map(&m_W, W, (size_t)V, (size_t)D, (size_t)D))) return rc;
     if ((rc = make_map(&m_d, d, (size_t)R, (size_t)V, (size_t)Vp))) return rc;
     if ((rc = make_map(&m_Wt, Wt, (size_t)D, (size_t)V, (size_t)Vp))) return rc;
-    if ((rc = make_map(&m_dT, dT, (size_t)V, (size_t)R, (size_t)R))) return rc;
-    if ((rc = make_map(&m_hT, hT, (size_t)D, (size_t)R, (size_t)R))) return rc;
+    // dW = d^T h contracts over the ROWS of d and h: both are read as they lie (MN-major operands), no transposed copies
+    if ((rc = make_map(&m_d_mn, d, (size_t)R, (size_t)V, (size_t)Vp, 1))) return rc;
+    if ((rc = make_map(&m_h_mn, h, (size_t)rows, (size_t)D, (size_t)D, 1))) return rc;
 
     int splits_used = 1;
     for (int r0 = 0, chunk = 0; r0 < rows; r0 += R, ++chunk) {
@@ -256,26 +256,24 @@ int ha_head_ctc_bwd(const float* h, const float* W, const float* bias, int N, in
         p.meta = (const int4*)(sb + w.meta); p.cls2pos = (const int*)(sb + w.cls2pos); p.dupnext = (const int*)(sb + w.dupnext);
         p.Sp = w.Sp; p.V = V; p.em = (float*)(sb + w.em); p.E = w.E;
         p.lse2 = (const float*)(sb + w.lse2); p.loss = (const float*)(sb + w.loss); p.gout = grad_loss;
-        p.out = d; p.ldo = Vp; p.outT = dT; p.ldt = R;
-        if ((rc = launch_gemm<kEpiBwdD>(m_h, m_W, p, st, "head_gemm_kernel<bwd d>"))) return rc;
-        {
-            const dim3 grid((D + 31) / 32, (crp + 31) / 32), block(32, 8);
-            head_transpose_kernel<<<grid, block, 0, st>>>(h, r0, rows, D, hT, R);
-            if ((rc = host_check_launch("head_transpose_kernel(h)"))) return rc;
-        }
+        p.out = d; p.ldo = Vp; p.Mpad = crp;                         // rows cr .. crp of d are written as zeros (dW reads them)
+        if ((rc = launch_gemm<kEpiBwdD>(m_h, m_W, p, st, "umma_gemm_kernel<head bwd d>"))) return rc;
         if (db) {
-            head_colsum_kernel<<<(V + 7) / 8, 256, 0, st>>>(dT, R, crp, V, db, chunk > 0);
+            head_colsum_kernel<<<dim3((V + 31) / 32, kColSplits), dim3(32, 8), 0, st>>>(d, Vp, cr, V, colpart);
             if ((rc = host_check_launch("head_colsum_kernel"))) return rc;
+            head_colsum_finish_kernel<<<(V + 255) / 256, 256, 0, st>>>(colpart, V, db, chunk > 0);
+            if ((rc = host_check_launch("head_colsum_finish_kernel"))) return rc;
         }
         HeadGemmParams q{};
         q.M = cr; q.N = D; q.K = V; q.a_row0 = 0; q.splits = 1; q.nprod = precision; q.rows_total = cr;
         q.out = dh + (size_t)r0 * D; q.ldo = D;
-        if ((rc = launch_gemm<kEpiStore>(m_d, m_Wt, q, st, "head_gemm_kernel<dh>"))) return rc;
+        if ((rc = launch_gemm<kEpiStore>(m_d, m_Wt, q, st, "umma_gemm_kernel<head dh>"))) return rc;
         HeadGemmParams u{};
         u.M = V; u.N = D; u.K = crp; u.a_row0 = 0; u.nprod = precision; u.rows_total = V;
+        u.a_mn = 1; u.b_mn = 1; u.a_k0 = 0; u.b_k0 = r0;
         u.splits = w.splits_max; u.out = part; u.ldo = D; u.accumulate = chunk > 0;
         // a shorter last chunk cuts K differently; each partial buffer still has exactly one writer per launch
-        if ((rc = launch_gemm<kEpiAccum>(m_dT, m_hT, u, st, "head_gemm_kernel<dW>"))) return rc;
+        if ((rc = launch_gemm<kEpiAccum>(m_d_mn, m_h_mn, u, st, "umma_gemm_kernel<head dW>"))) return rc;
         if (chunk == 0) {
             const int nkb = (crp + kHK - 1) / kHK;
             int s = w.splits_max > nkb ? nkb : w.splits_max;

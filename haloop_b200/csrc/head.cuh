@@ -6,9 +6,10 @@
 //   kEpiFwd    S = h W^T + b   per 128 x 128 tile: row max / sum-exp partials and the blank + label logits of the
 //                              row's utterance gathered into the CTC emission rows (logits never leave the SM)
 //   kEpiBwdD   S again (recomputed), d = g (softmax(S) - occupancy): written for ONE chunk of rows (an L2-sized
-//                              ring, not an (N,T,V) gradient), plain and transposed
+//                              ring, not an (N,T,V) gradient)
 //   kEpiStore  dh = d W        plain store
-//   kEpiAccum  dW += d^T h     split-K partial accumulators, one writer per element (deterministic)
+//   kEpiAccum  dW += d^T h     both operands read as they lie (MN-major: the contraction runs over their rows);
+//                              split-K partial accumulators, one writer per element (deterministic)
 //
 // The GEMM engine (TMA operand ring, tf32 x 3 split in shared memory, chunked TMEM accumulation) is umma_gemm.cuh.
 #pragma once
@@ -27,6 +28,8 @@ struct HeadGemmParams {
     int M, N, K;                 // rows of A this launch covers, rows of B (= output columns), contraction length
     int a_row0;                  // added to A's row coordinate (start of the row chunk)
     int splits;                  // split-K request (dW)
+    int a_mn, b_mn, a_k0, b_k0;  // MN-major operands and their K-coordinate offsets (GemmCore)
+    int Mpad;                    // kEpiBwdD: rows of `out` this launch may write (M rounded up to the tile: zeros beyond M)
     int nprod;                   // 3: error-compensated tf32 x 3; 1: plain tf32
     // epilogue data
     const float* bias;           // (N) or null
@@ -36,7 +39,6 @@ struct HeadGemmParams {
     float2* stats;               // fwd: [tiles_n][rows_total] (max, sum exp) partials
     const float* lse2; const float* loss; const float* gout;
     float* out; long long ldo;   // kEpiBwdD: d (M x N chunk), kEpiStore: dh, kEpiAccum: partials [splits][M][N]
-    float* outT; long long ldt;  // kEpiBwdD: d^T (N x ldt)
     int accumulate;              // kEpiAccum: add to what is there (every chunk but the first)
 };
 
@@ -119,18 +121,12 @@ struct HeadEpi {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         dv[j] = (live && n0 + c0 + j < p.N) ? g * (ex2f(fmaf(v[j], kLog2e, -l2)) - o[j]) : 0.0f;
-                    if (rl < p.M) {
+                    if (rl < p.Mpad) {
                         float* drow = p.out + (size_t)rl * p.ldo + n0 + c0;
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4)
                             if (n0 + c0 + 4 * j4 < p.N)
                                 *(float4*)(drow + 4 * j4) = make_float4(dv[4 * j4], dv[4 * j4 + 1], dv[4 * j4 + 2], dv[4 * j4 + 3]);
-                    }
-                    // transposed copy: the 32 lanes of a warp are 32 consecutive rows -> one 128-byte line per column
-                    if (rl < p.ldt) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (n0 + c0 + j < p.N) p.outT[(size_t)(n0 + c0 + j) * p.ldt + rl] = dv[j];
                     }
                 }
             }
@@ -232,15 +228,33 @@ __global__ void __launch_bounds__(256) head_transpose_kernel(const float* src, l
     }
 }
 
-// grid ceil(V / 8), block 256 (warp per class): db[c] (+)= sum over the chunk's rows of d^T[c][:]
-__global__ void __launch_bounds__(256) head_colsum_kernel(const float* dT, int ldt, int rows, int V, float* db, int accumulate) {
-    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (c >= V) return;
-    const float* r = dT + (size_t)c * ldt;
+// bias gradient: column sums of the chunk's d (rows x V, row-major).  grid (ceil(V / 32), kColSplits), block (32, 8):
+// a block sums its slice of the rows for 32 classes (coalesced 128-byte reads) into part[split][V]; the finish kernel
+// adds the splits in a fixed order (deterministic) onto db.
+constexpr int kColSplits = 32;
+__global__ void __launch_bounds__(256) head_colsum_kernel(const float* d, int ldd, int rows, int V, float* part) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int per = (rows + kColSplits - 1) / kColSplits;
+    const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
     float s = 0.0f;
-    for (int i = lane; i < rows; i += 32) s += r[i];
-    s = warp_sum(s);
-    if (lane == 0) db[c] = accumulate ? db[c] + s : s;
+    if (c < V)
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) s += d[(size_t)r * ldd + c];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < V) {
+        float t = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        part[(size_t)blockIdx.y * V + c] = t;
+    }
+}
+__global__ void __launch_bounds__(256) head_colsum_finish_kernel(const float* part, int V, float* db, int accumulate) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= V) return;
+    float s = 0.0f;
+    for (int k = 0; k < kColSplits; ++k) s += part[(size_t)k * V + c];
+    db[c] = accumulate ? db[c] + s : s;
 }
 
 // dW[i] = sum over the split-K partials

@@ -34,9 +34,10 @@ int ctc_trellis_for_head(int T, int N, int S, int Sp, int E, int SPX, int JWp, c
                          const int* tgt, float* em, float* tr, float* loss, float* loss_ws, cudaStream_t st);
 
 // ---- tensor maps for the GEMM engine (head.cu) ----
-// (rows x cols) fp32 matrix, cols contiguous (the contraction index), leading dimension ld floats; box 128 rows x 32 cols,
-// SWIZZLE_128B.  `map` points at a CUtensorMap.
-int host_make_map(void* map, const float* ptr, size_t rows, size_t cols, size_t ld);
+// (rows x cols) fp32 matrix, cols contiguous, leading dimension ld floats.  mn = 0: a K-major operand (cols = the
+// contraction index), box 128 rows x 32 cols, SWIZZLE_128B; mn = 1: an MN-major operand (rows = the contraction index), box
+// 32 x 32, SWIZZLE_128B_ATOM_32B.  `map` points at a CUtensorMap.
+int host_make_map(void* map, const float* ptr, size_t rows, size_t cols, size_t ld, int mn = 0);
 int host_sm_count();
 
 }  // namespace hab

@@ -40,6 +40,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3ffff) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
 }
+// MN-major descriptor for a 128 (MN) x 32 (K) fp32 tile stored as four 32 (MN) x 32 (K) boxes of 4096 bytes, each written
+// by TMA with the 32-byte-atom 128-byte swizzle (layout type SWIZZLE_128B_BASE32B = 1): a K row is one 128-byte line of
+// 32 consecutive MN elements, 4 K rows form a 512-byte swizzle atom.  LBO = distance between the atoms along MN (the
+// boxes: 4096 B), SBO = distance between the 4-row atoms along K (512 B).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffff) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+           (1ull << 61);
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -52,6 +60,13 @@ struct GemmCore {
     int a_row0;                  // added to A's row coordinate
     int tiles_m, tiles_n, splits, kb_per_split;
     int batches, a_batch_rows, b_batch_rows;     // independent problems: row offsets of batch b in the A and B tensor maps
+    // An operand may also be given "MN-major": stored (K x MN) row-major, i.e. the matrix the caller already has when the
+    // contraction runs over its ROW index (d^T h, W^T F): no transposed copy is made, the tile is loaded as four
+    // 32 (MN) x 32 (K) boxes and the MMA reads it through an MN-major descriptor.  For such an operand the tensor map has
+    // box 32 x 32 and the 32-byte-atom 128-byte swizzle (the only MN-major layout kind::tf32 accepts); `*_row0` /
+    // `*_batch_rows` offset the MN coordinate (columns) and `*_k0` / `*_batch_k` the K coordinate (rows).
+    int a_mn, b_mn;
+    int a_k0, b_k0, a_batch_k, b_batch_k, b_row0;
     int nprod;                   // 3: error-compensated tf32 x 3; 1: plain tf32
     int chunk_kb;                // k-blocks per accumulation chunk
 };
@@ -98,14 +113,22 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     mbar_wait(&empty[s], ((it / kHStages) & 1u) ^ 1u);
                     mbar_expect_tx(&raw_full[s], 2u * kHTile);
                     const uint32_t st = base + (uint32_t)s * kHStageBytes;
-                    tma_load_2d(st, &mapA, kb * kHK, p.a_row0 + bt * p.a_batch_rows + mb * kHM, &raw_full[s]);
-                    tma_load_2d(st + kHTile, &mapB, kb * kHK, bt * p.b_batch_rows + nb * kHN, &raw_full[s]);
+                    const int ka = p.a_k0 + bt * p.a_batch_k + kb * kHK, ra = p.a_row0 + bt * p.a_batch_rows + mb * kHM;
+                    const int kbb = p.b_k0 + bt * p.b_batch_k + kb * kHK, rb = p.b_row0 + bt * p.b_batch_rows + nb * kHN;
+                    if (!p.a_mn) tma_load_2d(st, &mapA, ka, ra, &raw_full[s]);
+                    else
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) tma_load_2d(st + i * 4096, &mapA, ra + 32 * i, ka, &raw_full[s]);
+                    if (!p.b_mn) tma_load_2d(st + kHTile, &mapB, kbb, rb, &raw_full[s]);
+                    else
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) tma_load_2d(st + kHTile + i * 4096, &mapB, rb + 32 * i, kbb, &raw_full[s]);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(kHM, kHN);
+            const uint32_t idesc = umma_idesc_tf32(kHM, kHN) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
             uint32_t it = 0, lt = 0, gc = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
                 const int sp = (tile / (p.tiles_n * p.tiles_m)) % p.splits;
@@ -128,10 +151,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         const uint32_t st = base + (uint32_t)s * kHStageBytes;
 #pragma unroll
                         for (int ks = 0; ks < kHK / 8; ++ks) {
-                            const uint64_t ah = umma_desc_sw128(st + ks * 32), bh = umma_desc_sw128(st + kHTile + ks * 32);
+                            // k-step inside the stage: 32 bytes along the 128-byte row (K-major) or 8 rows of 128 bytes (MN-major)
+                            const uint32_t oa = p.a_mn ? ks * 1024 : ks * 32, ob = p.b_mn ? ks * 1024 : ks * 32;
+                            const uint64_t ah = p.a_mn ? umma_desc_sw128_mn(st + oa) : umma_desc_sw128(st + oa);
+                            const uint64_t bh = p.b_mn ? umma_desc_sw128_mn(st + kHTile + ob) : umma_desc_sw128(st + kHTile + ob);
                             umma_tf32(d_main, ah, bh, idesc, (kb > kc || ks > 0) ? 1u : 0u);
                             if (p.nprod == 3) {
-                                const uint64_t al = umma_desc_sw128(st + 2 * kHTile + ks * 32), bl = umma_desc_sw128(st + 3 * kHTile + ks * 32);
+                                const uint64_t al = p.a_mn ? umma_desc_sw128_mn(st + 2 * kHTile + oa) : umma_desc_sw128(st + 2 * kHTile + oa);
+                                const uint64_t bl = p.b_mn ? umma_desc_sw128_mn(st + 3 * kHTile + ob) : umma_desc_sw128(st + 3 * kHTile + ob);
                                 umma_tf32(d_small, al, bh, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
                                 umma_tf32(d_small, ah, bl, idesc, 1u);
                             }
