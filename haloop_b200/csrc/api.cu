@@ -92,19 +92,25 @@ int common_checks(const void* x, int T, int N, int V, int S, const void* ws, siz
     return HA_OK;
 }
 
-// one contraction of the joint-free RNN-T on the GEMM engine: every utterance is a batch entry of the same two tensor maps
+// one contraction of the joint-free RNN-T on the GEMM engine: every utterance is a batch entry of the same two tensor maps.
+// An operand is (rows x cols) per utterance, row-major; K-major (mn = 0): rows index the output, cols the contraction;
+// MN-major (mn = 1): rows index the contraction, cols the output (the matrix is used as it lies, no transposed copy).
+struct FgOperand { const float* ptr; size_t rows, cols; int mn; };
 template <int MODE>
-int fg_engine_launch(const float* A, size_t a_rows, size_t a_cols, const float* B, size_t b_rows, size_t b_cols,
-                            int batches, int tiles_m, int ncols, int K, const FgUmmaParams& q, cudaStream_t st, const char* what) {
+int fg_engine_launch(FgOperand A, FgOperand B, int batches, int tiles_m, int ncols, int K, const FgUmmaParams& q,
+                     cudaStream_t st, const char* what) {
     alignas(64) CUtensorMap ma, mb;
     int rc;
-    if ((rc = host_make_map(&ma, A, (size_t)batches * a_rows, a_cols, a_cols))) return rc;
-    if ((rc = host_make_map(&mb, B, (size_t)batches * b_rows, b_cols, b_cols))) return rc;
+    if ((rc = host_make_map(&ma, A.ptr, (size_t)batches * A.rows, A.cols, A.cols, A.mn))) return rc;
+    if ((rc = host_make_map(&mb, B.ptr, (size_t)batches * B.rows, B.cols, B.cols, B.mn))) return rc;
     if ((rc = set_smem(umma_gemm_kernel<FgEpi<MODE>>, kHSmem, what))) return rc;
     GemmCore c{};
     c.N = ncols; c.K = K; c.a_row0 = 0; c.nprod = 3; c.chunk_kb = kFgChunkKb;
     c.tiles_m = tiles_m; c.tiles_n = (ncols + kHN - 1) / kHN; c.splits = 1; c.kb_per_split = (K + kHK - 1) / kHK;
-    c.batches = batches; c.a_batch_rows = (int)a_rows; c.b_batch_rows = (int)b_rows;
+    c.batches = batches;
+    c.a_mn = A.mn; c.b_mn = B.mn;
+    c.a_batch_rows = A.mn ? 0 : (int)A.rows; c.a_batch_k = A.mn ? (int)A.rows : 0;      // the batch offsets the ROW coordinate
+    c.b_batch_rows = B.mn ? 0 : (int)B.rows; c.b_batch_k = B.mn ? (int)B.rows : 0;
     const int ntiles = c.tiles_m * c.tiles_n * batches;
     const int grid = ntiles < host_sm_count() ? ntiles : host_sm_count();
     FgEpi<MODE> epi{q};
@@ -614,7 +620,8 @@ int ha_rnnt_fg_fwd(const float* f, const float* g, int N, int T, int U1, int V,
         fg_rows_kernel<<<dim3((uw.Tp + uw.Um + 7) / 8, N), 256, 0, st>>>(q);
         if ((rc = check_launch("fg_rows_kernel"))) return rc;
         // E = F G^T: rows of F (Tp per utterance) x rows of G (Um per utterance, Uk columns of E used), K = V
-        if ((rc = fg_engine_launch<kUmmaE>(q.Fh, uw.Tp, V, q.Gh, uw.Um, V, N, uw.Tp / kHM, uw.Uk, V, q, st, "umma_gemm_kernel<fg E>"))) return rc;
+        if ((rc = fg_engine_launch<kUmmaE>({q.Fh, (size_t)uw.Tp, (size_t)V, 0}, {q.Gh, (size_t)uw.Um, (size_t)V, 0}, N, uw.Tp / kHM, uw.Uk, V, q, st,
+                                           "umma_gemm_kernel<fg E>"))) return rc;
         fg_arc_kernel<<<dim3((T + 7) / 8, N), 256, 0, st>>>(q);
         if ((rc = check_launch("fg_arc_kernel"))) return rc;
     } else {
@@ -654,18 +661,15 @@ int ha_rnnt_fg_bwd(const float* f, const float* g, int N, int T, int U1, int V,
         // (the forward call took the same branch: it depends on V and on the alignment of f and g only)
         const FgUmmaWs uw = fg_umma_ws_layout(N, T, U1, V);
         const FgUmmaParams q = fg_umma_params(p, uw, base + w.total);
-        FgTransposeParams tp{q.Fh, q.Fth, uw.Tp, V, uw.Tk, uw.Tp};
-        fg_transpose_kernel<<<dim3((V + 31) / 32, (uw.Tk + 31) / 32, N), dim3(32, 8), 0, st>>>(tp);
-        if ((rc = check_launch("fg_transpose_kernel<F>"))) return rc;
-        FgTransposeParams tg{q.Gh, q.Gth, uw.Um, V, uw.Uk, uw.Um};
-        fg_transpose_kernel<<<dim3((V + 31) / 32, (uw.Uk + 31) / 32, N), dim3(32, 8), 0, st>>>(tg);
-        if ((rc = check_launch("fg_transpose_kernel<G>"))) return rc;
         fg_w_kernel<<<dim3((uw.Tp + 7) / 8, N), 256, 0, st>>>(q);
         if ((rc = check_launch("fg_w_kernel"))) return rc;
-        // DF = (W G) (.) F: rows of W (Tp x Uk) x rows of G^T (V x Uk), K = Uk;  DG = (W^T F) (.) G: rows of W^T (Um x Tk) x
-        // rows of F^T (V x Tk), K = Tk
-        if ((rc = fg_engine_launch<kUmmaDF>(q.Wh, uw.Tp, uw.Uk, q.Gth, V, uw.Uk, N, uw.Tp / kHM, V, uw.Uk, q, st, "umma_gemm_kernel<fg DF>"))) return rc;
-        if ((rc = fg_engine_launch<kUmmaDG>(q.Wth, uw.Um, uw.Tk, q.Fth, V, uw.Tk, N, uw.Um / kHM, V, uw.Tk, q, st, "umma_gemm_kernel<fg DG>"))) return rc;
+        // DF = (W G) (.) F: rows of W (Tp x Uk, K-major) against G (Um x V) read as it lies (MN-major: the contraction runs over
+        // its rows u), K = Uk.  DG = (W^T F) (.) G: W (Tp x Uk) and F (Tp x V) both as they lie (the contraction runs over
+        // their rows t), K = Tk.  No transposed copies of F, G or W exist.
+        if ((rc = fg_engine_launch<kUmmaDF>({q.Wh, (size_t)uw.Tp, (size_t)uw.Uk, 0}, {q.Gh, (size_t)uw.Um, (size_t)V, 1}, N, uw.Tp / kHM, V, uw.Uk, q, st,
+                                            "umma_gemm_kernel<fg DF>"))) return rc;
+        if ((rc = fg_engine_launch<kUmmaDG>({q.Wh, (size_t)uw.Tp, (size_t)uw.Uk, 1}, {q.Fh, (size_t)uw.Tp, (size_t)V, 1}, N, uw.Um / kHM, V, uw.Tk, q, st,
+                                            "umma_gemm_kernel<fg DG>"))) return rc;
     } else {
         rnnt_fg_gemm_kernel<kDF><<<dim3((T + kGM - 1) / kGM, (V + kGN - 1) / kGN, N), 256, 0, st>>>(p);
         if ((rc = check_launch("rnnt_fg_gemm_kernel<DF>"))) return rc;

@@ -8,8 +8,8 @@
 //
 // Operands are exponentials of shifted logits (F, G) or occupancy ratios (W): small row kernels form them once as
 // plain fp32 (kind::tf32 reads the high half of an fp32 word by itself; the engine's split warps derive the low half),
-// K-major (and transposed where the contraction runs over the other index), zero-padded to whole tiles; every
-// utterance is one batch entry of the engine.  A gradient needs 1e-5 absolute, so the accumulation chunks are short
+// zero-padded to whole tiles, and used as they lie: K-major where the contraction runs over their columns, MN-major
+// where it runs over their rows (no transposed copies); every utterance is one batch entry of the engine.  A gradient needs 1e-5 absolute, so the accumulation chunks are short
 // (16 k-blocks = 64 accumulating MMAs between round-to-nearest folds).
 #pragma once
 #include "common.cuh"
@@ -35,10 +35,10 @@ __host__ inline FgUmmaWs fg_umma_ws_layout(int N, int T, int U1, int V) {
     auto take = [&](size_t floats) { size_t at = o; o = round_up_sz(o + floats * 4 * (size_t)N, 256); return at; };
     w.Fh = take((size_t)w.Tp * V); w.Fl = take(0);                         // the low halves are formed in shared memory
     w.Gh = take((size_t)w.Um * V); w.Gl = take(0);                         // Um rows: G is also the M operand's epilogue source
-    w.Fth = take((size_t)V * w.Tk); w.Ftl = take(0);
-    w.Gth = take((size_t)V * w.Uk); w.Gtl = take(0);
+    w.Fth = take(0); w.Ftl = take(0);                                       // no transposed copies: MN-major operands
+    w.Gth = take(0); w.Gtl = take(0);
     w.Wh = take((size_t)w.Tp * w.Uk); w.Wl = take(0);
-    w.Wth = take((size_t)w.Um * w.Tk); w.Wtl = take(0);
+    w.Wth = take(0); w.Wtl = take(0);
     w.total = o;
     return w;
 }
@@ -95,27 +95,8 @@ __global__ void __launch_bounds__(256) fg_rows_kernel(FgUmmaParams p) {
     }
 }
 
-// grid (ceil(C / 32), ceil(Rd / 32), N), block (32, 8): dst[c][r] = src[r][c] for r < Rs (else 0), r < Rd
-struct FgTransposeParams { const float* sh; float* dh; int Rs, C, Rd, lds_rows; };
-__global__ void __launch_bounds__(256) fg_transpose_kernel(FgTransposeParams p) {
-    __shared__ float tile[32][33];
-    const int n = blockIdx.z;
-    const float* src = p.sh + (size_t)n * p.lds_rows * p.C;
-    float* dst = p.dh + (size_t)n * p.C * p.Rd;
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int r = r0 + i, c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (r < p.Rs && c < p.C) ? src[(size_t)r * p.C + c] : 0.0f;
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int c = c0 + i, r = r0 + threadIdx.x;
-        if (c < p.C && r < p.Rd) dst[(size_t)c * p.Rd + r] = tile[threadIdx.x][i];
-    }
-}
-
 // grid (ceil(Tp / 8), N), block 256 (one warp per padded frame): W[t][u] = (occ_blank + occ_label)[t][u] / E[t][u],
-// as W (Tp x Uk) and W^T (Um x Tk); zero outside the utterance
+// as W (Tp x Uk); zero outside the utterance
 __global__ void __launch_bounds__(256) fg_w_kernel(FgUmmaParams p) {
     const int n = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * 8 + warp;
@@ -125,15 +106,14 @@ __global__ void __launch_bounds__(256) fg_w_kernel(FgUmmaParams p) {
     const int Tn = (mt.z || !(lossn < CUDART_INF_F)) ? 0 : mt.x, Un = mt.y;
     const float2* occ = p.occ + (size_t)n * p.D * p.U1;
     const float* Em = p.E + (size_t)n * p.T * p.U1;
-    for (int u = lane; u < p.Um; u += 32) {
+    for (int u = lane; u < p.Uk; u += 32) {
         float w = 0.0f;
         if (t < Tn && u <= Un) {
             const float2 o = occ[(size_t)(t + u) * p.U1 + u];
             const float e = Em[(size_t)t * p.U1 + u];
             if (e > 0.0f) w = (o.x + o.y) / e;
         }
-        if (u < p.Uk) p.Wh[((size_t)n * p.Tp + t) * p.Uk + u] = w;
-        if (t < p.Tk) p.Wth[((size_t)n * p.Um + u) * p.Tk + t] = w;
+        p.Wh[((size_t)n * p.Tp + t) * p.Uk + u] = w;
     }
 }
 
