@@ -16,7 +16,7 @@ struct HeadWs {
     // forward scratch
     size_t stats, tr, fwd_total;
     // backward scratch
-    size_t d, Wt, part, colpart, bwd_total;
+    size_t d, part, colpart, bwd_total;
     int Sp, E, JWp, SPX, tiles_n, R, splits_max;
 };
 
@@ -80,7 +80,6 @@ HeadWs head_ws_layout(int N, int T, int D, int V, int S) {
     o = 256;
     const int Vp = round_up(V, 4);                                   // leading dimension of the class-contiguous scratch matrices
     w.d = take(sizeof(float) * (size_t)w.R * Vp);
-    w.Wt = take(sizeof(float) * (size_t)D * Vp);
     w.part = take(sizeof(float) * (size_t)w.splits_max * V * D);
     w.colpart = take(sizeof(float) * (size_t)kColSplits * V);
     w.bwd_total = o;
@@ -227,21 +226,16 @@ int ha_head_ctc_bwd(const float* h, const float* W, const float* bias, int N, in
     unsigned char* cb = (unsigned char*)scratch;
     const int rows = N * T;
     float* d = (float*)(cb + w.d);
-    float* Wt = (float*)(cb + w.Wt);
     float* part = (float*)(cb + w.part);
     float* colpart = (float*)(cb + w.colpart);
     const int R = w.R, Vp = round_up(V, 4);
 
-    {   // W^T (D x V): the B operand of dh = d W, contraction index (classes) contiguous
-        const dim3 grid((D + 31) / 32, (V + 31) / 32), block(32, 8);
-        head_transpose_kernel<<<grid, block, 0, st>>>(W, 0, V, D, Wt, Vp);
-        if ((rc = host_check_launch("head_transpose_kernel(W)"))) return rc;
-    }
-    CUtensorMap m_h, m_W, m_d, m_Wt, m_d_mn, m_h_mn;
+    CUtensorMap m_h, m_W, m_d, m_W_mn, m_d_mn, m_h_mn;
     if ((rc = make_map(&m_h, h, (size_t)rows, (size_t)D, (size_t)D))) return rc;
     if ((rc = make_map(&m_W, W, (size_t)V, (size_t)D, (size_t)D))) return rc;
     if ((rc = make_map(&m_d, d, (size_t)R, (size_t)V, (size_t)Vp))) return rc;
-    if ((rc = make_map(&m_Wt, Wt, (size_t)D, (size_t)V, (size_t)Vp))) return rc;
+    // dh = d W contracts over the ROWS of W (classes): W is read as it lies (MN-major B operand)
+    if ((rc = make_map(&m_W_mn, W, (size_t)V, (size_t)D, (size_t)D, 1))) return rc;
     // dW = d^T h contracts over the ROWS of d and h: both are read as they lie (MN-major operands), no transposed copies
     if ((rc = make_map(&m_d_mn, d, (size_t)R, (size_t)V, (size_t)Vp, 1))) return rc;
     if ((rc = make_map(&m_h_mn, h, (size_t)rows, (size_t)D, (size_t)D, 1))) return rc;
@@ -266,8 +260,8 @@ int ha_head_ctc_bwd(const float* h, const float* W, const float* bias, int N, in
         }
         HeadGemmParams q{};
         q.M = cr; q.N = D; q.K = V; q.a_row0 = 0; q.splits = 1; q.nprod = precision; q.rows_total = cr;
-        q.out = dh + (size_t)r0 * D; q.ldo = D;
-        if ((rc = launch_gemm<kEpiStore>(m_d, m_Wt, q, st, "umma_gemm_kernel<head dh>"))) return rc;
+        q.out = dh + (size_t)r0 * D; q.ldo = D; q.b_mn = 1;
+        if ((rc = launch_gemm<kEpiStore>(m_d, m_W_mn, q, st, "umma_gemm_kernel<head dh>"))) return rc;
         HeadGemmParams u{};
         u.M = V; u.N = D; u.K = crp; u.a_row0 = 0; u.nprod = precision; u.rows_total = V;
         u.a_mn = 1; u.b_mn = 1; u.a_k0 = 0; u.b_k0 = r0;

@@ -7,7 +7,7 @@
 //                              row's utterance gathered into the CTC emission rows (logits never leave the SM)
 //   kEpiBwdD   S again (recomputed), d = g (softmax(S) - occupancy): written for ONE chunk of rows (an L2-sized
 //                              ring, not an (N,T,V) gradient)
-//   kEpiStore  dh = d W        plain store
+//   kEpiStore  dh = d W        W read as it lies (MN-major B operand); plain store
 //   kEpiAccum  dW += d^T h     both operands read as they lie (MN-major: the contraction runs over their rows);
 //                              split-K partial accumulators, one writer per element (deterministic)
 //
@@ -209,22 +209,6 @@ __global__ void __launch_bounds__(256) head_finalize_kernel(HeadFinalizeParams p
         float K, f;
         emission_split(erow[1], l2, ct, K, f);
         *(float4*)erow = make_float4(ct, emission_linear(K, f), 0.0f, 0.0f);
-    }
-}
-
-// grid (ceil(C / 32), ceil(Rd / 32)), block (32, 8): dst[c][r] = src[r0 + r][c] for r0 + r < Rs (else 0), r < Rd
-__global__ void __launch_bounds__(256) head_transpose_kernel(const float* src, long long r0, long long Rs, int C, float* dst, int Rd) {
-    __shared__ float tile[32][33];
-    const int c0 = blockIdx.x * 32, rb = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const long long r = r0 + rb + i;
-        const int c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (r < Rs && c < C) ? src[(size_t)r * C + c] : 0.0f;
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int c = c0 + i, r = rb + threadIdx.x;
-        if (c < C && r < Rd) dst[(size_t)c * Rd + r] = tile[threadIdx.x][i];
     }
 }
 
