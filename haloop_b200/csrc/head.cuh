@@ -47,7 +47,7 @@ struct HeadGemmParams {
 template <int EPI>
 struct HeadEpi {
     HeadGemmParams p;
-    __device__ __forceinline__ void operator()(uint32_t trow, int mb, int nb, int sp, int /*batch*/, int q, int lane, float* /*stage*/) const {
+    __device__ __forceinline__ void operator()(uint32_t trow, int mb, int nb, int sp, int /*batch*/, int q, int lane, float* stg) const {
             const int rl = mb * kHM + 32 * q + lane;             // row inside this launch's A range
         const int n0 = nb * kHN;
 
@@ -121,30 +121,43 @@ struct HeadEpi {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         dv[j] = (live && n0 + c0 + j < p.N) ? g * (ex2f(fmaf(v[j], kLog2e, -l2)) - o[j]) : 0.0f;
-                    if (rl < p.Mpad) {
-                        float* drow = p.out + (size_t)rl * p.ldo + n0 + c0;
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4)
-                            if (n0 + c0 + 4 * j4 < p.N)
-                                *(float4*)(drow + 4 * j4) = make_float4(dv[4 * j4], dv[4 * j4 + 1], dv[4 * j4 + 2], dv[4 * j4 + 3]);
+                    for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = dv[j];
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int r = it * 8 + (lane >> 2), cq = (lane & 3) * 4;
+                        const int mm = mb * kHM + 32 * q + r, c = n0 + c0 + cq;
+                        if (mm < p.Mpad && c < p.N) {
+                            const float* a4 = stg + r * 17 + cq;
+                            *(float4*)(p.out + (size_t)mm * p.ldo + c) = make_float4(a4[0], a4[1], a4[2], a4[3]);
+                        }
                     }
+                    __syncwarp();
                 }
             }
             if (EPI == kEpiFwd && inside) p.stats[(size_t)nb * p.rows_total + row] = make_float2(m, ssum);
         } else {
-            float* orow = (EPI == kEpiAccum) ? p.out + ((size_t)sp * p.M + rl) * p.ldo + n0
-                                             : p.out + ((size_t)p.a_row0 + rl) * p.ldo + n0;
+            // thread = accumulator row (fixed by the TMEM lane mapping), but a row-per-thread store touches 32 rows of 16
+            // bytes per instruction: the 32 x 16 block of a warp goes through its staging block in shared memory and
+            // leaves (or is read-modify-written) as 64-byte row segments, 8 rows per instruction
+            float* obase = (EPI == kEpiAccum) ? p.out + (size_t)sp * p.M * p.ldo : p.out + (size_t)p.a_row0 * p.ldo;
+            const int m_w = mb * kHM + 32 * q;
             for (int c0 = 0; c0 < kHN && n0 + c0 < p.N; c0 += 16) {
                 float a[16];
                 tmem_ld16_nowait(trow + c0, a);
                 tmem_ld_wait();
-                if (rl < p.M && (EPI == kEpiAccum || p.a_row0 + rl < p.rows_total)) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        if (n0 + c0 + 4 * j4 >= p.N) continue;
-                        float4 o;
-                        o.x = a[4 * j4]; o.y = a[4 * j4 + 1]; o.z = a[4 * j4 + 2]; o.w = a[4 * j4 + 3];
-                        float4* dst = (float4*)(orow + c0 + 4 * j4);
+                for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = a[j];
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int r = it * 8 + (lane >> 2), cq = (lane & 3) * 4;
+                    const int mm = m_w + r, c = n0 + c0 + cq;
+                    if (mm < p.M && c < p.N && (EPI == kEpiAccum || p.a_row0 + mm < p.rows_total)) {
+                        const float* a4 = stg + r * 17 + cq;
+                        float4 o = make_float4(a4[0], a4[1], a4[2], a4[3]);
+                        float4* dst = (float4*)(obase + (size_t)mm * p.ldo + c);
                         if (EPI == kEpiAccum && p.accumulate) {
                             const float4 old = *dst;
                             o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
@@ -152,6 +165,7 @@ struct HeadEpi {
                         *dst = o;
                     }
                 }
+                __syncwarp();
             }
         }
     }
