@@ -37,11 +37,11 @@ timeout 600 ncu --set full --clock-control none -k regex:'rnnt_(grad|rows|lattic
     python bench.py --workload rnnt --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-library-baseline > $O/ncu_rnnt_$R.log 2>&1; echo "ncu rnnt rc=$?"
 timeout 600 ncu --set full --clock-control none -k regex:'star_(grad|rows|trellis)' -s 4 -c 3 -o $O/prof_star_$R \
     python bench.py --workload star --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-library-baseline > $O/ncu_star_$R.log 2>&1; echo "ncu star rc=$?"
-timeout 600 ncu --set full --clock-control none -k regex:'fg_umma_gemm|fg_rows|fg_w_' -s 10 -c 5 -o $O/prof_rnnt_fg_$R \
+timeout 600 ncu --set full --clock-control none -k regex:'umma_gemm|fg_rows|fg_arc|fg_w_' -s 12 -c 6 -o $O/prof_rnnt_fg_$R \
     python bench.py --workload rnnt_fg --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-library-baseline > $O/ncu_rnnt_fg_$R.log 2>&1; echo "ncu rnnt_fg rc=$?"
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'head_|ctc_' --csv --log-file $O/launches_head_$R.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'umma_gemm|head_|ctc_' --csv --log-file $O/launches_head_$R.csv \
     python tools/head_check.py perf > /dev/null 2>&1; echo "launches head rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'head_gemm' -c 6 -o $O/prof_head_$R \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'umma_gemm' -c 6 -o $O/prof_head_$R \
     python tools/head_check.py prof > $O/ncu_head_$R.log 2>&1; echo "ncu head rc=$?"
 # the reports are summarised on the box (gpurun brings back at most 64 MiB) and dropped
 for w in ctc star rnnt rnnt_fg head; do
