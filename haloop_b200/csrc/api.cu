@@ -316,8 +316,8 @@ int ha_ctc_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V, 
 
 // -------------------------------------------------------------------------------- star-CTC ---
 size_t ha_star_workspace_bytes(int T, int N, int V, int S) {
-    (void)V;
     if (T <= 0 || N <= 0 || S < 0) return 0;
+    if (star2_eligible(T, N, V, S)) return star2_workspace_bytes(T, N, S);
     return star_ws_layout(T, N, S).total;
 }
 
@@ -362,6 +362,13 @@ int ha_star_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
                 const void* in_len, const void* tgt_len, int lengths_i64,
                 float star_penalty, int from_logits, float* loss,
                 void* ws, size_t ws_bytes, void* stream) {
+    if (star2_eligible(T, N, V, S)) {
+        int rc2 = common_checks(x, T, N, V, S, ws, ws_bytes, 0);
+        if (rc2) return rc2;
+        if (!in_len || !tgt_len || !loss || (S > 0 && !targets)) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+        return star2_fwd(x, sx_t, sx_n, T, N, V, targets, tgt_stride, S, targets_i64, in_len, tgt_len, lengths_i64,
+                         star_penalty, from_logits, loss, ws, ws_bytes, (cudaStream_t)stream);
+    }
     const StarWs w = star_ws_layout(T, N, S);
     int rc = common_checks(x, T, N, V, S, ws, ws_bytes, w.total);
     if (rc) return rc;
@@ -414,6 +421,12 @@ int ha_star_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
                 const float* grad_loss, int from_logits,
                 float* gx, int64_t sg_t, int64_t sg_n,
                 void* ws, size_t ws_bytes, void* stream) {
+    if (star2_eligible(T, N, V, S)) {
+        int rc2 = common_checks(gx, T, N, V, S, ws, ws_bytes, 0);
+        if (rc2) return rc2;
+        if (!grad_loss) return fail(HA_ERR_INVALID_ARGUMENT, "null pointer");
+        return star2_bwd(x, sx_t, sx_n, T, N, V, S, grad_loss, from_logits, gx, sg_t, sg_n, ws, ws_bytes, (cudaStream_t)stream);
+    }
     const StarWs w = star_ws_layout(T, N, S);
     int rc = common_checks(gx, T, N, V, S, ws, ws_bytes, w.total);
     if (rc) return rc;

@@ -292,13 +292,15 @@ struct Prep2Params {
     const void* in_len; const void* tgt_len; int len64;
     int T, N, V, S, Sp, NF;
     int4* meta; int* order; int* tgt; int* nflist; int2* nfhdr; int* cnt; int4* zinfo;
+    int star;   // star-CTC (star2.cuh): occurrence ranks also cover position L_n (< S), whose star reads targets[n, L_n]
+                // (ha/star.py:46), and a label 0 needs no extra frame
 };
 
 // grid N, block 256.  meta[n] = {T_n, L_n, invalid, frames an alignment needs beyond L_n}; tgt[n][k] = label |
 // kNotFirst; nflist[n] = the positions whose label occurred before, as (label << 10 | position): occurrence ranks
 // 1 .. kRcap-1 in groups padded to 32 entries (-1) — the classes of a group are distinct, so the gradient kernel
 // updates one group per instruction — then any higher ranks in position order (a serial tail).
-__global__ void __launch_bounds__(256) ctc2_prep_kernel(Prep2Params p) {
+static __global__ void __launch_bounds__(256) ctc2_prep_kernel(Prep2Params p) {
     extern __shared__ __align__(16) int s_y[];          // [Sp] labels, [Sp] occurrence ranks
     __shared__ int s_bad, s_rank, s_rep, s_cnt[kRcap], s_off[kRcap], s_fill[kRcap];
     int* s_rk = s_y + p.Sp;
@@ -319,10 +321,11 @@ __global__ void __launch_bounds__(256) ctc2_prep_kernel(Prep2Params p) {
     for (int k = threadIdx.x; k < p.NF; k += blockDim.x) nfl[k] = -1;
     __syncthreads();
     const int L4 = (L + 3) & ~3;
+    const int Lc = p.star ? min(L + 1, p.S) : L;
     for (int k = threadIdx.x; k < p.Sp; k += blockDim.x) {
         const int y = s_y[k];
         int rk = 0;                                     // earlier positions with my label (branch-free vector scan)
-        if (k < L) {
+        if (k < Lc) {
             const int4* y4 = (const int4*)s_y;
 #pragma unroll 4
             for (int j4 = 0; j4 < (L4 >> 2); ++j4) {
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(256) ctc2_prep_kernel(Prep2Params p) {
         p.tgt[(size_t)n * p.Sp + k] = (y < 0 ? 0 : y) | (rk ? kNotFirst : 0);
         // a blank must separate equal neighbours, and a label 0 can only be entered from the blank before
         // it (ha/ctc.py:140: no skip into a blank-valued state): one extra frame each
-        if (k >= 1 && k < L && (s_y[k - 1] == y || y == 0)) atomicAdd(&s_rep, 1);
+        if (k >= 1 && k < L && (s_y[k - 1] == y || (!p.star && y == 0))) atomicAdd(&s_rep, 1);
     }
     {   // longest-first work order (rank by counting; N is a batch size)
         const long long mine = lenbad ? 0 : Tn * (Ln + 1);
@@ -360,13 +363,13 @@ __global__ void __launch_bounds__(256) ctc2_prep_kernel(Prep2Params p) {
         p.zinfo[n] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+    for (int k = threadIdx.x; k < Lc; k += blockDim.x) {
         const int rk = s_rk[k];
         if (rk >= 1 && rk < kRcap) nfl[s_off[rk - 1] + atomicAdd(&s_fill[rk - 1], 1)] = (s_y[k] << 10) | k;
     }
     if (threadIdx.x == 0 && s_cnt[kRcap - 1] > 0) {     // rare: a label occurring more than kRcap times
         int o = s_off[kRcap - 1];
-        for (int k = 0; k < L; ++k)
+        for (int k = 0; k < Lc; ++k)
             if (s_rk[k] >= kRcap) nfl[o++] = (s_y[k] << 10) | k;
     }
 }

@@ -25,6 +25,17 @@ int ctc2_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V, in
              const float* grad_loss, int from_logits, float* gx, int64_t sg_t, int64_t sg_n,
              void* ws, size_t ws_bytes, cudaStream_t st);
 
+// ---- fused star-CTC path (star2.cu) ----
+bool star2_eligible(int T, int N, int V, int S);
+size_t star2_workspace_bytes(int T, int N, int S);
+int star2_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
+              const void* targets, int64_t tgt_stride, int S, int targets_i64,
+              const void* in_len, const void* tgt_len, int lengths_i64,
+              float star_penalty, int from_logits, float* loss, void* ws, size_t ws_bytes, cudaStream_t st);
+int star2_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V, int S,
+              const float* grad_loss, int from_logits, float* gx, int64_t sg_t, int64_t sg_n,
+              void* ws, size_t ws_bytes, cudaStream_t st);
+
 // ---- classifier head + CTC (head.cu) reuses the CTC prep and trellis kernels instantiated in api.cu ----
 void ctc_head_dims(int S, int* Sp, int* E, int* JWp, int* SPX);
 int ctc_prep_for_head(const void* targets, int64_t tgt_stride, int S, int targets_i64,
