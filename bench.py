@@ -855,11 +855,15 @@ def main():
         # the first half of both sweeps in one kernel), the backward call is ctc2_bwd (second half of the sweeps,
         # occupancies and the gradient rows in one kernel); emissions and occupancies never reach HBM
         names = ["ctc2_prep_kernel", "ctc2_fwd_kernel", "ctc2_bwd_kernel"]
+    if kind == "star":
+        # the same two-kernel shape for star-CTC (csrc/star2.cuh, round 2): quads (blank, star, blank, label) per position,
+        # the dense-over-V gradient formed in the row ring
+        names = ["ctc2_prep_kernel", "star2_fwd_kernel", "star2_bwd_kernel"]
     if kind == "rnnt_fg":
         names = ["rnnt_fg_stats_kernel + rnnt_fg_gemm_kernel<E>", "rnnt_lattice_kernel",
                  "rnnt_fg_gemm_kernel<DF> + rnnt_fg_gemm_kernel<DG> + rnnt_fg_fix_kernel"]
     tr = [ncu_traffic(k) if args.workload in ("ctc", "star", "rnnt") else None for k in names]
-    launches_per_step = {"ctc": 3, "star": 4, "rnnt": 5, "rnnt_fg": 8}[kind]
+    launches_per_step = {"ctc": 3, "star": 3, "rnnt": 5, "rnnt_fg": 8}[kind]
     step_gbs = ab / (ms_step * 1e-3) / 1e9
     grad_gbs = ab / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else None      # --graph: forward and backward are one replay
     out = {
@@ -881,12 +885,12 @@ def main():
                 names[2]: {"ms": bwd_ms, "achieved": grad_gbs, "frac": (grad_gbs / peak) if grad_gbs else None, "traffic": tr[2],
                            "note": "the backward call = this one kernel (timed live by CUDA events): reads the logits, "
                                    "writes the gradient; its algorithmic bytes are the step's"
-                                   + ("; it also runs the second half of both sweeps" if kind == "ctc" else "")},
+                                   + ("; it also runs the second half of both sweeps" if kind in ("ctc", "star") else "")},
                 "forward (" + names[0] + " + " + names[1] + ")": {
                     "ms": fwd_ms, "traffic": ((tr[0] or 0) + tr[1]) if tr[1] is not None else None,
                     "note": ("one fused kernel: logit rows in through TMA, row statistics + emission gather by the row "
                              "warps, first half of the alpha and beta sweeps by the trellis warps (profiles/, DESIGN.md)"
-                             if kind == "ctc" else
+                             if kind in ("ctc", "star") else
                              "rows kernel is HBM-bound; the " + mid + " kernel is instruction-issue / latency bound "
                              "(profiles/, DESIGN.md section 5)")},
             },

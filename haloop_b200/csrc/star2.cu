@@ -10,34 +10,47 @@ namespace hab {
 
 namespace {
 
-struct CfgS { int W, R, NS; size_t smem_fwd, smem_bwd; bool ok; };
+struct CfgS { int W, R, J, NS; size_t smem_fwd, smem_bwd; bool ok; };
 
 int env_int(const char* name) {
     const char* e = getenv(name);
     return e ? atoi(e) : 0;
 }
 
-// trellis warps for the longest target the batch may hold, row warps and the ring depth of each.  The backward kernel
-// wants rows in flight (a row occupies its stage from the load until its gradient has been stored): 8 row warps with
-// 3 stages where two CTAs still fit an SM, then fewer.
+// Quads per lane J and trellis warps W for the longest target the batch may hold (fewer quads per lane = more warps
+// sharing a step's arithmetic), row warps R and the ring depth of each.  The backward kernel wants rows in flight (a
+// row occupies its stage from the load until its gradient has been stored): 8 row warps with 3 stages where two CTAs
+// still fit an SM, then fewer.
 CfgS pick_cfg_s(int V, int S) {
-    CfgS c{0, 0, 0, 0, 0, false};
+    CfgS c{0, 0, 0, 0, 0, 0, false};
+    if (V % 4 != 0 || V < 4) return c;
     const int Sp = round_up(S > 0 ? S : 1, 4);
-    const int NLmax = S / 4 + 2;
-    const int Wn = (NLmax + 31) / 32;
-    static const int kW[] = {1, 2, 3, 5};
-    for (int w : kW) if (!c.W && w >= Wn) c.W = w;
-    if (!c.W || V % 4 != 0 || V < 4) return c;
-    static const int force_r = env_int("HA_B200_STAR_R"), force_ns = env_int("HA_B200_STAR_NS");      // tuning only
+    const int NLmax = S / 4 + 2, NAmax = 4 * NLmax;
+    static const int force_r = env_int("HA_B200_STAR_R"), force_ns = env_int("HA_B200_STAR_NS"),
+                     force_j = env_int("HA_B200_STAR_J");                                              // tuning only
+    // instantiated (J, W) pairs, most parallel first
+    static const struct { int J, W; } kJW[] = {{2, 2}, {2, 4}, {2, 5}, {4, 1}, {4, 2}, {4, 3}, {4, 5}};
+    static const struct { int J, W; } kJW1[] = {{1, 4}, {1, 7}};
+    auto fits = [&](int J, int W) { return (NAmax / J + 31) / 32 <= W; };
+    if (force_j == 1) for (const auto& t : kJW1) if (!c.W && fits(t.J, t.W)) { c.J = t.J; c.W = t.W; }
+    for (const auto& t : kJW) {
+        if (c.W) break;
+        if (force_j && t.J != force_j) continue;
+        if (fits(t.J, t.W)) { c.J = t.J; c.W = t.W; }
+    }
+    if (!c.W) for (const auto& t : kJW) if (!c.W && fits(t.J, t.W)) { c.J = t.J; c.W = t.W; }
+    if (!c.W) return c;
     static const struct { int R, NS; size_t cap; } kTry[] = {
         {8, 3, 112 * 1024}, {4, 3, 112 * 1024}, {4, 2, 112 * 1024}, {4, 2, 200 * 1024}, {4, 1, 224 * 1024}};
     for (const auto& t : kTry) {
         if (c.ok) break;
         int R = t.R, NS = t.NS; size_t cap = t.cap;
         if ((force_r == 4 || force_r == 8) && force_ns >= 1 && force_ns <= 4) { R = force_r; NS = force_ns; cap = 224 * 1024; }
+        if (c.J == 1 && R != 8) continue;
         const size_t f = star2_smem(c.W, R, NS, V, Sp, NLmax, false).total, b = star2_smem(c.W, R, NS, V, Sp, NLmax, true).total;
         if (b <= cap) { c.R = R; c.NS = NS; c.smem_fwd = f; c.smem_bwd = b; c.ok = true; }
     }
+    if (!c.ok && c.J == 1) { c.J = 0; c.W = 0; }
     return c;
 }
 
@@ -65,7 +78,10 @@ Star2Params base_params(const Star2Ws& w, unsigned char* base, int T, int N, int
     return p;
 }
 
-#define HAB_SW_CASES(X) X(1, 4, 4) X(2, 4, 3) X(3, 4, 3) X(5, 4, 2) X(1, 8, 2) X(2, 8, 2) X(3, 8, 2) X(5, 8, 1)
+// (W, R, J, min CTAs per SM)
+#define HAB_SW_CASES(X)                                                                                     \
+    X(1, 4, 4, 4) X(2, 4, 4, 3) X(3, 4, 4, 3) X(5, 4, 4, 2) X(1, 8, 4, 2) X(2, 8, 4, 2) X(3, 8, 4, 2) X(5, 8, 4, 1) \
+    X(2, 4, 2, 3) X(4, 4, 2, 2) X(5, 4, 2, 2) X(2, 8, 2, 2) X(4, 8, 2, 2) X(5, 8, 2, 1) X(4, 8, 1, 2) X(7, 8, 1, 2)
 
 }  // namespace
 
@@ -107,16 +123,16 @@ int star2_fwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
     cudaGetDevice(&dev);
     dev &= 63;
     bool hit = false;
-#define HAB_CASE(WW, RR, MB)                                                                          \
-    if (!hit && c.W == WW && c.R == RR) {                                                             \
+#define HAB_CASE(WW, RR, JJ, MB)                                                                            \
+    if (!hit && c.W == WW && c.R == RR && c.J == JJ) {                                                         \
         hit = true;                                                                                   \
         static bool attr[64] = {};                                                                    \
-        if (!attr[dev]) { if ((rc = set_smem_s(star2_fwd_kernel<WW, RR, MB>, kMaxSmemOptin, "star2_fwd"))) return rc; attr[dev] = true; } \
-        star2_fwd_kernel<WW, RR, MB><<<grid, 32 * (WW + RR), c.smem_fwd, st>>>(p);                        \
+        if (!attr[dev]) { if ((rc = set_smem_s(star2_fwd_kernel<WW, RR, JJ, MB>, kMaxSmemOptin, "star2_fwd"))) return rc; attr[dev] = true; } \
+        star2_fwd_kernel<WW, RR, JJ, MB><<<grid, 32 * (WW + RR), c.smem_fwd, st>>>(p);                        \
     }
     HAB_SW_CASES(HAB_CASE)
 #undef HAB_CASE
-    if (!hit) return host_fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: star2 W=%d R=%d", c.W, c.R);
+    if (!hit) return host_fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: star2 W=%d R=%d J=%d", c.W, c.R, c.J);
     return host_check_launch("star2_fwd_kernel");
 }
 
@@ -139,16 +155,16 @@ int star2_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V, i
     cudaGetDevice(&dev);
     dev &= 63;
     bool hit = false;
-#define HAB_CASE(WW, RR, MB)                                                                          \
-    if (!hit && c.W == WW && c.R == RR) {                                                             \
+#define HAB_CASE(WW, RR, JJ, MB)                                                                            \
+    if (!hit && c.W == WW && c.R == RR && c.J == JJ) {                                                         \
         hit = true;                                                                                   \
         static bool attr[64] = {};                                                                    \
-        if (!attr[dev]) { if ((rc = set_smem_s(star2_bwd_kernel<WW, RR, MB>, kMaxSmemOptin, "star2_bwd"))) return rc; attr[dev] = true; } \
-        star2_bwd_kernel<WW, RR, MB><<<grid, 32 * (WW + RR), c.smem_bwd, st>>>(p);                        \
+        if (!attr[dev]) { if ((rc = set_smem_s(star2_bwd_kernel<WW, RR, JJ, MB>, kMaxSmemOptin, "star2_bwd"))) return rc; attr[dev] = true; } \
+        star2_bwd_kernel<WW, RR, JJ, MB><<<grid, 32 * (WW + RR), c.smem_bwd, st>>>(p);                        \
     }
     HAB_SW_CASES(HAB_CASE)
 #undef HAB_CASE
-    if (!hit) return host_fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: star2 W=%d R=%d", c.W, c.R);
+    if (!hit) return host_fail(HA_ERR_UNSUPPORTED_SHAPE, "internal: star2 W=%d R=%d J=%d", c.W, c.R, c.J);
     return host_check_launch("star2_bwd_kernel");
 }
 

@@ -169,34 +169,57 @@ __device__ __forceinline__ void star_gather_row(float* em, int NA, const float* 
     }
 }
 
+// J consecutive words of a slot / stored row / boundary (J = 4, 2, 1: one 16-, 8- or 4-byte access)
+template <int J, typename T> __device__ __forceinline__ void ldv(const void* p, T (&v)[J]) {
+    if constexpr (J == 4) { const int4 t = *(const int4*)p; const int w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = std::is_same<T, float>::value ? (T)__int_as_float(w[c]) : (T)w[c]; }
+    else if constexpr (J == 2) { const int2 t = *(const int2*)p; const int w[2] = {t.x, t.y};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) v[c] = std::is_same<T, float>::value ? (T)__int_as_float(w[c]) : (T)w[c]; }
+    else { const int w = *(const int*)p; v[0] = std::is_same<T, float>::value ? (T)__int_as_float(w) : (T)w; }
+}
+template <int J> __device__ __forceinline__ int wbits(float x) { return __float_as_int(x); }
+template <int J> __device__ __forceinline__ int wbits(int x) { return x; }
+template <int J, typename T> __device__ __forceinline__ void stv(void* p, const T (&v)[J]) {
+    if constexpr (J == 4) *(int4*)p = make_int4(wbits<J>(v[0]), wbits<J>(v[1]), wbits<J>(v[2]), wbits<J>(v[3]));
+    else if constexpr (J == 2) *(int2*)p = make_int2(wbits<J>(v[0]), wbits<J>(v[1]));
+    else *(int*)p = wbits<J>(v[0]);
+}
+
+// label indices a = position + 4 of an utterance (positions -4 .. L), padded to a multiple of 4
+__host__ __device__ inline int star2_na(int L) { return (L + 8) & ~3; }
+
 struct QCfg {
-    int g;             // my position group (clamped into the slot): positions 4 g - 4 .. 4 g - 1
-    unsigned allowed;  // skip-transition bits of my 4 quads
+    int g;             // my position group (clamped into the slot): positions J g - 4 .. J g + J - 5
+    unsigned allowed;  // skip-transition bits of my J quads
     bool live;         // the lane owns a group of the stored rows
 };
+template <int J>
 __device__ __forceinline__ QCfg star_lane_cfg(int gl, int dir, int L, int NL, int NLmax, const int* y) {
     QCfg cf;
     cf.live = gl < NL;
     const int g = dir ? NL - 1 - gl : gl;
-    cf.g = min(max(g, 0), NLmax - 1);
-    cf.allowed = s2_allowed(g, dir, L, y, kLabelMask);
+    cf.g = min(max(g, 0), 4 * NLmax / J - 1);
+    cf.allowed = s2_allowed<J>(g, dir, L, y, kLabelMask);
     return cf;
 }
 // the virtual source: mass 1 on the label below the first quad (alpha) / above the final quad (beta)
-__device__ __forceinline__ void star_inject(QLane& s, int gl, int dir, int L, int NL) {
+template <int J>
+__device__ __forceinline__ void star_inject(QLane<J>& s, int gl, int dir, int L, int NL) {
     const int a_inj = dir ? L + 4 : 3;
-    const int gi = a_inj >> 2, ci = a_inj & 3;
+    const int gi = a_inj / J, ci = a_inj % J;
     if (gl == (dir ? NL - 1 - gi : gi)) {
 #pragma unroll
-        for (int c = 0; c < kQJ; ++c)
+        for (int c = 0; c < J; ++c)
             if (c == ci) { s.lb[c] = 1.0f; s.e[c] = 0; }
     }
 }
 
 // neighbour values entering my lane: from the previous lane of the side, or the mailbox the warp below filled last step
-template <int DIR>
-__device__ __forceinline__ void star_fetch(const QLane& s, int w, int lane, const int4* mail_prev, float& n0, float& nl, int& ne) {
-    constexpr int C = DIR ? 0 : kQJ - 1;
+template <int DIR, int J>
+__device__ __forceinline__ void star_fetch(const QLane<J>& s, int w, int lane, const int4* mail_prev, float& n0, float& nl, int& ne) {
+    constexpr int C = DIR ? 0 : J - 1;
     nl = __shfl_up_sync(0xffffffffu, s.lb[C], 1);
     ne = __shfl_up_sync(0xffffffffu, s.e[C], 1);
     n0 = DIR ? __shfl_up_sync(0xffffffffu, s.b0[C], 1) : 0.0f;
@@ -206,15 +229,15 @@ __device__ __forceinline__ void star_fetch(const QLane& s, int w, int lane, cons
         n0 = __int_as_float(in.x); nl = __int_as_float(in.y); ne = in.z;
     }
 }
-template <int DIR>
-__device__ __forceinline__ int4 star_mail(const QLane& s) {
-    constexpr int C = DIR ? 0 : kQJ - 1;
+template <int DIR, int J>
+__device__ __forceinline__ int4 star_mail(const QLane<J>& s) {
+    constexpr int C = DIR ? 0 : J - 1;
     return make_int4(__float_as_int(s.b0[C]), __float_as_int(s.lb[C]), s.e[C], 0);
 }
 
 // ------------------------------------------------------------------------------------ forward ---
 // grid 2N (CTA c: utterance order[c / 2], direction c % 2), block 32 (W + R).
-template <int W, int R, int MINB>
+template <int W, int R, int J, int MINB>
 __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Params p) {
     constexpr int kSR = R, kSNE = 2 * R;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -231,7 +254,7 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
         }
         return;
     }
-    const int NL = L / 4 + 2;
+    const int NA_n = star2_na(L), NL = NA_n / J;   // label indices and lanes (groups of J quads) of this utterance
     const int Wn = (NL + 31) >> 5;                 // trellis warps this utterance needs
     const int NS = p.NS, V = p.V, EMF = p.EMF, NA = p.NA;
     const Star2Smem sm = star2_smem(W, R, NS, V, p.Sp, p.NLmax, false);
@@ -287,11 +310,11 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
             const float* row = wrows + stg * V;
             mbar_wait(&wbar[stg], par);
             const float4 nm = star_row_norms(star_row_stats(row, V4, lane), p.from_logits);
-            if (lane == 0) p.stat[(size_t)n * p.T + t] = nm;
             const int slot = i & (kSNE - 1), use = i / kSNE;
             if (use > 0) mbar_wait_sleep(&em_empty[slot], (uint32_t)(use - 1) & 1u, 128);
             star_gather_row(s_em + slot * EMF, NA, row, s_off, L, lane, nm);
             mbar_arrive(&em_full[slot]);
+            if (lane == 0) p.stat[(size_t)n * p.T + t] = nm;
             __syncwarp();
             if (k + NS < nrows) issue(k + NS, stg);
             if (++stg == NS) { stg = 0; par ^= 1u; }
@@ -304,32 +327,32 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
     const int w = warp;
     const int nthr = 32 * Wn;
     const int gl = 32 * w + lane;
-    const QCfg cfg = star_lane_cfg(gl, dir, L, NL, p.NLmax, p.tgt + (size_t)n * p.Sp);
-    QLane s;
+    const QCfg cfg = star_lane_cfg<J>(gl, dir, L, NL, p.NLmax, p.tgt + (size_t)n * p.Sp);
+    QLane<J> s;
     s2_lane_clear(s);
     star_inject(s, gl, dir, L, NL);
     if (lane == 31) mail[1 * W + w] = dir ? star_mail<1>(s) : star_mail<0>(s);
     side_barrier(nthr);
-    const float* emp = s_em + 4 + 4 * cfg.g;                // my four label emissions in slot 0
+    const float* emp = s_em + 4 + J * cfg.g;                // my J label emissions in slot 0
     const float pen = p.pen;
 
     auto sweep = [&](auto dirc) {
         constexpr int DIR = decltype(dirc)::value;
-        int* trow = p.tr + ((size_t)n * p.T + (DIR ? Tn - 1 : 0)) * p.SPL + 4 * cfg.g;
-        const int NL4 = 4 * NL;
+        int* trow = p.tr + ((size_t)n * p.T + (DIR ? Tn - 1 : 0)) * p.SPL + J * cfg.g;
+        const int NL4 = NA_n;
         const long long tstep = DIR ? -(long long)p.SPL : (long long)p.SPL;
         S2P_DECL(4);
         // The slot of step i + 1 is tested (non-blocking) before the arithmetic of step i and, when it is there, read
         // before the step's barrier: the latency of the phase test and of the loads is off the step's critical path.
-        float pb = 0.0f; float4 pl4 = make_float4(0.f, 0.f, 0.f, 0.f), ps4 = pl4;
-        auto load_slot = [&](int slot, float& b, float4& l4, float4& s4) {
+        float pb = 0.0f, pl[J] = {}, ps[J] = {};
+        auto load_slot = [&](int slot, float& b, float (&l)[J], float (&sx)[J]) {
             b = s_em[slot * EMF];
-            l4 = *(const float4*)(emp + slot * EMF);
-            s4 = *(const float4*)(emp + NA + slot * EMF);
+            ldv<J>(emp + slot * EMF, l);
+            ldv<J>(emp + NA + slot * EMF, sx);
         };
         if (steps1 > 0) {
             mbar_wait_sleep(&em_full[0], 0u, 32);
-            load_slot(0, pb, pl4, ps4);
+            load_slot(0, pb, pl, ps);
             mbar_arrive(&em_empty[0]);
         }
         for (int i = 0; i < steps1; ++i) {
@@ -337,21 +360,23 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
             const uint32_t par1 = (uint32_t)(i1 / kSNE) & 1u;
             const bool more = i1 < steps1;
             S2P_MARK(3);
-            const bool rdy = more && mbar_test(&em_full[slot1], par1);
+            const bool rdy = more & mbar_test(&em_full[slot1], par1);
             S2P_MARK(0);
-            const float pl[kQJ] = {pl4.x, pl4.y, pl4.z, pl4.w}, ps[kQJ] = {ps4.x, ps4.y, ps4.z, ps4.w};
             float n0, nl; int ne;
             star_fetch<DIR>(s, w, lane, mail + ((i + 1) & 1) * W, n0, nl, ne);
-            QSums q;
+            QSums<J> q;
             s2_quad_sums<DIR>(s, cfg.allowed, n0, nl, ne, q);
             s2_quad_emit(s, q, pb, pl, ps, pen);
             if (lane == 31) mail[(i & 1) * W + w] = star_mail<DIR>(s);
-            float npb = 0.0f; float4 npl = make_float4(0.f, 0.f, 0.f, 0.f), nps = npl;
-            if (rdy) load_slot(slot1, npb, npl, nps);
+            float npb = 0.0f, npl[J] = {}, nps[J] = {};
+            if (rdy) {        // (before this step's global stores: the release of the arrival would wait for them)
+                load_slot(slot1, npb, npl, nps);
+                mbar_arrive(&em_empty[slot1]);
+            }
             if (cfg.live) {
-                *(float4*)trow = make_float4(s.lb[0], s.lb[1], s.lb[2], s.lb[3]);
-                *(float4*)(trow + NL4) = make_float4(s.st[0], s.st[1], s.st[2], s.st[3]);
-                *(int4*)(trow + 2 * NL4) = make_int4(s.e[0], s.e[1], s.e[2], s.e[3]);
+                stv<J>(trow, s.lb);
+                stv<J>(trow + NL4, s.st);
+                stv<J>(trow + 2 * NL4, s.e);
             }
             trow += tstep;
             S2P_MARK(1);
@@ -361,9 +386,11 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
                 if (!rdy) {
                     mbar_wait_sleep(&em_full[slot1], par1, 32);
                     load_slot(slot1, npb, npl, nps);
+                    mbar_arrive(&em_empty[slot1]);
                 }
-                mbar_arrive(&em_empty[slot1]);
-                pb = npb; pl4 = npl; ps4 = nps;
+                pb = npb;
+#pragma unroll
+                for (int c = 0; c < J; ++c) { pl[c] = npl[c]; ps[c] = nps[c]; }
             }
         }
         if (w == 0) S2P_DUMP(16 + 8 * (int)blockIdx.x, 4, steps1);      // [em wait, compute, barrier, loop]
@@ -372,13 +399,13 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
 
     // ---- the meeting: leave my boundary state; whoever arrives second forms Z from both ----
     int* mybound = p.bound + ((size_t)n * 2 + dir) * p.BW;
-    const int NL4 = 4 * NL;
+    const int NL4 = NA_n;
     if (cfg.live) {
-        *(float4*)(mybound + 4 * cfg.g) = make_float4(s.b0[0], s.b0[1], s.b0[2], s.b0[3]);
-        *(float4*)(mybound + NL4 + 4 * cfg.g) = make_float4(s.st[0], s.st[1], s.st[2], s.st[3]);
-        *(float4*)(mybound + 2 * NL4 + 4 * cfg.g) = make_float4(s.b1[0], s.b1[1], s.b1[2], s.b1[3]);
-        *(float4*)(mybound + 3 * NL4 + 4 * cfg.g) = make_float4(s.lb[0], s.lb[1], s.lb[2], s.lb[3]);
-        *(int4*)(mybound + 4 * NL4 + 4 * cfg.g) = make_int4(s.e[0], s.e[1], s.e[2], s.e[3]);
+        stv<J>(mybound + J * cfg.g, s.b0);
+        stv<J>(mybound + NL4 + J * cfg.g, s.st);
+        stv<J>(mybound + 2 * NL4 + J * cfg.g, s.b1);
+        stv<J>(mybound + 3 * NL4 + J * cfg.g, s.lb);
+        stv<J>(mybound + 4 * NL4 + J * cfg.g, s.e);
     }
     __threadfence();
     side_barrier(nthr);
@@ -390,12 +417,12 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
         // side gets here runs the SAME arithmetic on the two stored boundaries (bit-identical repeats).
         const int* ba = p.bound + ((size_t)n * 2 + 0) * p.BW;
         const int* ob = p.bound + ((size_t)n * 2 + 1) * p.BW;
-        const QCfg ca = star_lane_cfg(gl, 0, L, NL, p.NLmax, p.tgt + (size_t)n * p.Sp);
-        QLane sa;
-        float bo[4][kQJ]; int be[kQJ];
+        const QCfg ca = star_lane_cfg<J>(gl, 0, L, NL, p.NLmax, p.tgt + (size_t)n * p.Sp);
+        QLane<J> sa;
+        float bo[4][J]; int be[J];
 #pragma unroll
-        for (int c = 0; c < kQJ; ++c) {
-            const int a = 4 * ca.g + c;
+        for (int c = 0; c < J; ++c) {
+            const int a = J * ca.g + c;
             sa.b0[c] = ca.live ? __int_as_float(__ldcg(ba + a)) : 0.0f;
             sa.st[c] = ca.live ? __int_as_float(__ldcg(ba + NL4 + a)) : 0.0f;
             sa.b1[c] = ca.live ? __int_as_float(__ldcg(ba + 2 * NL4 + a)) : 0.0f;
@@ -409,12 +436,12 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
         side_barrier(nthr);
         float n0, nl; int ne;
         star_fetch<0>(sa, w, lane, mail, n0, nl, ne);
-        QSums q;
+        QSums<J> q;
         s2_quad_sums<0>(sa, ca.allowed, n0, nl, ne, q);
-        float zm[4 * kQJ]; int zx[4 * kQJ];
+        float zm[4 * J]; int zx[4 * J];
         int pm = 4 * kQVoidE;
 #pragma unroll
-        for (int c = 0; c < kQJ; ++c) {
+        for (int c = 0; c < J; ++c) {
             const float m[4] = {q.w0[c] * bo[0][c], q.vs[c] * bo[1][c], q.u1[c] * bo[2][c], q.vl[c] * bo[3][c]};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -431,7 +458,7 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
         const bool feasible = pm > kVoidETest;
         double sum = 0.0;
 #pragma unroll
-        for (int j = 0; j < 4 * kQJ; ++j) {
+        for (int j = 0; j < 4 * J; ++j) {
             if (zm[j] > 0.0f) {
                 const float mant = __int_as_float((__float_as_int(zm[j]) & 0x007fffff) | 0x3f800000);   // in [1, 2)
                 const int rel = zx[j] - pm;                                      // <= 0
@@ -466,7 +493,7 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
 // log-softmax and 0 at the log-prob boundary, G = sum_k h_k, H_c = the sum of h_k over the stars that exclude c,
 // occ_c the label occupancy of class c (the blank: one minus the label and star occupancies).  Rows t >= T_n and every
 // row of an infeasible or invalid utterance are zero.
-template <int W, int R, int MINB>
+template <int W, int R, int J, int MINB>
 __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Params p) {
     constexpr int kSR = R, kSNE = 2 * R;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -493,7 +520,7 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
     }
     if (nsteps2 <= 0) return;
 
-    const int NL = L / 4 + 2;
+    const int NA_n = star2_na(L), NL = NA_n / J;
     const int Wn = (NL + 31) >> 5;
     const int Ks = min(L + 1, p.S);
     const Star2Smem sm = star2_smem(W, R, NS, V, p.Sp, p.NLmax, true);
@@ -546,7 +573,7 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
         };
         // the row the OTHER side stored for the frame of my row k, into my stored-row slot: issued once the trellis warps
         // have read the slot for my row k - 1 (I have seen their occupancies), R steps before they need it
-        const uint32_t st_bytes = (uint32_t)(12 * NL) * 4u;
+        const uint32_t st_bytes = (uint32_t)(3 * NA_n) * 4u;
         const int* tr_n = p.tr + (size_t)n * p.T * p.SPL;
         auto issue_st = [&](int k) {
             if (lane == 0) {
@@ -555,11 +582,19 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
             }
         };
         if (nrows > 0) issue_st(0);
+        float4 nm_next = make_float4(0.f, 0.f, 0.f, 0.f);       // row statistics, fetched one row ahead
+        if (nrows > 0) nm_next = p.stat[(size_t)n * p.T + frame(0)];
+        // later occurrences of a class: the first four rank groups live in registers (a global load per group and row
+        // would sit on every row's critical path)
+        int nfe[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nfe[j] = (32 * j < nf.x) ? __ldg(nfl + 32 * j + lane) : -1;
         // pre(k): gather the emissions of row k for the trellis warps, then turn the row into g * p_c in place.
         auto pre = [&](int k, int stg, uint32_t par) {
             const int i2 = r + k * kSR, t = frame(k);
             float* row = wrows + stg * V;
-            const float4 nm = p.stat[(size_t)n * p.T + t];
+            const float4 nm = nm_next;
+            if (k + 1 < nrows) nm_next = p.stat[(size_t)n * p.T + frame(k + 1)];
             S2P_MARK(5);
             mbar_wait(&wbar[stg], par);
             S2P_MARK(0);
@@ -586,6 +621,7 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
             float* em = s_em + (i2 & (kSNE - 1)) * EMF;
             S2P_MARK(5);
             mbar_wait_sleep(&occ_full[i2 & (kSNE - 1)], (uint32_t)(i2 / kSNE) & 1u, 128);
+            if (k + 1 < nrows) issue_st(k + 1);
             S2P_MARK(2);
             // per position: a_k = g p_{y_k} h_k - g gamma(label k), parked in the label-occupancy word; bs = label + star
             // occupancies, G = sum of h
@@ -637,7 +673,14 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
             }
             __syncwarp();
             // later occurrences: by occurrence rank, one rank (distinct classes) per 32 entries: deterministic, no atomics
-            for (int e0 = 0; e0 < nf.x; e0 += 32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (32 * j < nf.x) {
+                    if (nfe[j] >= 0) row[nfe[j] >> 10] += em[8 + (nfe[j] & 1023)];
+                    __syncwarp();
+                }
+            }
+            for (int e0 = 128; e0 < nf.x; e0 += 32) {
                 const int e = __ldg(nfl + e0 + lane);
                 if (e >= 0) row[e >> 10] += em[8 + (e & 1023)];
                 __syncwarp();
@@ -647,7 +690,6 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
             fence_async_smem();
             __syncwarp();
             if (lane == 0) { bulk_s2g(gb + (long long)t * p.sg_t, row, (uint32_t)V * 4u); bulk_commit(); }
-            if (k + 1 < nrows) issue_st(k + 1);
             S2P_MARK(3);
         };
         auto next = [&](int& stg, uint32_t& par) { if (++stg == NS) { stg = 0; par ^= 1u; } };
@@ -702,28 +744,22 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
     const int w = warp;
     const int nthr = 32 * Wn;
     const int gl = 32 * w + lane;
-    const QCfg cfg = star_lane_cfg(gl, dir, L, NL, p.NLmax, p.tgt + (size_t)n * p.Sp);
-    const int NL4 = 4 * NL;
-    QLane s;
+    const QCfg cfg = star_lane_cfg<J>(gl, dir, L, NL, p.NLmax, p.tgt + (size_t)n * p.Sp);
+    const int NL4 = NA_n;
+    QLane<J> s;
     s2_lane_clear(s);
     if (cfg.live) {
-        const int* mybound = p.bound + ((size_t)n * 2 + dir) * p.BW + 4 * cfg.g;
-        const float4 a0 = *(const float4*)(mybound), a1 = *(const float4*)(mybound + NL4);
-        const float4 a2 = *(const float4*)(mybound + 2 * NL4), a3 = *(const float4*)(mybound + 3 * NL4);
-        const int4 ae = *(const int4*)(mybound + 4 * NL4);
-        s.b0[0] = a0.x; s.b0[1] = a0.y; s.b0[2] = a0.z; s.b0[3] = a0.w;
-        s.st[0] = a1.x; s.st[1] = a1.y; s.st[2] = a1.z; s.st[3] = a1.w;
-        s.b1[0] = a2.x; s.b1[1] = a2.y; s.b1[2] = a2.z; s.b1[3] = a2.w;
-        s.lb[0] = a3.x; s.lb[1] = a3.y; s.lb[2] = a3.z; s.lb[3] = a3.w;
-        s.e[0] = ae.x; s.e[1] = ae.y; s.e[2] = ae.z; s.e[3] = ae.w;
+        const int* mybound = p.bound + ((size_t)n * 2 + dir) * p.BW + J * cfg.g;
+        ldv<J>(mybound, s.b0); ldv<J>(mybound + NL4, s.st); ldv<J>(mybound + 2 * NL4, s.b1); ldv<J>(mybound + 3 * NL4, s.lb);
+        ldv<J>(mybound + 4 * NL4, s.e);
     }
     const int4 zi = p.zinfo[n];
     const int eZ = zi.x;
     const float rZ = __int_as_float(zi.y);
     const float pen = p.hdr[0];
     if (lane == 31) mail[((steps1 + 1) & 1) * W + w] = dir ? star_mail<1>(s) : star_mail<0>(s);
-    float* emp = s_em + 4 + 4 * cfg.g;                      // my four label emissions / occupancies in slot 0
-    const int* stp = s_st + 4 * cfg.g;                      // the other side's label states of my group in slot 0
+    float* emp = s_em + 4 + J * cfg.g;                      // my J label emissions / occupancies in slot 0
+    const int* stp = s_st + J * cfg.g;                      // the other side's label states of my group in slot 0
     side_barrier(nthr);
 
     auto sweep = [&](auto dirc) {
@@ -731,21 +767,23 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
         S2P_DECL(5);
         // software-pipelined slot hand-over as in the forward kernel; a step's inputs are its emission slot (i2 % 2R)
         // and the stored-row slot of the row warp that owns the frame (i2 % R)
-        float pb = 0.0f; float4 pl4 = make_float4(0.f, 0.f, 0.f, 0.f), ps4 = pl4, o4 = pl4, s4 = pl4;
-        int4 e4 = make_int4(kQVoidE, kQVoidE, kQVoidE, kQVoidE);
-        auto load_slot = [&](int slot, int ss, float& b, float4& l4, float4& p4, float4& oo, float4& so, int4& eo) {
+        float pb = 0.0f, pl[J] = {}, ps[J] = {}, lbo[J] = {}, sto[J] = {};
+        int eo[J];
+#pragma unroll
+        for (int c = 0; c < J; ++c) eo[c] = kQVoidE;
+        auto load_slot = [&](int slot, int ss, float& b, float (&l)[J], float (&sx)[J], float (&oo)[J], float (&so)[J], int (&ee)[J]) {
             b = s_em[slot * EMF];
-            l4 = *(const float4*)(emp + slot * EMF);
-            p4 = *(const float4*)(emp + NA + slot * EMF);
+            ldv<J>(emp + slot * EMF, l);
+            ldv<J>(emp + NA + slot * EMF, sx);
             if (cfg.live) {
-                oo = *(const float4*)(stp + ss * p.SPL); so = *(const float4*)(stp + ss * p.SPL + NL4);
-                eo = *(const int4*)(stp + ss * p.SPL + 2 * NL4);
+                ldv<J>(stp + ss * p.SPL, oo); ldv<J>(stp + ss * p.SPL + NL4, so);
+                ldv<J>(stp + ss * p.SPL + 2 * NL4, ee);
             }
         };
         if (nsteps2 > 0) {
             mbar_wait_sleep(&em_full[0], 0u, 32);
             mbar_wait(&st_full[0], 0u);
-            load_slot(0, 0, pb, pl4, ps4, o4, s4, e4);
+            load_slot(0, 0, pb, pl, ps, lbo, sto, eo);
         }
         for (int i2 = 0; i2 < nsteps2; ++i2) {
             const int i = steps1 + i2;
@@ -754,27 +792,26 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
             const uint32_t par1 = (uint32_t)(j1 / kSNE) & 1u, spar1 = (uint32_t)(j1 / kSR) & 1u;
             const bool more = j1 < nsteps2;
             S2P_MARK(4);
-            const bool rdy = more && mbar_test(&em_full[slot1], par1) && mbar_test(&st_full[ss1], spar1);
+            const bool t_em = mbar_test(&em_full[slot1], par1), t_st = mbar_test(&st_full[ss1], spar1);   // both in flight
+            const bool rdy = more & t_em & t_st;
             S2P_MARK(0);
-            const float pl[kQJ] = {pl4.x, pl4.y, pl4.z, pl4.w}, ps[kQJ] = {ps4.x, ps4.y, ps4.z, ps4.w};
-            const float lbo[kQJ] = {o4.x, o4.y, o4.z, o4.w}, sto[kQJ] = {s4.x, s4.y, s4.z, s4.w};
-            const int eo[kQJ] = {e4.x, e4.y, e4.z, e4.w};
-            S2P_MARK(1);
             float n0, nl; int ne;
             star_fetch<DIR>(s, w, lane, mail + ((i + 1) & 1) * W, n0, nl, ne);
-            QSums q;
+            QSums<J> q;
             s2_quad_sums<DIR>(s, cfg.allowed, n0, nl, ne, q);
-            float ogl[kQJ], ogs[kQJ], oh[kQJ];
+            float ogl[J], ogs[J], oh[J];
             s2_quad_occ(s, q, lbo, sto, eo, eZ, rZ, ps, ogl, ogs, oh);
             s2_quad_emit(s, q, pb, pl, ps, pen);
             if (lane == 31) mail[(i & 1) * W + w] = star_mail<DIR>(s);
             if (cfg.live) {
-                *(float4*)(emp + slot * EMF) = make_float4(ogl[0], ogl[1], ogl[2], ogl[3]);
-                *(float4*)(emp + NA + slot * EMF) = make_float4(oh[0], oh[1], oh[2], oh[3]);
-                *(float4*)(emp + 2 * NA + slot * EMF) = make_float4(ogs[0], ogs[1], ogs[2], ogs[3]);
+                stv<J>(emp + slot * EMF, ogl);
+                stv<J>(emp + NA + slot * EMF, oh);
+                stv<J>(emp + 2 * NA + slot * EMF, ogs);
             }
-            float npb = 0.0f; float4 npl = make_float4(0.f, 0.f, 0.f, 0.f), nps = npl, no4 = npl, ns4 = npl;
-            int4 ne4 = make_int4(kQVoidE, kQVoidE, kQVoidE, kQVoidE);
+            float npb = 0.0f, npl[J] = {}, nps[J] = {}, no4[J] = {}, ns4[J] = {};
+            int ne4[J];
+#pragma unroll
+            for (int c = 0; c < J; ++c) ne4[c] = kQVoidE;
             if (rdy) load_slot(slot1, ss1, npb, npl, nps, no4, ns4, ne4);
             mbar_arrive(&occ_full[slot]);
             S2P_MARK(2);
@@ -782,11 +819,16 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
             S2P_MARK(3);
             if (more) {
                 if (!rdy) {
+#ifdef HAB_STAR2_PROBE
+                    s2p_acc[1] += mbar_test(&em_full[slot1], par1) ? 1 : 1000;      // units: waited for the stored row; thousands: for the emissions
+#endif
                     mbar_wait_sleep(&em_full[slot1], par1, 32);
                     mbar_wait(&st_full[ss1], spar1);
                     load_slot(slot1, ss1, npb, npl, nps, no4, ns4, ne4);
                 }
-                pb = npb; pl4 = npl; ps4 = nps; o4 = no4; s4 = ns4; e4 = ne4;
+                pb = npb;
+#pragma unroll
+                for (int c = 0; c < J; ++c) { pl[c] = npl[c]; ps[c] = nps[c]; lbo[c] = no4[c]; sto[c] = ns4[c]; eo[c] = ne4[c]; }
             }
         }
         if (w == 0) S2P_DUMP(32 + 8 * (int)blockIdx.x, 5, nsteps2);     // [em wait, stored-row wait, compute, barrier, loop]

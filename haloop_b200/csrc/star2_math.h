@@ -7,8 +7,8 @@
 //     b0 <- lb[k-1], b0        st <- b0, st, b1 (x star_penalty)        b1 <- st, b1
 //     lb <- b0, st, b1, and lb[k-1] unless y_k == y_{k-1}               (labels have no self loop)
 //
-// Numbers: "quad-normalised" linear domain, the ctc2.cuh format with four states per exponent.  A lane owns 4
-// consecutive quads in POSITION order (component c is position 4 g + c - 4); the four states of a quad are plain
+// Numbers: "quad-normalised" linear domain, the ctc2.cuh format with four states per exponent.  A lane owns J (4, 2 or 1)
+// consecutive quads in POSITION order (component c is position J g + c - 4); the four states of a quad are plain
 // fp32 values sharing one int32 exponent, rescaled after every step so that the largest sits in [2^32, 2^33).
 #pragma once
 #include <math.h>
@@ -22,7 +22,6 @@
 
 namespace hab {
 
-constexpr int kQJ = 4;                    // quads per lane
 constexpr int kQLaneExp = 32 + 127;       // biased exponent the largest state of a quad is normalised to
 constexpr int kQAlignMax = 30;            // largest up-shift applied to a neighbour's state
 constexpr int kQVoidE = -(1 << 28);       // exponent of an all-zero quad (common.cuh kVoidE)
@@ -96,14 +95,15 @@ S2_HD float s2_scale_pow2(float x, int d) {
     return (d >= -126) ? x * s2_i2f((d + 127) << 23) : 0.0f;
 }
 
-struct QLane { float b0[kQJ], st[kQJ], b1[kQJ], lb[kQJ]; int e[kQJ]; };
-struct QSums { float w0[kQJ], vs[kQJ], u1[kQJ], vl[kQJ]; };      // pre-emission sums of b0, st, b1, lb; scale s.e[c]
+template <int J> struct QLane { float b0[J], st[J], b1[J], lb[J]; int e[J]; };
+template <int J> struct QSums { float w0[J], vs[J], u1[J], vl[J]; };      // pre-emission sums of b0, st, b1, lb; scale s.e[c]
 
-S2_HD void s2_lane_clear(QLane& s) {
+template <int J>
+S2_HD void s2_lane_clear(QLane<J>& s) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int c = 0; c < kQJ; ++c) { s.b0[c] = 0.0f; s.st[c] = 0.0f; s.b1[c] = 0.0f; s.lb[c] = 0.0f; s.e[c] = kQVoidE; }
+    for (int c = 0; c < J; ++c) { s.b0[c] = 0.0f; s.st[c] = 0.0f; s.b1[c] = 0.0f; s.lb[c] = 0.0f; s.e[c] = kQVoidE; }
 }
 
 // First half of a step.  DIR 0 (alpha, forward in time): nl / ne = the label state of the quad below my lowest one
@@ -112,24 +112,29 @@ S2_HD void s2_lane_clear(QLane& s) {
 //   beta    w0 = b0 + st + lb       vs = u1 = st + b1 + lb                         vl = b0[k+1] + [allowed] lb[k+1]
 // (ha/star.py:123-145; beta: the transposed arcs).  A quad dwarfed by its neighbour (the wavefront arrives) moves its
 // exponent up first.
-template <int DIR>
-S2_HD void s2_quad_sums(QLane& s, unsigned allowed, float n0, float nl, int ne, QSums& q) {
-    float xl[kQJ], x0[kQJ]; int d[kQJ];
+template <int DIR, int J>
+S2_HD void s2_quad_sums(QLane<J>& s, unsigned allowed, float n0, float nl, int ne, QSums<J>& q) {
+    float xl[J], x0[J]; int d[J];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int c = 0; c < kQJ; ++c) {
-        const bool edge = DIR ? (c == kQJ - 1) : (c == 0);
-        const int cb = DIR ? (c < kQJ - 1 ? c + 1 : c) : (c ? c - 1 : 0);
+    for (int c = 0; c < J; ++c) {
+        const bool edge = DIR ? (c == J - 1) : (c == 0);
+        const int cb = DIR ? (c < J - 1 ? c + 1 : c) : (c ? c - 1 : 0);
         xl[c] = edge ? nl : s.lb[cb];
         x0[c] = DIR ? (edge ? n0 : s.b0[cb]) : 0.0f;
         d[c] = (edge ? ne : s.e[cb]) - s.e[c];
     }
-    if (s2_max(s2_max(d[0], d[1]), s2_max(d[2], d[3])) > kQAlignMax) {
+    int dmax = d[0];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int c = 0; c < kQJ; ++c) {
+    for (int c = 1; c < J; ++c) dmax = s2_max(dmax, d[c]);
+    if (dmax > kQAlignMax) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int c = 0; c < J; ++c) {
             if (d[c] > kQAlignMax) {
                 const int sh = d[c] - kQAlignMax, dn = -s2_min(sh, 512);
                 s.b0[c] = s2_scale_pow2(s.b0[c], dn); s.st[c] = s2_scale_pow2(s.st[c], dn);
@@ -142,7 +147,7 @@ S2_HD void s2_quad_sums(QLane& s, unsigned allowed, float n0, float nl, int ne, 
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int c = 0; c < kQJ; ++c) {
+    for (int c = 0; c < J; ++c) {
         const int dd = s2_max(d[c], -512);
         const bool al = (allowed >> c) & 1u;
         const float cl = s2_scale_pow2(xl[c], dd);
@@ -161,11 +166,12 @@ S2_HD void s2_quad_sums(QLane& s, unsigned allowed, float n0, float nl, int ne, 
 
 // Second half: multiply by the emissions (pb blank, pl[c] label, ps[c] star, pen = exp(star_penalty), paid on every
 // arc into a star, ha/star.py:137) and renormalise each quad.
-S2_HD void s2_quad_emit(QLane& s, const QSums& q, float pb, const float (&pl)[kQJ], const float (&ps)[kQJ], float pen) {
+template <int J>
+S2_HD void s2_quad_emit(QLane<J>& s, const QSums<J>& q, float pb, const float (&pl)[J], const float (&ps)[J], float pen) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int c = 0; c < kQJ; ++c) {
+    for (int c = 0; c < J; ++c) {
         const float n0 = q.w0[c] * pb, ns = (q.vs[c] * ps[c]) * pen, n1 = q.u1[c] * pb, nl = q.vl[c] * pl[c];
         const float mx = fmaxf(fmaxf(n0, ns), fmaxf(n1, nl));
         const int delta = s2_min(kQLaneExp - (s2_f2i(mx) >> 23), 120);
@@ -178,12 +184,13 @@ S2_HD void s2_quad_emit(QLane& s, const QSums& q, float pb, const float (&pl)[kQ
 // Occupancies of a frame from my pre-emission sums and the OTHER side's stored (emission included) label and star
 // states of the same frame: gl = gamma(label k), gs = gamma(star k), h = gamma(star k) / (P - p_{y_k}).
 // eZ / rZ: exponent of Z and 1 / mantissa of Z.
-S2_HD void s2_quad_occ(const QLane& s, const QSums& q, const float (&lbo)[kQJ], const float (&sto)[kQJ], const int (&eo)[kQJ],
-                       int eZ, float rZ, const float (&ps)[kQJ], float (&gl)[kQJ], float (&gs)[kQJ], float (&h)[kQJ]) {
+template <int J>
+S2_HD void s2_quad_occ(const QLane<J>& s, const QSums<J>& q, const float (&lbo)[J], const float (&sto)[J], const int (&eo)[J],
+                       int eZ, float rZ, const float (&ps)[J], float (&gl)[J], float (&gs)[J], float (&h)[J]) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int c = 0; c < kQJ; ++c) {
+    for (int c = 0; c < J; ++c) {
         const int xs = s.e[c] + eo[c] - eZ;
         const float sc = (xs < -126) ? 0.0f : s2_i2f(s2_f2i(rZ) + (int)((unsigned)s2_min(xs, 90) << 23));
         gl[c] = (q.vl[c] * lbo[c]) * sc;
@@ -192,11 +199,12 @@ S2_HD void s2_quad_occ(const QLane& s, const QSums& q, const float (&lbo)[kQJ], 
     }
 }
 
-// skip-transition bits of a lane's 4 quads (group g, labels y[0..L)), by component   [ha/star.py:117-118, :139-140]
+// skip-transition bits of a lane's J quads (group g, labels y[0..L)), by component   [ha/star.py:117-118, :139-140]
+template <int J>
 S2_HD unsigned s2_allowed(int g, int dir, int L, const int* y, int label_mask) {
     unsigned allowed = 0;
-    for (int c = 0; c < kQJ; ++c) {
-        const int p = 4 * g + c - 4;                 // target position of the quad
+    for (int c = 0; c < J; ++c) {
+        const int p = J * g + c - 4;                 // target position of the quad
         bool al = false;
         if (!dir) {
             if (p == 0) al = true;                   // the virtual source below the first quad

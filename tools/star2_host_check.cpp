@@ -13,37 +13,42 @@ using namespace hab;
 
 namespace {
 
+template <int J>
 struct Side {
     int dir, NL;
-    std::vector<QLane> s;
+    std::vector<QLane<J>> s;
     std::vector<unsigned> allowed;
     std::vector<int> g;
 };
 
-void side_init(Side& sd, int dir, int L, const int* y) {
+inline int na_of(int L) { return (L + 5 + 3) / 4 * 4; }      // label indices a = position + 4 of an utterance, padded to 4
+
+template <int J>
+void side_init(Side<J>& sd, int dir, int L, const int* y) {
     sd.dir = dir;
-    sd.NL = L / 4 + 2;
+    sd.NL = na_of(L) / J;
     sd.s.resize(sd.NL);
     sd.allowed.resize(sd.NL);
     sd.g.resize(sd.NL);
     for (int gl = 0; gl < sd.NL; ++gl) {
         const int g = dir ? sd.NL - 1 - gl : gl;
         sd.g[gl] = g;
-        sd.allowed[gl] = s2_allowed(g, dir, L, y, 0x3fffffff);
+        sd.allowed[gl] = s2_allowed<J>(g, dir, L, y, 0x3fffffff);
         s2_lane_clear(sd.s[gl]);
     }
     // the virtual source: mass 1 on the label below the first quad (alpha) / above the final quad (beta)
     const int a_inj = dir ? L + 4 : 3;
-    const int gi = a_inj >> 2, ci = a_inj & 3;
+    const int gi = a_inj / J, ci = a_inj % J;
     const int gl = dir ? sd.NL - 1 - gi : gi;
     sd.s[gl].lb[ci] = 1.0f; sd.s[gl].e[ci] = 0;
 }
 
 // neighbour values entering lane gl of a side (the kernel: shuffle from lane - 1 / mailbox of the warp below)
-void fetch(const Side& sd, const std::vector<QLane>& old, int gl, float& n0, float& nl, int& ne) {
+template <int J>
+void fetch(const Side<J>& sd, const std::vector<QLane<J>>& old, int gl, float& n0, float& nl, int& ne) {
     if (gl == 0) { n0 = 0.0f; nl = 0.0f; ne = kQVoidE; return; }
-    const QLane& p = old[gl - 1];
-    const int c = sd.dir ? 0 : kQJ - 1;
+    const QLane<J>& p = old[gl - 1];
+    const int c = sd.dir ? 0 : J - 1;
     n0 = p.b0[c]; nl = p.lb[c]; ne = p.e[c];
 }
 
@@ -51,9 +56,10 @@ struct Frame { float pb; std::vector<float> pl, ps; float l2; };
 
 }  // namespace
 
-extern "C" int star2_host(const float* x, int T, int V, const int* y, int S, int L, int Tn, float star_penalty,
-                          int from_logits, float gout, float* loss_out, float* grad /* [T][V] */) {
-    const int NL = L / 4 + 2, NA = 4 * NL;
+template <int J>
+int star2_host_j(const float* x, int T, int V, const int* y, int S, int L, int Tn, float star_penalty,
+                 int from_logits, float gout, float* loss_out, float* grad /* [T][V] */) {
+    const int NA = na_of(L), NL = NA / J;
     const float pen = expf(star_penalty);
     // ---- rows: statistics + gather (the row warps) ----
     std::vector<Frame> fr(Tn);
@@ -77,7 +83,7 @@ extern "C" int star2_host(const float* x, int T, int V, const int* y, int S, int
             f.ps[k + 4] = s2_star_emission(row[yk], yk != 0, s_nb, m2, pscale);
         }
     }
-    Side sd[2];
+    Side<J> sd[2];
     side_init(sd[0], 0, L, y);
     side_init(sd[1], 1, L, y);
     const int tm = Tn >> 1;
@@ -85,32 +91,32 @@ extern "C" int star2_host(const float* x, int T, int V, const int* y, int S, int
     std::vector<float> tr_lb((size_t)Tn * NA), tr_st((size_t)Tn * NA);
     std::vector<int> tr_e((size_t)Tn * NA);
 
-    auto step = [&](Side& S_, int t, bool phase2, std::vector<float>* GL, std::vector<float>* GS, std::vector<float>* H,
+    auto step = [&](Side<J>& S_, int t, bool phase2, std::vector<float>* GL, std::vector<float>* GS, std::vector<float>* H,
                     int eZ, float rZ) {
-        std::vector<QLane> old = S_.s;
+        std::vector<QLane<J>> old = S_.s;
         for (int gl = 0; gl < S_.NL; ++gl) {
             float n0, nl; int ne;
             fetch(S_, old, gl, n0, nl, ne);
-            QLane& s = S_.s[gl];
+            QLane<J>& s = S_.s[gl];
             const int g = S_.g[gl];
-            QSums q;
+            QSums<J> q;
             if (S_.dir) s2_quad_sums<1>(s, S_.allowed[gl], n0, nl, ne, q); else s2_quad_sums<0>(s, S_.allowed[gl], n0, nl, ne, q);
-            float pl[kQJ], ps[kQJ];
-            for (int c = 0; c < kQJ; ++c) { pl[c] = fr[t].pl[4 * g + c]; ps[c] = fr[t].ps[4 * g + c]; }
+            float pl[J], ps[J];
+            for (int c = 0; c < J; ++c) { pl[c] = fr[t].pl[J * g + c]; ps[c] = fr[t].ps[J * g + c]; }
             if (phase2) {
-                float lbo[kQJ], sto[kQJ], gl4[kQJ], gs4[kQJ], h4[kQJ]; int eo[kQJ];
-                for (int c = 0; c < kQJ; ++c) {
-                    lbo[c] = tr_lb[(size_t)t * NA + 4 * g + c]; sto[c] = tr_st[(size_t)t * NA + 4 * g + c];
-                    eo[c] = tr_e[(size_t)t * NA + 4 * g + c];
+                float lbo[J], sto[J], gl4[J], gs4[J], h4[J]; int eo[J];
+                for (int c = 0; c < J; ++c) {
+                    lbo[c] = tr_lb[(size_t)t * NA + J * g + c]; sto[c] = tr_st[(size_t)t * NA + J * g + c];
+                    eo[c] = tr_e[(size_t)t * NA + J * g + c];
                 }
                 s2_quad_occ(s, q, lbo, sto, eo, eZ, rZ, ps, gl4, gs4, h4);
-                for (int c = 0; c < kQJ; ++c) { (*GL)[4 * g + c] = gl4[c]; (*GS)[4 * g + c] = gs4[c]; (*H)[4 * g + c] = h4[c]; }
+                for (int c = 0; c < J; ++c) { (*GL)[J * g + c] = gl4[c]; (*GS)[J * g + c] = gs4[c]; (*H)[J * g + c] = h4[c]; }
             }
             s2_quad_emit(s, q, fr[t].pb, pl, ps, pen);
             if (!phase2) {
-                for (int c = 0; c < kQJ; ++c) {
-                    tr_lb[(size_t)t * NA + 4 * g + c] = s.lb[c]; tr_st[(size_t)t * NA + 4 * g + c] = s.st[c];
-                    tr_e[(size_t)t * NA + 4 * g + c] = s.e[c];
+                for (int c = 0; c < J; ++c) {
+                    tr_lb[(size_t)t * NA + J * g + c] = s.lb[c]; tr_st[(size_t)t * NA + J * g + c] = s.st[c];
+                    tr_e[(size_t)t * NA + J * g + c] = s.e[c];
                 }
             }
         }
@@ -120,18 +126,18 @@ extern "C" int star2_host(const float* x, int T, int V, const int* y, int S, int
 
     // ---- the meeting: Z = sum over the states of (alpha's pre-emission sums of frame tm) x (beta's boundary) ----
     // boundaries in position order
-    std::vector<QLane> ba(NL), bb(NL);
+    std::vector<QLane<J>> ba(NL), bb(NL);
     for (int gl = 0; gl < NL; ++gl) { ba[sd[0].g[gl]] = sd[0].s[gl]; bb[sd[1].g[gl]] = sd[1].s[gl]; }
     double tot = 0.0; int pm = 4 * kQVoidE;
     std::vector<float> zm; std::vector<int> zx;
     {
-        std::vector<QLane> sa = ba;
+        std::vector<QLane<J>> sa = ba;
         for (int g = 0; g < NL; ++g) {
             float nl = 0.0f; int ne = kQVoidE;
-            if (g > 0) { nl = ba[g - 1].lb[kQJ - 1]; ne = ba[g - 1].e[kQJ - 1]; }
-            QSums q;
-            s2_quad_sums<0>(sa[g], s2_allowed(g, 0, L, y, 0x3fffffff), 0.0f, nl, ne, q);
-            for (int c = 0; c < kQJ; ++c) {
+            if (g > 0) { nl = ba[g - 1].lb[J - 1]; ne = ba[g - 1].e[J - 1]; }
+            QSums<J> q;
+            s2_quad_sums<0>(sa[g], s2_allowed<J>(g, 0, L, y, 0x3fffffff), 0.0f, nl, ne, q);
+            for (int c = 0; c < J; ++c) {
                 const float m[4] = {q.w0[c] * bb[g].b0[c], q.vs[c] * bb[g].st[c], q.u1[c] * bb[g].b1[c], q.vl[c] * bb[g].lb[c]};
                 for (int j = 0; j < 4; ++j) {
                     zm.push_back(m[j]);
@@ -180,4 +186,11 @@ extern "C" int star2_host(const float* x, int T, int V, const int* y, int S, int
     for (int i = tm; i < Tn; ++i) { step(sd[0], i, true, &GL, &GS, &H, eZ, rZ); grad_row(i); }
     for (int i = Tn - tm; i < Tn; ++i) { const int t = Tn - 1 - i; step(sd[1], t, true, &GL, &GS, &H, eZ, rZ); grad_row(t); }
     return 0;
+}
+
+extern "C" int star2_host(const float* x, int T, int V, const int* y, int S, int L, int Tn, float star_penalty,
+                          int from_logits, float gout, float* loss_out, float* grad, int J) {
+    if (J == 1) return star2_host_j<1>(x, T, V, y, S, L, Tn, star_penalty, from_logits, gout, loss_out, grad);
+    if (J == 2) return star2_host_j<2>(x, T, V, y, S, L, Tn, star_penalty, from_logits, gout, loss_out, grad);
+    return star2_host_j<4>(x, T, V, y, S, L, Tn, star_penalty, from_logits, gout, loss_out, grad);
 }
