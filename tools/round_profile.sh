@@ -18,6 +18,20 @@ fi
 R=${1:-r01}
 O=gpurun_out
 export PYTHONPATH=.
+if [ "$2" = "star" ]; then      # refresh of the star-CTC artefacts only (+ the default line, which carries the star sub-record)
+  timeout 900 python bench.py > $O/bench_default_$R.json 2> $O/bench_default_$R.err; echo "bench default rc=$?"
+  timeout 500 python bench.py --workload star --steps 100 --warmup 5 > $O/bench_star_$R.json 2> $O/bench_star_$R.err; echo "bench star rc=$?"
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/launches_star_$R.csv \
+      python bench.py --workload star --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-library-baseline > /dev/null 2>&1; echo "launches star rc=$?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'star2_(fwd|bwd)' -s 4 -c 2 -o $O/prof_star_$R \
+      python bench.py --workload star --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-library-baseline > $O/ncu_star_$R.log 2>&1; echo "ncu star rc=$?"
+  python tools/ncu_summary.py $O/prof_star_$R.ncu-rep > $O/ncu_star_$R.txt 2>/dev/null
+  python tools/ncu_lines.py $O/prof_star_$R.ncu-rep "" 40 > $O/ncu_star_lines_$R.txt 2>/dev/null; rm -f $O/prof_star_$R.ncu-rep
+  for tool in memcheck racecheck synccheck; do
+    timeout 600 compute-sanitizer --tool $tool python tools/sanitize_cases.py star > $O/san_${tool}_star_$R.log 2>&1; echo "$tool star rc=$? $(grep -c "ERROR SUMMARY" $O/san_${tool}_star_$R.log)"
+  done
+  exit 0
+fi
 timeout 900 python bench.py > $O/bench_default_$R.json 2> $O/bench_default_$R.err; echo "bench default (headline + workloads) rc=$?"
 for w in ctc star rnnt rnnt_fg; do
   timeout 500 python bench.py --workload $w --steps 100 --warmup 5 > $O/bench_${w}_$R.json 2> $O/bench_${w}_$R.err; echo "bench $w rc=$?"
@@ -35,7 +49,7 @@ timeout 600 ncu --set full --clock-control none -k regex:'ctc2_(fwd|bwd)' -s 4 -
     python bench.py --workload ctc --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-library-baseline > $O/ncu_ctc_$R.log 2>&1; echo "ncu ctc rc=$?"
 timeout 600 ncu --set full --clock-control none -k regex:'rnnt_(grad|rows|lattice)' -s 4 -c 3 -o $O/prof_rnnt_$R \
     python bench.py --workload rnnt --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-library-baseline > $O/ncu_rnnt_$R.log 2>&1; echo "ncu rnnt rc=$?"
-timeout 600 ncu --set full --clock-control none -k regex:'star_(grad|rows|trellis)' -s 4 -c 3 -o $O/prof_star_$R \
+timeout 600 ncu --set full --clock-control none -k regex:'star2_(fwd|bwd)' -s 4 -c 2 -o $O/prof_star_$R \
     python bench.py --workload star --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-library-baseline > $O/ncu_star_$R.log 2>&1; echo "ncu star rc=$?"
 timeout 600 ncu --set full --clock-control none -k regex:'umma_gemm|fg_rows|fg_arc|fg_w_' -s 12 -c 6 -o $O/prof_rnnt_fg_$R \
     python bench.py --workload rnnt_fg --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-library-baseline > $O/ncu_rnnt_fg_$R.log 2>&1; echo "ncu rnnt_fg rc=$?"

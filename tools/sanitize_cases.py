@@ -4,6 +4,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import haloop_b200 as hb
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
+if len(sys.argv) > 1 and sys.argv[1] == "star":          # the fused star-CTC kernels only: 1 .. 4 trellis warps, repeats, L = 0 / S, T_n < T
+    for (T, N, V, S) in [(40, 3, 32, 9), (150, 2, 24, 70), (260, 2, 8, 200), (700, 1, 12, 400)]:
+        x = torch.randn(T, N, V, generator=g).to(dev).requires_grad_(True)
+        tg = torch.randint(1, min(V, 6), (N, S), generator=g).to(dev)
+        il = torch.tensor([T, T - 7][:N] + [T // 2] * max(0, N - 2)).to(dev); tl = torch.tensor([S, S // 2][:N] + [0] * max(0, N - 2)).to(dev)
+        hb.star_ctc_forward_score(x, tg, il, tl, from_logits=True).sum().backward()
+    torch.cuda.synchronize()
+    print("done")
+    sys.exit(0)
 for (T, N, V, S) in [(40, 3, 32, 9), (150, 2, 24, 70), (33, 2, 37, 5)]:
     x = torch.randn(T, N, V, generator=g).to(dev).requires_grad_(True)
     tg = torch.randint(1, V, (N, S), generator=g).to(dev)
