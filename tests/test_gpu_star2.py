@@ -71,6 +71,31 @@ def test_star2_ragged_vs_oracle(hb, oracle, cfg):
     _run(hb, oracle, x, tg, il, tl, cfg["pen"], go=go)
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(T=50, N=3, V=4096, S=20),       # rows of 16 KB: 4 row warps, two ring stages
+    dict(T=40, N=2, V=8192, S=20),       # rows of 32 KB: one stage per row warp
+    dict(T=30, N=3, V=4, S=6),           # the smallest class count of the fused path
+])
+def test_star2_row_ring_configurations(hb, oracle, cfg):
+    g = torch.Generator().manual_seed(cfg["V"])
+    T, N, V, S = cfg["T"], cfg["N"], cfg["V"], cfg["S"]
+    x = torch.randn(T, N, V, generator=g)
+    tg = torch.randint(1, V, (N, S), generator=g)
+    il = torch.randint(T // 2 + S, T + 1, (N,), generator=g); il[0] = T
+    tl = torch.randint(1, S + 1, (N,), generator=g); tl[0] = S
+    _run(hb, oracle, x, tg, il, tl, -0.5)
+
+
+def test_star2_empty_target_dimension(hb, oracle):
+    """S = 0: every utterance is the all-star .* (ha/star.py:47) around blanks"""
+    g = torch.Generator().manual_seed(3)
+    T, N, V = 25, 3, 16
+    x = torch.randn(T, N, V, generator=g)
+    tg = torch.zeros(N, 0, dtype=torch.long)
+    il = torch.tensor([25, 1, 12]); tl = torch.zeros(N, dtype=torch.long)
+    _run(hb, oracle, x, tg, il, tl, -0.5)
+
+
 def test_star2_label_zero_and_repeats(hb, oracle):
     g = torch.Generator().manual_seed(5)
     T, N, V, S = 150, 6, 8, 40
