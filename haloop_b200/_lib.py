@@ -71,8 +71,8 @@ SIGNATURES = {
                            _vp, _vp, _sz, _vp]),
     "ha_star_bwd": (_i32, [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _sz, _vp]),
     "ha_rnnt_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
-    "ha_rnnt_fwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
-    "ha_rnnt_bwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "ha_rnnt_fwd": (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "ha_rnnt_bwd": (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "ha_rnnt_fg_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ha_rnnt_fg_fwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "ha_rnnt_fg_bwd": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -465,7 +465,7 @@ size_t ha_rnnt_workspace_bytes(int N, int T, int U1, int V) {
     return rnnt_ws_layout(N, T, U1).total;
 }
 
-int ha_rnnt_fwd(const float* joint, int N, int T, int U1, int V,
+int ha_rnnt_fwd(const float* joint, int64_t sj_n, int64_t sj_t, int64_t sj_u, int N, int T, int U1, int V,
                 const void* targets, int64_t tgt_stride, int targets_i64,
                 const void* in_len, const void* tgt_len, int lengths_i64,
                 int from_logits, float* loss, void* ws, size_t ws_bytes, void* stream) {
@@ -488,11 +488,11 @@ int ha_rnnt_fwd(const float* joint, int N, int T, int U1, int V,
     if ((rc = check_launch("rnnt_prep_kernel"))) return rc;
 
     RnntRowsParams rp{};
-    rp.x = joint; rp.N = N; rp.T = T; rp.U1 = U1; rp.V = V;
+    rp.x = joint; rp.sx_n = sj_n; rp.sx_t = sj_t; rp.sx_u = sj_u; rp.N = N; rp.T = T; rp.U1 = U1; rp.V = V;
     rp.meta = pp.meta; rp.tgt = pp.tgt; rp.Up = w.Up;
     rp.lse2 = (float*)(base + w.lse2); rp.bl = (float2*)(base + w.bl); rp.lb = (float2*)(base + w.lb); rp.D = w.D;
     rp.from_logits = from_logits;
-    const bool vec = (V % 4 == 0) && aligned16(joint);
+    const bool vec = (V % 4 == 0) && aligned16(joint) && (sj_n % 4 == 0) && (sj_t % 4 == 0) && (sj_u % 4 == 0);
     rp.use_bulk = vec ? 1 : 0;
     const int nodes = T * U1;
     RowCfg rc_ = pick_row_cfg(nodes, [&](int ns, int nw) { return rnnt_rows_smem_bytes(V, ns, nw); }, 2, 4);
@@ -523,8 +523,8 @@ int ha_rnnt_fwd(const float* joint, int N, int T, int U1, int V,
     return check_launch("rnnt_lattice_kernel");
 }
 
-int ha_rnnt_bwd(const float* joint, int N, int T, int U1, int V,
-                const float* grad_loss, int from_logits, float* gjoint,
+int ha_rnnt_bwd(const float* joint, int64_t sj_n, int64_t sj_t, int64_t sj_u, int N, int T, int U1, int V,
+                const float* grad_loss, int from_logits, float* gjoint, int64_t sg_n, int64_t sg_t, int64_t sg_u,
                 void* ws, size_t ws_bytes, void* stream) {
     if (U1 <= 0) return fail(HA_ERR_INVALID_ARGUMENT, "U1 must be >= 1");
     const RnntWs w = rnnt_ws_layout(N, T, U1);
@@ -535,10 +535,12 @@ int ha_rnnt_bwd(const float* joint, int N, int T, int U1, int V,
     unsigned char* base = (unsigned char*)ws;
     RnntGradParams gp{};
     gp.x = joint; gp.gx = gjoint; gp.N = N; gp.T = T; gp.U1 = U1; gp.V = V;
+    gp.sx_n = sj_n; gp.sx_t = sj_t; gp.sx_u = sj_u; gp.sg_n = sg_n; gp.sg_t = sg_t; gp.sg_u = sg_u;
     gp.meta = (const int4*)(base + w.meta); gp.tgt = (const int*)(base + w.tgt); gp.Up = w.Up;
     gp.lse2 = (const float*)(base + w.lse2); gp.occ = (const float2*)(base + w.occ); gp.D = w.D;
     gp.gout = grad_loss; gp.loss = (const float*)(base + w.loss); gp.from_logits = from_logits;
-    const bool vec = (V % 4 == 0) && aligned16(gjoint) && (!from_logits || aligned16(joint));
+    const bool vec = (V % 4 == 0) && aligned16(gjoint) && (sg_n % 4 == 0) && (sg_t % 4 == 0) && (sg_u % 4 == 0) &&
+                     (!from_logits || (aligned16(joint) && (sj_n % 4 == 0) && (sj_t % 4 == 0) && (sj_u % 4 == 0)));
     gp.use_bulk = vec ? 1 : 0;
     const int nodes = T * U1;
     RowCfg rc_ = pick_row_cfg(nodes, [&](int ns, int nw) { return rnnt_rows_smem_bytes(V, ns, nw); });

@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(128) rnnt_prep_kernel(RnntPrepParams p) {
 
 // ------------------------------------------------------------------------------------ rows ---
 struct RnntRowsParams {
-    const float* x;            // (N,T,U1,V) contiguous
+    const float* x;            // (N,T,U1,V) view: element strides sx_n, sx_t, sx_u, unit class stride
+    long long sx_n, sx_t, sx_u;
     int N, T, U1, V;
     const int4* meta; const int* tgt; int Up;
     float* lse2; float2* bl; float2* lb; int D;
@@ -107,14 +108,14 @@ __global__ void __launch_bounds__(256) rnnt_rows_kernel(RnntRowsParams p) {
 
     int nrows = 0;
     if (v0 + warp < nvalid) nrows = min(p.rows_per_warp, (nvalid - 1 - v0 - warp) / nw + 1);
-    const float* xb = p.x + (size_t)n * p.T * p.U1 * V;
+    const float* xb = p.x + (long long)n * p.sx_n;
     const int* y = p.tgt + (size_t)n * p.Up;
 
     auto issue = [&](int r) {
         const int stage = r % nstage;
         const int v = v0 + warp + nw * r;
         const int t = v / W, u = v - t * W;
-        const float* src = xb + ((size_t)t * p.U1 + u) * V;
+        const float* src = xb + (long long)t * p.sx_t + (long long)u * p.sx_u;
         if (p.use_bulk) {
             if (lane == 0) {
                 mbar_expect_tx(&wbar[stage], (uint32_t)V * 4u);
@@ -375,6 +376,7 @@ __global__ void __launch_bounds__(MAXT) rnnt_lattice_kernel(RnntLatticeParams p)
 // ------------------------------------------------------------------------------------ grad ---
 struct RnntGradParams {
     const float* x; float* gx;
+    long long sx_n, sx_t, sx_u, sg_n, sg_t, sg_u;      // element strides of the joint view and of its gradient
     int N, T, U1, V;
     const int4* meta; const int* tgt; int Up;
     const float* lse2; const float2* occ; int D;
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(256) rnnt_grad_kernel(RnntGradParams p) {
         if (!p.from_logits) return;
         const int stage = r % nstage;
         int t, u; node(r, t, u);
-        const float* src = p.x + (ubase + (size_t)t * p.U1 + u) * V;
+        const float* src = p.x + (long long)n * p.sx_n + (long long)t * p.sx_t + (long long)u * p.sx_u;
         if (p.use_bulk) {
             if (lane == 0) {
                 mbar_expect_tx(&wbar[stage], (uint32_t)V * 4u);
@@ -459,7 +461,7 @@ __global__ void __launch_bounds__(256) rnnt_grad_kernel(RnntGradParams p) {
             row[0] -= g * o.x;
             if (u < W - 1) row[y[u]] -= g * o.y;                 // both land on class 0 if y[u] == 0
         }
-        float* dst = p.gx + (ubase + (size_t)t * p.U1 + u) * V;
+        float* dst = p.gx + (long long)n * p.sg_n + (long long)t * p.sg_t + (long long)u * p.sg_u;
         if (p.use_bulk) {
             fence_async_smem();
             __syncwarp();
@@ -484,7 +486,7 @@ __global__ void __launch_bounds__(256) rnnt_zero_kernel(RnntGradParams p) {
     for (int r = r0 + warp; r < min(r0 + 64, p.T * p.U1); r += 8) {
         const int t = r / p.U1, u = r - t * p.U1;
         if (t < Tn && u < W) continue;
-        float* dst = p.gx + ((size_t)n * p.T * p.U1 + r) * p.V;
+        float* dst = p.gx + (long long)n * p.sg_n + (long long)t * p.sg_t + (long long)u * p.sg_u;
         if ((p.V & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int c = lane; c < (p.V >> 2); c += 32) ((float4*)dst)[c] = z;

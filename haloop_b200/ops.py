@@ -272,7 +272,7 @@ def _register_time_major_vmap(fwd, bwd, n_extra):
 def rnnt_fwd(joint: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, tgt_len: torch.Tensor,
              from_logits: bool) -> tuple[torch.Tensor, torch.Tensor]:
     _check_cuda_f32(joint, "joint")
-    joint = joint.contiguous()
+    joint = _unit_class_stride(joint)            # any (n, t, u) strides are taken as they are: no copy of the joint
     N, T, U1, V = joint.shape
     tg, tg64 = _idx(targets, joint.device, "targets")
     il, il64 = _idx(in_len, joint.device, "joint_lengths")
@@ -286,7 +286,7 @@ def rnnt_fwd(joint: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, t
     ws = torch.empty(nbytes, dtype=torch.uint8, device=joint.device)
     loss = torch.empty(N, dtype=_F32, device=joint.device)
     with torch.cuda.device(joint.device):
-        rc = L.ha_rnnt_fwd(joint.data_ptr(), N, T, U1, V,
+        rc = L.ha_rnnt_fwd(joint.data_ptr(), joint.stride(0), joint.stride(1), joint.stride(2), N, T, U1, V,
                            tg.data_ptr() if U1 > 1 else None, tg.stride(0) if U1 > 1 else 0, tg64,
                            il.data_ptr(), tl.data_ptr(), il64, int(from_logits),
                            loss.data_ptr(), ws.data_ptr(), nbytes, _stream(joint))
@@ -304,13 +304,14 @@ def _(joint, targets, in_len, tgt_len, from_logits):
 @torch.library.custom_op("ha_b200::rnnt_bwd", mutates_args=())
 def rnnt_bwd(joint: torch.Tensor, ws: torch.Tensor, grad_loss: torch.Tensor,
              from_logits: bool) -> torch.Tensor:
-    joint = joint.contiguous()
+    joint = _unit_class_stride(joint)
     N, T, U1, V = joint.shape
-    gj = torch.empty_like(joint, memory_format=torch.contiguous_format)
+    gj = _empty_like_strided(joint)              # the gradient takes the strides of the joint view
     g = grad_loss.to(_F32).contiguous()
     L = _lib.lib()
     with torch.cuda.device(joint.device):
-        rc = L.ha_rnnt_bwd(joint.data_ptr(), N, T, U1, V, g.data_ptr(), int(from_logits), gj.data_ptr(),
+        rc = L.ha_rnnt_bwd(joint.data_ptr(), joint.stride(0), joint.stride(1), joint.stride(2), N, T, U1, V,
+                           g.data_ptr(), int(from_logits), gj.data_ptr(), gj.stride(0), gj.stride(1), gj.stride(2),
                            ws.data_ptr(), ws.numel(), _stream(joint))
     _lib.check(rc, "ha_rnnt_bwd")
     return gj

@@ -68,13 +68,14 @@ int ha_star_bwd(const float* x, int64_t sx_t, int64_t sx_n, int T, int N, int V,
 
 /* ---- RNN-T: ha/transducer.py:175-205 transducer_forward_score (+ ha/scan.py:88-126) --------- */
 size_t ha_rnnt_workspace_bytes(int N, int T, int U1, int V);
-/* joint (N,T,U1,V) contiguous, U1 = U+1; targets (N,U) */
-int ha_rnnt_fwd(const float* joint, int N, int T, int U1, int V,
+/* joint: a (N,T,U1,V) view with element strides sj_n, sj_t, sj_u and unit class stride, U1 = U+1 (a contiguous joint:
+ * T*U1*V, U1*V, V); targets (N,U); gjoint: the gradient, a view of the same shape with strides sg_* */
+int ha_rnnt_fwd(const float* joint, int64_t sj_n, int64_t sj_t, int64_t sj_u, int N, int T, int U1, int V,
                 const void* targets, int64_t tgt_stride, int targets_i64,
                 const void* in_len, const void* tgt_len, int lengths_i64,
                 int from_logits, float* loss, void* ws, size_t ws_bytes, void* stream);
-int ha_rnnt_bwd(const float* joint, int N, int T, int U1, int V,
-                const float* grad_loss, int from_logits, float* gjoint,
+int ha_rnnt_bwd(const float* joint, int64_t sj_n, int64_t sj_t, int64_t sj_u, int N, int T, int U1, int V,
+                const float* grad_loss, int from_logits, float* gjoint, int64_t sg_n, int64_t sg_t, int64_t sg_u,
                 void* ws, size_t ws_bytes, void* stream);
 
 /* ---- joint-free RNN-T: the reference's joint is a broadcast sum, ha/recognizer.py:104-114 ------

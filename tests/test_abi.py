@@ -51,7 +51,7 @@ def test_argument_validation_without_gpu(L):
     p = (p + 15) // 16 * 16
     rc = L.ha_ctc_fwd(p, 16, 8, 4, 2, 8, p, 2, 2, 1, p, p, 1, 1, p, p, 16, None)
     assert rc == 2 and b"workspace" in L.ha_b200_last_error()
-    rc = L.ha_rnnt_fwd(p, 2, 4, 0, 8, p, 1, 1, p, p, 1, 1, p, p, 16, None)
+    rc = L.ha_rnnt_fwd(p, 0, 0, 8, 2, 4, 0, 8, p, 1, 1, p, p, 1, 1, p, p, 16, None)
     assert rc == 1
 
 

@@ -338,3 +338,35 @@ def test_rnnt_joint_free_with_disagreeing_peaky_factors(hb):
     assert (l1 / l2 - 1).abs().max() < LOSS_RTOL
     l1.sum().backward()
     assert torch.isfinite(fd.grad).all() and torch.isfinite(gd.grad).all()
+
+
+# ------------------------------------------------------------ strided RNN-T joints (no copy) ---
+@pytest.mark.parametrize("layout", ["permuted", "padded", "unaligned"])
+def test_rnnt_takes_joint_views_as_they_are(hb, oracle, layout):
+    """The joint is read through its (n, t, u) strides and the gradient comes back with the strides of the view
+    (`joint.contiguous()` was a silent copy of the whole lattice): a (N,U+1,T,V) buffer viewed as
+    (N,T,U+1,V), a joint sliced out of a wider-U buffer, and a slice whose rows are not 16-byte aligned (plain loads
+    instead of bulk copies)."""
+    g = torch.Generator().manual_seed(77)
+    N, T, U, V = 3, 21, 7, 16
+    x = torch.randn(N, T, U + 1, V, generator=g)
+    tg = torch.randint(0, V, (N, U), generator=g)
+    il = torch.tensor([21, 13, 20]); tl = torch.tensor([7, 7, 3])
+    ol, og = oracle.rnnt(x.numpy(), tg.numpy(), il.numpy(), tl.numpy())
+    if layout == "permuted":
+        base = x.permute(0, 2, 1, 3).contiguous().to(dev())
+        view = base.permute(0, 2, 1, 3)
+    elif layout == "padded":
+        base = torch.zeros(N, T, U + 4, V, device=dev()); base[:, :, :U + 1] = x.to(dev())
+        view = base[:, :, :U + 1]
+    else:
+        base = torch.zeros(N, T, U + 1, V + 2, device=dev()); base[..., 1:V + 1] = x.to(dev())
+        view = base[..., 1:V + 1]
+    assert not view.is_contiguous()
+    from haloop_b200 import ops
+    loss, ws = ops.rnnt_fwd(view, tg.to(dev()), il.to(dev()), tl.to(dev()), True)
+    gr = ops.rnnt_bwd(view, ws, torch.ones(N, device=dev()), True)
+    np.testing.assert_allclose(loss.double().cpu().numpy(), ol, rtol=LOSS_RTOL)
+    assert np.abs(gr.double().cpu().numpy() - og).max() < GRAD_ATOL
+    if layout == "permuted":
+        assert gr.stride() == view.stride(), "the gradient of a dense permuted view keeps its strides"

@@ -29,6 +29,9 @@ want = [
     ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_sb"),
     ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall_wait"),
     ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall_math"),
+    ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall_no_inst"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall_not_selected"),
+    ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall_branch"),
 ]
 idx = {n: hdr.index(n) for n, _ in want if n in hdr}
 print(f"# {rep}: ncu --set full --clock-control none (per-launch values; cold cache, serialised replays)")
