@@ -6,6 +6,8 @@ Forward ops return (loss, workspace); the workspace tensor is the saved-for-back
 return the gradient with the SAME strides as the input view (ha/recognizer.py:70,78 hands the loss
 a permuted view of an (N,T,C) buffer), multiplied by the per-utterance grad_output.
 """
+import contextlib
+
 import torch
 
 from . import _lib
@@ -34,6 +36,15 @@ def _idx(t, device, name):
     if t.device != device:
         t = t.to(device)
     return t.contiguous(), int(t.dtype == torch.int64)
+
+
+_NULL = contextlib.nullcontext()
+
+
+def _on(device):
+    """Device guard for the C ABI call; the context manager is skipped (it costs more than the call) when the tensor's
+    device already is the current one."""
+    return _NULL if device.index == torch.cuda.current_device() else torch.cuda.device(device)
 
 
 def _unit_class_stride(x):
@@ -89,7 +100,7 @@ def ctc_fwd(x: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, tgt_le
     nbytes = L.ha_ctc_workspace_bytes(T, N, V, S)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     loss = torch.empty(N, dtype=_F32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         rc = L.ha_ctc_fwd(x.data_ptr(), x.stride(0), x.stride(1), T, N, V,
                           tg.data_ptr() if S else None, tg.stride(0) if S else 0, S, tg64,
                           il.data_ptr(), tl.data_ptr(), il64, int(from_logits),
@@ -113,7 +124,7 @@ def ctc_bwd(x: torch.Tensor, ws: torch.Tensor, grad_loss: torch.Tensor, S: int,
     gx = _empty_like_strided(xs)
     g = grad_loss.to(_F32).contiguous()
     L = _lib.lib()
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         rc = L.ha_ctc_bwd(xs.data_ptr(), xs.stride(0), xs.stride(1), T, N, V, S, g.data_ptr(),
                           int(from_logits), gx.data_ptr(), gx.stride(0), gx.stride(1),
                           ws.data_ptr(), ws.numel(), _stream(x))
@@ -147,7 +158,7 @@ ctc_fwd.register_autograd(_ctc_backward, setup_context=_ctc_setup)
 def star_fwd(x: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, tgt_len: torch.Tensor,
              star_penalty: float, from_logits: bool) -> tuple[torch.Tensor, torch.Tensor]:
     _check_cuda_f32(x, "emissions")
-    x = _unit_class_stride(x)
+    x = _tma_view(x)
     T, N, V = x.shape
     tg, tg64 = _idx(targets, x.device, "targets")
     il, il64 = _idx(in_len, x.device, "emission_lengths")
@@ -161,7 +172,7 @@ def star_fwd(x: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, tgt_l
     nbytes = L.ha_star_workspace_bytes(T, N, V, S)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     loss = torch.empty(N, dtype=_F32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         rc = L.ha_star_fwd(x.data_ptr(), x.stride(0), x.stride(1), T, N, V,
                            tg.data_ptr() if S else None, tg.stride(0) if S else 0, S, tg64,
                            il.data_ptr(), tl.data_ptr(), il64, float(star_penalty), int(from_logits),
@@ -180,12 +191,12 @@ def _(x, targets, in_len, tgt_len, star_penalty, from_logits):
 @torch.library.custom_op("ha_b200::star_bwd", mutates_args=())
 def star_bwd(x: torch.Tensor, ws: torch.Tensor, grad_loss: torch.Tensor, S: int,
              from_logits: bool) -> torch.Tensor:
-    xs = _unit_class_stride(x)
+    xs = _tma_view(x)
     T, N, V = xs.shape
     gx = _empty_like_strided(xs)
     g = grad_loss.to(_F32).contiguous()
     L = _lib.lib()
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         rc = L.ha_star_bwd(xs.data_ptr(), xs.stride(0), xs.stride(1), T, N, V, S, g.data_ptr(),
                            int(from_logits), gx.data_ptr(), gx.stride(0), gx.stride(1),
                            ws.data_ptr(), ws.numel(), _stream(x))
@@ -285,7 +296,7 @@ def rnnt_fwd(joint: torch.Tensor, targets: torch.Tensor, in_len: torch.Tensor, t
     nbytes = L.ha_rnnt_workspace_bytes(N, T, U1, V)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=joint.device)
     loss = torch.empty(N, dtype=_F32, device=joint.device)
-    with torch.cuda.device(joint.device):
+    with _on(joint.device):
         rc = L.ha_rnnt_fwd(joint.data_ptr(), joint.stride(0), joint.stride(1), joint.stride(2), N, T, U1, V,
                            tg.data_ptr() if U1 > 1 else None, tg.stride(0) if U1 > 1 else 0, tg64,
                            il.data_ptr(), tl.data_ptr(), il64, int(from_logits),
@@ -309,7 +320,7 @@ def rnnt_bwd(joint: torch.Tensor, ws: torch.Tensor, grad_loss: torch.Tensor,
     gj = _empty_like_strided(joint)              # the gradient takes the strides of the joint view
     g = grad_loss.to(_F32).contiguous()
     L = _lib.lib()
-    with torch.cuda.device(joint.device):
+    with _on(joint.device):
         rc = L.ha_rnnt_bwd(joint.data_ptr(), joint.stride(0), joint.stride(1), joint.stride(2), N, T, U1, V,
                            g.data_ptr(), int(from_logits), gj.data_ptr(), gj.stride(0), gj.stride(1), gj.stride(2),
                            ws.data_ptr(), ws.numel(), _stream(joint))
@@ -359,7 +370,7 @@ def rnnt_fg_fwd(f: torch.Tensor, g: torch.Tensor, targets: torch.Tensor, in_len:
     nbytes = L.ha_rnnt_fg_workspace_bytes(N, T, U1, V)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=f.device)
     loss = torch.empty(N, dtype=_F32, device=f.device)
-    with torch.cuda.device(f.device):
+    with _on(f.device):
         rc = L.ha_rnnt_fg_fwd(f.data_ptr(), g.data_ptr(), N, T, U1, V,
                               tg.data_ptr() if U1 > 1 else None, tg.stride(0) if U1 > 1 else 0, tg64,
                               il.data_ptr(), tl.data_ptr(), il64,
@@ -385,7 +396,7 @@ def rnnt_fg_bwd(f: torch.Tensor, g: torch.Tensor, ws: torch.Tensor,
     gg = torch.empty_like(g, memory_format=torch.contiguous_format)
     go = grad_loss.to(_F32).contiguous()
     L = _lib.lib()
-    with torch.cuda.device(f.device):
+    with _on(f.device):
         rc = L.ha_rnnt_fg_bwd(f.data_ptr(), g.data_ptr(), N, T, U1, V, go.data_ptr(), gf.data_ptr(), gg.data_ptr(),
                               ws.data_ptr(), ws.numel(), _stream(f))
     _lib.check(rc, "ha_rnnt_fg_bwd")
@@ -469,7 +480,7 @@ def head_ctc_fwd(h: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | Non
     saved = torch.empty(saved_b, dtype=torch.uint8, device=h.device)
     scratch = torch.empty(fwd_b, dtype=torch.uint8, device=h.device)
     loss = torch.empty(N, dtype=_F32, device=h.device)
-    with torch.cuda.device(h.device):
+    with _on(h.device):
         rc = _lib.lib().ha_head_ctc_fwd(h.data_ptr(), weight.data_ptr(), b.data_ptr() if b is not None else None,
                                         N, T, D, V, tg.data_ptr() if S else None, tg.stride(0) if S else 0, S, tg64,
                                         il.data_ptr(), tl.data_ptr(), il64, int(precision), loss.data_ptr(),
@@ -498,7 +509,7 @@ def head_ctc_bwd(h: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | Non
     dh = torch.empty_like(h)
     dW = torch.empty_like(weight)
     db = torch.empty(V, dtype=_F32, device=h.device)
-    with torch.cuda.device(h.device):
+    with _on(h.device):
         rc = _lib.lib().ha_head_ctc_bwd(h.data_ptr(), weight.data_ptr(), b.data_ptr() if b is not None else None,
                                         N, T, D, V, S, g.data_ptr(), int(precision), dh.data_ptr(), dW.data_ptr(),
                                         db.data_ptr(), saved.data_ptr(), saved.numel(), scratch.data_ptr(), bwd_b,

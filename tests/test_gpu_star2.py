@@ -96,6 +96,25 @@ def test_star2_empty_target_dimension(hb, oracle):
     _run(hb, oracle, x, tg, il, tl, -0.5)
 
 
+def test_star2_unaligned_and_permuted_views(hb, oracle):
+    """a class-sliced view (rows not 16-byte aligned: copied once by the shim, as for CTC) and the (N,T,C) buffer the
+    reference hands the loss as a permuted (T,N,C) view (taken as it is, gradient with the same strides)"""
+    g = torch.Generator().manual_seed(11)
+    T, N, V, S = 40, 3, 16, 6
+    x = torch.randn(T, N, V, generator=g)
+    tg = torch.randint(1, V, (N, S), generator=g)
+    il = torch.tensor([40, 33, 21]); tl = torch.tensor([6, 4, 2])
+    ol, og = oracle.star(x.numpy(), tg.numpy(), il.numpy(), tl.numpy(), star_penalty=-0.5)
+    wide = torch.zeros(T, N, V + 2, device=dev()); wide[..., 1:V + 1] = x.to(dev())
+    ntc = x.permute(1, 0, 2).contiguous().to(dev())
+    for view in (wide[..., 1:V + 1], ntc.permute(1, 0, 2)):
+        xd = view.detach().requires_grad_(True)
+        loss = hb.star_ctc_forward_score(xd, tg.to(dev()), il.to(dev()), tl.to(dev()), star_penalty=-0.5, from_logits=True)
+        loss.sum().backward()
+        np.testing.assert_allclose(loss.detach().double().cpu().numpy(), ol, rtol=LOSS_RTOL)
+        assert np.abs(xd.grad.double().cpu().numpy() - og).max() < GRAD_ATOL
+
+
 def test_star2_label_zero_and_repeats(hb, oracle):
     g = torch.Generator().manual_seed(5)
     T, N, V, S = 150, 6, 8, 40
