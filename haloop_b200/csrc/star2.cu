@@ -72,7 +72,7 @@ Star2Params base_params(const Star2Ws& w, unsigned char* base, int T, int N, int
     p.meta = (const int4*)(base + w.meta); p.order = (const int*)(base + w.order);
     p.tgt = (const int*)(base + w.tgt); p.nflist = (const int*)(base + w.nflist); p.nfhdr = (const int2*)(base + w.nfhdr); p.NF = w.NF;
     p.stat = (float4*)(base + w.stat); p.tr = (int*)(base + w.tr); p.SPL = w.SPL;
-    p.bound = (int*)(base + w.bound); p.BW = w.BW; p.zinfo = (int4*)(base + w.zinfo); p.cnt = (int*)(base + w.cnt);
+    p.bound = (int*)(base + w.bound); p.BW = w.BW; p.scr = (int*)(base + w.scr); p.zinfo = (int4*)(base + w.zinfo); p.cnt = (int*)(base + w.cnt);
     p.loss_ws = (float*)(base + w.loss); p.hdr = (float*)base;
     p.NS = c.NS; p.NLmax = w.NLmax; p.NA = 4 * w.NLmax; p.EMF = star2_em_floats(w.NLmax);
     return p;

@@ -39,7 +39,7 @@ namespace hab {
 // while the occupancies of its previous one are still in their slot)
 
 struct Star2Ws {                  // workspace layout (byte offsets); the 256-byte header holds exp(star_penalty)
-    size_t meta, order, tgt, nflist, nfhdr, loss, zinfo, cnt, stat, bound, tr, total;
+    size_t meta, order, tgt, nflist, nfhdr, loss, zinfo, cnt, stat, bound, scr, tr, total;
     int Sp, NLmax, SPL, BW, NF;
 };
 __host__ inline Star2Ws star2_ws_layout(int T, int N, int S) {
@@ -61,6 +61,7 @@ __host__ inline Star2Ws star2_ws_layout(int T, int N, int S) {
     w.cnt = take(sizeof(int) * (size_t)N);
     w.stat = take(sizeof(float4) * (size_t)N * T);      // per frame {l2, non-blank sum, shift m2, star scale}
     w.bound = take(sizeof(int) * (size_t)N * 2 * w.BW);
+    w.scr = take(sizeof(int) * (size_t)N * 2 * 32 * 16);   // 64 bytes per lane of a side's last warp: where lanes without a group store
     w.tr = take(sizeof(int) * (size_t)N * T * w.SPL);
     w.total = o;
     return w;
@@ -71,7 +72,7 @@ struct Star2Params {
     float* gx; long long sg_t, sg_n;
     int T, N, V, S, Sp;
     const int4* meta; const int* order; const int* tgt; const int* nflist; const int2* nfhdr; int NF;
-    float4* stat; int* tr; int SPL; int* bound; int BW; int4* zinfo; int* cnt;
+    float4* stat; int* tr; int SPL; int* bound; int BW; int* scr; int4* zinfo; int* cnt;
     float* loss; float* loss_ws; const float* gout; float* hdr;
     float pen;                            // exp(star_penalty) (forward; the backward reads it from the header)
     int from_logits, NS, NLmax, NA, EMF;  // ring stages per row warp; lanes of the longest target; 4 NLmax; floats per slot
@@ -338,9 +339,12 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
 
     auto sweep = [&](auto dirc) {
         constexpr int DIR = decltype(dirc)::value;
-        int* trow = p.tr + ((size_t)n * p.T + (DIR ? Tn - 1 : 0)) * p.SPL + J * cfg.g;
-        const int NL4 = NA_n;
-        const long long tstep = DIR ? -(long long)p.SPL : (long long)p.SPL;
+        // lanes without a group of their own store to 64 scratch bytes of their own instead of branching around the stores
+        // (a divergent branch needs a convergence barrier: see s2_quad_sums)
+        int* trow = cfg.live ? p.tr + ((size_t)n * p.T + (DIR ? Tn - 1 : 0)) * p.SPL + J * cfg.g
+                             : p.scr + (((size_t)n * 2 + DIR) * 32 + lane) * 16;
+        const int NL4 = cfg.live ? NA_n : 4;
+        const long long tstep = !cfg.live ? 0 : (DIR ? -(long long)p.SPL : (long long)p.SPL);
         S2P_DECL(4);
         // The slot of step i + 1 is tested (non-blocking) before the arithmetic of step i and, when it is there, read
         // before the step's barrier: the latency of the phase test and of the loads is off the step's critical path.
@@ -368,16 +372,12 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
             s2_quad_sums<DIR>(s, cfg.allowed, n0, nl, ne, q);
             s2_quad_emit(s, q, pb, pl, ps, pen);
             if (lane == 31) mail[(i & 1) * W + w] = star_mail<DIR>(s);
-            float npb = 0.0f, npl[J] = {}, nps[J] = {};
-            if (rdy) {        // (before this step's global stores: the release of the arrival would wait for them)
-                load_slot(slot1, npb, npl, nps);
-                mbar_arrive(&em_empty[slot1]);
-            }
-            if (cfg.live) {
-                stv<J>(trow, s.lb);
-                stv<J>(trow + NL4, s.st);
-                stv<J>(trow + 2 * NL4, s.e);
-            }
+            float npb, npl[J], nps[J];
+            load_slot(slot1, npb, npl, nps);          // (stale words when the slot is not there yet: read again below)
+            if (rdy) mbar_arrive(&em_empty[slot1]);   // (before this step's global stores: the release would wait for them)
+            stv<J>(trow, s.lb);
+            stv<J>(trow + NL4, s.st);
+            stv<J>(trow + 2 * NL4, s.e);
             trow += tstep;
             S2P_MARK(1);
             side_barrier(nthr);
@@ -759,6 +759,7 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
     const float pen = p.hdr[0];
     if (lane == 31) mail[((steps1 + 1) & 1) * W + w] = dir ? star_mail<1>(s) : star_mail<0>(s);
     float* emp = s_em + 4 + J * cfg.g;                      // my J label emissions / occupancies in slot 0
+    float* s_scratch = (float*)(smem + sm.red);             // (the Z reduction area is idle in this kernel)
     const int* stp = s_st + J * cfg.g;                      // the other side's label states of my group in slot 0
     side_barrier(nthr);
 
@@ -775,10 +776,10 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
             b = s_em[slot * EMF];
             ldv<J>(emp + slot * EMF, l);
             ldv<J>(emp + NA + slot * EMF, sx);
-            if (cfg.live) {
-                ldv<J>(stp + ss * p.SPL, oo); ldv<J>(stp + ss * p.SPL + NL4, so);
-                ldv<J>(stp + ss * p.SPL + 2 * NL4, ee);
-            }
+            // (lanes without a group of their own read whatever lies at their clamped position: their occupancies go to
+            // the scratch word)
+            ldv<J>(stp + ss * p.SPL, oo); ldv<J>(stp + ss * p.SPL + NL4, so);
+            ldv<J>(stp + ss * p.SPL + 2 * NL4, ee);
         };
         if (nsteps2 > 0) {
             mbar_wait_sleep(&em_full[0], 0u, 32);
@@ -803,16 +804,17 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
             s2_quad_occ(s, q, lbo, sto, eo, eZ, rZ, ps, ogl, ogs, oh);
             s2_quad_emit(s, q, pb, pl, ps, pen);
             if (lane == 31) mail[(i & 1) * W + w] = star_mail<DIR>(s);
-            if (cfg.live) {
-                stv<J>(emp + slot * EMF, ogl);
-                stv<J>(emp + NA + slot * EMF, oh);
-                stv<J>(emp + 2 * NA + slot * EMF, ogs);
+            {   // lanes without a group of their own write a scratch word instead of branching around the stores
+                float* o0 = cfg.live ? emp + slot * EMF : s_scratch;
+                stv<J>(o0, ogl);
+                stv<J>(cfg.live ? o0 + NA : s_scratch, oh);
+                stv<J>(cfg.live ? o0 + 2 * NA : s_scratch, ogs);
             }
-            float npb = 0.0f, npl[J] = {}, nps[J] = {}, no4[J] = {}, ns4[J] = {};
+            float npb, npl[J], nps[J], no4[J] = {}, ns4[J] = {};
             int ne4[J];
 #pragma unroll
             for (int c = 0; c < J; ++c) ne4[c] = kQVoidE;
-            if (rdy) load_slot(slot1, ss1, npb, npl, nps, no4, ns4, ne4);
+            load_slot(slot1, ss1, npb, npl, nps, no4, ns4, ne4);      // (stale when the slot is not there yet: read again below)
             mbar_arrive(&occ_full[slot]);
             S2P_MARK(2);
             side_barrier(nthr);
