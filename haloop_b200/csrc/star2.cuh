@@ -82,7 +82,7 @@ struct Star2Params {
 //   [4 + a] label emission -> label occupancy     [4 + NA + a] star emission -> h     [4 + 2 NA + a] -> star occupancy
 __host__ __device__ inline int star2_em_floats(int NLmax) { return 4 + 12 * NLmax; }
 
-struct Star2Smem { int bars, mail, red, tgt, em, st, rows, total; };
+struct Star2Smem { int bars, mail, red, tscr, tgt, em, st, rows, total; };
 __host__ __device__ inline Star2Smem star2_smem(int W, int R, int NS, int V, int Sp, int NLmax, bool bwd) {
     const int kSR = R, kSNE = 2 * R;
     Star2Smem s;
@@ -91,6 +91,7 @@ __host__ __device__ inline Star2Smem star2_smem(int W, int R, int NS, int V, int
     s.bars = take(8 * (kSR * NS + 2 * kSNE + kSR));
     s.mail = take(16 * 2 * W);
     s.red = take(16 * W + 16);
+    s.tscr = take(bwd ? 16 * 32 : 0);            // 16 scratch bytes per lane: where lanes without a group put their occupancies
     s.tgt = take(4 * round_up(Sp + 1, 128));
     s.em = take(4 * kSNE * star2_em_floats(NLmax));
     s.st = take(bwd ? 4 * kSR * 12 * NLmax : 0);          // stored rows of the other side: one slot per row warp
@@ -372,9 +373,11 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
             s2_quad_sums<DIR>(s, cfg.allowed, n0, nl, ne, q);
             s2_quad_emit(s, q, pb, pl, ps, pen);
             if (lane == 31) mail[(i & 1) * W + w] = star_mail<DIR>(s);
-            float npb, npl[J], nps[J];
-            load_slot(slot1, npb, npl, nps);          // (stale words when the slot is not there yet: read again below)
-            if (rdy) mbar_arrive(&em_empty[slot1]);   // (before this step's global stores: the release would wait for them)
+            float npb = 0.0f, npl[J] = {}, nps[J] = {};
+            if (rdy) {        // warp-uniform; (before this step's global stores: the release of the arrival would wait for them)
+                load_slot(slot1, npb, npl, nps);
+                mbar_arrive(&em_empty[slot1]);
+            }
             stv<J>(trow, s.lb);
             stv<J>(trow + NL4, s.st);
             stv<J>(trow + 2 * NL4, s.e);
@@ -759,7 +762,7 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
     const float pen = p.hdr[0];
     if (lane == 31) mail[((steps1 + 1) & 1) * W + w] = dir ? star_mail<1>(s) : star_mail<0>(s);
     float* emp = s_em + 4 + J * cfg.g;                      // my J label emissions / occupancies in slot 0
-    float* s_scratch = (float*)(smem + sm.red);             // (the Z reduction area is idle in this kernel)
+    float* s_scratch = (float*)(smem + sm.tscr) + 4 * lane;
     const int* stp = s_st + J * cfg.g;                      // the other side's label states of my group in slot 0
     side_barrier(nthr);
 
@@ -810,11 +813,11 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
                 stv<J>(cfg.live ? o0 + NA : s_scratch, oh);
                 stv<J>(cfg.live ? o0 + 2 * NA : s_scratch, ogs);
             }
-            float npb, npl[J], nps[J], no4[J] = {}, ns4[J] = {};
+            float npb = 0.0f, npl[J] = {}, nps[J] = {}, no4[J] = {}, ns4[J] = {};
             int ne4[J];
 #pragma unroll
             for (int c = 0; c < J; ++c) ne4[c] = kQVoidE;
-            load_slot(slot1, ss1, npb, npl, nps, no4, ns4, ne4);      // (stale when the slot is not there yet: read again below)
+            if (rdy) load_slot(slot1, ss1, npb, npl, nps, no4, ns4, ne4);      // warp-uniform
             mbar_arrive(&occ_full[slot]);
             S2P_MARK(2);
             side_barrier(nthr);
