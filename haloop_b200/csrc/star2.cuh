@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_fwd_kernel(Star2Para
             s2_quad_sums<DIR>(s, cfg.allowed, n0, nl, ne, q);
             s2_quad_emit(s, q, pb, pl, ps, pen);
             if (lane == 31) mail[(i & 1) * W + w] = star_mail<DIR>(s);
-            float npb = 0.0f, npl[J] = {}, nps[J] = {};
+            float npb, npl[J], nps[J];          // (assigned on both ways to their only use, behind `more`)
             if (rdy) {        // warp-uniform; (before this step's global stores: the release of the arrival would wait for them)
                 load_slot(slot1, npb, npl, nps);
                 mbar_arrive(&em_empty[slot1]);
@@ -813,10 +813,8 @@ __global__ void __launch_bounds__(32 * (W + R), MINB) star2_bwd_kernel(Star2Para
                 stv<J>(cfg.live ? o0 + NA : s_scratch, oh);
                 stv<J>(cfg.live ? o0 + 2 * NA : s_scratch, ogs);
             }
-            float npb = 0.0f, npl[J] = {}, nps[J] = {}, no4[J] = {}, ns4[J] = {};
+            float npb, npl[J], nps[J], no4[J], ns4[J];      // (assigned on both ways to their only use, behind `more`)
             int ne4[J];
-#pragma unroll
-            for (int c = 0; c < J; ++c) ne4[c] = kQVoidE;
             if (rdy) load_slot(slot1, ss1, npb, npl, nps, no4, ns4, ne4);      // warp-uniform
             mbar_arrive(&occ_full[slot]);
             S2P_MARK(2);
